@@ -1,0 +1,153 @@
+/* made_b200 — C ABI of the B200-native MaDe inference + scoring hot path.
+ *
+ * The reference (xxayt/MGSV) is pure Python/PyTorch, so the "FFI" a maintainer binds is ctypes
+ * from the Python modules named below (see INTEGRATION.md for the stubs).  Every entry point:
+ *   - takes plain device pointers (contiguous, row-major, 16-byte aligned) and sizes,
+ *   - enqueues on the given CUDA stream (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and never synchronises,
+ *   - returns MADE_OK or a negative MADE_E* code; made_last_error_string() gives the text
+ *     (thread-local).  The Python shim raises ValueError for MADE_EINVAL / MADE_EUNSUPPORTED and
+ *     RuntimeError otherwise, matching the reference's exception conventions
+ *     (model_Uni.py:275, span_utils.py:107-108).
+ * The caller owns every buffer.  A made_ctx owns packed weights and a workspace; one ctx per
+ * (process, device), calls on it serialised by the caller (the reference is single-threaded).
+ */
+#ifndef MADE_B200_H_
+#define MADE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MADE_ABI_VERSION 1
+
+#define MADE_OK 0
+#define MADE_EINVAL (-1)        /* bad shape / pointer / argument            */
+#define MADE_ECUDA (-2)         /* CUDA runtime or driver error              */
+#define MADE_ENOMEM (-3)        /* workspace allocation failed               */
+#define MADE_EUNSUPPORTED (-4)  /* config outside the shipped MaDe config    */
+#define MADE_ESTATE (-5)        /* weights not loaded / ctx misuse           */
+
+#define MADE_DTYPE_F32 0
+#define MADE_DTYPE_BF16 1
+
+#define MADE_VIDEO 0
+#define MADE_MUSIC 1
+
+typedef struct made_ctx made_ctx;
+
+const char* made_last_error_string(void);
+int made_abi_version(void);
+/* MADE_OK iff `device` is an sm_100 part. */
+int made_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * span utilities — music_detr/span_utils.py, bit-exact fp32
+ * ------------------------------------------------------------------------------------------- */
+/* span_cw_to_se (span_utils.py:15-24): cw [n,2] -> se [n,2] */
+int made_span_cw_to_se(const float* cw, float* se, int64_t n, void* stream);
+/* generalized_temporal_iou (span_utils.py:86-115): spans1_se [n,2], spans2_se [m,2] -> giou [n,m] */
+int made_giou(const float* spans1_se, int64_t n, const float* spans2_se, int64_t m, float* giou,
+              void* stream);
+/* temporal_iou (span_utils.py:39-66): -> iou [n,m], union [n,m] */
+int made_temporal_iou(const float* spans1_se, int64_t n, const float* spans2_se, int64_t m,
+                      float* iou, float* uni, void* stream);
+/* HungarianMatcher cost matrix (matcher.py:66-88) for (c,w) spans given the foreground softmax
+ * probabilities: C = w_span*L1 + w_giou*(-gIoU) + w_class*(-p_fg), [n,m].  The caller has already
+ * dropped zero-width targets (matcher.py:59). */
+int made_matcher_cost(const float* prob_fg, const float* out_spans_cw, int64_t n,
+                      const float* tgt_spans_cw, int64_t m, float w_span, float w_giou,
+                      float w_class, float* cost, void* stream);
+/* Driver post-processing (test-MaDe.py:306-316) fused with detr_iou (span_utils.py:147-170,
+ * 119-145): logits [n,2], spans_cw [n,2], gt_moment [n,2] seconds, m_duration [n]
+ * -> pred_st, pred_ed (seconds), score (foreground prob), iou (nullable). */
+int made_moment_postproc(const float* pred_logits, const float* pred_spans_cw,
+                         const float* gt_moment, const float* m_duration, float max_m_duration,
+                         int64_t n, float* pred_st, float* pred_ed, float* score, float* iou,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ranking — utils/util_test.py:32-97 (Recall_metrics, dedup=True) + test-MaDe.py:401-403
+ * ------------------------------------------------------------------------------------------- */
+/* Scores are double(single[r,c]) + double(dual[r,c]) (dual nullable).  Per row r:
+ *   rank_out[r]  = number of distinct music ids strictly ahead of the ground truth, where the GT
+ *                  score is the best column of the GT id: gt_col[r] must be the LAST column
+ *                  carrying that id and prev_same[c] the previous column with the same id as c
+ *                  (-1 if none; prev_same nullable = all ids distinct).  If gt_score_in is given
+ *                  (multi-GPU: the GT lives on another shard) it replaces the gt_col walk.
+ *   topk_idx/topk_score [n_rows,k] = exact top-k, score descending, lower column first on ties;
+ *                  indices are column + col_offset. k <= 256. */
+int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n_rows,
+                   int64_t n_cols, const int32_t* gt_col, const double* gt_score_in,
+                   const int32_t* prev_same, int32_t col_offset, int k, int32_t* topk_idx,
+                   double* topk_score, int32_t* rank_out, double* gt_score_out, void* stream);
+/* Merge per-shard candidates [n_rows, n_cand] (idx -1 = empty) into the global top-k. */
+int made_topk_merge(const double* cand_score, const int32_t* cand_idx, int64_t n_rows, int n_cand,
+                    int k, int32_t* out_idx, double* out_score, void* stream);
+/* cal_distance(..., "COS") (modules/loss.py:52-56): out[i,j] = <a_i/|a_i|, b_j/|b_j|>, fp32. */
+int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d, float* out,
+                    int64_t ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * model context — model/model_Uni.py:14 (Uni_model), shipped config only
+ * ------------------------------------------------------------------------------------------- */
+int made_ctx_create(made_ctx** out, int device);
+int made_ctx_destroy(made_ctx* ctx);
+/* Weights by reference state_dict key (util_train.py:51-53): n host fp32 arrays.
+ * Packs bf16 GEMM operands and the folded X-Pool / decoder weights. */
+int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const float* const* host_ptrs,
+                          const int64_t* numels, void* stream);
+
+/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32 or bf16),
+ * masks [B,L] float {0,1}; L,Din = 50,512 (MADE_VIDEO) or 96,768 (MADE_MUSIC).
+ * -> seq_bf16 [B,L,256] bf16, seq_f32 [B,L,256] (nullable), pooled [B,256] fp32 (L2-normalised). */
+int made_encode(made_ctx* ctx, int modality, const void* feats, int feats_dtype, const float* masks,
+                int64_t B, void* seq_bf16, float* seq_f32, float* pooled, void* stream);
+
+/* Per-track X-Pool operands from encoded segments (modules/transformer.py:165, 102-106 folded):
+ * seg_bf16 [N,96,256], seg_masks [N,96] -> kz [N*96,768] bf16 (K | V'' | Z''),
+ * gram [N*96,96] bf16, maskbits [N,4] u32. */
+int made_gallery_prepare(made_ctx* ctx, const void* seg_bf16, const float* seg_masks, int64_t N,
+                         void* kz, void* gram, uint32_t* maskbits, void* stream);
+/* Per-query X-Pool operands (modules/transformer.py:164, 98; metrics.py:19):
+ * video_feats [N,256] fp32 -> q [N,256] bf16 (q_proj(LN1(v))/16), vhat [N,256] fp16. */
+int made_query_prepare(made_ctx* ctx, const float* video_feats, int64_t N, void* q, void* vhat,
+                       void* stream);
+/* Transformer_XA + sim_matrix_music_pooling fused (modules/transformer.py:156-180,
+ * modules/metrics.py:10-24): sim[v, col_offset + m] for v < N_v, m < N_m; sim row stride ld. */
+int made_xpool_score(made_ctx* ctx, const void* q, const void* vhat, int64_t n_queries,
+                     const void* kz, const void* gram, const uint32_t* maskbits, int64_t n_tracks,
+                     float* sim, int64_t ld, int64_t col_offset, void* stream);
+
+/* Moment detection for B (query, track) pairs — model_Uni.py:207-227 + calc_output :117-150:
+ * concat fusion, PositionEmbeddingSine, DETR encoder x2 / decoder x6, heads.
+ * frame_bf16 [Bv,50,256], frame_masks [Bv,50], seg_bf16 [Nm,96,256], seg_masks [Nm,96],
+ * track_idx [B] (nullable = identity) picks the track paired with query b, video_feats [B,256].
+ * -> hs [6,B,256] (through decoder.norm), pred_logits [6,B,2], pred_spans [6,B,2] (sigmoid (c,w)),
+ *    proj_queries [6,B,256] (nullable), proj_vid_mem [B,50,256] (nullable), memory [B,146,256]
+ *    fp32 (nullable). */
+int made_detr_detect(made_ctx* ctx, const void* frame_bf16, const float* frame_masks,
+                     const void* seg_bf16, const float* seg_masks, const int32_t* track_idx,
+                     const float* video_feats, int64_t B, float* hs, float* pred_logits,
+                     float* pred_spans, float* proj_queries, float* proj_vid_mem, float* memory,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * building blocks exported for the parity tests
+ * ------------------------------------------------------------------------------------------- */
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias (+ residual)) with optional LayerNorm over N (N == 256).
+ * A, W bf16; bias/gamma/beta fp32 (nullable); residual fp32 [M,N] (nullable);
+ * act: 0 none, 1 GELU(erf), 2 ReLU; out_bf16 / out_f32 nullable (at least one). */
+int made_gemm_bf16(const void* A, const void* W, int64_t M, int N, int K, const float* bias,
+                   const float* residual, int act, const float* ln_gamma, const float* ln_beta,
+                   void* out_bf16, float* out_f32, void* stream);
+/* softmax(Q K^T / sqrt(32) + key mask) V for 8 heads of 32: q,k,v,out [B*L, 256] bf16. */
+int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B,
+                  int L, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADE_B200_H_ */

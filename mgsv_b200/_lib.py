@@ -1,0 +1,97 @@
+"""ctypes binding of libmade_b200.so (include/made_b200.h).  No CPU fallback: if the library is
+missing it is built with nvcc; if that fails, importing raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+_LIB: Optional[C.CDLL] = None
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
+F32, BF16 = 0, 1
+VIDEO, MUSIC = 0, 1
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int
+_f = C.c_float
+
+# name -> argtypes, in the order of include/made_b200.h
+SIGNATURES = {
+    "made_abi_version": [],
+    "made_device_check": [_i32],
+    "made_span_cw_to_se": [_p, _p, _i64, _p],
+    "made_giou": [_p, _i64, _p, _i64, _p, _p],
+    "made_temporal_iou": [_p, _i64, _p, _i64, _p, _p, _p],
+    "made_matcher_cost": [_p, _p, _i64, _p, _i64, _f, _f, _f, _p, _p],
+    "made_moment_postproc": [_p, _p, _p, _p, _f, _i64, _p, _p, _p, _p, _p],
+    "made_rank_topk": [_p, _p, _i64, _i64, _i64, _p, _p, _p, C.c_int32, _i32, _p, _p, _p, _p, _p],
+    "made_topk_merge": [_p, _p, _i64, _i32, _i32, _p, _p, _p],
+    "made_cosine_sim": [_p, _i64, _p, _i64, _i32, _p, _i64, _p],
+    "made_ctx_create": [C.POINTER(_p), _i32],
+    "made_ctx_destroy": [_p],
+    "made_ctx_load_weights": [_p, _i32, C.POINTER(C.c_char_p), C.POINTER(_p), C.POINTER(_i64), _p],
+    "made_encode": [_p, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p],
+    "made_gallery_prepare": [_p, _p, _p, _i64, _p, _p, _p, _p],
+    "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
+    "made_xpool_score": [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _p],
+    "made_detr_detect": [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "made_gemm_bf16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
+    "made_mha_core": [_p, _p, _p, _p, _i64, _i32, _p, _p],
+}
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if _build.needs_build():
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    lib.made_last_error_string.restype = C.c_char_p
+    lib.made_last_error_string.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Map MADE_E* to the reference's exception conventions (ValueError for unsupported/invalid
+    arguments, RuntimeError for runtime failures)."""
+    if rc == OK:
+        return
+    msg = load().made_last_error_string().decode("utf-8", "replace")
+    if rc in (EINVAL, EUNSUPPORTED):
+        raise ValueError(f"made_b200: {msg}")
+    raise RuntimeError(f"made_b200 (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("made_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError("made_b200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("made_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

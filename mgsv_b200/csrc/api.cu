@@ -1,0 +1,827 @@
+// C ABI entry points that own state: the model context (packed weights + workspace) and the
+// host-side orchestration of the encoder / X-Pool / DETR kernel sequences.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "prep.cuh"
+
+using namespace made;
+
+namespace {
+
+constexpr int D = 256, DFF = 1024, LV = 50, LM = 96, LD = 146, NENC = 2, NDEC = 6;
+
+uint16_t f2bf(float f) {  // round-to-nearest-even, NaN-preserving
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+struct Lin {            // y = x W^T + b, W [out,in] bf16 on device, b fp32
+  __nv_bfloat16* w = nullptr;
+  float* b = nullptr;
+};
+struct LNp {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+
+struct EncW {
+  int L = 0, din = 0;
+  Lin proj, in_proj, out_proj, ff1, ff2, fin;
+  LNp ln1, ln2;
+  float* pe = nullptr;  // [L,256]
+};
+struct DetrEncW {
+  Lin qk, v, out, ff1, ff2;
+  LNp n1, n2;
+};
+struct DetrDecW {
+  Lin sa, q, out, ff1, ff2;
+  LNp n1, n2, n3;
+};
+
+}  // namespace
+
+struct made_ctx {
+  int device = 0;
+  bool loaded = false;
+  std::unordered_map<std::string, std::vector<float>> host;
+  std::vector<void*> allocs;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0, ws_off = 0;
+
+  EncW enc[2];
+  LNp xp_ln1;
+  Lin xp_q, xp_kvz;
+  DetrEncW denc[NENC];
+  DetrDecW ddec[NDEC];
+  Lin dec_kall, dec_vall;
+  LNp dec_norm;
+  Lin span0, span1, pq, pv;
+  float *span2_w = nullptr, *span2_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  float* inv_dim_t = nullptr;
+
+  // ---- workspace arena ----
+  int reserve(size_t bytes) {
+    ws_off = 0;
+    if (bytes <= ws_bytes) return MADE_OK;
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    ws_bytes = 0;
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&ws, want);
+    if (e != cudaSuccess) {
+      set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return MADE_ENOMEM;
+    }
+    ws_bytes = want;
+    return MADE_OK;
+  }
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(ws + ws_off);
+    ws_off += bytes;
+    return p;
+  }
+};
+
+namespace {
+
+size_t padded(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+
+// ---- weight upload helpers -------------------------------------------------------------------
+int get(made_ctx* c, const std::string& key, size_t numel, const std::vector<float>** out) {
+  auto it = c->host.find(key);
+  if (it == c->host.end()) {
+    set_error("load_weights: missing state_dict key '%s'", key.c_str());
+    return MADE_EINVAL;
+  }
+  if (it->second.size() != numel) {
+    set_error("load_weights: key '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+    return MADE_EINVAL;
+  }
+  *out = &it->second;
+  return MADE_OK;
+}
+
+int up_f32(made_ctx* c, const float* src, size_t n, float** dst) {
+  void* p = nullptr;
+  MADE_CUDA(cudaMalloc(&p, n * 4));
+  c->allocs.push_back(p);
+  MADE_CUDA(cudaMemcpy(p, src, n * 4, cudaMemcpyHostToDevice));
+  *dst = static_cast<float*>(p);
+  return MADE_OK;
+}
+
+int up_bf16(made_ctx* c, const float* src, size_t n, __nv_bfloat16** dst) {
+  std::vector<uint16_t> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = f2bf(src[i]);
+  void* p = nullptr;
+  MADE_CUDA(cudaMalloc(&p, n * 2));
+  c->allocs.push_back(p);
+  MADE_CUDA(cudaMemcpy(p, tmp.data(), n * 2, cudaMemcpyHostToDevice));
+  *dst = static_cast<__nv_bfloat16*>(p);
+  return MADE_OK;
+}
+
+int up_lin(made_ctx* c, const float* w, const float* b, size_t out_f, size_t in_f, Lin* lin) {
+  MADE_TRY(up_bf16(c, w, out_f * in_f, &lin->w));
+  MADE_TRY(up_f32(c, b, out_f, &lin->b));
+  return MADE_OK;
+}
+
+int load_lin(made_ctx* c, const std::string& prefix, size_t out_f, size_t in_f, Lin* lin,
+             const char* wname = ".weight", const char* bname = ".bias") {
+  const std::vector<float>*w, *b;
+  MADE_TRY(get(c, prefix + wname, out_f * in_f, &w));
+  MADE_TRY(get(c, prefix + bname, out_f, &b));
+  return up_lin(c, w->data(), b->data(), out_f, in_f, lin);
+}
+
+int load_ln(made_ctx* c, const std::string& prefix, LNp* ln) {
+  const std::vector<float>*g, *b;
+  MADE_TRY(get(c, prefix + ".weight", D, &g));
+  MADE_TRY(get(c, prefix + ".bias", D, &b));
+  MADE_TRY(up_f32(c, g->data(), D, &ln->g));
+  MADE_TRY(up_f32(c, b->data(), D, &ln->b));
+  return MADE_OK;
+}
+
+// C[n x m] = A[n x k] * B[k x m] in double
+std::vector<double> matmul(const std::vector<double>& A, const std::vector<double>& B, int n, int k, int m) {
+  std::vector<double> C(static_cast<size_t>(n) * m, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int kk = 0; kk < k; ++kk) {
+      const double a = A[static_cast<size_t>(i) * k + kk];
+      const double* br = &B[static_cast<size_t>(kk) * m];
+      double* cr = &C[static_cast<size_t>(i) * m];
+      for (int j = 0; j < m; ++j) cr[j] += a * br[j];
+    }
+  return C;
+}
+std::vector<double> to_d(const float* p, size_t n) { return std::vector<double>(p, p + n); }
+std::vector<float> to_f(const std::vector<double>& v) { return std::vector<float>(v.begin(), v.end()); }
+
+int load_encoder(made_ctx* c, int modality) {
+  EncW& e = c->enc[modality];
+  const bool vid = modality == MADE_VIDEO;
+  e.L = vid ? LV : LM;
+  e.din = vid ? 512 : 768;
+  const std::string tr = vid ? "video_transformer" : "audio_transformer";
+  MADE_TRY(load_lin(c, vid ? "vit_proj" : "ast_proj", D, e.din, &e.proj));
+  MADE_TRY(load_ln(c, tr + ".layers.0.0", &e.ln1));
+  MADE_TRY(load_lin(c, tr + ".layers.0.1", 3 * D, D, &e.in_proj, ".in_proj_weight", ".in_proj_bias"));
+  MADE_TRY(load_lin(c, tr + ".layers.0.1.out_proj", D, D, &e.out_proj));
+  MADE_TRY(load_ln(c, tr + ".layers.0.2", &e.ln2));
+  MADE_TRY(load_lin(c, tr + ".layers.0.3.0", DFF, D, &e.ff1));
+  MADE_TRY(load_lin(c, tr + ".layers.0.3.3", D, DFF, &e.ff2));
+  MADE_TRY(load_lin(c, tr + ".final_linear", D, D, &e.fin));
+  const std::vector<float>* pe;
+  const size_t pe_len = vid ? 250 : 300;
+  MADE_TRY(get(c, vid ? "video_position_embedding.pe" : "audio_position_embedding.pe", pe_len * D, &pe));
+  MADE_TRY(up_f32(c, pe->data(), static_cast<size_t>(e.L) * D, &e.pe));  // first L rows (model_Base.py:533)
+  return MADE_OK;
+}
+
+int load_xpool(made_ctx* c, cudaStream_t st) {
+  const std::string x = "video_guided_to_music_pooling_cross_transformer";
+  MADE_TRY(load_ln(c, x + ".layer_norm1", &c->xp_ln1));
+  const std::vector<float>*wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo, *wl, *bl, *g2, *b2, *g3, *b3;
+  MADE_TRY(get(c, x + ".cross_attn.q_proj.weight", D * D, &wq));
+  MADE_TRY(get(c, x + ".cross_attn.q_proj.bias", D, &bq));
+  MADE_TRY(get(c, x + ".cross_attn.k_proj.weight", D * D, &wk));
+  MADE_TRY(get(c, x + ".cross_attn.k_proj.bias", D, &bk));
+  MADE_TRY(get(c, x + ".cross_attn.v_proj.weight", D * D, &wv));
+  MADE_TRY(get(c, x + ".cross_attn.v_proj.bias", D, &bv));
+  MADE_TRY(get(c, x + ".cross_attn.out_proj.weight", D * D, &wo));
+  MADE_TRY(get(c, x + ".cross_attn.out_proj.bias", D, &bo));
+  MADE_TRY(get(c, x + ".linear_proj.weight", D * D, &wl));
+  MADE_TRY(get(c, x + ".linear_proj.bias", D, &bl));
+  MADE_TRY(get(c, x + ".layer_norm2.weight", D, &g2));
+  MADE_TRY(get(c, x + ".layer_norm2.bias", D, &b2));
+  MADE_TRY(get(c, x + ".layer_norm3.weight", D, &g3));
+  MADE_TRY(get(c, x + ".layer_norm3.bias", D, &b3));
+  // q = (Wq LN1(v) + bq) / sqrt(256)   (modules/transformer.py:98,111) — exact power-of-two scale
+  {
+    std::vector<float> w(D * D), b(D);
+    for (int i = 0; i < D * D; ++i) w[i] = (*wq)[i] * 0.0625f;
+    for (int i = 0; i < D; ++i) b[i] = (*bq)[i] * 0.0625f;
+    MADE_TRY(up_lin(c, w.data(), b.data(), D, D, &c->xp_q));
+  }
+  // V'' = centre_d( Wo (Wv s + bv) + bo ),  Z'' = W' V'',  W' = (I + Wl) diag(gamma2)
+  std::vector<double> Wo = to_d(wo->data(), D * D), Wv = to_d(wv->data(), D * D);
+  std::vector<double> Wvo = matmul(Wo, Wv, D, D, D);
+  std::vector<double> bvo(D, 0.0);
+  for (int i = 0; i < D; ++i) {
+    double s = (*bo)[i];
+    for (int k = 0; k < D; ++k) s += Wo[static_cast<size_t>(i) * D + k] * (*bv)[k];
+    bvo[i] = s;
+  }
+  for (int j = 0; j < D; ++j) {
+    double m = 0;
+    for (int i = 0; i < D; ++i) m += Wvo[static_cast<size_t>(i) * D + j];
+    m /= D;
+    for (int i = 0; i < D; ++i) Wvo[static_cast<size_t>(i) * D + j] -= m;
+  }
+  {
+    double m = 0;
+    for (int i = 0; i < D; ++i) m += bvo[i];
+    m /= D;
+    for (int i = 0; i < D; ++i) bvo[i] -= m;
+  }
+  std::vector<double> Wp(static_cast<size_t>(D) * D);
+  std::vector<float> bprime(D);
+  for (int n = 0; n < D; ++n) {
+    double s = (*b2)[n] + (*bl)[n];
+    for (int d = 0; d < D; ++d) {
+      Wp[static_cast<size_t>(n) * D + d] = ((n == d ? 1.0 : 0.0) + (*wl)[static_cast<size_t>(n) * D + d]) * (*g2)[d];
+      s += static_cast<double>((*wl)[static_cast<size_t>(n) * D + d]) * (*b2)[d];
+    }
+    bprime[n] = static_cast<float>(s);
+  }
+  std::vector<double> Wz = matmul(Wp, Wvo, D, D, D);
+  std::vector<double> bz(D, 0.0);
+  for (int n = 0; n < D; ++n) {
+    double s = 0;
+    for (int d = 0; d < D; ++d) s += Wp[static_cast<size_t>(n) * D + d] * bvo[d];
+    bz[n] = s;
+  }
+  std::vector<float> w(static_cast<size_t>(3) * D * D), b(3 * D);
+  memcpy(w.data(), wk->data(), sizeof(float) * D * D);
+  for (int i = 0; i < D * D; ++i) {
+    w[static_cast<size_t>(D) * D + i] = static_cast<float>(Wvo[i]);
+    w[static_cast<size_t>(2) * D * D + i] = static_cast<float>(Wz[i]);
+  }
+  for (int i = 0; i < D; ++i) {
+    b[i] = (*bk)[i];
+    b[D + i] = static_cast<float>(bvo[i]);
+    b[2 * D + i] = static_cast<float>(bz[i]);
+  }
+  MADE_TRY(up_lin(c, w.data(), b.data(), 3 * D, D, &c->xp_kvz));
+  MADE_TRY(xpool_set_constants(bprime.data(), g3->data(), b3->data(), st));
+  MADE_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  return MADE_OK;
+}
+
+int load_detr(made_ctx* c) {
+  for (int l = 0; l < NENC; ++l) {
+    const std::string p = "detr_transformer.encoder.layers." + std::to_string(l);
+    const std::vector<float>*w, *b;
+    MADE_TRY(get(c, p + ".self_attn.in_proj_weight", 3 * D * D, &w));
+    MADE_TRY(get(c, p + ".self_attn.in_proj_bias", 3 * D, &b));
+    MADE_TRY(up_lin(c, w->data(), b->data(), 2 * D, D, &c->denc[l].qk));
+    MADE_TRY(up_lin(c, w->data() + 2 * D * D, b->data() + 2 * D, D, D, &c->denc[l].v));
+    MADE_TRY(load_lin(c, p + ".self_attn.out_proj", D, D, &c->denc[l].out));
+    MADE_TRY(load_lin(c, p + ".linear1", DFF, D, &c->denc[l].ff1));
+    MADE_TRY(load_lin(c, p + ".linear2", D, DFF, &c->denc[l].ff2));
+    MADE_TRY(load_ln(c, p + ".norm1", &c->denc[l].n1));
+    MADE_TRY(load_ln(c, p + ".norm2", &c->denc[l].n2));
+  }
+  const std::vector<float>* qpos;
+  MADE_TRY(get(c, "decoder_query_embed.weight", D, &qpos));
+  std::vector<float> wk_all(static_cast<size_t>(NDEC) * D * D), bk_all(NDEC * D), wv_all(static_cast<size_t>(NDEC) * D * D),
+      bv_all(NDEC * D);
+  for (int l = 0; l < NDEC; ++l) {
+    const std::string p = "detr_transformer.decoder.layers." + std::to_string(l);
+    const std::vector<float>*sw, *sb, *so, *sob, *cw, *cb;
+    MADE_TRY(get(c, p + ".self_attn.in_proj_weight", 3 * D * D, &sw));
+    MADE_TRY(get(c, p + ".self_attn.in_proj_bias", 3 * D, &sb));
+    MADE_TRY(get(c, p + ".self_attn.out_proj.weight", D * D, &so));
+    MADE_TRY(get(c, p + ".self_attn.out_proj.bias", D, &sob));
+    // single query: softmax over one key = 1, so SA(tgt) = Wo (Wv tgt + bv) + bo  
+    std::vector<double> Wsa = matmul(to_d(so->data(), D * D), to_d(sw->data() + 2 * D * D, D * D), D, D, D);
+    std::vector<float> bsa(D);
+    for (int i = 0; i < D; ++i) {
+      double s = (*sob)[i];
+      for (int k = 0; k < D; ++k) s += static_cast<double>((*so)[static_cast<size_t>(i) * D + k]) * (*sb)[2 * D + k];
+      bsa[i] = static_cast<float>(s);
+    }
+    std::vector<float> wsa = to_f(Wsa);
+    MADE_TRY(up_lin(c, wsa.data(), bsa.data(), D, D, &c->ddec[l].sa));
+    MADE_TRY(get(c, p + ".multihead_attn.in_proj_weight", 3 * D * D, &cw));
+    MADE_TRY(get(c, p + ".multihead_attn.in_proj_bias", 3 * D, &cb));
+    // q = Wq (tgt + query_pos) + bq = Wq tgt + (bq + Wq query_pos)
+    std::vector<float> bq(D);
+    for (int i = 0; i < D; ++i) {
+      double s = (*cb)[i];
+      for (int k = 0; k < D; ++k) s += static_cast<double>((*cw)[static_cast<size_t>(i) * D + k]) * (*qpos)[k];
+      bq[i] = static_cast<float>(s);
+    }
+    MADE_TRY(up_lin(c, cw->data(), bq.data(), D, D, &c->ddec[l].q));
+    memcpy(&wk_all[static_cast<size_t>(l) * D * D], cw->data() + D * D, sizeof(float) * D * D);
+    memcpy(&bk_all[l * D], cb->data() + D, sizeof(float) * D);
+    memcpy(&wv_all[static_cast<size_t>(l) * D * D], cw->data() + 2 * D * D, sizeof(float) * D * D);
+    memcpy(&bv_all[l * D], cb->data() + 2 * D, sizeof(float) * D);
+    MADE_TRY(load_lin(c, p + ".multihead_attn.out_proj", D, D, &c->ddec[l].out));
+    MADE_TRY(load_lin(c, p + ".linear1", DFF, D, &c->ddec[l].ff1));
+    MADE_TRY(load_lin(c, p + ".linear2", D, DFF, &c->ddec[l].ff2));
+    MADE_TRY(load_ln(c, p + ".norm1", &c->ddec[l].n1));
+    MADE_TRY(load_ln(c, p + ".norm2", &c->ddec[l].n2));
+    MADE_TRY(load_ln(c, p + ".norm3", &c->ddec[l].n3));
+  }
+  MADE_TRY(up_lin(c, wk_all.data(), bk_all.data(), NDEC * D, D, &c->dec_kall));
+  MADE_TRY(up_lin(c, wv_all.data(), bv_all.data(), NDEC * D, D, &c->dec_vall));
+  MADE_TRY(load_ln(c, "detr_transformer.decoder.norm", &c->dec_norm));
+  MADE_TRY(load_lin(c, "span_embed.layers.0", D, D, &c->span0));
+  MADE_TRY(load_lin(c, "span_embed.layers.1", D, D, &c->span1));
+  MADE_TRY(load_lin(c, "contrastive_align_projection_query", D, D, &c->pq));
+  MADE_TRY(load_lin(c, "contrastive_align_projection_vid", D, D, &c->pv));
+  const std::vector<float>*w, *b;
+  MADE_TRY(get(c, "span_embed.layers.2.weight", 2 * D, &w));
+  MADE_TRY(get(c, "span_embed.layers.2.bias", 2, &b));
+  MADE_TRY(up_f32(c, w->data(), 2 * D, &c->span2_w));
+  MADE_TRY(up_f32(c, b->data(), 2, &c->span2_b));
+  MADE_TRY(get(c, "class_embed.weight", 2 * D, &w));
+  MADE_TRY(get(c, "class_embed.bias", 2, &b));
+  MADE_TRY(up_f32(c, w->data(), 2 * D, &c->cls_w));
+  MADE_TRY(up_f32(c, b->data(), 2, &c->cls_b));
+  // position_encoding.py:65-66: dim_t = 10000 ** (2 * (i // 2) / 256), fp32
+  std::vector<float> inv(D);
+  for (int i = 0; i < D; ++i) inv[i] = 1.0f / powf(10000.0f, static_cast<float>(2 * (i / 2)) / 256.0f);
+  MADE_TRY(up_f32(c, inv.data(), D, &c->inv_dim_t));
+  return MADE_OK;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+// plain linear helper: out = act(A W^T + b)
+int linear(const __nv_bfloat16* A, int64_t lda, const Lin& w, int64_t M, int N, int K, GemmEpilogue epi,
+           cudaStream_t st) {
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  epi.bias = w.b;
+  p.epi = epi;
+  return gemm_bf16_tc(A, lda, w.w, K, N, p, 256, st);
+}
+
+#define CTX_READY(ctx)                                                       \
+  do {                                                                       \
+    if (!(ctx)) { set_error("null made_ctx"); return MADE_EINVAL; }          \
+    if (!(ctx)->loaded) { set_error("made_ctx has no weights loaded"); return MADE_ESTATE; } \
+    MADE_CUDA(cudaSetDevice((ctx)->device));                                 \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int made_ctx_create(made_ctx** out, int device) {
+  MADE_REQUIRE(out, "ctx_create: null out");
+  MADE_TRY(made_device_check(device));
+  MADE_CUDA(cudaSetDevice(device));
+  made_ctx* c = new made_ctx();
+  c->device = device;
+  *out = c;
+  return MADE_OK;
+}
+
+int made_ctx_destroy(made_ctx* c) {
+  if (!c) return MADE_OK;
+  cudaSetDevice(c->device);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->ws) cudaFree(c->ws);
+  delete c;
+  return MADE_OK;
+}
+
+int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const float* const* host_ptrs,
+                          const int64_t* numels, void* stream) {
+  MADE_REQUIRE(c && names && host_ptrs && numels, "load_weights: null argument");
+  MADE_CUDA(cudaSetDevice(c->device));
+  for (void* p : c->allocs) cudaFree(p);
+  c->allocs.clear();
+  c->host.clear();
+  c->loaded = false;
+  for (int i = 0; i < n; ++i) c->host[names[i]] = std::vector<float>(host_ptrs[i], host_ptrs[i] + numels[i]);
+  MADE_TRY(load_encoder(c, MADE_VIDEO));
+  MADE_TRY(load_encoder(c, MADE_MUSIC));
+  MADE_TRY(load_xpool(c, static_cast<cudaStream_t>(stream)));
+  MADE_TRY(load_detr(c));
+  c->host.clear();
+  c->loaded = true;
+  return MADE_OK;
+}
+
+int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, const float* masks, int64_t B,
+                void* seq_bf16, float* seq_f32, float* pooled, void* stream) {
+  CTX_READY(c);
+  MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode: bad modality %d", modality);
+  MADE_REQUIRE(feats_dtype == MADE_DTYPE_F32 || feats_dtype == MADE_DTYPE_BF16, "encode: bad dtype");
+  if (B == 0) return MADE_OK;
+  MADE_REQUIRE(feats && masks && seq_bf16 && pooled, "encode: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const EncW& e = c->enc[modality];
+  const int64_t T = B * e.L;
+  MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
+  size_t need = padded(T * e.din, 2) + padded(T * D, 2) * 4 + padded(T * D, 4) * 3 + padded(T * 3 * D, 2) +
+                padded(T * DFF, 2);
+  MADE_TRY(c->reserve(need));
+  __nv_bfloat16* x0 = c->take<__nv_bfloat16>(T * e.din);
+  __nv_bfloat16* x1 = c->take<__nv_bfloat16>(T * D);
+  float* x1f = c->take<float>(T * D);
+  __nv_bfloat16* qkv = c->take<__nv_bfloat16>(T * 3 * D);
+  __nv_bfloat16* att = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* x2 = c->take<__nv_bfloat16>(T * D);
+  float* x2f = c->take<float>(T * D);
+  __nv_bfloat16* h = c->take<__nv_bfloat16>(T * DFF);
+  __nv_bfloat16* x3 = c->take<__nv_bfloat16>(T * D);
+  float* seqf = seq_f32 ? seq_f32 : c->take<float>(T * D);
+
+  // model_Base.py:556/595 masked_fill, cast to the GEMM operand type
+  MADE_TRY(cast_mask_rows(feats, feats_dtype == MADE_DTYPE_BF16, masks, T, e.din, x0, st));
+  {  // :559/598 projection, :533 += pe[:L], Transformer_enhancement norm1 (:86)
+    GemmEpilogue ep;
+    ep.row_table = e.pe;
+    ep.row_mod = e.L;
+    ep.ln_gamma = e.ln1.g;
+    ep.ln_beta = e.ln1.b;
+    ep.out_bf16 = x1;
+    ep.ld_bf16 = D;
+    ep.out_f32 = x1f;
+    ep.ld_f32 = D;
+    MADE_TRY(linear(x0, e.din, e.proj, T, D, e.din, ep, st));
+  }
+  {  // packed in_proj (nn.MultiheadAttention)
+    GemmEpilogue ep;
+    ep.out_bf16 = qkv;
+    ep.ld_bf16 = 3 * D;
+    MADE_TRY(linear(x1, D, e.in_proj, T, 3 * D, D, ep, st));
+  }
+  MADE_TRY(mha_core(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, masks, B, e.L, att, D, st));
+  {  // out_proj + residual (from the normed tensor, Q2) + norm2 (:87-88)
+    GemmEpilogue ep;
+    ep.residual = x1f;
+    ep.residual_f32 = 1;
+    ep.res_ld = D;
+    ep.ln_gamma = e.ln2.g;
+    ep.ln_beta = e.ln2.b;
+    ep.out_bf16 = x2;
+    ep.ld_bf16 = D;
+    ep.out_f32 = x2f;
+    ep.ld_f32 = D;
+    MADE_TRY(linear(att, D, e.out_proj, T, D, D, ep, st));
+  }
+  {  // FF: Linear -> GELU(erf)
+    GemmEpilogue ep;
+    ep.act = 1;
+    ep.out_bf16 = h;
+    ep.ld_bf16 = DFF;
+    MADE_TRY(linear(x2, D, e.ff1, T, DFF, D, ep, st));
+  }
+  {  // FF: Linear + residual (:89)
+    GemmEpilogue ep;
+    ep.residual = x2f;
+    ep.residual_f32 = 1;
+    ep.res_ld = D;
+    ep.out_bf16 = x3;
+    ep.ld_bf16 = D;
+    MADE_TRY(linear(h, DFF, e.ff2, T, D, DFF, ep, st));
+  }
+  {  // final_linear (:91) + masked_fill (:541)
+    GemmEpilogue ep;
+    ep.row_mask = masks;
+    ep.out_bf16 = static_cast<__nv_bfloat16*>(seq_bf16);
+    ep.ld_bf16 = D;
+    ep.out_f32 = seqf;
+    ep.ld_f32 = D;
+    MADE_TRY(linear(x3, D, e.fin, T, D, D, ep, st));
+  }
+  // masked mean + F.normalize (:579-580 / :615-616)
+  MADE_TRY(pool_norm(seqf, masks, B, e.L, pooled, st));
+  return MADE_OK;
+}
+
+int made_gallery_prepare(made_ctx* c, const void* seg_bf16, const float* seg_masks, int64_t N, void* kz,
+                         void* gram, uint32_t* maskbits, void* stream) {
+  CTX_READY(c);
+  if (N == 0) return MADE_OK;
+  MADE_REQUIRE(seg_bf16 && seg_masks && kz && gram && maskbits, "gallery_prepare: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = N * LM;
+  MADE_REQUIRE(T < (1LL << 31), "gallery_prepare: too many tracks in one call; chunk it");
+  MADE_TRY(c->reserve(padded(T * D, 2)));
+  __nv_bfloat16* sp = c->take<__nv_bfloat16>(T * D);
+  // shared LayerNorm1 on the segments (modules/transformer.py:165)
+  MADE_TRY(layernorm_rows(seg_bf16, 1, D, T, c->xp_ln1.g, c->xp_ln1.b, sp, nullptr, st));
+  __nv_bfloat16* kzb = static_cast<__nv_bfloat16*>(kz);
+  {
+    GemmEpilogue ep;
+    ep.out_bf16 = kzb;
+    ep.ld_bf16 = 3 * D;
+    MADE_TRY(linear(sp, D, c->xp_kvz, T, 3 * D, D, ep, st));
+  }
+  {  // per-track Gram matrix G = V'' V''^T (96 x 96), batched over tracks
+    GemmParams p;
+    p.M = T;
+    p.N = LM;
+    p.K = D;
+    p.m_stride = LM;
+    p.m_valid = LM;
+    p.b_batched = 1;
+    p.epi.out_bf16 = static_cast<__nv_bfloat16*>(gram);
+    p.epi.ld_bf16 = LM;
+    MADE_TRY(gemm_bf16_tc(kzb + D, 3 * D, kzb + D, 3 * D, T, p, 96, st));
+  }
+  MADE_TRY(mask_bits(seg_masks, N, maskbits, st));
+  return MADE_OK;
+}
+
+int made_query_prepare(made_ctx* c, const float* video_feats, int64_t N, void* q, void* vhat, void* stream) {
+  CTX_READY(c);
+  if (N == 0) return MADE_OK;
+  MADE_REQUIRE(video_feats && q && vhat, "query_prepare: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MADE_TRY(c->reserve(padded(N * D, 2)));
+  __nv_bfloat16* vp = c->take<__nv_bfloat16>(N * D);
+  MADE_TRY(layernorm_rows(video_feats, 0, D, N, c->xp_ln1.g, c->xp_ln1.b, vp, nullptr, st));
+  GemmEpilogue ep;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(q);
+  ep.ld_bf16 = D;
+  MADE_TRY(linear(vp, D, c->xp_q, N, D, D, ep, st));
+  MADE_TRY(vhat_rows(video_feats, N, static_cast<__half*>(vhat), st));
+  return MADE_OK;
+}
+
+int made_xpool_score(made_ctx* c, const void* q, const void* vhat, int64_t n_queries, const void* kz,
+                     const void* gram, const uint32_t* maskbits, int64_t n_tracks, float* sim, int64_t ld,
+                     int64_t col_offset, void* stream) {
+  CTX_READY(c);
+  MADE_REQUIRE(ld >= col_offset + n_tracks, "xpool_score: ld=%lld too small", (long long)ld);
+  return xpool_score(static_cast<const __nv_bfloat16*>(q), static_cast<const __half*>(vhat), n_queries,
+                     static_cast<const __nv_bfloat16*>(kz), 3 * D, 2 * D, static_cast<const __nv_bfloat16*>(gram),
+                     maskbits, n_tracks, sim, ld, col_offset, static_cast<cudaStream_t>(stream));
+}
+
+int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_masks, const void* seg_bf16,
+                     const float* seg_masks, const int32_t* track_idx, const float* video_feats, int64_t B,
+                     float* hs, float* pred_logits, float* pred_spans, float* proj_queries, float* proj_vid_mem,
+                     float* memory, void* stream) {
+  CTX_READY(c);
+  if (B == 0) return MADE_OK;
+  MADE_REQUIRE(frame_bf16 && frame_masks && seg_bf16 && seg_masks && video_feats && hs && pred_logits && pred_spans,
+               "detr_detect: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t T = B * LD;
+  MADE_REQUIRE(T < (1LL << 31), "detr_detect: batch too large; chunk the call");
+  const int64_t R = NDEC * B;
+  size_t need = padded(T * D, 2) * 8 + padded(T, 4) + padded(T * 2 * D, 2) + padded(T * D, 4) * 2 + padded(T * DFF, 2) +
+                padded(T * NDEC * D, 2) * 2 + padded(B * D, 2) * 6 + padded(B * D, 4) * 4 + padded(B * DFF, 2) +
+                padded(R * D, 4) + padded(R * D, 2) * 3;
+  MADE_TRY(c->reserve(need));
+  __nv_bfloat16* src = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* pos = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* srcpos = c->take<__nv_bfloat16>(T * D);
+  float* mask = c->take<float>(T);
+  __nv_bfloat16* qk = c->take<__nv_bfloat16>(T * 2 * D);
+  __nv_bfloat16* v = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* att = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* s1 = c->take<__nv_bfloat16>(T * D);
+  float* s1f = c->take<float>(T * D);
+  __nv_bfloat16* hbuf = c->take<__nv_bfloat16>(T * DFF);
+  __nv_bfloat16* src2 = c->take<__nv_bfloat16>(T * D);
+  __nv_bfloat16* srcpos2 = c->take<__nv_bfloat16>(T * D);
+  float* srcf = c->take<float>(T * D);
+  __nv_bfloat16* kall = c->take<__nv_bfloat16>(T * NDEC * D);
+  __nv_bfloat16* vall = c->take<__nv_bfloat16>(T * NDEC * D);
+  __nv_bfloat16* tgt = c->take<__nv_bfloat16>(B * D);
+  __nv_bfloat16* t1 = c->take<__nv_bfloat16>(B * D);
+  float* t1f = c->take<float>(B * D);
+  float* qf = c->take<float>(B * D);
+  __nv_bfloat16* ob = c->take<__nv_bfloat16>(B * D);
+  __nv_bfloat16* t2 = c->take<__nv_bfloat16>(B * D);
+  float* t2f = c->take<float>(B * D);
+  __nv_bfloat16* hdec = c->take<__nv_bfloat16>(B * DFF);
+  __nv_bfloat16* t3 = c->take<__nv_bfloat16>(B * D);
+  float* t3all = c->take<float>(R * D);
+  __nv_bfloat16* hsb = c->take<__nv_bfloat16>(R * D);
+  __nv_bfloat16* sp0 = c->take<__nv_bfloat16>(R * D);
+  __nv_bfloat16* sp1 = c->take<__nv_bfloat16>(R * D);
+
+  const __nv_bfloat16* fr = static_cast<const __nv_bfloat16*>(frame_bf16);
+  MADE_TRY(detr_prep(fr, frame_masks, static_cast<const __nv_bfloat16*>(seg_bf16), seg_masks, track_idx,
+                     c->inv_dim_t, B, src, pos, srcpos, mask, st));
+  // ---------------- encoder (forward_post, music_detr/transformer.py:191-210) ----------------
+  __nv_bfloat16 *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
+  for (int l = 0; l < NENC; ++l) {
+    const DetrEncW& w = c->denc[l];
+    {
+      GemmEpilogue ep;
+      ep.out_bf16 = qk;
+      ep.ld_bf16 = 2 * D;
+      MADE_TRY(linear(curpos, D, w.qk, T, 2 * D, D, ep, st));   // q = k = src + pos
+    }
+    {
+      GemmEpilogue ep;
+      ep.out_bf16 = v;
+      ep.ld_bf16 = D;
+      MADE_TRY(linear(cur, D, w.v, T, D, D, ep, st));           // value = src
+    }
+    MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, mask, B, LD, att, D, st));
+    {
+      GemmEpilogue ep;
+      if (l == 0) {
+        ep.residual = cur;
+        ep.residual_f32 = 0;
+      } else {
+        ep.residual = srcf;
+        ep.residual_f32 = 1;
+      }
+      ep.res_ld = D;
+      ep.ln_gamma = w.n1.g;
+      ep.ln_beta = w.n1.b;
+      ep.out_bf16 = s1;
+      ep.ld_bf16 = D;
+      ep.out_f32 = s1f;
+      ep.ld_f32 = D;
+      MADE_TRY(linear(att, D, w.out, T, D, D, ep, st));
+    }
+    {
+      GemmEpilogue ep;
+      ep.act = 2;
+      ep.out_bf16 = hbuf;
+      ep.ld_bf16 = DFF;
+      MADE_TRY(linear(s1, D, w.ff1, T, DFF, D, ep, st));
+    }
+    {
+      GemmEpilogue ep;
+      ep.residual = s1f;
+      ep.residual_f32 = 1;
+      ep.res_ld = D;
+      ep.ln_gamma = w.n2.g;
+      ep.ln_beta = w.n2.b;
+      ep.out_bf16 = nxt;
+      ep.ld_bf16 = D;
+      ep.out_f32 = srcf;
+      ep.ld_f32 = D;
+      ep.add2 = pos;
+      ep.add2_ld = D;
+      ep.out2_bf16 = nxtpos;
+      ep.ld_out2 = D;
+      MADE_TRY(linear(hbuf, DFF, w.ff2, T, D, DFF, ep, st));
+    }
+    __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+    t = curpos; curpos = nxtpos; nxtpos = t;
+  }
+  if (memory) MADE_CUDA(cudaMemcpyAsync(memory, srcf, static_cast<size_t>(T) * D * 4, cudaMemcpyDeviceToDevice, st));
+  // ---------------- decoder K/V of the memory for all six layers at once ----------------
+  {
+    GemmEpilogue ep;
+    ep.out_bf16 = kall;
+    ep.ld_bf16 = NDEC * D;
+    MADE_TRY(linear(curpos, D, c->dec_kall, T, NDEC * D, D, ep, st));   // key = memory + pos
+  }
+  {
+    GemmEpilogue ep;
+    ep.out_bf16 = vall;
+    ep.ld_bf16 = NDEC * D;
+    MADE_TRY(linear(cur, D, c->dec_vall, T, NDEC * D, D, ep, st));      // value = memory
+  }
+  // ---------------- decoder (forward_post :273-307), one moment query per sequence ----------------
+  cast_f32_bf16_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
+  MADE_CHECK_LAUNCH();
+  const __nv_bfloat16* tin = tgt;
+  const float* tinf = video_feats;
+  for (int l = 0; l < NDEC; ++l) {
+    const DetrDecW& w = c->ddec[l];
+    float* t3f = t3all + static_cast<size_t>(l) * B * D;
+    {
+      GemmEpilogue ep;   // self-attention on a single query (folded) + norm1
+      ep.residual = tinf;
+      ep.residual_f32 = 1;
+      ep.res_ld = D;
+      ep.ln_gamma = w.n1.g;
+      ep.ln_beta = w.n1.b;
+      ep.out_bf16 = t1;
+      ep.ld_bf16 = D;
+      ep.out_f32 = t1f;
+      ep.ld_f32 = D;
+      MADE_TRY(linear(tin, D, w.sa, B, D, D, ep, st));
+    }
+    {
+      GemmEpilogue ep;
+      ep.out_f32 = qf;
+      ep.ld_f32 = D;
+      MADE_TRY(linear(t1, D, w.q, B, D, D, ep, st));
+    }
+    MADE_TRY(dec_cross_attn(qf, kall + l * D, vall + l * D, NDEC * D, mask, B, LD, ob, st));
+    {
+      GemmEpilogue ep;
+      ep.residual = t1f;
+      ep.residual_f32 = 1;
+      ep.res_ld = D;
+      ep.ln_gamma = w.n2.g;
+      ep.ln_beta = w.n2.b;
+      ep.out_bf16 = t2;
+      ep.ld_bf16 = D;
+      ep.out_f32 = t2f;
+      ep.ld_f32 = D;
+      MADE_TRY(linear(ob, D, w.out, B, D, D, ep, st));
+    }
+    {
+      GemmEpilogue ep;
+      ep.act = 2;
+      ep.out_bf16 = hdec;
+      ep.ld_bf16 = DFF;
+      MADE_TRY(linear(t2, D, w.ff1, B, DFF, D, ep, st));
+    }
+    {
+      GemmEpilogue ep;
+      ep.residual = t2f;
+      ep.residual_f32 = 1;
+      ep.res_ld = D;
+      ep.ln_gamma = w.n3.g;
+      ep.ln_beta = w.n3.b;
+      ep.out_bf16 = t3;
+      ep.ld_bf16 = D;
+      ep.out_f32 = t3f;
+      ep.ld_f32 = D;
+      MADE_TRY(linear(hdec, DFF, w.ff2, B, D, DFF, ep, st));
+    }
+    // t3 is consumed by the next layer's first GEMM before this layer's buffers are rewritten
+    MADE_CUDA(cudaMemcpyAsync(tgt, t3, static_cast<size_t>(B) * D * 2, cudaMemcpyDeviceToDevice, st));
+    tin = tgt;
+    tinf = t3f;
+  }
+  // decoder.norm on every layer's output (:136), then the heads (model_Uni.py:131-149)
+  MADE_TRY(layernorm_rows(t3all, 0, D, R, c->dec_norm.g, c->dec_norm.b, hsb, hs, st));
+  {
+    GemmEpilogue ep;
+    ep.act = 2;
+    ep.out_bf16 = sp0;
+    ep.ld_bf16 = D;
+    MADE_TRY(linear(hsb, D, c->span0, R, D, D, ep, st));
+  }
+  {
+    GemmEpilogue ep;
+    ep.act = 2;
+    ep.out_bf16 = sp1;
+    ep.ld_bf16 = D;
+    MADE_TRY(linear(sp0, D, c->span1, R, D, D, ep, st));
+  }
+  MADE_TRY(heads_final(hs, sp1, R, c->cls_w, c->cls_b, c->span2_w, c->span2_b, pred_logits, pred_spans, st));
+  if (proj_queries) {
+    GemmEpilogue ep;
+    ep.l2norm = 1;
+    ep.out_f32 = proj_queries;
+    ep.ld_f32 = D;
+    MADE_TRY(linear(hsb, D, c->pq, R, D, D, ep, st));
+  }
+  if (proj_vid_mem) {
+    GemmEpilogue ep;
+    ep.l2norm = 1;
+    ep.out_f32 = proj_vid_mem;
+    ep.ld_f32 = D;
+    MADE_TRY(linear(fr, D, c->pv, B * LV, D, D, ep, st));
+  }
+  return MADE_OK;
+}
+
+int made_gemm_bf16(const void* A, const void* W, int64_t M, int N, int K, const float* bias, const float* residual,
+                   int act, const float* ln_gamma, const float* ln_beta, void* out_bf16, float* out_f32,
+                   void* stream) {
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi.bias = bias;
+  p.epi.residual = residual;
+  p.epi.residual_f32 = 1;
+  p.epi.res_ld = N;
+  p.epi.act = act;
+  p.epi.ln_gamma = ln_gamma;
+  p.epi.ln_beta = ln_beta;
+  p.epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
+  p.epi.ld_bf16 = N;
+  p.epi.out_f32 = out_f32;
+  p.epi.ld_f32 = N;
+  return gemm_bf16_tc(static_cast<const __nv_bfloat16*>(A), K, static_cast<const __nv_bfloat16*>(W), K, N, p, 256,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B, int L, void* out,
+                  void* stream) {
+  return mha_core(static_cast<const __nv_bfloat16*>(q), D, static_cast<const __nv_bfloat16*>(k), D,
+                  static_cast<const __nv_bfloat16*>(v), D, key_mask, B, L, static_cast<__nv_bfloat16*>(out), D,
+                  static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// tcgen05 / TMA / TMEM GEMM with fused epilogues (see gemm_tc.cuh).
+#include "gemm_tc.cuh"
+
+namespace made {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kBTileBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kAccStride = BN <= 128 ? 128 : 256;      // TMEM columns per acc stage
+  static constexpr uint32_t kTmemCols = kAccStride * kAccStages;  // 256 or 512
+  static constexpr int kChunks = BN / 32;
+  // dynamic smem: tiles + barriers + tmem slot + LN partials
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + 4 * 128 * 4;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+  float* ln_part = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [2 halves][2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_blocks = p.N / BN;
+  const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
+  const int64_t n_tiles = m_tiles * n_blocks;
+  const int k_blocks = (p.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m_blk = tile / n_blocks;
+        const int n_blk = static_cast<int>(tile % n_blocks);
+        const int32_t row_a = static_cast<int32_t>(m_blk * p.m_stride);
+        const int32_t row_b = p.b_batched ? row_a : n_blk * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row_a);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int as = static_cast<int>(it & 1);
+        const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kATileBytes;
+          const uint64_t adesc = umma_smem_desc(sa, 0, 1024);
+          const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) tc_commit(&tmem_full[as]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    const GemmEpilogue& e = p.epi;
+    const int ew = warp - 4;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // which column chunks (even/odd) this warp owns
+    const int r_in_tile = q * 32 + lane;
+    const bool do_ln = e.ln_gamma != nullptr;
+    const bool two_pass = do_ln || e.l2norm;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int as = static_cast<int>(it & 1);
+      const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
+      const int64_t m_blk = tile / n_blocks;
+      const int n_blk = static_cast<int>(tile % n_blocks);
+      const int64_t grow = m_blk * p.m_stride + r_in_tile;
+      const bool row_ok = r_in_tile < p.m_valid && grow < p.M;
+      const int64_t srow = row_ok ? grow : 0;   // safe row for loads
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      float keep = 1.f;
+      if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
+
+      float psum = 0.f;
+      // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
+      for (int c = half; c < Cfg::kChunks; c += 2) {
+        uint32_t acc[32];
+        tmem_ld_x32(t_acc + c * 32, acc);
+        tmem_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+        if (e.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 t = __ldg(b4 + i);
+            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+          }
+        }
+        if (e.row_table) {
+          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (srow % e.row_mod) * p.N + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 t = __ldg(t4 + i);
+            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+          }
+        }
+        if (e.residual) {
+          if (e.residual_f32) {
+            const float4* r4 = reinterpret_cast<const float4*>(
+                static_cast<const float*>(e.residual) + srow * e.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(r4 + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          } else {
+            const uint4* r4 = reinterpret_cast<const uint4*>(
+                static_cast<const __nv_bfloat16*>(e.residual) + srow * e.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 t = __ldg(r4 + i);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(h[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (e.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        } else if (e.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (two_pass) {
+          uint32_t st[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            psum += do_ln ? v[i] : v[i] * v[i];
+            st[i] = __float_as_uint(v[i]);
+          }
+          tmem_st_x32(t_acc + c * 32, st);
+        } else {
+          // ---------- direct store ----------
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= keep;
+          if (row_ok) {
+            if (e.out_bf16) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.ld_bf16 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            if (e.out_f32) {
+              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (e.out2_bf16) {
+              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_bf16 + grow * e.ld_out2 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t = __ldg(a4 + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+                float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+                float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                o[i] = make_uint4(pack_bf16x2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_bf16x2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_bf16x2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_bf16x2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+              }
+            }
+          }
+        }
+      }
+      if (two_pass) {
+        tmem_wait_st();
+        // ---------- row statistics across the two column halves ----------
+        float mean = 0.f, scale;
+        float* slot_a = ln_part + (0 * 2 + half) * 128 + r_in_tile;
+        float* slot_b = ln_part + (1 * 2 + half) * 128 + r_in_tile;
+        *slot_a = psum;
+        named_bar_sync(1, kEpiThreads);
+        float tot = ln_part[(0 * 2 + 0) * 128 + r_in_tile] + ln_part[(0 * 2 + 1) * 128 + r_in_tile];
+        if (do_ln) {
+          mean = tot * (1.0f / BN);
+          float psq = 0.f;
+          for (int c = half; c < Cfg::kChunks; c += 2) {
+            uint32_t acc[32];
+            tmem_ld_x32(t_acc + c * 32, acc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float d = __uint_as_float(acc[i]) - mean;
+              psq = fmaf(d, d, psq);
+            }
+          }
+          *slot_b = psq;
+          named_bar_sync(1, kEpiThreads);
+          float var = (ln_part[(1 * 2 + 0) * 128 + r_in_tile] + ln_part[(1 * 2 + 1) * 128 + r_in_tile]) * (1.0f / BN);
+          scale = rsqrtf(var + e.ln_eps);
+        } else {
+          scale = 1.0f / fmaxf(sqrtf(tot), 1e-12f);   // F.normalize
+        }
+        // ---------- pass 3: normalise + store ----------
+        for (int c = half; c < Cfg::kChunks; c += 2) {
+          uint32_t acc[32];
+          tmem_ld_x32(t_acc + c * 32, acc);
+          tmem_wait_ld();
+          const int col0 = n_blk * BN + c * 32;
+          float v[32];
+          if (do_ln) {
+            const float4* g4 = reinterpret_cast<const float4*>(e.ln_gamma + col0);
+            const float4* b4 = reinterpret_cast<const float4*>(e.ln_beta + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+              v[4 * i] = (__uint_as_float(acc[4 * i]) - mean) * scale * g.x + b.x;
+              v[4 * i + 1] = (__uint_as_float(acc[4 * i + 1]) - mean) * scale * g.y + b.y;
+              v[4 * i + 2] = (__uint_as_float(acc[4 * i + 2]) - mean) * scale * g.z + b.z;
+              v[4 * i + 3] = (__uint_as_float(acc[4 * i + 3]) - mean) * scale * g.w + b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * scale;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= keep;
+          if (row_ok) {
+            if (e.out_bf16) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.ld_bf16 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            if (e.out_f32) {
+              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (e.out2_bf16) {
+              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_bf16 + grow * e.ld_out2 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t = __ldg(a4 + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+                float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+                float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                o[i] = make_uint4(pack_bf16x2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_bf16x2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_bf16x2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_bf16x2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+              }
+            }
+          }
+        }
+        // the partial-sum slots are reused by the next tile: all readers must be done
+        named_bar_sync(1, kEpiThreads);
+      }
+      // release the accumulator stage
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MADE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
+  const int64_t n_tiles = m_tiles * (p.N / BN);
+  int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  MADE_CHECK_LAUNCH();
+  return MADE_OK;
+}
+
+int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldb,
+                 int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream) {
+  if (p.M == 0) return MADE_OK;
+  MADE_REQUIRE(A && W, "gemm: null operand");
+  MADE_REQUIRE(block_n == 256 || block_n == 96, "gemm: block_n=%d unsupported", block_n);
+  MADE_REQUIRE(p.N % block_n == 0, "gemm: N=%d not a multiple of %d", p.N, block_n);
+  MADE_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8");
+  MADE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  const GemmEpilogue& e = p.epi;
+  MADE_REQUIRE(!(e.ln_gamma || e.l2norm) || (p.N == block_n && block_n == 256),
+               "gemm: LayerNorm/L2 epilogue needs N == 256");
+  MADE_REQUIRE(!(e.ln_gamma && e.l2norm), "gemm: LayerNorm and L2 epilogues are exclusive");
+  MADE_REQUIRE(!e.ln_gamma || e.ln_beta, "gemm: LayerNorm needs beta");
+  MADE_REQUIRE(!e.out2_bf16 || e.add2, "gemm: out2 needs add2");
+  MADE_REQUIRE(e.out_bf16 || e.out_f32 || e.out2_bf16, "gemm: no output");
+  MADE_REQUIRE(p.m_valid >= 1 && p.m_valid <= 128 && p.m_stride >= 1 && p.m_stride <= 128,
+               "gemm: bad tile geometry");
+  CUtensorMap ta, tb;
+  MADE_TRY(encode_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M),
+                               static_cast<uint64_t>(lda) * 2, kBlockK, kBlockM));
+  MADE_TRY(encode_tmap_2d_bf16(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
+                               static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
+  if (block_n == 256) return launch_gemm<256>(ta, tb, p, stream);
+  return launch_gemm<96>(ta, tb, p, stream);
+}
+
+}  // namespace made

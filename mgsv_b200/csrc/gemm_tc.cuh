@@ -1,0 +1,48 @@
+// Persistent tcgen05 GEMM with fused epilogues:  C = epilogue(A[M,K] * W[N,K]^T).
+// A and W are bf16, K-contiguous ("K-major"), staged by TMA (128-byte swizzle) through a 4-stage
+// mbarrier ring; accumulators are fp32 in TMEM (two stages, so the epilogue of tile i overlaps
+// the MMAs of tile i+1); one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4).., column half w/4).
+#pragma once
+#include "common.cuh"
+
+namespace made {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;          // [N]
+  const float* row_table = nullptr;     // [row_mod, N] fp32, added by (row % row_mod)
+  int row_mod = 1;
+  const void* residual = nullptr;       // [M, N], row stride res_ld elements
+  int residual_f32 = 0;
+  int64_t res_ld = 0;
+  int act = 0;                          // 0 none, 1 GELU(erf), 2 ReLU
+  const float* ln_gamma = nullptr;      // LayerNorm over the full row (needs N == 256)
+  const float* ln_beta = nullptr;
+  float ln_eps = 1e-5f;
+  int l2norm = 0;                       // F.normalize(p=2, eps=1e-12) over the row (N == 256)
+  const float* row_mask = nullptr;      // [M]; rows with mask == 0 are written as 0
+  __nv_bfloat16* out_bf16 = nullptr;
+  int64_t ld_bf16 = 0;
+  float* out_f32 = nullptr;
+  int64_t ld_f32 = 0;
+  const __nv_bfloat16* add2 = nullptr;  // second output: bf16(result + add2[row, col])
+  int64_t add2_ld = 0;
+  __nv_bfloat16* out2_bf16 = nullptr;
+  int64_t ld_out2 = 0;
+};
+
+struct GemmParams {
+  int64_t M = 0;
+  int N = 0, K = 0;
+  int m_stride = 128;   // rows between consecutive M tiles (96 for per-track batched tiles)
+  int m_valid = 128;    // rows of each tile that are stored
+  int b_batched = 0;    // 1: B rows start at tile_m * m_stride (per-tile B, e.g. Gram matrix)
+  GemmEpilogue epi;
+};
+
+// Host launcher. A: [M, K] bf16 with row stride lda; W: [N(or M for batched), K] bf16, stride ldb.
+int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldb,
+                 int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream);
+
+}  // namespace made

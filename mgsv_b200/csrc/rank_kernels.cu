@@ -1,0 +1,392 @@
+// Similarity -> top-k selection and ground-truth rank, replacing the full argsort + python walk
+// of utils/util_test.py:32-97 (Recall_metrics, dedup=True) and the fp64 sum of
+// test-MaDe.py:401-403.
+//
+// One CTA per query row.  Scores are s = double(single) + double(dual) exactly as the reference
+// forms them (numpy float32 + float64 -> float64).  Work per row:
+//   1. s* = max score over the ground-truth id's columns (chain walk over prev_same),
+//   2. rank = number of DISTINCT music ids whose best column beats s* (strictly) — a column counts
+//      iff s > s* and no earlier column of the same id also has s > s* (prev_same chain),
+//   3. exact top-k by an 8-pass MSB radix select on order-preserving 64-bit keys, ties broken by
+//      the lower column index, then a bitonic sort of the k winners.
+// The row is staged once in shared memory (up to kMaxSmemCols columns; beyond that the passes
+// re-read global memory), so HBM traffic is the algorithmic 8 B per (query, track).
+#include "common.cuh"
+
+namespace made {
+
+constexpr int kRankThreads = 256;
+constexpr int kMaxK = 256;
+constexpr int kMaxSmemCols = 24576;  // 24576 * 8 B = 192 KB of keys
+
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+
+struct RowView {
+  const float* a;
+  const float* b;  // may be null
+  const unsigned long long* cache;  // smem keys or null
+  __device__ __forceinline__ unsigned long long key(int64_t j) const {
+    if (cache) return cache[j];
+    double s = static_cast<double>(a[j]);
+    if (b) s += static_cast<double>(b[j]);
+    return f64_key(s);
+  }
+};
+
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (kRankThreads / 32) ? red[threadIdx.x] : 0;
+    t = __reduce_add_sync(0xffffffffu, t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  __syncthreads();
+  return t;
+}
+
+// bitonic sort of n (power of two) (key, idx) pairs: key descending, idx ascending
+__device__ void bitonic_sort_desc(unsigned long long* keys, int* idx, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        int lo = (t / stride) * stride * 2 + (t % stride);
+        int hi = lo + stride;
+        bool desc_block = ((lo & size) == 0);
+        unsigned long long kl = keys[lo], kh = keys[hi];
+        int il = idx[lo], ih = idx[hi];
+        // "lo should come first" when (key larger) or (equal and idx smaller)
+        bool lo_first = (kl > kh) || (kl == kh && il < ih);
+        if (lo_first != desc_block) {
+          keys[lo] = kh; keys[hi] = kl;
+          idx[lo] = ih; idx[hi] = il;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
+                 int64_t n_cols, const int32_t* __restrict__ gt_col,
+                 const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
+                 int32_t col_offset, int k, int use_cache, int32_t* __restrict__ topk_idx,
+                 double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
+                 double* __restrict__ gt_score_out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ int hist[256];
+  __shared__ int red[kRankThreads / 32];
+  __shared__ unsigned long long sel_keys[kMaxK];
+  __shared__ int sel_idx[kMaxK];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ int sh_krem, sh_count, sh_eq_taken;
+  __shared__ unsigned long long sh_gt_key;
+
+  const int64_t row = blockIdx.x;
+  RowView rv;
+  rv.a = single + row * ld;
+  rv.b = dual ? dual + row * ld : nullptr;
+  rv.cache = nullptr;
+  if (use_cache) {
+    unsigned long long* cache = reinterpret_cast<unsigned long long*>(dyn_smem);
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) cache[j] = rv.key(j);
+    __syncthreads();
+    rv.cache = cache;
+  }
+
+  // ---- 1. ground-truth score ------------------------------------------------------------
+  const bool want_rank = rank_out != nullptr;
+  if (want_rank) {
+    if (threadIdx.x == 0) {
+      unsigned long long best = 0;  // smaller than any real key
+      if (gt_score_in) {
+        best = f64_key(gt_score_in[row]);
+      } else {
+        int32_t g = gt_col ? gt_col[row] : -1;
+        int32_t guard = 0;
+        while (g >= 0 && g < n_cols && guard++ < (1 << 20)) {
+          unsigned long long kk = rv.key(g);
+          best = kk > best ? kk : best;
+          g = prev_same ? prev_same[g] : -1;
+        }
+      }
+      sh_gt_key = best;
+    }
+    __syncthreads();
+    // ---- 2. distinct ids ahead of the ground truth --------------------------------------
+    const unsigned long long gk = sh_gt_key;
+    int cnt = 0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+      if (rv.key(j) > gk) {
+        bool first = true;
+        if (prev_same) {
+          int32_t p = prev_same[j];
+          int32_t guard = 0;
+          while (p >= 0 && guard++ < (1 << 20)) {
+            if (rv.key(p) > gk) { first = false; break; }
+            p = prev_same[p];
+          }
+        }
+        cnt += first ? 1 : 0;
+      }
+    }
+    cnt = block_sum_int(cnt, red);
+    if (threadIdx.x == 0) {
+      rank_out[row] = cnt;
+      if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
+    }
+  }
+  if (k <= 0 || topk_idx == nullptr) return;
+
+  // ---- 3. top-k: radix select of the k-th largest key -----------------------------------
+  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
+  if (threadIdx.x == 0) {
+    sh_prefix = 0ull;
+    sh_krem = kk;
+    sh_count = 0;
+    sh_eq_taken = 0;
+  }
+  __syncthreads();
+  for (int pass = 7; pass >= 0; --pass) {
+    hist[threadIdx.x] = 0;  // kRankThreads == 256 buckets
+    __syncthreads();
+    const unsigned long long prefix = sh_prefix;
+    const int shift = pass * 8;
+    const unsigned long long himask = pass == 7 ? 0ull : (~0ull << (shift + 8));
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+      unsigned long long key = rv.key(j);
+      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int rem = sh_krem, b = 255, acc = 0;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= rem) break;
+        acc += hist[b];
+      }
+      sh_krem = rem - acc;  // still needed inside bucket b
+      sh_prefix = prefix | (static_cast<unsigned long long>(b) << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned long long thr = sh_prefix;  // exact k-th largest key
+  const int need_eq = sh_krem;               // how many == thr to take (lowest indices first)
+  // strictly-greater elements: unordered append
+  for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+    unsigned long long key = rv.key(j);
+    if (key > thr) {
+      int slot = atomicAdd(&sh_count, 1);
+      if (slot < kMaxK) { sel_keys[slot] = key; sel_idx[slot] = static_cast<int>(j); }
+    }
+  }
+  __syncthreads();
+  const int n_gt = sh_count;
+  // ties: ordered append, chunk by chunk
+  for (int64_t base = 0; base < n_cols; base += kRankThreads) {
+    if (sh_eq_taken >= need_eq) break;
+    int64_t j = base + threadIdx.x;
+    bool eq = j < n_cols && rv.key(j) == thr;
+    unsigned ballot = __ballot_sync(0xffffffffu, eq);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+      if (w < warp) before += red[w];
+      total += red[w];
+    }
+    before += __popc(ballot & ((1u << lane) - 1u));
+    int taken = sh_eq_taken;
+    if (eq && taken + before < need_eq) {
+      int slot = n_gt + taken + before;
+      if (slot < kMaxK) { sel_keys[slot] = thr; sel_idx[slot] = static_cast<int>(j); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh_eq_taken = taken + total;
+    __syncthreads();
+  }
+  // pad to a power of two and sort
+  int n_pow = 1;
+  while (n_pow < kk) n_pow <<= 1;
+  for (int t = kk + threadIdx.x; t < n_pow; t += kRankThreads) {
+    sel_keys[t] = 0ull;
+    sel_idx[t] = 0x7FFFFFFF;
+  }
+  bitonic_sort_desc(sel_keys, sel_idx, n_pow);
+  for (int t = threadIdx.x; t < k; t += kRankThreads) {
+    if (t < kk) {
+      topk_idx[row * k + t] = sel_idx[t] + col_offset;
+      if (topk_score) topk_score[row * k + t] = key_f64(sel_keys[t]);
+    } else {
+      topk_idx[row * k + t] = -1;
+      if (topk_score) topk_score[row * k + t] = -INFINITY;
+    }
+  }
+}
+
+// Merge G per-shard candidate lists per row ([n_rows, n_cand] scores + global indices, -1 = empty)
+// into the global top-k: score descending, index ascending.
+__global__ void __launch_bounds__(kRankThreads)
+topk_merge_kernel(const double* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                  int n_cand, int k, int32_t* __restrict__ out_idx, double* __restrict__ out_score) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  int n_pow = 1;
+  while (n_pow < n_cand) n_pow <<= 1;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(dyn_smem);
+  int* idx = reinterpret_cast<int*>(keys + n_pow);
+  const int64_t row = blockIdx.x;
+  for (int t = threadIdx.x; t < n_pow; t += kRankThreads) {
+    if (t < n_cand && cand_idx[row * n_cand + t] >= 0) {
+      keys[t] = f64_key(cand_score[row * n_cand + t]);
+      idx[t] = cand_idx[row * n_cand + t];
+    } else {
+      keys[t] = 0ull;
+      idx[t] = 0x7FFFFFFF;
+    }
+  }
+  bitonic_sort_desc(keys, idx, n_pow);
+  for (int t = threadIdx.x; t < k; t += kRankThreads) {
+    bool ok = t < n_pow && idx[t] != 0x7FFFFFFF;
+    out_idx[row * k + t] = ok ? idx[t] : -1;
+    out_score[row * k + t] = ok ? key_f64(keys[t]) : -INFINITY;
+  }
+}
+
+// dual-tower cosine (modules/loss.py:52-56): out[i,j] = <a_i/|a_i|, b_j/|b_j|>, all fp32.
+// 64x64 output tile per CTA, 256 threads, 4x4 outputs per thread, D = 256 staged in two halves.
+constexpr int kCosTile = 64;
+__global__ void __launch_bounds__(256)
+cosine_sim_kernel(const float* __restrict__ a, int64_t n, const float* __restrict__ b, int64_t m,
+                  int d, float* __restrict__ out, int64_t ld) {
+  __shared__ float sa[kCosTile][33], sb[kCosTile][33];
+  __shared__ float na[kCosTile], nb[kCosTile];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * kCosTile;
+  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * kCosTile;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  // row norms (one warp handles 8 rows of each side)
+  {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < 2 * kCosTile; r += 8) {
+      bool is_a = r < kCosTile;
+      int rr = is_a ? r : r - kCosTile;
+      int64_t g = (is_a ? i0 : j0) + rr;
+      int64_t lim = is_a ? n : m;
+      const float* p = (is_a ? a : b) + g * d;
+      float s = 0.f;
+      if (g < lim)
+        for (int c = lane; c < d; c += 32) { float v = p[c]; s = fmaf(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) (is_a ? na : nb)[rr] = sqrtf(s);
+    }
+  }
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < d; c0 += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < kCosTile * 32; t += 256) {
+      int r = t / 32, c = t % 32;
+      int64_t gi = i0 + r, gj = j0 + r;
+      // normalise on load: x / |x| (one rounding, like the reference's elementwise divide)
+      sa[r][c] = (gi < n && c0 + c < d) ? __fdiv_rn(a[gi * d + c0 + c], na[r]) : 0.f;
+      sb[r][c] = (gj < m && c0 + c < d) ? __fdiv_rn(b[gj * d + c0 + c], nb[r]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { av[u] = sa[ty * 4 + u][c]; bv[u] = sb[tx * 4 + u][c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      int64_t gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + v;
+      if (gi < n && gj < m) out[gi * ld + gj] = acc[u][v];
+    }
+}
+
+}  // namespace made
+
+using namespace made;
+
+extern "C" {
+
+int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n_rows,
+                   int64_t n_cols, const int32_t* gt_col, const double* gt_score_in,
+                   const int32_t* prev_same, int32_t col_offset, int k, int32_t* topk_idx,
+                   double* topk_score, int32_t* rank_out, double* gt_score_out, void* stream) {
+  if (n_rows == 0) return MADE_OK;
+  MADE_REQUIRE(single, "rank_topk: null similarity matrix");
+  MADE_REQUIRE(k >= 0 && k <= kMaxK, "rank_topk: k=%d outside [0,%d]", k, kMaxK);
+  MADE_REQUIRE(n_cols > 0 && n_cols < (1LL << 31), "rank_topk: n_cols=%lld unsupported",
+               (long long)n_cols);
+  MADE_REQUIRE(k == 0 || topk_idx, "rank_topk: k>0 needs topk_idx");
+  MADE_REQUIRE(!rank_out || gt_col || gt_score_in, "rank_topk: rank needs gt_col or gt_score_in");
+  int use_cache = n_cols <= kMaxSmemCols;
+  size_t smem = use_cache ? static_cast<size_t>(n_cols) * 8 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MADE_CUDA(cudaFuncSetAttribute(rank_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kMaxSmemCols * 8));
+    attr_set = true;
+  }
+  rank_topk_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem,
+                     static_cast<cudaStream_t>(stream)>>>(
+      single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, use_cache, topk_idx,
+      topk_score, rank_out, gt_score_out);
+  MADE_CHECK_LAUNCH();
+  return MADE_OK;
+}
+
+int made_topk_merge(const double* cand_score, const int32_t* cand_idx, int64_t n_rows, int n_cand,
+                    int k, int32_t* out_idx, double* out_score, void* stream) {
+  if (n_rows == 0) return MADE_OK;
+  MADE_REQUIRE(cand_score && cand_idx && out_idx && out_score, "topk_merge: null pointer");
+  MADE_REQUIRE(n_cand > 0 && n_cand <= 4096 && k > 0 && k <= n_cand,
+               "topk_merge: n_cand=%d k=%d unsupported", n_cand, k);
+  int n_pow = 1;
+  while (n_pow < n_cand) n_pow <<= 1;
+  size_t smem = static_cast<size_t>(n_pow) * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MADE_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   4096 * 12));
+    attr_set = true;
+  }
+  topk_merge_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem,
+                      static_cast<cudaStream_t>(stream)>>>(cand_score, cand_idx, n_cand, k, out_idx,
+                                                           out_score);
+  MADE_CHECK_LAUNCH();
+  return MADE_OK;
+}
+
+int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d, float* out,
+                    int64_t ld, void* stream) {
+  if (n == 0 || m == 0) return MADE_OK;
+  MADE_REQUIRE(a && b && out && d > 0 && ld >= m, "cosine_sim: bad arguments");
+  dim3 grid(static_cast<unsigned>(ceil_div64(m, kCosTile)),
+            static_cast<unsigned>(ceil_div64(n, kCosTile)));
+  cosine_sim_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, n, b, m, d, out, ld);
+  MADE_CHECK_LAUNCH();
+  return MADE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+"""made_ctx wrapper: packed weights + the stateful ops (encoders, X-Pool scoring, DETR detection).
+
+Host logic only — every tensor op below is a C-ABI call into libmade_b200.so.  There is no CPU or
+eager-PyTorch fallback: constructing an Engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from . import config as cfg
+
+
+class Engine:
+    def __init__(self, device: Optional[torch.device] = None):
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("made_b200 needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.made_ctx_create(C.byref(h), self.device.index))
+        self._h = h
+        self.loaded = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.made_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -----------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Reference key names.  Frozen `vit_model.*` / `ast_model.*` entries of
+        real checkpoints are ignored (the feature path never uses them)."""
+        names, arrs = [], []
+        for k, v in sd.items():
+            if k.startswith(("vit_model.", "ast_model.")):
+                continue
+            names.append(k.encode())
+            arrs.append(v.detach().to("cpu", torch.float32).contiguous())
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_ptrs = (C.c_void_p * n)(*[a.data_ptr() for a in arrs])
+        c_num = (C.c_int64 * n)(*[a.numel() for a in arrs])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.made_ctx_load_weights(self._h, n, c_names, c_ptrs, c_num, _lib.stream_ptr()))
+        self.loaded = True
+
+    # -----------------------------------------------------------------------------------------
+    def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True):
+        """forward_{video,audio}_encoder_feature → (seq_bf16 [B,L,256], seq_f32 or None, pooled [B,256])."""
+        L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
+        if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
+            raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
+        if tuple(masks.shape) != (feats.shape[0], L):
+            raise ValueError(f"expected masks of shape [B,{L}], got {tuple(masks.shape)}")
+        if feats.dtype == torch.float32:
+            dt = _lib.F32
+        elif feats.dtype == torch.bfloat16:
+            dt = _lib.BF16
+        else:
+            raise ValueError(f"unsupported feature dtype {feats.dtype}")
+        feats = feats.contiguous()
+        masks = masks.to(torch.float32).contiguous()
+        B = feats.shape[0]
+        dev = feats.device
+        seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.bfloat16, device=dev)
+        seq32 = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
+        pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
+        _lib.check(self._lib.made_encode(self._h, modality, _lib.ptr(feats), dt, _lib.ptr(masks), B, _lib.ptr(seq),
+                                         _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
+        return seq, seq32, pooled
+
+    def gallery_prepare(self, seg_bf16: torch.Tensor, seg_masks: torch.Tensor):
+        """Per-track X-Pool operands: kz [N*96,768] bf16, gram [N*96,96] bf16, maskbits [N,4] int32."""
+        N = seg_bf16.shape[0]
+        dev = seg_bf16.device
+        if seg_bf16.dtype != torch.bfloat16:
+            raise ValueError("gallery_prepare takes the bf16 encoded segments")
+        kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.bfloat16, device=dev)
+        gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.bfloat16, device=dev)
+        bits = torch.empty((N, 4), dtype=torch.int32, device=dev)
+        masks = seg_masks.to(torch.float32).contiguous()
+        _lib.check(self._lib.made_gallery_prepare(self._h, _lib.ptr(seg_bf16.contiguous()), _lib.ptr(masks), N,
+                                                  _lib.ptr(kz), _lib.ptr(gram), _lib.ptr(bits), _lib.stream_ptr()))
+        return kz, gram, bits
+
+    def query_prepare(self, video_feats: torch.Tensor):
+        N = video_feats.shape[0]
+        vf = video_feats.to(torch.float32).contiguous()
+        q = torch.empty((N, cfg.D_MODEL), dtype=torch.bfloat16, device=vf.device)
+        vhat = torch.empty((N, cfg.D_MODEL), dtype=torch.float16, device=vf.device)
+        _lib.check(self._lib.made_query_prepare(self._h, _lib.ptr(vf), N, _lib.ptr(q), _lib.ptr(vhat),
+                                                _lib.stream_ptr()))
+        return q, vhat
+
+    def xpool_score(self, q, vhat, kz, gram, bits, out: Optional[torch.Tensor] = None, col_offset: int = 0):
+        n_q, n_m = q.shape[0], bits.shape[0]
+        if out is None:
+            out = torch.empty((n_q, n_m), dtype=torch.float32, device=q.device)
+            col_offset = 0
+        _lib.check(self._lib.made_xpool_score(self._h, _lib.ptr(q), _lib.ptr(vhat), n_q, _lib.ptr(kz), _lib.ptr(gram),
+                                              _lib.ptr(bits), n_m, _lib.ptr(out), out.stride(0), col_offset,
+                                              _lib.stream_ptr()))
+        return out
+
+    def detr_detect(self, frame_bf16, frame_masks, seg_bf16, seg_masks, video_feats, track_idx=None,
+                    want_proj: bool = False, want_memory: bool = False):
+        """→ dict(hs [6,B,256], pred_logits [6,B,2], pred_spans [6,B,2], proj_queries?, proj_vid_mem?, memory?)."""
+        B = video_feats.shape[0]
+        dev = video_feats.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        hs = torch.empty((cfg.DETR_DEC_LAYERS, B, cfg.D_MODEL), **f32)
+        logits = torch.empty((cfg.DETR_DEC_LAYERS, B, 2), **f32)
+        spans = torch.empty((cfg.DETR_DEC_LAYERS, B, 2), **f32)
+        pq = torch.empty((cfg.DETR_DEC_LAYERS, B, cfg.D_MODEL), **f32) if want_proj else None
+        pv = torch.empty((B, cfg.L_V, cfg.D_MODEL), **f32) if want_proj else None
+        mem = torch.empty((B, cfg.L_DETR, cfg.D_MODEL), **f32) if want_memory else None
+        if track_idx is not None:
+            track_idx = track_idx.to(torch.int32).contiguous()
+        _lib.check(self._lib.made_detr_detect(
+            self._h, _lib.ptr(frame_bf16.contiguous()), _lib.ptr(frame_masks.to(torch.float32).contiguous()),
+            _lib.ptr(seg_bf16.contiguous()), _lib.ptr(seg_masks.to(torch.float32).contiguous()), _lib.ptr(track_idx),
+            _lib.ptr(video_feats.to(torch.float32).contiguous()), B, _lib.ptr(hs), _lib.ptr(logits), _lib.ptr(spans),
+            _lib.ptr(pq), _lib.ptr(pv), _lib.ptr(mem), _lib.stream_ptr()))
+        return dict(hs=hs, pred_logits=logits, pred_spans=spans, proj_queries=pq, proj_vid_mem=pv, memory=mem)

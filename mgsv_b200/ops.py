@@ -1,0 +1,189 @@
+"""Torch-tensor front ends of the stateless C-ABI kernels (same names and argument meaning as the
+reference's free functions).  Tensors must live on the CUDA device; outputs are fresh tensors
+allocated by torch and filled by the kernels on the current stream."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MAX_M_DURATION = 240.0
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# music_detr/span_utils.py
+# ---------------------------------------------------------------------------------------------
+def span_cw_to_se(cw_spans: torch.Tensor) -> torch.Tensor:
+    """span_utils.py:15-24."""
+    cw = _f32c(cw_spans)
+    out = torch.empty_like(cw)
+    _lib.check(_lib.load().made_span_cw_to_se(_lib.ptr(cw), _lib.ptr(out), cw.shape[0], _lib.stream_ptr()))
+    return out
+
+
+def _check_spans(s: torch.Tensor, name: str) -> torch.Tensor:
+    if s.dim() != 2 or s.shape[1] != 2:
+        raise ValueError(f"{name} must be [n,2], got {tuple(s.shape)}")
+    return _f32c(s)
+
+
+def generalized_temporal_iou(spans1: torch.Tensor, spans2: torch.Tensor, check: bool = True) -> torch.Tensor:
+    """span_utils.py:86-115.  `check=True` keeps the reference's `assert e >= s` (which costs a
+    device sync, as it does in the reference)."""
+    s1, s2 = _check_spans(spans1, "spans1"), _check_spans(spans2, "spans2")
+    if check:
+        assert (s1[:, 1] >= s1[:, 0]).all()
+        assert (s2[:, 1] >= s2[:, 0]).all()
+    out = torch.empty((s1.shape[0], s2.shape[0]), dtype=torch.float32, device=s1.device)
+    _lib.check(_lib.load().made_giou(_lib.ptr(s1), s1.shape[0], _lib.ptr(s2), s2.shape[0], _lib.ptr(out),
+                                     _lib.stream_ptr()))
+    return out
+
+
+def temporal_iou(spans1: torch.Tensor, spans2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """span_utils.py:39-66 → (iou, union)."""
+    s1, s2 = _check_spans(spans1, "spans1"), _check_spans(spans2, "spans2")
+    iou = torch.empty((s1.shape[0], s2.shape[0]), dtype=torch.float32, device=s1.device)
+    uni = torch.empty_like(iou)
+    _lib.check(_lib.load().made_temporal_iou(_lib.ptr(s1), s1.shape[0], _lib.ptr(s2), s2.shape[0], _lib.ptr(iou),
+                                             _lib.ptr(uni), _lib.stream_ptr()))
+    return iou, uni
+
+
+def matcher_cost(prob_fg: torch.Tensor, out_spans_cw: torch.Tensor, tgt_spans_cw: torch.Tensor,
+                 cost_span: float = 10.0, cost_giou: float = 1.0, cost_class: float = 4.0) -> torch.Tensor:
+    """Cost matrix of HungarianMatcher.forward (matcher.py:66-88) with build_matcher's weights."""
+    p = _f32c(prob_fg)
+    a, b = _check_spans(out_spans_cw, "out_spans"), _check_spans(tgt_spans_cw, "tgt_spans")
+    if p.shape[0] != a.shape[0]:
+        raise ValueError("prob_fg and out_spans disagree on the number of predictions")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().made_matcher_cost(_lib.ptr(p), _lib.ptr(a), a.shape[0], _lib.ptr(b), b.shape[0],
+                                             cost_span, cost_giou, cost_class, _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def moment_postproc(pred_logits: torch.Tensor, pred_spans: torch.Tensor, gt_moment: Optional[torch.Tensor] = None,
+                    m_duration: Optional[torch.Tensor] = None, max_m_duration: float = MAX_M_DURATION):
+    """test-MaDe.py:306-316 + detr_iou (span_utils.py:147-170): logits [n,1,2] or [n,2], spans
+    (c,w) likewise, gt_moment [n,1,2] seconds → (pred_st, pred_ed, score, iou or None)."""
+    lg = _f32c(pred_logits.reshape(-1, 2))
+    sp = _f32c(pred_spans.reshape(-1, 2))
+    n = lg.shape[0]
+    st = torch.empty(n, dtype=torch.float32, device=lg.device)
+    ed, sc = torch.empty_like(st), torch.empty_like(st)
+    iou = gt = md = None
+    if gt_moment is not None:
+        gt = _f32c(gt_moment.reshape(-1, 2))
+        md = _f32c(m_duration.reshape(-1))
+        iou = torch.empty_like(st)
+    _lib.check(_lib.load().made_moment_postproc(_lib.ptr(lg), _lib.ptr(sp), _lib.ptr(gt), _lib.ptr(md),
+                                                max_m_duration, n, _lib.ptr(st), _lib.ptr(ed), _lib.ptr(sc),
+                                                _lib.ptr(iou), _lib.stream_ptr()))
+    return st, ed, sc, iou
+
+
+# ---------------------------------------------------------------------------------------------
+# ranking (utils/util_test.py:32-97) and similarities (modules/loss.py:52-56)
+# ---------------------------------------------------------------------------------------------
+def dedup_tables(music_ids: Sequence[str], gt_ids: Optional[Sequence[str]] = None):
+    """Host-side id bookkeeping for Recall_metrics(dedup=True): prev_same[c] = previous column with
+    the same music id (-1 if none); gt_col[r] = LAST column carrying row r's ground-truth id
+    (row r's GT id defaults to music_ids[r], the reference's square layout, Q13)."""
+    last = {}
+    prev = np.full(len(music_ids), -1, dtype=np.int32)
+    for c, mid in enumerate(music_ids):
+        if mid in last:
+            prev[c] = last[mid]
+        last[mid] = c
+    if gt_ids is None:
+        gt_ids = music_ids
+    gt_col = np.array([last.get(g, -1) for g in gt_ids], dtype=np.int32)
+    has_dups = bool((prev >= 0).any())
+    return prev, gt_col, has_dups
+
+
+def rank_topk(single: torch.Tensor, dual: Optional[torch.Tensor], gt_col: Optional[torch.Tensor] = None,
+              prev_same: Optional[torch.Tensor] = None, k: int = 0, col_offset: int = 0,
+              gt_score_in: Optional[torch.Tensor] = None, n_cols: Optional[int] = None):
+    """Exact top-k and dedup-aware ground-truth rank of rows of (double(single) + double(dual)).
+    Returns dict(topk_idx [n,k] int32, topk_score [n,k] f64, rank [n] int32, gt_score [n] f64)."""
+    if single.dtype != torch.float32 or (dual is not None and dual.dtype != torch.float32):
+        raise ValueError("rank_topk takes fp32 similarity matrices")
+    n_rows, ld = single.shape[0], single.stride(0)
+    n_cols = single.shape[1] if n_cols is None else n_cols
+    if dual is not None and (dual.stride(0) != ld or dual.shape[0] != n_rows):
+        raise ValueError("single and dual must share their layout")
+    dev = single.device
+    out = {}
+    topk_idx = topk_score = rank = gt_score = None
+    if k > 0:
+        topk_idx = torch.empty((n_rows, k), dtype=torch.int32, device=dev)
+        topk_score = torch.empty((n_rows, k), dtype=torch.float64, device=dev)
+    if gt_col is not None or gt_score_in is not None:
+        rank = torch.empty(n_rows, dtype=torch.int32, device=dev)
+        gt_score = torch.empty(n_rows, dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().made_rank_topk(
+        single.data_ptr(), None if dual is None else dual.data_ptr(), ld, n_rows, n_cols, _lib.ptr(gt_col),
+        _lib.ptr(gt_score_in), _lib.ptr(prev_same), col_offset, k, _lib.ptr(topk_idx), _lib.ptr(topk_score),
+        _lib.ptr(rank), _lib.ptr(gt_score), _lib.stream_ptr()))
+    out.update(topk_idx=topk_idx, topk_score=topk_score, rank=rank, gt_score=gt_score)
+    return out
+
+
+def topk_merge(cand_score: torch.Tensor, cand_idx: torch.Tensor, k: int):
+    """Merge per-shard candidate lists [n_rows, n_cand] into the global top-k."""
+    cs, ci = cand_score.to(torch.float64).contiguous(), cand_idx.to(torch.int32).contiguous()
+    n_rows, n_cand = cs.shape
+    oi = torch.empty((n_rows, k), dtype=torch.int32, device=cs.device)
+    os_ = torch.empty((n_rows, k), dtype=torch.float64, device=cs.device)
+    _lib.check(_lib.load().made_topk_merge(_lib.ptr(cs), _lib.ptr(ci), n_rows, n_cand, k, _lib.ptr(oi),
+                                           _lib.ptr(os_), _lib.stream_ptr()))
+    return oi, os_
+
+
+def cal_distance(x: torch.Tensor, y: torch.Tensor, distance_type: str = "COS", out: Optional[torch.Tensor] = None,
+                 col_offset: int = 0) -> torch.Tensor:
+    """modules/loss.py:30-62, COS branch only (the shipped config; L2 raises ValueError)."""
+    if distance_type != "COS":
+        raise ValueError(f"distance_type={distance_type!r} is not supported by made_b200 (COS only)")
+    assert x.shape[1] == y.shape[1], "The second dimension of x and y must be the same."
+    x, y = _f32c(x), _f32c(y)
+    if out is None:
+        out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
+        col_offset = 0
+    _lib.check(_lib.load().made_cosine_sim(_lib.ptr(x), x.shape[0], _lib.ptr(y), y.shape[0], x.shape[1],
+                                           out.data_ptr() + 4 * col_offset, out.stride(0), _lib.stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks exported for tests
+# ---------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, act: int = 0, ln=None,
+              out_dtype=torch.bfloat16) -> torch.Tensor:
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    g, b = (ln if ln is not None else (None, None))
+    _lib.check(_lib.load().made_gemm_bf16(
+        _lib.ptr(a), _lib.ptr(w), M, N, K, _lib.ptr(bias), _lib.ptr(residual), act, _lib.ptr(g), _lib.ptr(b),
+        _lib.ptr(out) if out_dtype == torch.bfloat16 else None,
+        _lib.ptr(out) if out_dtype == torch.float32 else None, _lib.stream_ptr()))
+    return out
+
+
+def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: torch.Tensor) -> torch.Tensor:
+    """q,k,v [B,L,256] bf16, key_mask [B,L] float (1 = valid) → [B,L,256] bf16."""
+    B, L, _ = q.shape
+    out = torch.empty_like(q)
+    _lib.check(_lib.load().made_mha_core(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(key_mask), B, L,
+                                         _lib.ptr(out), _lib.stream_ptr()))
+    return out
