@@ -134,6 +134,19 @@ int made_detr_detect(made_ctx* ctx, const void* frame_bf16, const float* frame_m
                      float* pred_spans, float* proj_queries, float* proj_vid_mem, float* memory,
                      void* stream);
 
+/* Evaluation-time loss scalars of Uni_model.forward (forward values only).
+ * SetCriterion (loss_detr.py:74-169) for n_layers decoder outputs with one moment query:
+ * pred_logits/pred_spans [n_layers,B,2], proj_queries [n_layers,B,256] and proj_vid_mem [B,50,256]
+ * (both nullable), targets_cw [B,2]; w_fg/w_bg = criterion.empty_weight; out [n_layers,5] =
+ * {loss_span, loss_giou, loss_label, class_error, loss_contrastive_align}. */
+int made_detr_losses(const float* pred_logits, const float* pred_spans, const float* proj_queries,
+                     const float* proj_vid_mem, const float* targets_cw, int64_t B, int n_layers,
+                     float w_fg, float w_bg, float temperature, float* out, void* stream);
+/* InfoNCELoss(dual) + CLIPLoss(single) (modules/loss.py:5-24,66-123; model_Uni.py:255-262) on
+ * in-batch [n,n] similarity matrices with row stride ld -> out[0]. */
+int made_retrieval_loss(const float* dual, const float* single, int64_t ld, int n, float logit_scale,
+                        float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * building blocks exported for the parity tests
  * ------------------------------------------------------------------------------------------- */

@@ -41,6 +41,8 @@ SIGNATURES = {
     "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
     "made_xpool_score": [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _p],
     "made_detr_detect": [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "made_detr_losses": [_p, _p, _p, _p, _p, _i64, _i32, _f, _f, _f, _p, _p],
+    "made_retrieval_loss": [_p, _p, _i64, _i32, _f, _p, _p],
     "made_gemm_bf16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
     "made_mha_core": [_p, _p, _p, _p, _i64, _i32, _p, _p],
 }

@@ -441,13 +441,15 @@ def summarize_ranks(ind: np.ndarray):
 
 
 def iou_metrics(iou_list):
-    """util_test.py:101-111 (strict >, Q9)."""
-    n = len(iou_list)
+    """util_test.py:101-111 (strict >, Q9).  The reference's list holds 0-d fp32 tensors, so the
+    thresholds compare in fp32 and python's sum() accumulates sequentially in fp32."""
+    t = [torch.as_tensor(float(i), dtype=torch.float32) for i in iou_list]
+    n = len(t)
     return {
-        "mIoU": float(sum(float(i) for i in iou_list) / n),
-        "IoU@0.3": sum(1 for i in iou_list if i > 0.3) * 100 / n,
-        "IoU@0.5": sum(1 for i in iou_list if i > 0.5) * 100 / n,
-        "IoU@0.7": sum(1 for i in iou_list if i > 0.7) * 100 / n,
+        "mIoU": float(sum(t) / n),
+        "IoU@0.3": sum(1 for i in t if i > 0.3) * 100 / n,
+        "IoU@0.5": sum(1 for i in t if i > 0.5) * 100 / n,
+        "IoU@0.7": sum(1 for i in t if i > 0.7) * 100 / n,
     }
 
 

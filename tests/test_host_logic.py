@@ -1,0 +1,130 @@
+"""CPU tests: host logic, ABI surface, metric bookkeeping (no CUDA compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mgsv_b200 import _lib, config, metrics, ops, synth
+from mgsv_b200.parallel import owner_of, shard_bounds
+from oracle import build_c
+from oracle import made_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_check_args_accepts_shipped_and_rejects_other_branches():
+    config.check_args(config.default_args())
+    for k, bad in (("vmr_fusion", "XA-video"), ("mml_fusion", "CA"), ("detr_dec_layers", 2),
+                   ("agg_module", "mlp"), ("fusion_mask", 0), ("num_moment_queries", 5)):
+        with pytest.raises(ValueError):
+            config.check_args(config.default_args(**{k: bad}))
+
+
+def test_state_dict_spec_matches_reference_inventory():
+    spec = synth.state_dict_spec()
+    keys = [k for k, _, _ in spec]
+    assert len(keys) == len(set(keys)) == 199          # 199 entries
+    n_param = sum(int(np.prod(s)) if s else 1 for k, s, kind in spec if kind not in ("pe", "empty_weight"))
+    assert n_param == 10_534_917
+    sd = synth.make_state_dict(0)
+    sd2 = synth.make_state_dict(0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert torch.allclose(sd["logit_scale"], torch.tensor(np.log(1 / 0.03), dtype=torch.float32))
+
+
+def test_synthetic_inputs_shape_and_masks():
+    v, m, ids = synth.make_eval_set(32, 64, 5)
+    assert v["frame_feats"].shape == (32, 50, 512) and m["segment_feats"].shape == (64, 96, 768)
+    assert (v["frame_mask"].sum(1) >= 6).all() and (m["segment_mask"].sum(1) >= 13).all()
+    # padded rows zeroed, masks are prefixes
+    assert (v["frame_feats"][v["frame_mask"] == 0] == 0).all()
+    assert ((m["segment_mask"][:, 1:] <= m["segment_mask"][:, :-1])).all()
+    assert (m["gt_moment"][:, 0, 1] <= m["m_duration"]).all()
+    v2, _, _ = synth.make_eval_set(32, 64, 5)
+    assert torch.equal(v["frame_feats"], v2["frame_feats"])
+
+
+def test_c_oracle_matches_torch_oracle_bitwise():
+    a, b, logits = synth.make_span_pairs(300, 200, 21)
+    g_c = build_c.giou(build_c.cw_to_se(a.numpy()), build_c.cw_to_se(b.numpy()))
+    g_t = O.generalized_temporal_iou(O.span_cw_to_se(a), O.span_cw_to_se(b)).numpy()
+    assert np.array_equal(g_c, g_t, equal_nan=True)
+    prob = logits.softmax(-1)[:, 0]
+    tgt = b[b[:, 1] != 0]
+    assert np.array_equal(build_c.matcher_cost(prob.numpy(), a.numpy(), tgt.numpy()),
+                          O.matcher_cost(prob, a, tgt).numpy(), equal_nan=True)
+    st, ed = torch.rand(50) * 200 - 10, torch.rand(50) * 260
+    gt = torch.sort(torch.rand(50, 1, 2) * 240, dim=-1)[0]
+    md = torch.rand(50) * 200 + 40
+    assert np.array_equal(build_c.detr_iou(st.numpy(), ed.numpy(), gt.numpy(), md.numpy()),
+                          O.detr_iou(st, ed, gt, md).numpy())
+
+
+def test_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, "include", "made_b200.h")).read()
+    declared = set(re.findall(r"\b(made_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/made_b200.h but not exported"
+    assert set(_lib.SIGNATURES) | {"made_last_error_string"} == declared
+    assert lib.made_abi_version() == 1
+
+
+def test_product_path_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from mgsv_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine()
+    with pytest.raises(RuntimeError):
+        ops.span_cw_to_se(torch.zeros(4, 2))
+
+
+def test_uni_model_interface_on_cpu():
+    from mgsv_b200.model import Uni_model
+    model = Uni_model(config.default_args(), torch.device("cpu"), None)
+    sd = model.state_dict()
+    ref = synth.make_state_dict(0)
+    assert list(sd.keys()) != [] and set(sd.keys()) == set(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in ref)
+    assert model.criterion.foreground_label == 0
+    assert len(model.criterion.weight_dict) == 24
+    assert hasattr(model, "video_guided_to_music_pooling_cross_transformer")
+    assert sum(p.numel() for p in model.parameters()) == 10_534_917
+    groups = model.get_temporal_parameter() + model.get_matching_parameter() + model.get_detection_parameter()
+    # every parameter except decoder_query_embed (absent from the reference's groups too) is in a group
+    assert sum(p.numel() for p in groups) == 10_534_917 - 256
+    model.load_state_dict(synth.make_state_dict(3))
+    model.eval().float()
+    with pytest.raises(ValueError):
+        Uni_model(config.default_args(vmr_loss="dual"), torch.device("cpu"), None)
+
+
+def test_dedup_tables_and_rank_summary():
+    ids = ["a", "b", "a", "c", "b"]
+    prev, gt_col, has = ops.dedup_tables(ids)
+    assert list(prev) == [-1, -1, 0, -1, 1] and list(gt_col) == [2, 4, 2, 3, 4] and has
+    ind = np.array([0, 4, 11, 0, 99, 150])
+    assert metrics.summarize_ranks(ind) == O.summarize_ranks(ind)
+    iou = np.array([0.0, 0.31, 0.5, 0.71, 0.9, 0.3], dtype=np.float32)
+    a, b = metrics.IoU_metrics(list(iou)), O.iou_metrics(list(iou))
+    assert all(abs(a[k] - b[k]) < 1e-9 for k in a)
+    c1, c2 = metrics.Composite_metrics(ind, iou), O.composite_metrics(list(ind), list(iou))
+    assert list(c1.keys()) == list(c2.keys())
+    assert all(abs(c1[k] - c2[k]) < 1e-6 for k in c1)
+
+
+def test_shard_bounds_partition():
+    for n in (4000, 4001, 7, 2000):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            cols = torch.arange(n)
+            own = owner_of(cols, n, w)
+            for r in range(w):
+                assert (own[b[r][0]:b[r][1]] == r).all()
