@@ -9,6 +9,8 @@
  *     (thread-local).  The Python shim raises ValueError for MADE_EINVAL / MADE_EUNSUPPORTED and
  *     RuntimeError otherwise, matching the reference's exception conventions
  *     (model_Uni.py:275, span_utils.py:107-108).
+ * All 16-bit activation/operand buffers are IEEE fp16 (the path's GEMM operand type: fp16 operands,
+ * fp32 accumulation; DESIGN.md "numerics").
  * The caller owns every buffer.  A made_ctx owns packed weights and a workspace; one ctx per
  * (process, device), calls on it serialised by the caller (the reference is single-threaded).
  */
@@ -32,6 +34,7 @@ extern "C" {
 
 #define MADE_DTYPE_F32 0
 #define MADE_DTYPE_BF16 1
+#define MADE_DTYPE_F16 2
 
 #define MADE_VIDEO 0
 #define MADE_MUSIC 1
@@ -96,23 +99,24 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
 int made_ctx_create(made_ctx** out, int device);
 int made_ctx_destroy(made_ctx* ctx);
 /* Weights by reference state_dict key (util_train.py:51-53): n host fp32 arrays.
- * Packs bf16 GEMM operands and the folded X-Pool / decoder weights. */
+ * Packs fp16 GEMM operands and the folded X-Pool / decoder weights. */
 int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const float* const* host_ptrs,
                           const int64_t* numels, void* stream);
 
-/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32 or bf16),
+/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16 or fp16; rows with mask 0 are
+ * never read),
  * masks [B,L] float {0,1}; L,Din = 50,512 (MADE_VIDEO) or 96,768 (MADE_MUSIC).
- * -> seq_bf16 [B,L,256] bf16, seq_f32 [B,L,256] (nullable), pooled [B,256] fp32 (L2-normalised). */
+ * -> seq16 [B,L,256] fp16, seq_f32 [B,L,256] (nullable), pooled [B,256] fp32 (L2-normalised). */
 int made_encode(made_ctx* ctx, int modality, const void* feats, int feats_dtype, const float* masks,
-                int64_t B, void* seq_bf16, float* seq_f32, float* pooled, void* stream);
+                int64_t B, void* seq16, float* seq_f32, float* pooled, void* stream);
 
 /* Per-track X-Pool operands from encoded segments (modules/transformer.py:165, 102-106 folded):
- * seg_bf16 [N,96,256], seg_masks [N,96] -> kz [N*96,768] bf16 (K | V'' | Z''),
- * gram [N*96,96] bf16, maskbits [N,4] u32. */
-int made_gallery_prepare(made_ctx* ctx, const void* seg_bf16, const float* seg_masks, int64_t N,
+ * seg16 [N,96,256], seg_masks [N,96] -> kz [N*96,768] fp16 (K | V'' | Z''),
+ * gram [N*96,96] fp16, maskbits [N,4] u32. */
+int made_gallery_prepare(made_ctx* ctx, const void* seg16, const float* seg_masks, int64_t N,
                          void* kz, void* gram, uint32_t* maskbits, void* stream);
 /* Per-query X-Pool operands (modules/transformer.py:164, 98; metrics.py:19):
- * video_feats [N,256] fp32 -> q [N,256] bf16 (q_proj(LN1(v))/16), vhat [N,256] fp16. */
+ * video_feats [N,256] fp32 -> q [N,256] fp16 (q_proj(LN1(v))/16), vhat [N,256] fp16. */
 int made_query_prepare(made_ctx* ctx, const float* video_feats, int64_t N, void* q, void* vhat,
                        void* stream);
 /* Transformer_XA + sim_matrix_music_pooling fused (modules/transformer.py:156-180,
@@ -123,13 +127,13 @@ int made_xpool_score(made_ctx* ctx, const void* q, const void* vhat, int64_t n_q
 
 /* Moment detection for B (query, track) pairs — model_Uni.py:207-227 + calc_output :117-150:
  * concat fusion, PositionEmbeddingSine, DETR encoder x2 / decoder x6, heads.
- * frame_bf16 [Bv,50,256], frame_masks [Bv,50], seg_bf16 [Nm,96,256], seg_masks [Nm,96],
+ * frame16 [Bv,50,256], frame_masks [Bv,50], seg16 [Nm,96,256], seg_masks [Nm,96],
  * track_idx [B] (nullable = identity) picks the track paired with query b, video_feats [B,256].
  * -> hs [6,B,256] (through decoder.norm), pred_logits [6,B,2], pred_spans [6,B,2] (sigmoid (c,w)),
  *    proj_queries [6,B,256] (nullable), proj_vid_mem [B,50,256] (nullable), memory [B,146,256]
  *    fp32 (nullable). */
-int made_detr_detect(made_ctx* ctx, const void* frame_bf16, const float* frame_masks,
-                     const void* seg_bf16, const float* seg_masks, const int32_t* track_idx,
+int made_detr_detect(made_ctx* ctx, const void* frame16, const float* frame_masks,
+                     const void* seg16, const float* seg_masks, const int32_t* track_idx,
                      const float* video_feats, int64_t B, float* hs, float* pred_logits,
                      float* pred_spans, float* proj_queries, float* proj_vid_mem, float* memory,
                      void* stream);
@@ -151,12 +155,12 @@ int made_retrieval_loss(const float* dual, const float* single, int64_t ld, int 
  * building blocks exported for the parity tests
  * ------------------------------------------------------------------------------------------- */
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias (+ residual)) with optional LayerNorm over N (N == 256).
- * A, W bf16; bias/gamma/beta fp32 (nullable); residual fp32 [M,N] (nullable);
- * act: 0 none, 1 GELU(erf), 2 ReLU; out_bf16 / out_f32 nullable (at least one). */
-int made_gemm_bf16(const void* A, const void* W, int64_t M, int N, int K, const float* bias,
+ * A, W fp16; bias/gamma/beta fp32 (nullable); residual fp32 [M,N] (nullable);
+ * act: 0 none, 1 GELU(erf), 2 ReLU; out16 / out_f32 nullable (at least one). */
+int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const float* bias,
                    const float* residual, int act, const float* ln_gamma, const float* ln_beta,
-                   void* out_bf16, float* out_f32, void* stream);
-/* softmax(Q K^T / sqrt(32) + key mask) V for 8 heads of 32: q,k,v,out [B*L, 256] bf16. */
+                   void* out16, float* out_f32, void* stream);
+/* softmax(Q K^T / sqrt(32) + key mask) V for 8 heads of 32: q,k,v,out [B*L, 256] fp16. */
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B,
                   int L, void* out, void* stream);
 

@@ -13,7 +13,7 @@ from . import build as _build
 _LIB: Optional[C.CDLL] = None
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 VIDEO, MUSIC = 0, 1
 
 _p = C.c_void_p
@@ -43,7 +43,7 @@ SIGNATURES = {
     "made_detr_detect": [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "made_detr_losses": [_p, _p, _p, _p, _p, _i64, _i32, _f, _f, _f, _p, _p],
     "made_retrieval_loss": [_p, _p, _i64, _i32, _f, _p, _p],
-    "made_gemm_bf16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
+    "made_gemm_f16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
     "made_mha_core": [_p, _p, _p, _p, _i64, _i32, _p, _p],
 }
 

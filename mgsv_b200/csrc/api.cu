@@ -16,16 +16,18 @@ namespace {
 
 constexpr int D = 256, DFF = 1024, LV = 50, LM = 96, LD = 146, NENC = 2, NDEC = 6;
 
-uint16_t f2bf(float f) {  // round-to-nearest-even, NaN-preserving
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>(u >> 16);
+uint16_t f2h(float f) {  // fp32 -> IEEE fp16 bits, round-to-nearest-even, saturating to +-65504
+  if (f != f) return 0x7E00;
+  const float lim = 65504.0f;
+  f = f > lim ? lim : (f < -lim ? -lim : f);
+  const __half h = __float2half_rn(f);   // host path of cuda_fp16.h: RNE incl. subnormals
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
 }
 
-struct Lin {            // y = x W^T + b, W [out,in] bf16 on device, b fp32
-  __nv_bfloat16* w = nullptr;
+struct Lin {            // y = x W^T + b, W [out,in] fp16 on device, b fp32
+  op_t* w = nullptr;
   float* b = nullptr;
 };
 struct LNp {
@@ -123,19 +125,19 @@ int up_f32(made_ctx* c, const float* src, size_t n, float** dst) {
   return MADE_OK;
 }
 
-int up_bf16(made_ctx* c, const float* src, size_t n, __nv_bfloat16** dst) {
+int up_op(made_ctx* c, const float* src, size_t n, op_t** dst) {
   std::vector<uint16_t> tmp(n);
-  for (size_t i = 0; i < n; ++i) tmp[i] = f2bf(src[i]);
+  for (size_t i = 0; i < n; ++i) tmp[i] = f2h(src[i]);
   void* p = nullptr;
   MADE_CUDA(cudaMalloc(&p, n * 2));
   c->allocs.push_back(p);
   MADE_CUDA(cudaMemcpy(p, tmp.data(), n * 2, cudaMemcpyHostToDevice));
-  *dst = static_cast<__nv_bfloat16*>(p);
+  *dst = static_cast<op_t*>(p);
   return MADE_OK;
 }
 
 int up_lin(made_ctx* c, const float* w, const float* b, size_t out_f, size_t in_f, Lin* lin) {
-  MADE_TRY(up_bf16(c, w, out_f * in_f, &lin->w));
+  MADE_TRY(up_op(c, w, out_f * in_f, &lin->w));
   MADE_TRY(up_f32(c, b, out_f, &lin->b));
   return MADE_OK;
 }
@@ -352,17 +354,17 @@ int load_detr(made_ctx* c) {
   return MADE_OK;
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+__global__ void cast_f32_op_kernel(const float* __restrict__ in, op_t* __restrict__ out, int64_t n) {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16(in[i]);
+  if (i < n) out[i] = f2op(in[i]);
 }
-__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+__global__ void cast_op_f32_kernel(const op_t* __restrict__ in, float* __restrict__ out, int64_t n) {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i < n) out[i] = op2f(in[i]);
 }
 
 // plain linear helper: out = act(A W^T + b)
-int linear(const __nv_bfloat16* A, int64_t lda, const Lin& w, int64_t M, int N, int K, GemmEpilogue epi,
+int linear(const op_t* A, int64_t lda, const Lin& w, int64_t M, int N, int K, GemmEpilogue epi,
            cudaStream_t st) {
   GemmParams p;
   p.M = M;
@@ -370,7 +372,7 @@ int linear(const __nv_bfloat16* A, int64_t lda, const Lin& w, int64_t M, int N, 
   p.K = K;
   epi.bias = w.b;
   p.epi = epi;
-  return gemm_bf16_tc(A, lda, w.w, K, N, p, 256, st);
+  return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
 }
 
 #define CTX_READY(ctx)                                                       \
@@ -422,12 +424,13 @@ int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const fl
 }
 
 int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, const float* masks, int64_t B,
-                void* seq_bf16, float* seq_f32, float* pooled, void* stream) {
+                void* seq16, float* seq_f32, float* pooled, void* stream) {
   CTX_READY(c);
   MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode: bad modality %d", modality);
-  MADE_REQUIRE(feats_dtype == MADE_DTYPE_F32 || feats_dtype == MADE_DTYPE_BF16, "encode: bad dtype");
+  MADE_REQUIRE(feats_dtype == MADE_DTYPE_F32 || feats_dtype == MADE_DTYPE_BF16 || feats_dtype == MADE_DTYPE_F16,
+               "encode: bad feature dtype %d", feats_dtype);
   if (B == 0) return MADE_OK;
-  MADE_REQUIRE(feats && masks && seq_bf16 && pooled, "encode: null pointer");
+  MADE_REQUIRE(feats && masks && seq16 && pooled, "encode: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const EncW& e = c->enc[modality];
   const int64_t T = B * e.L;
@@ -435,35 +438,35 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   size_t need = padded(T * e.din, 2) + padded(T * D, 2) * 4 + padded(T * D, 4) * 3 + padded(T * 3 * D, 2) +
                 padded(T * DFF, 2);
   MADE_TRY(c->reserve(need));
-  __nv_bfloat16* x0 = c->take<__nv_bfloat16>(T * e.din);
-  __nv_bfloat16* x1 = c->take<__nv_bfloat16>(T * D);
+  op_t* x0 = c->take<op_t>(T * e.din);
+  op_t* x1 = c->take<op_t>(T * D);
   float* x1f = c->take<float>(T * D);
-  __nv_bfloat16* qkv = c->take<__nv_bfloat16>(T * 3 * D);
-  __nv_bfloat16* att = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* x2 = c->take<__nv_bfloat16>(T * D);
+  op_t* qkv = c->take<op_t>(T * 3 * D);
+  op_t* att = c->take<op_t>(T * D);
+  op_t* x2 = c->take<op_t>(T * D);
   float* x2f = c->take<float>(T * D);
-  __nv_bfloat16* h = c->take<__nv_bfloat16>(T * DFF);
-  __nv_bfloat16* x3 = c->take<__nv_bfloat16>(T * D);
+  op_t* h = c->take<op_t>(T * DFF);
+  op_t* x3 = c->take<op_t>(T * D);
   float* seqf = seq_f32 ? seq_f32 : c->take<float>(T * D);
 
   // model_Base.py:556/595 masked_fill, cast to the GEMM operand type
-  MADE_TRY(cast_mask_rows(feats, feats_dtype == MADE_DTYPE_BF16, masks, T, e.din, x0, st));
+  MADE_TRY(cast_mask_rows(feats, feats_dtype, masks, T, e.din, x0, st));
   {  // :559/598 projection, :533 += pe[:L], Transformer_enhancement norm1 (:86)
     GemmEpilogue ep;
     ep.row_table = e.pe;
     ep.row_mod = e.L;
     ep.ln_gamma = e.ln1.g;
     ep.ln_beta = e.ln1.b;
-    ep.out_bf16 = x1;
-    ep.ld_bf16 = D;
+    ep.out_h = x1;
+    ep.ld_h = D;
     ep.out_f32 = x1f;
     ep.ld_f32 = D;
     MADE_TRY(linear(x0, e.din, e.proj, T, D, e.din, ep, st));
   }
   {  // packed in_proj (nn.MultiheadAttention)
     GemmEpilogue ep;
-    ep.out_bf16 = qkv;
-    ep.ld_bf16 = 3 * D;
+    ep.out_h = qkv;
+    ep.ld_h = 3 * D;
     MADE_TRY(linear(x1, D, e.in_proj, T, 3 * D, D, ep, st));
   }
   MADE_TRY(mha_core(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, masks, B, e.L, att, D, st));
@@ -474,8 +477,8 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
     ep.res_ld = D;
     ep.ln_gamma = e.ln2.g;
     ep.ln_beta = e.ln2.b;
-    ep.out_bf16 = x2;
-    ep.ld_bf16 = D;
+    ep.out_h = x2;
+    ep.ld_h = D;
     ep.out_f32 = x2f;
     ep.ld_f32 = D;
     MADE_TRY(linear(att, D, e.out_proj, T, D, D, ep, st));
@@ -483,8 +486,8 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   {  // FF: Linear -> GELU(erf)
     GemmEpilogue ep;
     ep.act = 1;
-    ep.out_bf16 = h;
-    ep.ld_bf16 = DFF;
+    ep.out_h = h;
+    ep.ld_h = DFF;
     MADE_TRY(linear(x2, D, e.ff1, T, DFF, D, ep, st));
   }
   {  // FF: Linear + residual (:89)
@@ -492,15 +495,15 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
     ep.residual = x2f;
     ep.residual_f32 = 1;
     ep.res_ld = D;
-    ep.out_bf16 = x3;
-    ep.ld_bf16 = D;
+    ep.out_h = x3;
+    ep.ld_h = D;
     MADE_TRY(linear(h, DFF, e.ff2, T, D, DFF, ep, st));
   }
   {  // final_linear (:91) + masked_fill (:541)
     GemmEpilogue ep;
     ep.row_mask = masks;
-    ep.out_bf16 = static_cast<__nv_bfloat16*>(seq_bf16);
-    ep.ld_bf16 = D;
+    ep.out_h = static_cast<op_t*>(seq16);
+    ep.ld_h = D;
     ep.out_f32 = seqf;
     ep.ld_f32 = D;
     MADE_TRY(linear(x3, D, e.fin, T, D, D, ep, st));
@@ -510,23 +513,23 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   return MADE_OK;
 }
 
-int made_gallery_prepare(made_ctx* c, const void* seg_bf16, const float* seg_masks, int64_t N, void* kz,
+int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks, int64_t N, void* kz,
                          void* gram, uint32_t* maskbits, void* stream) {
   CTX_READY(c);
   if (N == 0) return MADE_OK;
-  MADE_REQUIRE(seg_bf16 && seg_masks && kz && gram && maskbits, "gallery_prepare: null pointer");
+  MADE_REQUIRE(seg16 && seg_masks && kz && gram && maskbits, "gallery_prepare: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = N * LM;
   MADE_REQUIRE(T < (1LL << 31), "gallery_prepare: too many tracks in one call; chunk it");
   MADE_TRY(c->reserve(padded(T * D, 2)));
-  __nv_bfloat16* sp = c->take<__nv_bfloat16>(T * D);
+  op_t* sp = c->take<op_t>(T * D);
   // shared LayerNorm1 on the segments (modules/transformer.py:165)
-  MADE_TRY(layernorm_rows(seg_bf16, 1, D, T, c->xp_ln1.g, c->xp_ln1.b, sp, nullptr, st));
-  __nv_bfloat16* kzb = static_cast<__nv_bfloat16*>(kz);
+  MADE_TRY(layernorm_rows(seg16, 1, D, T, c->xp_ln1.g, c->xp_ln1.b, sp, nullptr, st));
+  op_t* kzb = static_cast<op_t*>(kz);
   {
     GemmEpilogue ep;
-    ep.out_bf16 = kzb;
-    ep.ld_bf16 = 3 * D;
+    ep.out_h = kzb;
+    ep.ld_h = 3 * D;
     MADE_TRY(linear(sp, D, c->xp_kvz, T, 3 * D, D, ep, st));
   }
   {  // per-track Gram matrix G = V'' V''^T (96 x 96), batched over tracks
@@ -537,9 +540,9 @@ int made_gallery_prepare(made_ctx* c, const void* seg_bf16, const float* seg_mas
     p.m_stride = LM;
     p.m_valid = LM;
     p.b_batched = 1;
-    p.epi.out_bf16 = static_cast<__nv_bfloat16*>(gram);
-    p.epi.ld_bf16 = LM;
-    MADE_TRY(gemm_bf16_tc(kzb + D, 3 * D, kzb + D, 3 * D, T, p, 96, st));
+    p.epi.out_h = static_cast<op_t*>(gram);
+    p.epi.ld_h = LM;
+    MADE_TRY(gemm_f16_tc(kzb + D, 3 * D, kzb + D, 3 * D, T, p, 96, st));
   }
   MADE_TRY(mask_bits(seg_masks, N, maskbits, st));
   return MADE_OK;
@@ -551,11 +554,11 @@ int made_query_prepare(made_ctx* c, const float* video_feats, int64_t N, void* q
   MADE_REQUIRE(video_feats && q && vhat, "query_prepare: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MADE_TRY(c->reserve(padded(N * D, 2)));
-  __nv_bfloat16* vp = c->take<__nv_bfloat16>(N * D);
+  op_t* vp = c->take<op_t>(N * D);
   MADE_TRY(layernorm_rows(video_feats, 0, D, N, c->xp_ln1.g, c->xp_ln1.b, vp, nullptr, st));
   GemmEpilogue ep;
-  ep.out_bf16 = static_cast<__nv_bfloat16*>(q);
-  ep.ld_bf16 = D;
+  ep.out_h = static_cast<op_t*>(q);
+  ep.ld_h = D;
   MADE_TRY(linear(vp, D, c->xp_q, N, D, D, ep, st));
   MADE_TRY(vhat_rows(video_feats, N, static_cast<__half*>(vhat), st));
   return MADE_OK;
@@ -566,18 +569,18 @@ int made_xpool_score(made_ctx* c, const void* q, const void* vhat, int64_t n_que
                      int64_t col_offset, void* stream) {
   CTX_READY(c);
   MADE_REQUIRE(ld >= col_offset + n_tracks, "xpool_score: ld=%lld too small", (long long)ld);
-  return xpool_score(static_cast<const __nv_bfloat16*>(q), static_cast<const __half*>(vhat), n_queries,
-                     static_cast<const __nv_bfloat16*>(kz), 3 * D, 2 * D, static_cast<const __nv_bfloat16*>(gram),
+  return xpool_score(static_cast<const op_t*>(q), static_cast<const __half*>(vhat), n_queries,
+                     static_cast<const op_t*>(kz), 3 * D, 2 * D, static_cast<const op_t*>(gram),
                      maskbits, n_tracks, sim, ld, col_offset, static_cast<cudaStream_t>(stream));
 }
 
-int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_masks, const void* seg_bf16,
+int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks, const void* seg16,
                      const float* seg_masks, const int32_t* track_idx, const float* video_feats, int64_t B,
                      float* hs, float* pred_logits, float* pred_spans, float* proj_queries, float* proj_vid_mem,
                      float* memory, void* stream) {
   CTX_READY(c);
   if (B == 0) return MADE_OK;
-  MADE_REQUIRE(frame_bf16 && frame_masks && seg_bf16 && seg_masks && video_feats && hs && pred_logits && pred_spans,
+  MADE_REQUIRE(frame16 && frame_masks && seg16 && seg_masks && video_feats && hs && pred_logits && pred_spans,
                "detr_detect: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = B * LD;
@@ -587,52 +590,52 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
                 padded(T * NDEC * D, 2) * 2 + padded(B * D, 2) * 6 + padded(B * D, 4) * 4 + padded(B * DFF, 2) +
                 padded(R * D, 4) + padded(R * D, 2) * 3;
   MADE_TRY(c->reserve(need));
-  __nv_bfloat16* src = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* pos = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* srcpos = c->take<__nv_bfloat16>(T * D);
+  op_t* src = c->take<op_t>(T * D);
+  op_t* pos = c->take<op_t>(T * D);
+  op_t* srcpos = c->take<op_t>(T * D);
   float* mask = c->take<float>(T);
-  __nv_bfloat16* qk = c->take<__nv_bfloat16>(T * 2 * D);
-  __nv_bfloat16* v = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* att = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* s1 = c->take<__nv_bfloat16>(T * D);
+  op_t* qk = c->take<op_t>(T * 2 * D);
+  op_t* v = c->take<op_t>(T * D);
+  op_t* att = c->take<op_t>(T * D);
+  op_t* s1 = c->take<op_t>(T * D);
   float* s1f = c->take<float>(T * D);
-  __nv_bfloat16* hbuf = c->take<__nv_bfloat16>(T * DFF);
-  __nv_bfloat16* src2 = c->take<__nv_bfloat16>(T * D);
-  __nv_bfloat16* srcpos2 = c->take<__nv_bfloat16>(T * D);
+  op_t* hbuf = c->take<op_t>(T * DFF);
+  op_t* src2 = c->take<op_t>(T * D);
+  op_t* srcpos2 = c->take<op_t>(T * D);
   float* srcf = c->take<float>(T * D);
-  __nv_bfloat16* kall = c->take<__nv_bfloat16>(T * NDEC * D);
-  __nv_bfloat16* vall = c->take<__nv_bfloat16>(T * NDEC * D);
-  __nv_bfloat16* tgt = c->take<__nv_bfloat16>(B * D);
-  __nv_bfloat16* t1 = c->take<__nv_bfloat16>(B * D);
+  op_t* kall = c->take<op_t>(T * NDEC * D);
+  op_t* vall = c->take<op_t>(T * NDEC * D);
+  op_t* tgt = c->take<op_t>(B * D);
+  op_t* t1 = c->take<op_t>(B * D);
   float* t1f = c->take<float>(B * D);
   float* qf = c->take<float>(B * D);
-  __nv_bfloat16* ob = c->take<__nv_bfloat16>(B * D);
-  __nv_bfloat16* t2 = c->take<__nv_bfloat16>(B * D);
+  op_t* ob = c->take<op_t>(B * D);
+  op_t* t2 = c->take<op_t>(B * D);
   float* t2f = c->take<float>(B * D);
-  __nv_bfloat16* hdec = c->take<__nv_bfloat16>(B * DFF);
-  __nv_bfloat16* t3 = c->take<__nv_bfloat16>(B * D);
+  op_t* hdec = c->take<op_t>(B * DFF);
+  op_t* t3 = c->take<op_t>(B * D);
   float* t3all = c->take<float>(R * D);
-  __nv_bfloat16* hsb = c->take<__nv_bfloat16>(R * D);
-  __nv_bfloat16* sp0 = c->take<__nv_bfloat16>(R * D);
-  __nv_bfloat16* sp1 = c->take<__nv_bfloat16>(R * D);
+  op_t* hsb = c->take<op_t>(R * D);
+  op_t* sp0 = c->take<op_t>(R * D);
+  op_t* sp1 = c->take<op_t>(R * D);
 
-  const __nv_bfloat16* fr = static_cast<const __nv_bfloat16*>(frame_bf16);
-  MADE_TRY(detr_prep(fr, frame_masks, static_cast<const __nv_bfloat16*>(seg_bf16), seg_masks, track_idx,
+  const op_t* fr = static_cast<const op_t*>(frame16);
+  MADE_TRY(detr_prep(fr, frame_masks, static_cast<const op_t*>(seg16), seg_masks, track_idx,
                      c->inv_dim_t, B, src, pos, srcpos, mask, st));
   // ---------------- encoder (forward_post, music_detr/transformer.py:191-210) ----------------
-  __nv_bfloat16 *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
+  op_t *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
   for (int l = 0; l < NENC; ++l) {
     const DetrEncW& w = c->denc[l];
     {
       GemmEpilogue ep;
-      ep.out_bf16 = qk;
-      ep.ld_bf16 = 2 * D;
+      ep.out_h = qk;
+      ep.ld_h = 2 * D;
       MADE_TRY(linear(curpos, D, w.qk, T, 2 * D, D, ep, st));   // q = k = src + pos
     }
     {
       GemmEpilogue ep;
-      ep.out_bf16 = v;
-      ep.ld_bf16 = D;
+      ep.out_h = v;
+      ep.ld_h = D;
       MADE_TRY(linear(cur, D, w.v, T, D, D, ep, st));           // value = src
     }
     MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, mask, B, LD, att, D, st));
@@ -648,8 +651,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
       ep.res_ld = D;
       ep.ln_gamma = w.n1.g;
       ep.ln_beta = w.n1.b;
-      ep.out_bf16 = s1;
-      ep.ld_bf16 = D;
+      ep.out_h = s1;
+      ep.ld_h = D;
       ep.out_f32 = s1f;
       ep.ld_f32 = D;
       MADE_TRY(linear(att, D, w.out, T, D, D, ep, st));
@@ -657,8 +660,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
     {
       GemmEpilogue ep;
       ep.act = 2;
-      ep.out_bf16 = hbuf;
-      ep.ld_bf16 = DFF;
+      ep.out_h = hbuf;
+      ep.ld_h = DFF;
       MADE_TRY(linear(s1, D, w.ff1, T, DFF, D, ep, st));
     }
     {
@@ -668,37 +671,37 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
       ep.res_ld = D;
       ep.ln_gamma = w.n2.g;
       ep.ln_beta = w.n2.b;
-      ep.out_bf16 = nxt;
-      ep.ld_bf16 = D;
+      ep.out_h = nxt;
+      ep.ld_h = D;
       ep.out_f32 = srcf;
       ep.ld_f32 = D;
       ep.add2 = pos;
       ep.add2_ld = D;
-      ep.out2_bf16 = nxtpos;
+      ep.out2_h = nxtpos;
       ep.ld_out2 = D;
       MADE_TRY(linear(hbuf, DFF, w.ff2, T, D, DFF, ep, st));
     }
-    __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+    op_t* t = cur; cur = nxt; nxt = t;
     t = curpos; curpos = nxtpos; nxtpos = t;
   }
   if (memory) MADE_CUDA(cudaMemcpyAsync(memory, srcf, static_cast<size_t>(T) * D * 4, cudaMemcpyDeviceToDevice, st));
   // ---------------- decoder K/V of the memory for all six layers at once ----------------
   {
     GemmEpilogue ep;
-    ep.out_bf16 = kall;
-    ep.ld_bf16 = NDEC * D;
+    ep.out_h = kall;
+    ep.ld_h = NDEC * D;
     MADE_TRY(linear(curpos, D, c->dec_kall, T, NDEC * D, D, ep, st));   // key = memory + pos
   }
   {
     GemmEpilogue ep;
-    ep.out_bf16 = vall;
-    ep.ld_bf16 = NDEC * D;
+    ep.out_h = vall;
+    ep.ld_h = NDEC * D;
     MADE_TRY(linear(cur, D, c->dec_vall, T, NDEC * D, D, ep, st));      // value = memory
   }
   // ---------------- decoder (forward_post :273-307), one moment query per sequence ----------------
-  cast_f32_bf16_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
+  cast_f32_op_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
   MADE_CHECK_LAUNCH();
-  const __nv_bfloat16* tin = tgt;
+  const op_t* tin = tgt;
   const float* tinf = video_feats;
   for (int l = 0; l < NDEC; ++l) {
     const DetrDecW& w = c->ddec[l];
@@ -710,8 +713,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
       ep.res_ld = D;
       ep.ln_gamma = w.n1.g;
       ep.ln_beta = w.n1.b;
-      ep.out_bf16 = t1;
-      ep.ld_bf16 = D;
+      ep.out_h = t1;
+      ep.ld_h = D;
       ep.out_f32 = t1f;
       ep.ld_f32 = D;
       MADE_TRY(linear(tin, D, w.sa, B, D, D, ep, st));
@@ -730,8 +733,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
       ep.res_ld = D;
       ep.ln_gamma = w.n2.g;
       ep.ln_beta = w.n2.b;
-      ep.out_bf16 = t2;
-      ep.ld_bf16 = D;
+      ep.out_h = t2;
+      ep.ld_h = D;
       ep.out_f32 = t2f;
       ep.ld_f32 = D;
       MADE_TRY(linear(ob, D, w.out, B, D, D, ep, st));
@@ -739,8 +742,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
     {
       GemmEpilogue ep;
       ep.act = 2;
-      ep.out_bf16 = hdec;
-      ep.ld_bf16 = DFF;
+      ep.out_h = hdec;
+      ep.ld_h = DFF;
       MADE_TRY(linear(t2, D, w.ff1, B, DFF, D, ep, st));
     }
     {
@@ -750,8 +753,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
       ep.res_ld = D;
       ep.ln_gamma = w.n3.g;
       ep.ln_beta = w.n3.b;
-      ep.out_bf16 = t3;
-      ep.ld_bf16 = D;
+      ep.out_h = t3;
+      ep.ld_h = D;
       ep.out_f32 = t3f;
       ep.ld_f32 = D;
       MADE_TRY(linear(hdec, DFF, w.ff2, B, D, DFF, ep, st));
@@ -766,15 +769,15 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
   {
     GemmEpilogue ep;
     ep.act = 2;
-    ep.out_bf16 = sp0;
-    ep.ld_bf16 = D;
+    ep.out_h = sp0;
+    ep.ld_h = D;
     MADE_TRY(linear(hsb, D, c->span0, R, D, D, ep, st));
   }
   {
     GemmEpilogue ep;
     ep.act = 2;
-    ep.out_bf16 = sp1;
-    ep.ld_bf16 = D;
+    ep.out_h = sp1;
+    ep.ld_h = D;
     MADE_TRY(linear(sp0, D, c->span1, R, D, D, ep, st));
   }
   MADE_TRY(heads_final(hs, sp1, R, c->cls_w, c->cls_b, c->span2_w, c->span2_b, pred_logits, pred_spans, st));
@@ -795,8 +798,8 @@ int made_detr_detect(made_ctx* c, const void* frame_bf16, const float* frame_mas
   return MADE_OK;
 }
 
-int made_gemm_bf16(const void* A, const void* W, int64_t M, int N, int K, const float* bias, const float* residual,
-                   int act, const float* ln_gamma, const float* ln_beta, void* out_bf16, float* out_f32,
+int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const float* bias, const float* residual,
+                   int act, const float* ln_gamma, const float* ln_beta, void* out_h, float* out_f32,
                    void* stream) {
   GemmParams p;
   p.M = M;
@@ -809,18 +812,18 @@ int made_gemm_bf16(const void* A, const void* W, int64_t M, int N, int K, const 
   p.epi.act = act;
   p.epi.ln_gamma = ln_gamma;
   p.epi.ln_beta = ln_beta;
-  p.epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
-  p.epi.ld_bf16 = N;
+  p.epi.out_h = static_cast<op_t*>(out_h);
+  p.epi.ld_h = N;
   p.epi.out_f32 = out_f32;
   p.epi.ld_f32 = N;
-  return gemm_bf16_tc(static_cast<const __nv_bfloat16*>(A), K, static_cast<const __nv_bfloat16*>(W), K, N, p, 256,
+  return gemm_f16_tc(static_cast<const op_t*>(A), K, static_cast<const op_t*>(W), K, N, p, 256,
                       static_cast<cudaStream_t>(stream));
 }
 
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B, int L, void* out,
                   void* stream) {
-  return mha_core(static_cast<const __nv_bfloat16*>(q), D, static_cast<const __nv_bfloat16*>(k), D,
-                  static_cast<const __nv_bfloat16*>(v), D, key_mask, B, L, static_cast<__nv_bfloat16*>(out), D,
+  return mha_core(static_cast<const op_t*>(q), D, static_cast<const op_t*>(k), D,
+                  static_cast<const op_t*>(v), D, key_mask, B, L, static_cast<op_t*>(out), D,
                   static_cast<cudaStream_t>(stream));
 }
 

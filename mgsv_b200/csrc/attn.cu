@@ -5,16 +5,16 @@
 // These are ~5-9 % of the path's FLOPs in 32-wide heads, too small for a 128-row tcgen05 tile, so
 // one warp owns one (sequence, head): K and V^T head slices live in padded shared memory
 // (conflict-free fragment loads), scores stay in registers (whole row, no online softmax), and the
-// two products run on mma.sync m16n8k16 bf16 with fp32 accumulation.
+// two products run on mma.sync m16n8k16 fp16 with fp32 accumulation.
 // The decoder's single-query cross-attention (1 x 146 per head) is a separate SIMT kernel.
 #include "common.cuh"
 
 namespace made {
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4],
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4],
                                                const uint32_t (&b)[2]) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
       "{%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
@@ -22,21 +22,21 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 constexpr int kHeadDim = 32;
 constexpr int kHeadsPerCta = 4;
-constexpr int kKStride = 40;  // bf16 elements per K row in smem (80 B: conflict-free 4-byte frags)
+constexpr int kKStride = 40;  // fp16 elements per K row in smem (80 B: conflict-free 4-byte frags)
 
 template <int LP>  // padded length, multiple of 16
 struct AttnSmem {
   static constexpr int kVStride = LP + 8;  // (LP+8)/2 words == 4 or 20 (mod 32): conflict-free
-  static constexpr int kPerWarp = LP * kKStride + kHeadDim * kVStride;  // bf16 elements
+  static constexpr int kPerWarp = LP * kKStride + kHeadDim * kVStride;  // fp16 elements
   static constexpr int kBytes = kHeadsPerCta * kPerWarp * 2 + LP * 4;
 };
 
 template <int LP>
 __global__ void __launch_bounds__(kHeadsPerCta * 32)
-mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfloat16* __restrict__ K,
-                int64_t ldk, const __nv_bfloat16* __restrict__ V, int64_t ldv,
+mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict__ K,
+                int64_t ldk, const op_t* __restrict__ V, int64_t ldv,
                 const float* __restrict__ key_mask, int L, float scale,
-                __nv_bfloat16* __restrict__ O, int64_t ldo) {
+                op_t* __restrict__ O, int64_t ldo) {
   using S = AttnSmem<LP>;
   constexpr int NT = LP / 8, KK = LP / 16;
   extern __shared__ __align__(16) uint8_t attn_smem[];
@@ -44,16 +44,16 @@ mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfl
   const int g = lane >> 2, t = lane & 3;
   const int64_t b = blockIdx.x;
   const int h = blockIdx.y * kHeadsPerCta + warp;
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem) + warp * S::kPerWarp;
-  __nv_bfloat16* Vt = Ks + LP * kKStride;
+  op_t* Ks = reinterpret_cast<op_t*>(attn_smem) + warp * S::kPerWarp;
+  op_t* Vt = Ks + LP * kKStride;
   float* smask = reinterpret_cast<float*>(attn_smem + kHeadsPerCta * S::kPerWarp * 2);
 
   for (int i = threadIdx.x; i < LP; i += blockDim.x)
     smask[i] = (i < L && key_mask[b * L + i] != 0.f) ? 0.f : -INFINITY;
 
   // ---- stage K (row-major) and V (transposed) head slices; rows >= L are zero ----
-  const __nv_bfloat16* Kg = K + (b * L) * ldk + h * kHeadDim;
-  const __nv_bfloat16* Vg = V + (b * L) * ldv + h * kHeadDim;
+  const op_t* Kg = K + (b * L) * ldk + h * kHeadDim;
+  const op_t* Vg = V + (b * L) * ldv + h * kHeadDim;
   for (int idx = lane; idx < LP * 4; idx += 32) {
     const int key = idx >> 2, ch = idx & 3;
     uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -62,13 +62,13 @@ mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfl
       vv = __ldg(reinterpret_cast<const uint4*>(Vg + key * ldv + ch * 8));
     }
     *reinterpret_cast<uint4*>(Ks + key * kKStride + ch * 8) = kv;
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+    const op_t* ve = reinterpret_cast<const op_t*>(&vv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) Vt[(ch * 8 + j) * S::kVStride + key] = ve[j];
   }
   __syncthreads();
 
-  const __nv_bfloat16* Qg = Q + (b * L) * ldq + h * kHeadDim;
+  const op_t* Qg = Q + (b * L) * ldq + h * kHeadDim;
   for (int rt = 0; rt < KK; ++rt) {
     const int r0 = rt * 16 + g, r1 = r0 + 8;
     if (rt * 16 >= L) break;
@@ -90,10 +90,10 @@ mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfl
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t kb[2];
-        const __nv_bfloat16* kp = Ks + (nt * 8 + g) * kKStride + ks * 16 + 2 * t;
+        const op_t* kp = Ks + (nt * 8 + g) * kKStride + ks * 16 + 2 * t;
         kb[0] = *reinterpret_cast<const uint32_t*>(kp);
         kb[1] = *reinterpret_cast<const uint32_t*>(kp + 8);
-        mma_bf16_16816(s[nt], qa[ks], kb);
+        mma_f16_16816(s[nt], qa[ks], kb);
       }
     }
     // ---- masked softmax over the whole row (rows g and g+8 of this tile) ----
@@ -116,11 +116,11 @@ mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfl
     uint32_t pa[KK][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      // unnormalised weights, rounded to bf16 for the MMA; the divisor is the sum of the ROUNDED
+      // unnormalised weights, rounded to fp16 for the MMA; the divisor is the sum of the ROUNDED
       // weights so that the weights used sum to one exactly
-      __nv_bfloat162 p01 = __floats2bfloat162_rn(__expf(s[nt][0] - mx0), __expf(s[nt][1] - mx0));
-      __nv_bfloat162 p23 = __floats2bfloat162_rn(__expf(s[nt][2] - mx1), __expf(s[nt][3] - mx1));
-      float2 f01 = __bfloat1622float2(p01), f23 = __bfloat1622float2(p23);
+      op2_t p01 = floats2op2(__expf(s[nt][0] - mx0), __expf(s[nt][1] - mx0));
+      op2_t p23 = floats2op2(__expf(s[nt][2] - mx1), __expf(s[nt][3] - mx1));
+      float2 f01 = op2_to_f2(p01), f23 = op2_to_f2(p23);
       sum0 += f01.x + f01.y;
       sum1 += f23.x + f23.y;
       pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&p01);
@@ -138,31 +138,31 @@ mha_core_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfl
 #pragma unroll
       for (int kk = 0; kk < KK; ++kk) {
         uint32_t vb[2];
-        const __nv_bfloat16* vp = Vt + (nd * 8 + g) * S::kVStride + kk * 16 + 2 * t;
+        const op_t* vp = Vt + (nd * 8 + g) * S::kVStride + kk * 16 + 2 * t;
         vb[0] = *reinterpret_cast<const uint32_t*>(vp);
         vb[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[nd], pa[kk], vb);
+        mma_f16_16816(o[nd], pa[kk], vb);
       }
     }
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-    __nv_bfloat16* Og = O + (b * L) * ldo + h * kHeadDim;
+    op_t* Og = O + (b * L) * ldo + h * kHeadDim;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
       const int c = nd * 8 + 2 * t;
-      if (r0 < L) *reinterpret_cast<uint32_t*>(Og + r0 * ldo + c) = pack_bf16x2(o[nd][0] * inv0, o[nd][1] * inv0);
-      if (r1 < L) *reinterpret_cast<uint32_t*>(Og + r1 * ldo + c) = pack_bf16x2(o[nd][2] * inv1, o[nd][3] * inv1);
+      if (r0 < L) *reinterpret_cast<uint32_t*>(Og + r0 * ldo + c) = pack_op2(o[nd][0] * inv0, o[nd][1] * inv0);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(Og + r1 * ldo + c) = pack_op2(o[nd][2] * inv1, o[nd][3] * inv1);
     }
   }
 }
 
 // Decoder cross-attention with ONE query per sequence (music_detr/transformer.py:289-292):
 // q [B,256] fp32 (already projected, includes the query-pos term), K/V slices of layer l inside
-// the batched [B*L, ldkv] projections; out [B,256] bf16.  One CTA (256 threads) per sequence.
+// the batched [B*L, ldkv] projections; out [B,256] fp16.  One CTA (256 threads) per sequence.
 __global__ void __launch_bounds__(256)
-dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ K,
-                      const __nv_bfloat16* __restrict__ V, int64_t ldkv,
+dec_cross_attn_kernel(const float* __restrict__ q, const op_t* __restrict__ K,
+                      const op_t* __restrict__ V, int64_t ldkv,
                       const float* __restrict__ key_mask, int L, float scale,
-                      __nv_bfloat16* __restrict__ out) {
+                      op_t* __restrict__ out) {
   __shared__ float sq[256];
   __shared__ float sp[8][160];
   const int64_t b = blockIdx.x;
@@ -170,7 +170,7 @@ dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restri
   sq[tid] = q[b * 256 + tid] * scale;
   __syncthreads();
   // scores: warp = head; lane strides over keys; 32-dim dot from a 64-byte contiguous slice
-  const __nv_bfloat16* Kb = K + (b * L) * ldkv + warp * 32;
+  const op_t* Kb = K + (b * L) * ldkv + warp * 32;
   float mx = -INFINITY;
   for (int key = lane; key < L; key += 32) {
     const uint4* kp = reinterpret_cast<const uint4*>(Kb + key * ldkv);
@@ -178,10 +178,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restri
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 kv = __ldg(kp + c);
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&kv);
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&kv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(hh[j]);
+        float2 f = op2_to_f2(hh[j]);
         acc = fmaf(f.x, sq[warp * 32 + c * 8 + 2 * j], acc);
         acc = fmaf(f.y, sq[warp * 32 + c * 8 + 2 * j + 1], acc);
       }
@@ -200,10 +200,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restri
   sum = warp_sum(sum);
   __syncthreads();
   // output: thread = output dim (head = tid/32), coalesced 512-byte V rows
-  const __nv_bfloat16* Vb = V + (b * L) * ldkv + tid;
+  const op_t* Vb = V + (b * L) * ldkv + tid;
   float acc = 0.f;
-  for (int key = 0; key < L; ++key) acc = fmaf(sp[warp][key], __bfloat162float(Vb[key * ldkv]), acc);
-  out[b * 256 + tid] = __float2bfloat16(acc / sum);
+  for (int key = 0; key < L; ++key) acc = fmaf(sp[warp][key], op2f(Vb[key * ldkv]), acc);
+  out[b * 256 + tid] = f2op(acc / sum);
 }
 
 }  // namespace made
@@ -211,9 +211,9 @@ dec_cross_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restri
 using namespace made;
 
 template <int LP>
-static int launch_mha(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* K, int64_t ldk,
-                      const __nv_bfloat16* V, int64_t ldv, const float* mask, int64_t B, int L,
-                      __nv_bfloat16* O, int64_t ldo, cudaStream_t st) {
+static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
+                      const op_t* V, int64_t ldv, const float* mask, int64_t B, int L,
+                      op_t* O, int64_t ldo, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     MADE_CUDA(cudaFuncSetAttribute(mha_core_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -228,9 +228,9 @@ static int launch_mha(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* 
 }
 
 namespace made {
-int mha_core(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* K, int64_t ldk,
-             const __nv_bfloat16* V, int64_t ldv, const float* key_mask, int64_t B, int L,
-             __nv_bfloat16* O, int64_t ldo, cudaStream_t st) {
+int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
+             const op_t* V, int64_t ldv, const float* key_mask, int64_t B, int L,
+             op_t* O, int64_t ldo, cudaStream_t st) {
   if (B == 0) return MADE_OK;
   MADE_REQUIRE(Q && K && V && key_mask && O, "mha_core: null pointer");
   MADE_REQUIRE(L > 0 && L <= 160, "mha_core: L=%d unsupported (max 160)", L);
@@ -240,8 +240,8 @@ int mha_core(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* K, int64_
   return launch_mha<160>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, O, ldo, st);
 }
 
-int dec_cross_attn(const float* q, const __nv_bfloat16* K, const __nv_bfloat16* V, int64_t ldkv,
-                   const float* key_mask, int64_t B, int L, __nv_bfloat16* out, cudaStream_t st) {
+int dec_cross_attn(const float* q, const op_t* K, const op_t* V, int64_t ldkv,
+                   const float* key_mask, int64_t B, int L, op_t* out, cudaStream_t st) {
   if (B == 0) return MADE_OK;
   MADE_REQUIRE(q && K && V && key_mask && out && L <= 160, "dec_cross_attn: bad arguments");
   dec_cross_attn_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(q, K, V, ldkv, key_mask, L,

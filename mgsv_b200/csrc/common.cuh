@@ -13,6 +13,14 @@
 
 namespace made {
 
+// The 16-bit GEMM operand type of the whole path.  IEEE fp16 (10-bit mantissa) rather than bf16
+// (7-bit): same tensor-pipe rate, 8x smaller rounding error, which is what brings the similarity
+// scores inside the 1e-3 relative bar (DESIGN.md "numerics", scripts/precision_study.py).
+// Activations of this model are LayerNorm-bounded, far inside fp16's range; conversions saturate.
+typedef __half op_t;
+typedef __half2 op2_t;
+constexpr uint32_t kUmmaOpFormat = 0;   // tcgen05 kind::f16 a/b format: 0 = F16, 1 = BF16
+
 // ------------------------------------------------------------------------------------------
 // host-side error plumbing (the C ABI returns codes; text via made_last_error_string)
 // ------------------------------------------------------------------------------------------
@@ -44,7 +52,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // TMA descriptor encode through the driver entry point (no link-time libcuda dependency).
-int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 int sm_count();
@@ -222,8 +230,8 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1
 //   bits [61,64) layout type (2 = SWIZZLE_128B)
-// K-major operand  (rows = M/N index, 128 B = 64 bf16 of K per row): SBO = 1024 (8 rows), LBO unused.
-// MN-major operand (rows = K index, 128 B = 64 bf16 of M/N per row): SBO = 1024 (8 k-rows),
+// K-major operand  (rows = M/N index, 128 B = 64 fp16 of K per row): SBO = 1024 (8 rows), LBO unused.
+// MN-major operand (rows = K index, 128 B = 64 fp16 of M/N per row): SBO = 1024 (8 k-rows),
 //                   LBO = byte distance between consecutive 64-element MN slabs.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes) {
@@ -235,13 +243,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= 2ull << 61;
   return d;
 }
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
-//   [4,6) c_format (1 = F32)  [7,10) a_format (1 = BF16)  [10,13) b_format (1 = BF16)
+// Instruction descriptor for kind::f16, fp16 x fp16 -> fp32.
+//   [4,6) c_format (1 = F32)  [7,10) a_format (0 = F16, 1 = BF16)  [10,13) b_format (same)
 //   [15] a_major (0 = K)  [16] b_major (0 = K, 1 = MN)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, uint32_t a_mn_major,
                                                        uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
-         ((n >> 3) << 17) | ((m >> 4) << 24);
+  return (1u << 4) | (kUmmaOpFormat << 7) | (kUmmaOpFormat << 10) | (a_mn_major << 15) |
+         (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
@@ -256,10 +264,24 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 }
 
 // ---- small math ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// ---- 16-bit operand type helpers (op_t = IEEE fp16) ------------------------------------------
+// Conversions to the operand type saturate to +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+__device__ __forceinline__ op2_t floats2op2(float lo, float hi) {
+  uint32_t r = pack_op2(lo, hi);
+  return *reinterpret_cast<op2_t*>(&r);
+}
+__device__ __forceinline__ op_t f2op(float x) {
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return __ushort_as_half(r);
+}
+__device__ __forceinline__ float op2f(op_t x) { return __half2float(x); }
+__device__ __forceinline__ float2 op2_to_f2(op2_t x) { return __half22float2(x); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

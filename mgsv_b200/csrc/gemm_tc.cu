@@ -4,7 +4,7 @@
 namespace made {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
@@ -95,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
@@ -114,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
+            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);
@@ -184,14 +184,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           } else {
             const uint4* r4 = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(e.residual) + srow * e.res_ld + col0);
+                static_cast<const op_t*>(e.residual) + srow * e.res_ld + col0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 t = __ldg(r4 + i);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                float2 f = __bfloat1622float2(h[j]);
+                float2 f = op2_to_f2(h[j]);
                 v[8 * i + 2 * j] += f.x;
                 v[8 * i + 2 * j + 1] += f.y;
               }
@@ -218,31 +218,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
           if (row_ok) {
-            if (e.out_bf16) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.ld_bf16 + col0);
+            if (e.out_h) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
             }
             if (e.out_f32) {
               float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            if (e.out2_bf16) {
+            if (e.out2_h) {
               const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_bf16 + grow * e.ld_out2 + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 uint4 t = __ldg(a4 + i);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
-                float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
-                float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
-                o[i] = make_uint4(pack_bf16x2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_bf16x2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_bf16x2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_bf16x2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
+                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
               }
             }
           }
@@ -302,31 +302,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
           if (row_ok) {
-            if (e.out_bf16) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + grow * e.ld_bf16 + col0);
+            if (e.out_h) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
             }
             if (e.out_f32) {
               float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            if (e.out2_bf16) {
+            if (e.out2_h) {
               const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_bf16 + grow * e.ld_out2 + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 uint4 t = __ldg(a4 + i);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
-                float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
-                float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
-                o[i] = make_uint4(pack_bf16x2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_bf16x2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_bf16x2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_bf16x2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
+                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
               }
             }
           }
@@ -367,7 +367,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return MADE_OK;
 }
 
-int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldb,
+int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                  int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream) {
   if (p.M == 0) return MADE_OK;
   MADE_REQUIRE(A && W, "gemm: null operand");
@@ -381,14 +381,14 @@ int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, in
                "gemm: LayerNorm/L2 epilogue needs N == 256");
   MADE_REQUIRE(!(e.ln_gamma && e.l2norm), "gemm: LayerNorm and L2 epilogues are exclusive");
   MADE_REQUIRE(!e.ln_gamma || e.ln_beta, "gemm: LayerNorm needs beta");
-  MADE_REQUIRE(!e.out2_bf16 || e.add2, "gemm: out2 needs add2");
-  MADE_REQUIRE(e.out_bf16 || e.out_f32 || e.out2_bf16, "gemm: no output");
+  MADE_REQUIRE(!e.out2_h || e.add2, "gemm: out2 needs add2");
+  MADE_REQUIRE(e.out_h || e.out_f32 || e.out2_h, "gemm: no output");
   MADE_REQUIRE(p.m_valid >= 1 && p.m_valid <= 128 && p.m_stride >= 1 && p.m_stride <= 128,
                "gemm: bad tile geometry");
   CUtensorMap ta, tb;
-  MADE_TRY(encode_tmap_2d_bf16(&ta, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M),
+  MADE_TRY(encode_tmap_2d_16b(&ta, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M),
                                static_cast<uint64_t>(lda) * 2, kBlockK, kBlockM));
-  MADE_TRY(encode_tmap_2d_bf16(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
+  MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
   if (block_n == 256) return launch_gemm<256>(ta, tb, p, stream);
   return launch_gemm<96>(ta, tb, p, stream);

@@ -1,5 +1,5 @@
 // Persistent tcgen05 GEMM with fused epilogues:  C = epilogue(A[M,K] * W[N,K]^T).
-// A and W are bf16, K-contiguous ("K-major"), staged by TMA (128-byte swizzle) through a 4-stage
+// A and W are fp16, K-contiguous ("K-major"), staged by TMA (128-byte swizzle) through a 4-stage
 // mbarrier ring; accumulators are fp32 in TMEM (two stages, so the epilogue of tile i overlaps
 // the MMAs of tile i+1); one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16).
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
@@ -22,13 +22,13 @@ struct GemmEpilogue {
   float ln_eps = 1e-5f;
   int l2norm = 0;                       // F.normalize(p=2, eps=1e-12) over the row (N == 256)
   const float* row_mask = nullptr;      // [M]; rows with mask == 0 are written as 0
-  __nv_bfloat16* out_bf16 = nullptr;
-  int64_t ld_bf16 = 0;
+  op_t* out_h = nullptr;
+  int64_t ld_h = 0;
   float* out_f32 = nullptr;
   int64_t ld_f32 = 0;
-  const __nv_bfloat16* add2 = nullptr;  // second output: bf16(result + add2[row, col])
+  const op_t* add2 = nullptr;  // second output: fp16(result + add2[row, col])
   int64_t add2_ld = 0;
-  __nv_bfloat16* out2_bf16 = nullptr;
+  op_t* out2_h = nullptr;
   int64_t ld_out2 = 0;
 };
 
@@ -41,8 +41,8 @@ struct GemmParams {
   GemmEpilogue epi;
 };
 
-// Host launcher. A: [M, K] bf16 with row stride lda; W: [N(or M for batched), K] bf16, stride ldb.
-int gemm_bf16_tc(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldb,
+// Host launcher. A: [M, K] fp16 with row stride lda; W: [N(or M for batched), K] fp16, stride ldb.
+int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                  int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream);
 
 }  // namespace made

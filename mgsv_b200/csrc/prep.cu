@@ -7,39 +7,48 @@
 
 namespace made {
 
-// x[t, :] = mask[t] ? in[t, :] : 0  -> bf16     (model_Base.py:556 / :595 masked_fill + cast)
-template <typename TIn>
-__global__ void cast_mask_rows_kernel(const TIn* __restrict__ in, const float* __restrict__ mask,
-                                      int64_t rows, int dim, __nv_bfloat16* __restrict__ out) {
+// x[t, :] = mask[t] ? in[t, :] : 0  -> fp16     (model_Base.py:556 / :595 masked_fill + cast)
+// Rows with mask == 0 are never read (the reference's dataloader zero-pads them and the model
+// overwrites them with 0 anyway), so a padded feature tensor costs only its valid rows of traffic.
+// kIn: 0 = fp32, 1 = bf16, 2 = fp16 (MADE_DTYPE_*).
+template <int kIn>
+__global__ void cast_mask_rows_kernel(const void* __restrict__ in_, const float* __restrict__ mask,
+                                      int64_t rows, int dim, op_t* __restrict__ out) {
   const int vec = dim / 8;
   const int64_t total = rows * vec;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t row = i / vec;
     const int c = static_cast<int>(i % vec) * 8;
-    const float keep = mask[row] != 0.f ? 1.f : 0.f;
-    float v[8];
-    if constexpr (sizeof(TIn) == 4) {
-      const float4* p = reinterpret_cast<const float4*>(in + row * dim + c);
-      float4 a = __ldcs(p), b = __ldcs(p + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-      uint4 a = __ldcs(reinterpret_cast<const uint4*>(in + row * dim + c));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (mask[row] != 0.f) {
+      float v[8];
+      if constexpr (kIn == MADE_DTYPE_F32) {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(in_) + row * dim + c);
+        float4 a = __ldcs(p), b = __ldcs(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else if constexpr (kIn == MADE_DTYPE_BF16) {
+        uint4 a = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(in_) + row * dim + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+      } else {
+        uint4 a = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __half*>(in_) + row * dim + c));
+        const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+      }
+      o = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
     }
-    uint4 o = make_uint4(pack_bf16x2(v[0] * keep, v[1] * keep), pack_bf16x2(v[2] * keep, v[3] * keep),
-                         pack_bf16x2(v[4] * keep, v[5] * keep), pack_bf16x2(v[6] * keep, v[7] * keep));
     *reinterpret_cast<uint4*>(out + row * dim + c) = o;
   }
 }
 
-// Row LayerNorm over 256 features: warp per row, 8 features per lane. in fp32 or bf16 -> bf16/fp32.
+// Row LayerNorm over 256 features: warp per row, 8 features per lane. in fp32 or fp16 -> fp16/fp32.
 template <typename TIn>
 __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in, int64_t rows,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float eps, __nv_bfloat16* __restrict__ out_bf16,
+                                      float eps, op_t* __restrict__ out_h,
                                       float* __restrict__ out_f32) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -51,9 +60,9 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
     uint4 a = *reinterpret_cast<const uint4*>(in + row * ld_in + lane * 8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const op2_t* h = reinterpret_cast<const op2_t*>(&a);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    for (int j = 0; j < 4; ++j) { float2 f = op2_to_f2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
   }
   float s = 0.f;
 #pragma unroll
@@ -69,9 +78,9 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bb[j];
-  if (out_bf16)
-    *reinterpret_cast<uint4*>(out_bf16 + row * 256 + lane * 8) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  if (out_h)
+    *reinterpret_cast<uint4*>(out_h + row * 256 + lane * 8) =
+        make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
   if (out_f32) {
     float4* o = reinterpret_cast<float4*>(out_f32 + row * 256 + lane * 8);
     o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -103,16 +112,16 @@ pool_norm_kernel(const float* __restrict__ seq, const float* __restrict__ mask, 
 }
 
 // DETR input assembly (model_Uni.py:207-216 + position_encoding.py:51-71):
-//   src[b]  = cat(frame_out[b] (50), seg_out[track_idx[b]] (96))           bf16 [B,146,256]
+//   src[b]  = cat(frame_out[b] (50), seg_out[track_idx[b]] (96))           fp16 [B,146,256]
 //   mask[b] = cat(frame_mask[b], seg_mask[track_idx[b]])                   f32  [B,146]
 //   pos[b,t,2j] = sin(x/dim_t), pos[b,t,2j+1] = cos(x/dim_t),  x = cumsum(mask)/(total+1e-6)*2pi
 // One CTA per sequence; warp per token row.
 __global__ void __launch_bounds__(256)
-detr_prep_kernel(const __nv_bfloat16* __restrict__ frame_out, const float* __restrict__ frame_mask,
-                 const __nv_bfloat16* __restrict__ seg_out, const float* __restrict__ seg_mask,
+detr_prep_kernel(const op_t* __restrict__ frame_out, const float* __restrict__ frame_mask,
+                 const op_t* __restrict__ seg_out, const float* __restrict__ seg_mask,
                  const int32_t* __restrict__ track_idx, const float* __restrict__ inv_dim_t,
-                 __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ pos,
-                 __nv_bfloat16* __restrict__ srcpos, float* __restrict__ mask_out) {
+                 op_t* __restrict__ src, op_t* __restrict__ pos,
+                 op_t* __restrict__ srcpos, float* __restrict__ mask_out) {
   constexpr int LV = 50, LM = 96, L = 146;
   __shared__ float sx[L];
   const int64_t b = blockIdx.x;
@@ -132,9 +141,9 @@ detr_prep_kernel(const __nv_bfloat16* __restrict__ frame_out, const float* __res
   }
   __syncthreads();
   for (int t = warp; t < L; t += 8) {
-    const __nv_bfloat16* sp = t < LV ? frame_out + (b * LV + t) * 256 : seg_out + (tr * LM + (t - LV)) * 256;
+    const op_t* sp = t < LV ? frame_out + (b * LV + t) * 256 : seg_out + (tr * LM + (t - LV)) * 256;
     uint4 raw = *reinterpret_cast<const uint4*>(sp + lane * 8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const op2_t* h = reinterpret_cast<const op2_t*>(&raw);
     const float x = sx[t];
     float pv[8], sv[8];
 #pragma unroll
@@ -142,24 +151,24 @@ detr_prep_kernel(const __nv_bfloat16* __restrict__ frame_out, const float* __res
       const float a = x * inv_dim_t[lane * 8 + 2 * j];   // same dim_t for the (sin, cos) pair
       pv[2 * j] = sinf(a);
       pv[2 * j + 1] = cosf(a);
-      float2 f = __bfloat1622float2(h[j]);
+      float2 f = op2_to_f2(h[j]);
       sv[2 * j] = f.x;
       sv[2 * j + 1] = f.y;
     }
     const int64_t o = (b * L + t) * 256 + lane * 8;
     *reinterpret_cast<uint4*>(src + o) = raw;
-    *reinterpret_cast<uint4*>(pos + o) = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]),
-                                                    pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+    *reinterpret_cast<uint4*>(pos + o) = make_uint4(pack_op2(pv[0], pv[1]), pack_op2(pv[2], pv[3]),
+                                                    pack_op2(pv[4], pv[5]), pack_op2(pv[6], pv[7]));
     *reinterpret_cast<uint4*>(srcpos + o) =
-        make_uint4(pack_bf16x2(sv[0] + pv[0], sv[1] + pv[1]), pack_bf16x2(sv[2] + pv[2], sv[3] + pv[3]),
-                   pack_bf16x2(sv[4] + pv[4], sv[5] + pv[5]), pack_bf16x2(sv[6] + pv[6], sv[7] + pv[7]));
+        make_uint4(pack_op2(sv[0] + pv[0], sv[1] + pv[1]), pack_op2(sv[2] + pv[2], sv[3] + pv[3]),
+                   pack_op2(sv[4] + pv[4], sv[5] + pv[5]), pack_op2(sv[6] + pv[6], sv[7] + pv[7]));
   }
 }
 
 // Output heads on hs rows (model_Uni.py:131-135): logits = class_embed(hs) [2];
-// spans = sigmoid(span_embed.layers.2(h2)) [2] with h2 = the MLP's second hidden layer (bf16).
+// spans = sigmoid(span_embed.layers.2(h2)) [2] with h2 = the MLP's second hidden layer (fp16).
 // Warp per row.
-__global__ void heads_final_kernel(const float* __restrict__ hs, const __nv_bfloat16* __restrict__ h2,
+__global__ void heads_final_kernel(const float* __restrict__ hs, const op_t* __restrict__ h2,
                                    int64_t rows, const float* __restrict__ w_cls, const float* __restrict__ b_cls,
                                    const float* __restrict__ w_sp, const float* __restrict__ b_sp,
                                    float* __restrict__ logits, float* __restrict__ spans) {
@@ -171,7 +180,7 @@ __global__ void heads_final_kernel(const float* __restrict__ hs, const __nv_bflo
   for (int j = 0; j < 8; ++j) {
     const int c = lane + 32 * j;
     const float x = hs[row * 256 + c];
-    const float y = __bfloat162float(h2[row * 256 + c]);
+    const float y = op2f(h2[row * 256 + c]);
     a[0] = fmaf(x, w_cls[c], a[0]);
     a[1] = fmaf(x, w_cls[256 + c], a[1]);
     a[2] = fmaf(y, w_sp[c], a[2]);
@@ -216,33 +225,34 @@ __global__ void vhat_kernel(const float* __restrict__ v, int64_t rows, __half* _
 }
 
 // ---- launchers ---------------------------------------------------------------------------
-int cast_mask_rows(const void* in, int in_is_bf16, const float* mask, int64_t rows, int dim,
-                   __nv_bfloat16* out, cudaStream_t st) {
+int cast_mask_rows(const void* in, int in_dtype, const float* mask, int64_t rows, int dim,
+                   op_t* out, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
   MADE_REQUIRE(dim % 8 == 0, "cast_mask_rows: dim must be a multiple of 8");
   const int64_t total = rows * (dim / 8);
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (in_is_bf16)
-    cast_mask_rows_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(in), mask, rows, dim, out);
+  const unsigned g = static_cast<unsigned>(blocks);
+  if (in_dtype == MADE_DTYPE_F32)
+    cast_mask_rows_kernel<MADE_DTYPE_F32><<<g, 256, 0, st>>>(in, mask, rows, dim, out);
+  else if (in_dtype == MADE_DTYPE_BF16)
+    cast_mask_rows_kernel<MADE_DTYPE_BF16><<<g, 256, 0, st>>>(in, mask, rows, dim, out);
   else
-    cast_mask_rows_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        static_cast<const float*>(in), mask, rows, dim, out);
+    cast_mask_rows_kernel<MADE_DTYPE_F16><<<g, 256, 0, st>>>(in, mask, rows, dim, out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
 
-int layernorm_rows(const void* in, int in_is_bf16, int64_t ld_in, int64_t rows, const float* gamma,
-                   const float* beta, __nv_bfloat16* out_bf16, float* out_f32, cudaStream_t st) {
+int layernorm_rows(const void* in, int in_is_op, int64_t ld_in, int64_t rows, const float* gamma,
+                   const float* beta, op_t* out_h, float* out_f32, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
   const unsigned blocks = static_cast<unsigned>(ceil_div64(rows, 8));
-  if (in_is_bf16)
-    layernorm_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), ld_in,
-                                                                 rows, gamma, beta, 1e-5f, out_bf16, out_f32);
+  if (in_is_op)
+    layernorm_rows_kernel<op_t><<<blocks, 256, 0, st>>>(static_cast<const op_t*>(in), ld_in,
+                                                                 rows, gamma, beta, 1e-5f, out_h, out_f32);
   else
     layernorm_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(in), ld_in, rows, gamma,
-                                                         beta, 1e-5f, out_bf16, out_f32);
+                                                         beta, 1e-5f, out_h, out_f32);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -254,9 +264,9 @@ int pool_norm(const float* seq, const float* mask, int64_t B, int L, float* pool
   return MADE_OK;
 }
 
-int detr_prep(const __nv_bfloat16* frame_out, const float* frame_mask, const __nv_bfloat16* seg_out,
+int detr_prep(const op_t* frame_out, const float* frame_mask, const op_t* seg_out,
               const float* seg_mask, const int32_t* track_idx, const float* inv_dim_t, int64_t B,
-              __nv_bfloat16* src, __nv_bfloat16* pos, __nv_bfloat16* srcpos, float* mask_out,
+              op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
               cudaStream_t st) {
   if (B == 0) return MADE_OK;
   detr_prep_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(frame_out, frame_mask, seg_out, seg_mask,
@@ -265,7 +275,7 @@ int detr_prep(const __nv_bfloat16* frame_out, const float* frame_mask, const __n
   return MADE_OK;
 }
 
-int heads_final(const float* hs, const __nv_bfloat16* h2, int64_t rows, const float* w_cls,
+int heads_final(const float* hs, const op_t* h2, int64_t rows, const float* w_cls,
                 const float* b_cls, const float* w_sp, const float* b_sp, float* logits, float* spans,
                 cudaStream_t st) {
   if (rows == 0) return MADE_OK;

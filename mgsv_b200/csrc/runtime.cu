@@ -41,7 +41,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {

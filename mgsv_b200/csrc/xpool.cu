@@ -9,7 +9,7 @@
 //   |o - mean(o)|^2      = a^T G a                    G   = V'' V''^T   (per track, 96x96)
 //   LN2 -> (I+Wl) + bl   = (1/sigma) sum_t a_t Z''_t + b'     Z'' = V'' W'^T,  W' = (I+Wl) diag(g2)
 // so per pair only three products remain:  S = q K^T (96),  T = e G (96),  Y = e Z'' (256), with
-// e = exp(S - max) kept unnormalised in bf16 and divided by the sum of the rounded weights.
+// e = exp(S - max) kept unnormalised in fp16 and divided by the sum of the rounded weights.
 //
 // One CTA owns a 128-query tile (Q resident in shared memory, v_hat resident in TMEM as fp16) and
 // streams tracks: TMA brings K/Z''/G of a track into 128B-swizzled shared memory, one thread issues
@@ -127,9 +127,9 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 96, 0, 0);    // S = Q K^T   (B K-major)
-      constexpr uint32_t idesc_y = umma_idesc_bf16(128, 256, 0, 1);   // Y = P Z''   (B MN-major)
-      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 96, 0, 1);    // T = P G     (B MN-major)
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, 0, 0);    // S = Q K^T   (B K-major)
+      constexpr uint32_t idesc_y = umma_idesc_f16(128, 256, 0, 1);   // Y = P Z''   (B MN-major)
+      constexpr uint32_t idesc_t = umma_idesc_f16(128, 96, 0, 1);    // T = P G     (B MN-major)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aZ = smem_u32(sZ), aG = smem_u32(sG),
                      aP = smem_u32(sP);
       mbar_wait(q_full, 0);
@@ -214,13 +214,13 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          __nv_bfloat162 e0 = __floats2bfloat162_rn(__expf(__uint_as_float(s0[2 * i]) - mx),
+          op2_t e0 = floats2op2(__expf(__uint_as_float(s0[2 * i]) - mx),
                                                     __expf(__uint_as_float(s0[2 * i + 1]) - mx));
-          __nv_bfloat162 e1 = __floats2bfloat162_rn(__expf(__uint_as_float(s1[2 * i]) - mx),
+          op2_t e1 = floats2op2(__expf(__uint_as_float(s1[2 * i]) - mx),
                                                     __expf(__uint_as_float(s1[2 * i + 1]) - mx));
-          __nv_bfloat162 e2 = __floats2bfloat162_rn(__expf(__uint_as_float(s2[2 * i]) - mx),
+          op2_t e2 = floats2op2(__expf(__uint_as_float(s2[2 * i]) - mx),
                                                     __expf(__uint_as_float(s2[2 * i + 1]) - mx));
-          float2 f0 = __bfloat1622float2(e0), f1 = __bfloat1622float2(e1), f2 = __bfloat1622float2(e2);
+          float2 f0 = op2_to_f2(e0), f1 = op2_to_f2(e1), f2 = op2_to_f2(e2);
           lsum += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y);
           pk[i] = *reinterpret_cast<uint32_t*>(&e0);
           pk[16 + i] = *reinterpret_cast<uint32_t*>(&e1);
@@ -249,7 +249,7 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c * 16 + i]));
+          float2 e = op2_to_f2(*reinterpret_cast<const op2_t*>(&pk[c * 16 + i]));
           qf = fmaf(e.x, __uint_as_float(tt[2 * i]), qf);
           qf = fmaf(e.y, __uint_as_float(tt[2 * i + 1]), qf);
         }
@@ -319,10 +319,10 @@ int xpool_set_constants(const float* bias_prime, const float* gamma3, const floa
   return MADE_OK;
 }
 
-// q [n_queries,256] bf16 (pre-scaled by 1/16), vhat fp16, kz [n_tracks*96, ldkz] bf16 with the K block
-// at column 0 and the Z'' block at column z_col, gram [n_tracks*96, 96] bf16.
-int xpool_score(const __nv_bfloat16* q, const __half* vhat, int64_t n_queries, const __nv_bfloat16* kz,
-                int64_t ldkz, int z_col, const __nv_bfloat16* gram, const uint32_t* maskbits,
+// q [n_queries,256] fp16 (pre-scaled by 1/16), vhat fp16, kz [n_tracks*96, ldkz] fp16 with the K block
+// at column 0 and the Z'' block at column z_col, gram [n_tracks*96, 96] fp16.
+int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t* kz,
+                int64_t ldkz, int z_col, const op_t* gram, const uint32_t* maskbits,
                 int64_t n_tracks, float* sim, int64_t ld, int64_t col_offset, cudaStream_t st) {
   if (n_queries == 0 || n_tracks == 0) return MADE_OK;
   MADE_REQUIRE(q && vhat && kz && gram && maskbits && sim, "xpool_score: null pointer");
@@ -334,10 +334,10 @@ int xpool_score(const __nv_bfloat16* q, const __half* vhat, int64_t n_queries, c
   }
   CUtensorMap tq, tk, tz, tg;
   const uint64_t T = static_cast<uint64_t>(n_tracks) * kXL;
-  MADE_TRY(encode_tmap_2d_bf16(&tq, q, kXD, static_cast<uint64_t>(n_queries), kXD * 2, 64, kXQ));
-  MADE_TRY(encode_tmap_2d_bf16(&tk, kz, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
-  MADE_TRY(encode_tmap_2d_bf16(&tz, kz + z_col, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
-  MADE_TRY(encode_tmap_2d_bf16(&tg, gram, kXL, T, kXL * 2, 64, kXL));
+  MADE_TRY(encode_tmap_2d_16b(&tq, q, kXD, static_cast<uint64_t>(n_queries), kXD * 2, 64, kXQ));
+  MADE_TRY(encode_tmap_2d_16b(&tk, kz, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
+  MADE_TRY(encode_tmap_2d_16b(&tz, kz + z_col, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
+  MADE_TRY(encode_tmap_2d_16b(&tg, gram, kXL, T, kXL * 2, 64, kXL));
   XpoolParams p;
   p.n_queries = n_queries;
   p.n_tracks = n_tracks;

@@ -59,7 +59,7 @@ class Engine:
 
     # -----------------------------------------------------------------------------------------
     def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True):
-        """forward_{video,audio}_encoder_feature → (seq_bf16 [B,L,256], seq_f32 or None, pooled [B,256])."""
+        """forward_{video,audio}_encoder_feature → (seq16 [B,L,256], seq_f32 or None, pooled [B,256])."""
         L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
         if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
             raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
@@ -69,37 +69,39 @@ class Engine:
             dt = _lib.F32
         elif feats.dtype == torch.bfloat16:
             dt = _lib.BF16
+        elif feats.dtype == torch.float16:
+            dt = _lib.F16
         else:
             raise ValueError(f"unsupported feature dtype {feats.dtype}")
         feats = feats.contiguous()
         masks = masks.to(torch.float32).contiguous()
         B = feats.shape[0]
         dev = feats.device
-        seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.bfloat16, device=dev)
+        seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float16, device=dev)
         seq32 = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
         pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
         _lib.check(self._lib.made_encode(self._h, modality, _lib.ptr(feats), dt, _lib.ptr(masks), B, _lib.ptr(seq),
                                          _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
         return seq, seq32, pooled
 
-    def gallery_prepare(self, seg_bf16: torch.Tensor, seg_masks: torch.Tensor):
-        """Per-track X-Pool operands: kz [N*96,768] bf16, gram [N*96,96] bf16, maskbits [N,4] int32."""
-        N = seg_bf16.shape[0]
-        dev = seg_bf16.device
-        if seg_bf16.dtype != torch.bfloat16:
-            raise ValueError("gallery_prepare takes the bf16 encoded segments")
-        kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.bfloat16, device=dev)
-        gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.bfloat16, device=dev)
+    def gallery_prepare(self, seg16: torch.Tensor, seg_masks: torch.Tensor):
+        """Per-track X-Pool operands: kz [N*96,768] fp16, gram [N*96,96] fp16, maskbits [N,4] int32."""
+        N = seg16.shape[0]
+        dev = seg16.device
+        if seg16.dtype != torch.float16:
+            raise ValueError("gallery_prepare takes the fp16 encoded segments")
+        kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev)
+        gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev)
         bits = torch.empty((N, 4), dtype=torch.int32, device=dev)
         masks = seg_masks.to(torch.float32).contiguous()
-        _lib.check(self._lib.made_gallery_prepare(self._h, _lib.ptr(seg_bf16.contiguous()), _lib.ptr(masks), N,
+        _lib.check(self._lib.made_gallery_prepare(self._h, _lib.ptr(seg16.contiguous()), _lib.ptr(masks), N,
                                                   _lib.ptr(kz), _lib.ptr(gram), _lib.ptr(bits), _lib.stream_ptr()))
         return kz, gram, bits
 
     def query_prepare(self, video_feats: torch.Tensor):
         N = video_feats.shape[0]
         vf = video_feats.to(torch.float32).contiguous()
-        q = torch.empty((N, cfg.D_MODEL), dtype=torch.bfloat16, device=vf.device)
+        q = torch.empty((N, cfg.D_MODEL), dtype=torch.float16, device=vf.device)
         vhat = torch.empty((N, cfg.D_MODEL), dtype=torch.float16, device=vf.device)
         _lib.check(self._lib.made_query_prepare(self._h, _lib.ptr(vf), N, _lib.ptr(q), _lib.ptr(vhat),
                                                 _lib.stream_ptr()))
@@ -115,7 +117,7 @@ class Engine:
                                               _lib.stream_ptr()))
         return out
 
-    def detr_detect(self, frame_bf16, frame_masks, seg_bf16, seg_masks, video_feats, track_idx=None,
+    def detr_detect(self, frame16, frame_masks, seg16, seg_masks, video_feats, track_idx=None,
                     want_proj: bool = False, want_memory: bool = False):
         """→ dict(hs [6,B,256], pred_logits [6,B,2], pred_spans [6,B,2], proj_queries?, proj_vid_mem?, memory?)."""
         B = video_feats.shape[0]
@@ -130,8 +132,8 @@ class Engine:
         if track_idx is not None:
             track_idx = track_idx.to(torch.int32).contiguous()
         _lib.check(self._lib.made_detr_detect(
-            self._h, _lib.ptr(frame_bf16.contiguous()), _lib.ptr(frame_masks.to(torch.float32).contiguous()),
-            _lib.ptr(seg_bf16.contiguous()), _lib.ptr(seg_masks.to(torch.float32).contiguous()), _lib.ptr(track_idx),
+            self._h, _lib.ptr(frame16.contiguous()), _lib.ptr(frame_masks.to(torch.float32).contiguous()),
+            _lib.ptr(seg16.contiguous()), _lib.ptr(seg_masks.to(torch.float32).contiguous()), _lib.ptr(track_idx),
             _lib.ptr(video_feats.to(torch.float32).contiguous()), B, _lib.ptr(hs), _lib.ptr(logits), _lib.ptr(spans),
             _lib.ptr(pq), _lib.ptr(pv), _lib.ptr(mem), _lib.stream_ptr()))
         return dict(hs=hs, pred_logits=logits, pred_spans=spans, proj_queries=pq, proj_vid_mem=pv, memory=mem)

@@ -5,7 +5,7 @@
 SURVEY.md §8b), but owns no compute: every tensor op is a C-ABI call into libmade_b200.so through
 `Engine`.  Parameters are held as ordinary nn.Parameters (fp32 masters, reference names) so that
 `.to()`, `.float()`, `.eval()`, `.state_dict()`, `.load_state_dict()` and the param-group getters
-behave; the engine repacks them (bf16 operands, folded X-Pool/decoder weights) whenever they change.
+behave; the engine repacks them (fp16 operands, folded X-Pool/decoder weights) whenever they change.
 """
 from __future__ import annotations
 
@@ -140,14 +140,14 @@ class Uni_model(nn.Module):
         """model_Base.py:544-581 → (frame_feats [B,50,256], video_feats [B,256], frame_masks)."""
         dev = self.engine().device
         seq, seq32, pooled = self.engine().encode(_lib.VIDEO, frame_feats.to(dev), frame_masks.to(dev))
-        self._last_frame_bf16 = seq
+        self._last_frame16 = seq
         return seq32, pooled, frame_masks
 
     def forward_audio_encoder_feature(self, segment_feats=None, segment_masks=None, music_ids=None):
         """model_Base.py:583-617."""
         dev = self.engine().device
         seq, seq32, pooled = self.engine().encode(_lib.MUSIC, segment_feats.to(dev), segment_masks.to(dev))
-        self._last_segment_bf16 = seq
+        self._last_segment16 = seq
         return seq32, pooled, segment_masks
 
     def score_gallery(self, video_feats, music_feats, segment_feats, segment_masks, out=None, col_offset=0):
@@ -156,8 +156,8 @@ class Uni_model(nn.Module):
         eng = self.engine()
         dev = eng.device
         seg = segment_feats.to(dev)
-        seg_bf16 = seg if seg.dtype == torch.bfloat16 else seg.to(torch.bfloat16)
-        kz, gram, bits = eng.gallery_prepare(seg_bf16, segment_masks.to(dev))
+        seg16 = seg if seg.dtype == torch.float16 else seg.to(torch.float16)
+        kz, gram, bits = eng.gallery_prepare(seg16, segment_masks.to(dev))
         q, vhat = eng.query_prepare(video_feats.to(dev))
         single = eng.xpool_score(q, vhat, kz, gram, bits)
         dual = ops.cal_distance(video_feats.to(dev), music_feats.to(dev))
@@ -182,7 +182,7 @@ class Uni_model(nn.Module):
         segment_masks = segment_masks.to(dev)
         frame_out, video_feats, _ = self.forward_video_encoder_feature(frame_feats, frame_masks)
         segment_out, music_feats, _ = self.forward_audio_encoder_feature(segment_feats, segment_masks)
-        det = eng.detr_detect(self._last_frame_bf16, frame_masks, self._last_segment_bf16, segment_masks,
+        det = eng.detr_detect(self._last_frame16, frame_masks, self._last_segment16, segment_masks,
                               video_feats, want_proj=True)
         L = cfg.DETR_DEC_LAYERS
         output_map = {
@@ -197,7 +197,7 @@ class Uni_model(nn.Module):
                 "proj_vid_mem": det["proj_vid_mem"],
             } for i in range(L - 1)],
         }
-        single, dual = self.score_gallery(video_feats, music_feats, self._last_segment_bf16, segment_masks)
+        single, dual = self.score_gallery(video_feats, music_feats, self._last_segment16, segment_masks)
         loss_map = self._eval_losses(output_map, single, dual, spans_target.to(dev))
         feat_map = {"video_feats": video_feats, "music_feats": music_feats, "frame_feats": frame_out,
                     "segment_feats": segment_out}

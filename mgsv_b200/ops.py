@@ -167,21 +167,21 @@ def cal_distance(x: torch.Tensor, y: torch.Tensor, distance_type: str = "COS", o
 # ---------------------------------------------------------------------------------------------
 # building blocks exported for tests
 # ---------------------------------------------------------------------------------------------
-def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, act: int = 0, ln=None,
-              out_dtype=torch.bfloat16) -> torch.Tensor:
+def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, act: int = 0, ln=None,
+              out_dtype=torch.float16) -> torch.Tensor:
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     g, b = (ln if ln is not None else (None, None))
-    _lib.check(_lib.load().made_gemm_bf16(
+    _lib.check(_lib.load().made_gemm_f16(
         _lib.ptr(a), _lib.ptr(w), M, N, K, _lib.ptr(bias), _lib.ptr(residual), act, _lib.ptr(g), _lib.ptr(b),
-        _lib.ptr(out) if out_dtype == torch.bfloat16 else None,
+        _lib.ptr(out) if out_dtype == torch.float16 else None,
         _lib.ptr(out) if out_dtype == torch.float32 else None, _lib.stream_ptr()))
     return out
 
 
 def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: torch.Tensor) -> torch.Tensor:
-    """q,k,v [B,L,256] bf16, key_mask [B,L] float (1 = valid) → [B,L,256] bf16."""
+    """q,k,v [B,L,256] fp16, key_mask [B,L] float (1 = valid) → [B,L,256] fp16."""
     B, L, _ = q.shape
     out = torch.empty_like(q)
     _lib.check(_lib.load().made_mha_core(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(key_mask), B, L,

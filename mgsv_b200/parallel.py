@@ -7,7 +7,7 @@ gallery is split into contiguous shards; the only exchange steps are tiny:
   3. all_reduce(SUM) of the "ids ahead of the GT" counts [N_v] i32,
   4. all_gather of the local top-k candidates [N_v, k] (score f64, global index i32) + merge kernel.
 Moment detection shards by query; a query's paired track may live on another shard, so the encoded
-segments of the paired tracks are exchanged with one all_gather of [N_v/G, 96, 256] bf16 slices.
+segments of the paired tracks are exchanged with one all_gather of [N_v/G, 96, 256] fp16 slices.
 """
 from __future__ import annotations
 

@@ -45,7 +45,7 @@ class GalleryEvaluator:
     # ---- stages -----------------------------------------------------------------------------------
     def encode_queries(self, frame_feats, frame_mask, on_host: bool):
         n = frame_feats.shape[0]
-        seq = torch.empty((n, cfg.L_V, cfg.D_MODEL), dtype=torch.bfloat16, device=self.dev)
+        seq = torch.empty((n, cfg.L_V, cfg.D_MODEL), dtype=torch.float16, device=self.dev)
         pooled = torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=self.dev)
         mask_d = self._to_dev(frame_mask, on_host)
         for s, e, feats_d in self._chunks(frame_feats, self.video_chunk, on_host):
@@ -57,10 +57,10 @@ class GalleryEvaluator:
 
     def encode_gallery(self, segment_feats, segment_mask, on_host: bool):
         n = segment_feats.shape[0]
-        seq = torch.empty((n, cfg.L_M, cfg.D_MODEL), dtype=torch.bfloat16, device=self.dev)
+        seq = torch.empty((n, cfg.L_M, cfg.D_MODEL), dtype=torch.float16, device=self.dev)
         pooled = torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=self.dev)
-        kz = torch.empty((n * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.bfloat16, device=self.dev)
-        gram = torch.empty((n * cfg.L_M, cfg.L_M), dtype=torch.bfloat16, device=self.dev)
+        kz = torch.empty((n * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=self.dev)
+        gram = torch.empty((n * cfg.L_M, cfg.L_M), dtype=torch.float16, device=self.dev)
         bits = torch.empty((n, 4), dtype=torch.int32, device=self.dev)
         mask_d = self._to_dev(segment_mask, on_host)
         for s, e, feats_d in self._chunks(segment_feats, self.music_chunk, on_host):

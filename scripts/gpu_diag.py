@@ -84,26 +84,26 @@ def stage_gemm():
     torch.manual_seed(0)
     for (M, N, K) in [(128, 256, 64), (128, 256, 256), (300, 256, 512), (1000, 768, 256), (5000, 1024, 256),
                       (4800, 256, 1024), (40000, 256, 768)]:
-        a = torch.randn(M, K).to(torch.bfloat16)
-        w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+        a = torch.randn(M, K).to(torch.float16)
+        w = (torch.randn(N, K) / K ** 0.5).to(torch.float16)
         bias = torch.randn(N)
         ref = a.float() @ w.float().t() + bias
         t0 = time.time()
-        out = ops.gemm_bf16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), out_dtype=torch.float32)
+        out = ops.gemm_f16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), out_dtype=torch.float32)
         torch.cuda.synchronize()
         stats(f"gemm {M}x{N}x{K} f32out", out, ref, f"{time.time() - t0:.3f}s")
     M, N, K = 1000, 256, 256
-    a = torch.randn(M, K).to(torch.bfloat16)
-    w = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    a = torch.randn(M, K).to(torch.float16)
+    w = (torch.randn(N, K) / K ** 0.5).to(torch.float16)
     bias, res = torch.randn(N), torch.randn(M, N)
     g, b = torch.randn(N), torch.randn(N)
     base = a.float() @ w.float().t() + bias
-    out = ops.gemm_bf16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), residual=res.to(DEV), ln=(g.to(DEV), b.to(DEV)),
+    out = ops.gemm_f16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), residual=res.to(DEV), ln=(g.to(DEV), b.to(DEV)),
                         out_dtype=torch.float32)
     stats("gemm +res +LN", out, torch.nn.functional.layer_norm(base + res, (N,), g, b))
-    out = ops.gemm_bf16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), act=1, out_dtype=torch.bfloat16)
+    out = ops.gemm_f16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), act=1, out_dtype=torch.float16)
     stats("gemm gelu bf16out", out.float(), torch.nn.functional.gelu(base))
-    out = ops.gemm_bf16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), act=2, out_dtype=torch.float32)
+    out = ops.gemm_f16(a.to(DEV), w.to(DEV), bias=bias.to(DEV), act=2, out_dtype=torch.float32)
     stats("gemm relu", out, torch.relu(base))
 
 
@@ -111,7 +111,7 @@ def stage_attn():
     torch.manual_seed(1)
     for L in (50, 96, 146):
         B = 7
-        q, k, v = [torch.randn(B, L, 256).to(torch.bfloat16) for _ in range(3)]
+        q, k, v = [torch.randn(B, L, 256).to(torch.float16) for _ in range(3)]
         n_valid = torch.randint(1, L + 1, (B,))
         n_valid[0] = L
         mask = (torch.arange(L)[None] < n_valid[:, None]).float()
@@ -141,7 +141,7 @@ def stage_encode():
         seq, seq32, pooled = eng.encode(mod, feats.to(DEV), mask.to(DEV))
         torch.cuda.synchronize()
         rs, rp = fn(sd, feats, mask)
-        rsb, rpb = fn(sdb, feats.to(torch.bfloat16).float(), mask)
+        rsb, rpb = fn(sdb, feats.to(torch.float16).float(), mask)
         stats(f"{name} seq vs fp32 oracle", seq32, rs)
         stats(f"{name} seq vs bf16w oracle", seq32, rsb)
         stats(f"{name} pooled vs fp32", pooled, rp)
@@ -157,7 +157,7 @@ def stage_xpool():
     fo, vf = O.encode_video(sd, v["frame_feats"], v["frame_mask"])
     so, mf = O.encode_music(sd, m["segment_feats"][:nm], m["segment_mask"][:nm])
     single, dual, total = O.gallery_similarity(sd, vf, mf, so, m["segment_mask"][:nm])
-    seg_bf16 = so.to(torch.bfloat16).to(DEV)
+    seg_bf16 = so.to(torch.float16).to(DEV)
     kz, gram, bits = eng.gallery_prepare(seg_bf16, m["segment_mask"][:nm].to(DEV))
     q, vhat = eng.query_prepare(vf.to(DEV))
     torch.cuda.synchronize()
@@ -183,7 +183,7 @@ def stage_detr():
     mask = torch.cat([v["frame_mask"], m["segment_mask"]], 1)
     hs, memory = O.detr_forward(sd, src, mask, O.position_embedding_sine(mask), vf.unsqueeze(1))
     om = O.calc_output(sd, hs, fo)
-    r = eng.detr_detect(fo.to(torch.bfloat16).to(DEV), v["frame_mask"].to(DEV), so.to(torch.bfloat16).to(DEV),
+    r = eng.detr_detect(fo.to(torch.float16).to(DEV), v["frame_mask"].to(DEV), so.to(torch.float16).to(DEV),
                         m["segment_mask"].to(DEV), vf.to(DEV), want_proj=True, want_memory=True)
     torch.cuda.synchronize()
     stats("memory", r["memory"], memory)
