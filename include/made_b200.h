@@ -35,6 +35,7 @@ extern "C" {
 #define MADE_DTYPE_F32 0
 #define MADE_DTYPE_BF16 1
 #define MADE_DTYPE_F16 2
+#define MADE_DTYPE_F16_MASKED 3 /* fp16 written by made_ingest_features: consumed in place */
 
 #define MADE_VIDEO 0
 #define MADE_MUSIC 1
@@ -103,8 +104,17 @@ int made_ctx_destroy(made_ctx* ctx);
 int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const float* const* host_ptrs,
                           const int64_t* numels, void* stream);
 
-/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16 or fp16; rows with mask 0 are
- * never read),
+/* Feature ingest = the masked_fill + cast at the top of forward_{video,audio}_encoder_feature
+ * (model_Base.py:556 / :595) on its own: feats [rows, dim] (fp32 / bf16 / fp16) -> out16 [rows, dim]
+ * fp16 with rows of mask == 0 written as zero and NEVER READ.  `feats` may be device memory or
+ * pinned host memory (unified addressing): in the latter case the kernel pulls only the valid rows
+ * over PCIe, which replaces the reference's per-batch H2D copy of the zero-padded tensors
+ * (test-MaDe.py:268-277).  masks and out16 are device memory.  dim % 8 == 0. */
+int made_ingest_features(const void* feats, int feats_dtype, const float* masks, int64_t rows, int dim,
+                         void* out16, void* stream);
+
+/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16, fp16 — rows with mask 0 are
+ * never read — or MADE_DTYPE_F16_MASKED = the output of made_ingest_features, used in place),
  * masks [B,L] float {0,1}; L,Din = 50,512 (MADE_VIDEO) or 96,768 (MADE_MUSIC).
  * -> seq16 [B,L,256] fp16, seq_f32 [B,L,256] (nullable), pooled [B,256] fp32 (L2-normalised). */
 int made_encode(made_ctx* ctx, int modality, const void* feats, int feats_dtype, const float* masks,

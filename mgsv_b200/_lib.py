@@ -13,7 +13,7 @@ from . import build as _build
 _LIB: Optional[C.CDLL] = None
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, F16_MASKED = 0, 1, 2, 3
 VIDEO, MUSIC = 0, 1
 
 _p = C.c_void_p
@@ -36,6 +36,7 @@ SIGNATURES = {
     "made_ctx_create": [C.POINTER(_p), _i32],
     "made_ctx_destroy": [_p],
     "made_ctx_load_weights": [_p, _i32, C.POINTER(C.c_char_p), C.POINTER(_p), C.POINTER(_i64), _p],
+    "made_ingest_features": [_p, _i32, _p, _i64, _i32, _p, _p],
     "made_encode": [_p, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p],
     "made_gallery_prepare": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
@@ -88,6 +89,17 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if not t.is_contiguous():
         raise ValueError("made_b200 needs contiguous tensors")
     return t.data_ptr()
+
+
+def ptr_any(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device tensor or PINNED host tensor (read in place over PCIe by made_ingest_features)."""
+    if t is not None and not t.is_cuda:
+        if not t.is_pinned():
+            raise RuntimeError("host tensors handed to made_b200 must be pinned (tensor.pin_memory())")
+        if not t.is_contiguous():
+            raise ValueError("made_b200 needs contiguous tensors")
+        return t.data_ptr()
+    return ptr(t)
 
 
 def stream_ptr() -> int:

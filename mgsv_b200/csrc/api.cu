@@ -46,7 +46,10 @@ struct DetrEncW {
   LNp n1, n2;
 };
 struct DetrDecW {
-  Lin sa, q, out, ff1, ff2;
+  Lin sa;        // folded single-query self-attention
+  Lin qfold;     // [8*256, 256]: per head Wk_h^T Wq_h / sqrt(32)  -> q~ (scores = q~_h . (mem+pos)_t)
+  Lin ovfold;    // [256, 8*256]: per head Wo[:, h] Wv_h            -> out = W_ov vec(mbar) + b_ov
+  Lin ff1, ff2;
   LNp n1, n2, n3;
 };
 
@@ -65,7 +68,6 @@ struct made_ctx {
   Lin xp_q, xp_kvz;
   DetrEncW denc[NENC];
   DetrDecW ddec[NDEC];
-  Lin dec_kall, dec_vall;
   LNp dec_norm;
   Lin span0, span1, pq, pv;
   float *span2_w = nullptr, *span2_b = nullptr, *cls_w = nullptr, *cls_b = nullptr;
@@ -291,11 +293,10 @@ int load_detr(made_ctx* c) {
   }
   const std::vector<float>* qpos;
   MADE_TRY(get(c, "decoder_query_embed.weight", D, &qpos));
-  std::vector<float> wk_all(static_cast<size_t>(NDEC) * D * D), bk_all(NDEC * D), wv_all(static_cast<size_t>(NDEC) * D * D),
-      bv_all(NDEC * D);
+  constexpr int H = 8, DH = 32;
   for (int l = 0; l < NDEC; ++l) {
     const std::string p = "detr_transformer.decoder.layers." + std::to_string(l);
-    const std::vector<float>*sw, *sb, *so, *sob, *cw, *cb;
+    const std::vector<float>*sw, *sb, *so, *sob, *cw, *cb, *ow, *ob;
     MADE_TRY(get(c, p + ".self_attn.in_proj_weight", 3 * D * D, &sw));
     MADE_TRY(get(c, p + ".self_attn.in_proj_bias", 3 * D, &sb));
     MADE_TRY(get(c, p + ".self_attn.out_proj.weight", D * D, &so));
@@ -310,29 +311,65 @@ int load_detr(made_ctx* c) {
     }
     std::vector<float> wsa = to_f(Wsa);
     MADE_TRY(up_lin(c, wsa.data(), bsa.data(), D, D, &c->ddec[l].sa));
+    // ---- cross-attention with ONE query per sequence, K/V projections folded away ----
+    // scores_h[t] = q_h . (Wk_h mp_t + bk_h) / sqrt(32) = (Wk_h^T q_h / sqrt(32)) . mp_t + const_h
+    //   (const_h is the same for every key t and cancels in the softmax), with
+    //   q = Wq (tgt + query_pos) + bq  and  mp = memory + pos;
+    // out = Wo concat_h(Wv_h mbar_h + bv_h) + bo,  mbar_h = sum_t a_{h,t} memory_t.
     MADE_TRY(get(c, p + ".multihead_attn.in_proj_weight", 3 * D * D, &cw));
     MADE_TRY(get(c, p + ".multihead_attn.in_proj_bias", 3 * D, &cb));
-    // q = Wq (tgt + query_pos) + bq = Wq tgt + (bq + Wq query_pos)
-    std::vector<float> bq(D);
+    MADE_TRY(get(c, p + ".multihead_attn.out_proj.weight", D * D, &ow));
+    MADE_TRY(get(c, p + ".multihead_attn.out_proj.bias", D, &ob));
+    const float* Wq = cw->data();
+    const float* Wk = cw->data() + D * D;
+    const float* Wv = cw->data() + 2 * D * D;
+    const double inv_sqrt_dh = 1.0 / std::sqrt(static_cast<double>(DH));
+    std::vector<float> wqf(static_cast<size_t>(H) * D * D), bqf(static_cast<size_t>(H) * D);
+    std::vector<float> wov(static_cast<size_t>(D) * H * D), bov(D);
+    std::vector<double> qb(D);   // Wq qpos + bq
     for (int i = 0; i < D; ++i) {
       double s = (*cb)[i];
-      for (int k = 0; k < D; ++k) s += static_cast<double>((*cw)[static_cast<size_t>(i) * D + k]) * (*qpos)[k];
-      bq[i] = static_cast<float>(s);
+      for (int k = 0; k < D; ++k) s += static_cast<double>(Wq[static_cast<size_t>(i) * D + k]) * (*qpos)[k];
+      qb[i] = s;
     }
-    MADE_TRY(up_lin(c, cw->data(), bq.data(), D, D, &c->ddec[l].q));
-    memcpy(&wk_all[static_cast<size_t>(l) * D * D], cw->data() + D * D, sizeof(float) * D * D);
-    memcpy(&bk_all[l * D], cb->data() + D, sizeof(float) * D);
-    memcpy(&wv_all[static_cast<size_t>(l) * D * D], cw->data() + 2 * D * D, sizeof(float) * D * D);
-    memcpy(&bv_all[l * D], cb->data() + 2 * D, sizeof(float) * D);
-    MADE_TRY(load_lin(c, p + ".multihead_attn.out_proj", D, D, &c->ddec[l].out));
+    for (int h = 0; h < H; ++h) {
+      for (int d = 0; d < D; ++d) {          // output row h*256+d of W~q: sum_j Wk[h*32+j, d] * Wq[h*32+j, :]
+        float* row = &wqf[(static_cast<size_t>(h) * D + d) * D];
+        std::vector<double> acc(D, 0.0);
+        double bacc = 0.0;
+        for (int j = 0; j < DH; ++j) {
+          const double kjd = Wk[static_cast<size_t>(h * DH + j) * D + d];
+          const float* wqrow = Wq + static_cast<size_t>(h * DH + j) * D;
+          for (int e = 0; e < D; ++e) acc[e] += kjd * wqrow[e];
+          bacc += kjd * qb[h * DH + j];
+        }
+        for (int e = 0; e < D; ++e) row[e] = static_cast<float>(acc[e] * inv_sqrt_dh);
+        bqf[static_cast<size_t>(h) * D + d] = static_cast<float>(bacc * inv_sqrt_dh);
+      }
+      for (int i = 0; i < D; ++i) {          // W_ov[i, h*256+d] = sum_j Wo[i, h*32+j] * Wv[h*32+j, d]
+        float* row = &wov[static_cast<size_t>(i) * H * D + static_cast<size_t>(h) * D];
+        std::vector<double> acc(D, 0.0);
+        for (int j = 0; j < DH; ++j) {
+          const double oij = (*ow)[static_cast<size_t>(i) * D + h * DH + j];
+          const float* wvrow = Wv + static_cast<size_t>(h * DH + j) * D;
+          for (int d = 0; d < D; ++d) acc[d] += oij * wvrow[d];
+        }
+        for (int d = 0; d < D; ++d) row[d] = static_cast<float>(acc[d]);
+      }
+    }
+    for (int i = 0; i < D; ++i) {
+      double s = (*ob)[i];
+      for (int k = 0; k < D; ++k) s += static_cast<double>((*ow)[static_cast<size_t>(i) * D + k]) * (*cb)[2 * D + k];
+      bov[i] = static_cast<float>(s);
+    }
+    MADE_TRY(up_lin(c, wqf.data(), bqf.data(), static_cast<size_t>(H) * D, D, &c->ddec[l].qfold));
+    MADE_TRY(up_lin(c, wov.data(), bov.data(), D, static_cast<size_t>(H) * D, &c->ddec[l].ovfold));
     MADE_TRY(load_lin(c, p + ".linear1", DFF, D, &c->ddec[l].ff1));
     MADE_TRY(load_lin(c, p + ".linear2", D, DFF, &c->ddec[l].ff2));
     MADE_TRY(load_ln(c, p + ".norm1", &c->ddec[l].n1));
     MADE_TRY(load_ln(c, p + ".norm2", &c->ddec[l].n2));
     MADE_TRY(load_ln(c, p + ".norm3", &c->ddec[l].n3));
   }
-  MADE_TRY(up_lin(c, wk_all.data(), bk_all.data(), NDEC * D, D, &c->dec_kall));
-  MADE_TRY(up_lin(c, wv_all.data(), bv_all.data(), NDEC * D, D, &c->dec_vall));
   MADE_TRY(load_ln(c, "detr_transformer.decoder.norm", &c->dec_norm));
   MADE_TRY(load_lin(c, "span_embed.layers.0", D, D, &c->span0));
   MADE_TRY(load_lin(c, "span_embed.layers.1", D, D, &c->span1));
@@ -358,11 +395,6 @@ __global__ void cast_f32_op_kernel(const float* __restrict__ in, op_t* __restric
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = f2op(in[i]);
 }
-__global__ void cast_op_f32_kernel(const op_t* __restrict__ in, float* __restrict__ out, int64_t n) {
-  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = op2f(in[i]);
-}
-
 // plain linear helper: out = act(A W^T + b)
 int linear(const op_t* A, int64_t lda, const Lin& w, int64_t M, int N, int K, GemmEpilogue epi,
            cudaStream_t st) {
@@ -423,11 +455,22 @@ int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const fl
   return MADE_OK;
 }
 
+int made_ingest_features(const void* feats, int feats_dtype, const float* masks, int64_t rows, int dim,
+                         void* out16, void* stream) {
+  if (rows == 0) return MADE_OK;
+  MADE_REQUIRE(feats && masks && out16, "ingest_features: null pointer");
+  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "ingest_features: bad dtype %d",
+               feats_dtype);
+  MADE_REQUIRE(dim > 0 && dim % 8 == 0, "ingest_features: dim=%d must be a positive multiple of 8", dim);
+  return cast_mask_rows(feats, feats_dtype, masks, rows, dim, static_cast<op_t*>(out16),
+                        static_cast<cudaStream_t>(stream));
+}
+
 int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, const float* masks, int64_t B,
                 void* seq16, float* seq_f32, float* pooled, void* stream) {
   CTX_READY(c);
   MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode: bad modality %d", modality);
-  MADE_REQUIRE(feats_dtype == MADE_DTYPE_F32 || feats_dtype == MADE_DTYPE_BF16 || feats_dtype == MADE_DTYPE_F16,
+  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16_MASKED,
                "encode: bad feature dtype %d", feats_dtype);
   if (B == 0) return MADE_OK;
   MADE_REQUIRE(feats && masks && seq16 && pooled, "encode: null pointer");
@@ -439,6 +482,7 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
                 padded(T * DFF, 2);
   MADE_TRY(c->reserve(need));
   op_t* x0 = c->take<op_t>(T * e.din);
+  if (feats_dtype == MADE_DTYPE_F16_MASKED) x0 = const_cast<op_t*>(static_cast<const op_t*>(feats));
   op_t* x1 = c->take<op_t>(T * D);
   float* x1f = c->take<float>(T * D);
   op_t* qkv = c->take<op_t>(T * 3 * D);
@@ -450,7 +494,7 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   float* seqf = seq_f32 ? seq_f32 : c->take<float>(T * D);
 
   // model_Base.py:556/595 masked_fill, cast to the GEMM operand type
-  MADE_TRY(cast_mask_rows(feats, feats_dtype, masks, T, e.din, x0, st));
+  if (feats_dtype != MADE_DTYPE_F16_MASKED) MADE_TRY(cast_mask_rows(feats, feats_dtype, masks, T, e.din, x0, st));
   {  // :559/598 projection, :533 += pe[:L], Transformer_enhancement norm1 (:86)
     GemmEpilogue ep;
     ep.row_table = e.pe;
@@ -583,33 +627,39 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   MADE_REQUIRE(frame16 && frame_masks && seg16 && seg_masks && video_feats && hs && pred_logits && pred_spans,
                "detr_detect: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t T = B * LD;
-  MADE_REQUIRE(T < (1LL << 31), "detr_detect: batch too large; chunk the call");
+  MADE_REQUIRE(B * LD < (1LL << 31), "detr_detect: batch too large; chunk the call");
+  // The encoder (token-wise GEMMs over B*146 rows) runs in chunks of kEncChunk sequences so that its
+  // scratch stays small and L2-friendly; the decoder (one query per sequence: tiny, latency-bound
+  // GEMMs) runs once over all B sequences.
+  constexpr int64_t kEncChunk = 512;
+  const int64_t Bc = B < kEncChunk ? B : kEncChunk;
+  const int64_t Tc = Bc * LD, Tall = B * LD;
   const int64_t R = NDEC * B;
-  size_t need = padded(T * D, 2) * 8 + padded(T, 4) + padded(T * 2 * D, 2) + padded(T * D, 4) * 2 + padded(T * DFF, 2) +
-                padded(T * NDEC * D, 2) * 2 + padded(B * D, 2) * 6 + padded(B * D, 4) * 4 + padded(B * DFF, 2) +
-                padded(R * D, 4) + padded(R * D, 2) * 3;
+  size_t need = padded(Tall * D, 2) * 2 + padded(Tall, 4) +                                  // mem, mp, mask
+                padded(Tc * D, 2) * 7 + padded(Tc * 2 * D, 2) + padded(Tc * D, 4) * 2 + padded(Tc * DFF, 2) +
+                padded(B * D, 2) * 4 + padded(B * D, 4) * 2 + padded(B * 8 * D, 4) + padded(B * 8 * D, 2) +
+                padded(B * DFF, 2) + padded(R * D, 4) + padded(R * D, 2) * 3;
   MADE_TRY(c->reserve(need));
-  op_t* src = c->take<op_t>(T * D);
-  op_t* pos = c->take<op_t>(T * D);
-  op_t* srcpos = c->take<op_t>(T * D);
-  float* mask = c->take<float>(T);
-  op_t* qk = c->take<op_t>(T * 2 * D);
-  op_t* v = c->take<op_t>(T * D);
-  op_t* att = c->take<op_t>(T * D);
-  op_t* s1 = c->take<op_t>(T * D);
-  float* s1f = c->take<float>(T * D);
-  op_t* hbuf = c->take<op_t>(T * DFF);
-  op_t* src2 = c->take<op_t>(T * D);
-  op_t* srcpos2 = c->take<op_t>(T * D);
-  float* srcf = c->take<float>(T * D);
-  op_t* kall = c->take<op_t>(T * NDEC * D);
-  op_t* vall = c->take<op_t>(T * NDEC * D);
+  op_t* mem_all = c->take<op_t>(Tall * D);     // encoder output (memory), fp16
+  op_t* mp_all = c->take<op_t>(Tall * D);      // memory + pos
+  float* mask = c->take<float>(Tall);
+  op_t* src = c->take<op_t>(Tc * D);
+  op_t* pos = c->take<op_t>(Tc * D);
+  op_t* srcpos = c->take<op_t>(Tc * D);
+  op_t* qk = c->take<op_t>(Tc * 2 * D);
+  op_t* v = c->take<op_t>(Tc * D);
+  op_t* att = c->take<op_t>(Tc * D);
+  op_t* s1 = c->take<op_t>(Tc * D);
+  float* s1f = c->take<float>(Tc * D);
+  op_t* hbuf = c->take<op_t>(Tc * DFF);
+  op_t* src2 = c->take<op_t>(Tc * D);
+  op_t* srcpos2 = c->take<op_t>(Tc * D);
+  float* srcf = c->take<float>(Tc * D);
   op_t* tgt = c->take<op_t>(B * D);
   op_t* t1 = c->take<op_t>(B * D);
   float* t1f = c->take<float>(B * D);
-  float* qf = c->take<float>(B * D);
-  op_t* ob = c->take<op_t>(B * D);
+  float* qt = c->take<float>(B * 8 * D);
+  op_t* mbar = c->take<op_t>(B * 8 * D);
   op_t* t2 = c->take<op_t>(B * D);
   float* t2f = c->take<float>(B * D);
   op_t* hdec = c->take<op_t>(B * DFF);
@@ -620,83 +670,81 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   op_t* sp1 = c->take<op_t>(R * D);
 
   const op_t* fr = static_cast<const op_t*>(frame16);
-  MADE_TRY(detr_prep(fr, frame_masks, static_cast<const op_t*>(seg16), seg_masks, track_idx,
-                     c->inv_dim_t, B, src, pos, srcpos, mask, st));
-  // ---------------- encoder (forward_post, music_detr/transformer.py:191-210) ----------------
-  op_t *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
-  for (int l = 0; l < NENC; ++l) {
-    const DetrEncW& w = c->denc[l];
-    {
-      GemmEpilogue ep;
-      ep.out_h = qk;
-      ep.ld_h = 2 * D;
-      MADE_TRY(linear(curpos, D, w.qk, T, 2 * D, D, ep, st));   // q = k = src + pos
-    }
-    {
-      GemmEpilogue ep;
-      ep.out_h = v;
-      ep.ld_h = D;
-      MADE_TRY(linear(cur, D, w.v, T, D, D, ep, st));           // value = src
-    }
-    MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, mask, B, LD, att, D, st));
-    {
-      GemmEpilogue ep;
-      if (l == 0) {
-        ep.residual = cur;
-        ep.residual_f32 = 0;
-      } else {
-        ep.residual = srcf;
-        ep.residual_f32 = 1;
+  static_assert(NENC % 2 == 0, "the encoder ping-pong below ends in the (src, srcpos) buffers");
+  // ---------------- encoder (forward_post, music_detr/transformer.py:191-210), chunked ----------------
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
+    const int64_t T = nb * LD;
+    float* mask_c = mask + b0 * LD;
+    MADE_TRY(detr_prep(fr + b0 * LV * D, frame_masks + b0 * LV, static_cast<const op_t*>(seg16), seg_masks,
+                       track_idx ? track_idx + b0 : nullptr, b0, c->inv_dim_t, nb, src, pos, srcpos, mask_c, st));
+    op_t *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
+    for (int l = 0; l < NENC; ++l) {
+      const DetrEncW& w = c->denc[l];
+      if (l == NENC - 1) {   // the last layer writes the memory straight into the all-sequence buffers
+        nxt = mem_all + b0 * LD * D;
+        nxtpos = mp_all + b0 * LD * D;
       }
-      ep.res_ld = D;
-      ep.ln_gamma = w.n1.g;
-      ep.ln_beta = w.n1.b;
-      ep.out_h = s1;
-      ep.ld_h = D;
-      ep.out_f32 = s1f;
-      ep.ld_f32 = D;
-      MADE_TRY(linear(att, D, w.out, T, D, D, ep, st));
+      {
+        GemmEpilogue ep;
+        ep.out_h = qk;
+        ep.ld_h = 2 * D;
+        MADE_TRY(linear(curpos, D, w.qk, T, 2 * D, D, ep, st));   // q = k = src + pos
+      }
+      {
+        GemmEpilogue ep;
+        ep.out_h = v;
+        ep.ld_h = D;
+        MADE_TRY(linear(cur, D, w.v, T, D, D, ep, st));           // value = src
+      }
+      MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, mask_c, nb, LD, att, D, st));
+      {
+        GemmEpilogue ep;
+        if (l == 0) {
+          ep.residual = cur;
+          ep.residual_f32 = 0;
+        } else {
+          ep.residual = srcf;
+          ep.residual_f32 = 1;
+        }
+        ep.res_ld = D;
+        ep.ln_gamma = w.n1.g;
+        ep.ln_beta = w.n1.b;
+        ep.out_h = s1;
+        ep.ld_h = D;
+        ep.out_f32 = s1f;
+        ep.ld_f32 = D;
+        MADE_TRY(linear(att, D, w.out, T, D, D, ep, st));
+      }
+      {
+        GemmEpilogue ep;
+        ep.act = 2;
+        ep.out_h = hbuf;
+        ep.ld_h = DFF;
+        MADE_TRY(linear(s1, D, w.ff1, T, DFF, D, ep, st));
+      }
+      {
+        GemmEpilogue ep;
+        ep.residual = s1f;
+        ep.residual_f32 = 1;
+        ep.res_ld = D;
+        ep.ln_gamma = w.n2.g;
+        ep.ln_beta = w.n2.b;
+        ep.out_h = nxt;
+        ep.ld_h = D;
+        if (l < NENC - 1 || memory) {
+          ep.out_f32 = (l == NENC - 1) ? memory + b0 * LD * D : srcf;
+          ep.ld_f32 = D;
+        }
+        ep.add2 = pos;
+        ep.add2_ld = D;
+        ep.out2_h = nxtpos;
+        ep.ld_out2 = D;
+        MADE_TRY(linear(hbuf, DFF, w.ff2, T, D, DFF, ep, st));
+      }
+      op_t* t = cur; cur = nxt; nxt = t;
+      t = curpos; curpos = nxtpos; nxtpos = t;
     }
-    {
-      GemmEpilogue ep;
-      ep.act = 2;
-      ep.out_h = hbuf;
-      ep.ld_h = DFF;
-      MADE_TRY(linear(s1, D, w.ff1, T, DFF, D, ep, st));
-    }
-    {
-      GemmEpilogue ep;
-      ep.residual = s1f;
-      ep.residual_f32 = 1;
-      ep.res_ld = D;
-      ep.ln_gamma = w.n2.g;
-      ep.ln_beta = w.n2.b;
-      ep.out_h = nxt;
-      ep.ld_h = D;
-      ep.out_f32 = srcf;
-      ep.ld_f32 = D;
-      ep.add2 = pos;
-      ep.add2_ld = D;
-      ep.out2_h = nxtpos;
-      ep.ld_out2 = D;
-      MADE_TRY(linear(hbuf, DFF, w.ff2, T, D, DFF, ep, st));
-    }
-    op_t* t = cur; cur = nxt; nxt = t;
-    t = curpos; curpos = nxtpos; nxtpos = t;
-  }
-  if (memory) MADE_CUDA(cudaMemcpyAsync(memory, srcf, static_cast<size_t>(T) * D * 4, cudaMemcpyDeviceToDevice, st));
-  // ---------------- decoder K/V of the memory for all six layers at once ----------------
-  {
-    GemmEpilogue ep;
-    ep.out_h = kall;
-    ep.ld_h = NDEC * D;
-    MADE_TRY(linear(curpos, D, c->dec_kall, T, NDEC * D, D, ep, st));   // key = memory + pos
-  }
-  {
-    GemmEpilogue ep;
-    ep.out_h = vall;
-    ep.ld_h = NDEC * D;
-    MADE_TRY(linear(cur, D, c->dec_vall, T, NDEC * D, D, ep, st));      // value = memory
   }
   // ---------------- decoder (forward_post :273-307), one moment query per sequence ----------------
   cast_f32_op_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
@@ -720,14 +768,14 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       MADE_TRY(linear(tin, D, w.sa, B, D, D, ep, st));
     }
     {
-      GemmEpilogue ep;
-      ep.out_f32 = qf;
-      ep.ld_f32 = D;
-      MADE_TRY(linear(t1, D, w.q, B, D, D, ep, st));
+      GemmEpilogue ep;   // q~ = per-head Wk_h^T q_h / sqrt(32)
+      ep.out_f32 = qt;
+      ep.ld_f32 = 8 * D;
+      MADE_TRY(linear(t1, D, w.qfold, B, 8 * D, D, ep, st));
     }
-    MADE_TRY(dec_cross_attn(qf, kall + l * D, vall + l * D, NDEC * D, mask, B, LD, ob, st));
+    MADE_TRY(dec_attn_folded(qt, mp_all, mem_all, mask, B, LD, mbar, st));
     {
-      GemmEpilogue ep;
+      GemmEpilogue ep;   // out_proj o v_proj folded, + residual + norm2
       ep.residual = t1f;
       ep.residual_f32 = 1;
       ep.res_ld = D;
@@ -737,7 +785,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       ep.ld_h = D;
       ep.out_f32 = t2f;
       ep.ld_f32 = D;
-      MADE_TRY(linear(ob, D, w.out, B, D, D, ep, st));
+      MADE_TRY(linear(mbar, 8 * D, w.ovfold, B, D, 8 * D, ep, st));
     }
     {
       GemmEpilogue ep;

@@ -6,7 +6,8 @@
 // one warp owns one (sequence, head): K and V^T head slices live in padded shared memory
 // (conflict-free fragment loads), scores stay in registers (whole row, no online softmax), and the
 // two products run on mma.sync m16n8k16 fp16 with fp32 accumulation.
-// The decoder's single-query cross-attention (1 x 146 per head) is a separate SIMT kernel.
+// The decoder's single-query cross-attention (1 x 146 per head) is a separate SIMT kernel that
+// works on the memory itself (K/V projections folded into the query side).
 #include "common.cuh"
 
 namespace made {
@@ -155,55 +156,83 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   }
 }
 
-// Decoder cross-attention with ONE query per sequence (music_detr/transformer.py:289-292):
-// q [B,256] fp32 (already projected, includes the query-pos term), K/V slices of layer l inside
-// the batched [B*L, ldkv] projections; out [B,256] fp16.  One CTA (256 threads) per sequence.
+// Decoder cross-attention with ONE query per sequence (music_detr/transformer.py:289-292) with the
+// per-layer K/V projections of the memory folded into the query side (api.cu load_detr):
+//   scores_h[t] = q~_h . (memory + pos)_t          q~ [B, 8*256] fp32 (includes 1/sqrt(32))
+//   mbar_h      = sum_t softmax_t(scores_h)[t] * memory_t   -> out [B, 8*256] fp16
+// so every layer reads the SAME two [146,256] fp16 matrices of a sequence (L1/L2 resident across
+// the 8 heads) and the [B*146, 6*512] K/V tensors of the reference are never formed.
+// One CTA per sequence, warp = head, lane = 8 consecutive features; only valid keys are visited.
 __global__ void __launch_bounds__(256)
-dec_cross_attn_kernel(const float* __restrict__ q, const op_t* __restrict__ K,
-                      const op_t* __restrict__ V, int64_t ldkv,
-                      const float* __restrict__ key_mask, int L, float scale,
-                      op_t* __restrict__ out) {
-  __shared__ float sq[256];
+dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp,
+                       const op_t* __restrict__ mem, const float* __restrict__ key_mask, int L,
+                       op_t* __restrict__ out) {
   __shared__ float sp[8][160];
+  __shared__ short vidx[160];
+  __shared__ int s_nvalid;
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  sq[tid] = q[b * 256 + tid] * scale;
+  if (warp == 0) {   // ordered compaction of the valid key positions
+    int base = 0;
+    for (int t0 = 0; t0 < L; t0 += 32) {
+      const int t = t0 + lane;
+      const bool ok = t < L && key_mask[b * L + t] != 0.f;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) vidx[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<short>(t);
+      base += __popc(bal);
+    }
+    if (lane == 0) s_nvalid = base;
+  }
+  float q[8];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qt + b * 2048 + warp * 256 + lane * 8);
+    const float4 a = __ldg(qp), c = __ldg(qp + 1);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = c.x; q[5] = c.y; q[6] = c.z; q[7] = c.w;
+  }
   __syncthreads();
-  // scores: warp = head; lane strides over keys; 32-dim dot from a 64-byte contiguous slice
-  const op_t* Kb = K + (b * L) * ldkv + warp * 32;
+  const int nv = s_nvalid;
+  const op_t* mpb = mp + b * L * 256 + lane * 8;
+  const op_t* memb = mem + b * L * 256 + lane * 8;
   float mx = -INFINITY;
-  for (int key = lane; key < L; key += 32) {
-    const uint4* kp = reinterpret_cast<const uint4*>(Kb + key * ldkv);
+  for (int i = 0; i < nv; ++i) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mpb + vidx[i] * 256));
+    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
     float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 kv = __ldg(kp + c);
-      const op2_t* hh = reinterpret_cast<const op2_t*>(&kv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = op2_to_f2(hh[j]);
-        acc = fmaf(f.x, sq[warp * 32 + c * 8 + 2 * j], acc);
-        acc = fmaf(f.y, sq[warp * 32 + c * 8 + 2 * j + 1], acc);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = op2_to_f2(hh[j]);
+      acc = fmaf(f.x, q[2 * j], acc);
+      acc = fmaf(f.y, q[2 * j + 1], acc);
     }
-    if (key_mask[b * L + key] == 0.f) acc = -INFINITY;
-    sp[warp][key] = acc;
+    acc = warp_sum(acc);
+    if (lane == 0) sp[warp][i] = acc;
     mx = fmaxf(mx, acc);
   }
-  mx = warp_max(mx);
+  __syncwarp();
   float sum = 0.f;
-  for (int key = lane; key < L; key += 32) {
-    float e = __expf(sp[warp][key] - mx);
-    sp[warp][key] = e;
+  for (int i = lane; i < nv; i += 32) {
+    const float e = __expf(sp[warp][i] - mx);
+    sp[warp][i] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  __syncthreads();
-  // output: thread = output dim (head = tid/32), coalesced 512-byte V rows
-  const op_t* Vb = V + (b * L) * ldkv + tid;
-  float acc = 0.f;
-  for (int key = 0; key < L; ++key) acc = fmaf(sp[warp][key], op2f(Vb[key * ldkv]), acc);
-  out[b * 256 + tid] = f2op(acc / sum);
+  __syncwarp();
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = 0; i < nv; ++i) {
+    const float a = sp[warp][i];
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(memb + vidx[i] * 256));
+    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = op2_to_f2(hh[j]);
+      o[2 * j] = fmaf(a, f.x, o[2 * j]);
+      o[2 * j + 1] = fmaf(a, f.y, o[2 * j + 1]);
+    }
+  }
+  const float inv = 1.f / sum;
+  *reinterpret_cast<uint4*>(out + b * 2048 + warp * 256 + lane * 8) =
+      make_uint4(pack_op2(o[0] * inv, o[1] * inv), pack_op2(o[2] * inv, o[3] * inv),
+                 pack_op2(o[4] * inv, o[5] * inv), pack_op2(o[6] * inv, o[7] * inv));
 }
 
 }  // namespace made
@@ -240,12 +269,11 @@ int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
   return launch_mha<160>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, O, ldo, st);
 }
 
-int dec_cross_attn(const float* q, const op_t* K, const op_t* V, int64_t ldkv,
-                   const float* key_mask, int64_t B, int L, op_t* out, cudaStream_t st) {
+int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const float* key_mask, int64_t B,
+                    int L, op_t* out, cudaStream_t st) {
   if (B == 0) return MADE_OK;
-  MADE_REQUIRE(q && K && V && key_mask && out && L <= 160, "dec_cross_attn: bad arguments");
-  dec_cross_attn_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(q, K, V, ldkv, key_mask, L,
-                                                                  0.17677669529663687f, out);
+  MADE_REQUIRE(qt && mp && mem && key_mask && out && L > 0 && L <= 160, "dec_attn_folded: bad arguments");
+  dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(qt, mp, mem, key_mask, L, out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

@@ -119,13 +119,13 @@ pool_norm_kernel(const float* __restrict__ seq, const float* __restrict__ mask, 
 __global__ void __launch_bounds__(256)
 detr_prep_kernel(const op_t* __restrict__ frame_out, const float* __restrict__ frame_mask,
                  const op_t* __restrict__ seg_out, const float* __restrict__ seg_mask,
-                 const int32_t* __restrict__ track_idx, const float* __restrict__ inv_dim_t,
-                 op_t* __restrict__ src, op_t* __restrict__ pos,
+                 const int32_t* __restrict__ track_idx, int64_t seq_offset,
+                 const float* __restrict__ inv_dim_t, op_t* __restrict__ src, op_t* __restrict__ pos,
                  op_t* __restrict__ srcpos, float* __restrict__ mask_out) {
   constexpr int LV = 50, LM = 96, L = 146;
   __shared__ float sx[L];
   const int64_t b = blockIdx.x;
-  const int64_t tr = track_idx ? track_idx[b] : b;
+  const int64_t tr = track_idx ? track_idx[b] : seq_offset + b;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < L) {
     float mk = tid < LV ? frame_mask[b * LV + tid] : seg_mask[tr * LM + (tid - LV)];
@@ -231,7 +231,16 @@ int cast_mask_rows(const void* in, int in_dtype, const float* mask, int64_t rows
   MADE_REQUIRE(dim % 8 == 0, "cast_mask_rows: dim must be a multiple of 8");
   const int64_t total = rows * (dim / 8);
   int64_t blocks = ceil_div64(total, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  // Pinned host memory (UVA): the kernel pulls the valid rows over PCIe itself.  Two CTAs per SM
+  // keep ~2 MB of reads in flight (far more than the link needs) while leaving the SMs' thread and
+  // shared-memory slots free for the GEMM kernels of the previous chunk running on another stream.
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, in) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+    cap = static_cast<int64_t>(sm_count()) * 2;
+  else
+    (void)cudaGetLastError();
+  if (blocks > cap) blocks = cap;
   const unsigned g = static_cast<unsigned>(blocks);
   if (in_dtype == MADE_DTYPE_F32)
     cast_mask_rows_kernel<MADE_DTYPE_F32><<<g, 256, 0, st>>>(in, mask, rows, dim, out);
@@ -265,12 +274,13 @@ int pool_norm(const float* seq, const float* mask, int64_t B, int L, float* pool
 }
 
 int detr_prep(const op_t* frame_out, const float* frame_mask, const op_t* seg_out,
-              const float* seg_mask, const int32_t* track_idx, const float* inv_dim_t, int64_t B,
-              op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
+              const float* seg_mask, const int32_t* track_idx, int64_t seq_offset, const float* inv_dim_t,
+              int64_t B, op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
               cudaStream_t st) {
   if (B == 0) return MADE_OK;
   detr_prep_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(frame_out, frame_mask, seg_out, seg_mask,
-                                                             track_idx, inv_dim_t, src, pos, srcpos, mask_out);
+                                                             track_idx, seq_offset, inv_dim_t, src, pos, srcpos,
+                                                             mask_out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

@@ -11,8 +11,8 @@ int layernorm_rows(const void* in, int in_is_op, int64_t ld_in, int64_t rows, co
                    const float* beta, op_t* out_h, float* out_f32, cudaStream_t st);
 int pool_norm(const float* seq, const float* mask, int64_t B, int L, float* pooled, cudaStream_t st);
 int detr_prep(const op_t* frame_out, const float* frame_mask, const op_t* seg_out,
-              const float* seg_mask, const int32_t* track_idx, const float* inv_dim_t, int64_t B,
-              op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
+              const float* seg_mask, const int32_t* track_idx, int64_t seq_offset, const float* inv_dim_t,
+              int64_t B, op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
               cudaStream_t st);
 int heads_final(const float* hs, const op_t* h2, int64_t rows, const float* w_cls,
                 const float* b_cls, const float* w_sp, const float* b_sp, float* logits, float* spans,
@@ -24,8 +24,8 @@ int vhat_rows(const float* v, int64_t rows, __half* out, cudaStream_t st);
 int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
              const op_t* V, int64_t ldv, const float* key_mask, int64_t B, int L,
              op_t* O, int64_t ldo, cudaStream_t st);
-int dec_cross_attn(const float* q, const op_t* K, const op_t* V, int64_t ldkv,
-                   const float* key_mask, int64_t B, int L, op_t* out, cudaStream_t st);
+int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const float* key_mask, int64_t B,
+                    int L, op_t* out, cudaStream_t st);
 
 // xpool.cu
 int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st);

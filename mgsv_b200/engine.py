@@ -58,14 +58,40 @@ class Engine:
         self.loaded = True
 
     # -----------------------------------------------------------------------------------------
-    def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True):
-        """forward_{video,audio}_encoder_feature → (seq16 [B,L,256], seq_f32 or None, pooled [B,256])."""
+    def ingest(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """Masked cast of raw features (device tensor or PINNED host tensor, fp32/bf16/fp16) into the
+        fp16 operand buffer consumed by `encode(..., ingested=True)`.  Padded rows are never read, so
+        a pinned host tensor costs only its valid rows of PCIe traffic.  `masks` is a device tensor."""
+        L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
+        if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
+            raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
+        if tuple(masks.shape) != (feats.shape[0], L) or masks.dtype != torch.float32 or not masks.is_cuda:
+            raise ValueError(f"expected a float32 device mask of shape [B,{L}]")
+        dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}.get(feats.dtype)
+        if dt is None:
+            raise ValueError(f"unsupported feature dtype {feats.dtype}")
+        B = feats.shape[0]
+        if out is None:
+            out = torch.empty((B, L, din), dtype=torch.float16, device=masks.device)
+        _lib.check(self._lib.made_ingest_features(_lib.ptr_any(feats), dt, _lib.ptr(masks.contiguous()), B * L, din,
+                                                  _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True,
+               ingested: bool = False, out=None):
+        """forward_{video,audio}_encoder_feature → (seq16 [B,L,256], seq_f32 or None, pooled [B,256]).
+        `ingested=True`: feats is the fp16 buffer written by `ingest` (used in place).
+        `out=(seq16, pooled)` writes into caller-provided (contiguous slices of) tensors."""
         L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
         if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
             raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
         if tuple(masks.shape) != (feats.shape[0], L):
             raise ValueError(f"expected masks of shape [B,{L}], got {tuple(masks.shape)}")
-        if feats.dtype == torch.float32:
+        if ingested:
+            if feats.dtype != torch.float16:
+                raise ValueError("ingested features must be the fp16 output of Engine.ingest")
+            dt = _lib.F16_MASKED
+        elif feats.dtype == torch.float32:
             dt = _lib.F32
         elif feats.dtype == torch.bfloat16:
             dt = _lib.BF16
@@ -77,22 +103,29 @@ class Engine:
         masks = masks.to(torch.float32).contiguous()
         B = feats.shape[0]
         dev = feats.device
-        seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float16, device=dev)
+        if out is not None:
+            seq, pooled = out
+        else:
+            seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float16, device=dev)
+            pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
         seq32 = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
-        pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
         _lib.check(self._lib.made_encode(self._h, modality, _lib.ptr(feats), dt, _lib.ptr(masks), B, _lib.ptr(seq),
                                          _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
         return seq, seq32, pooled
 
-    def gallery_prepare(self, seg16: torch.Tensor, seg_masks: torch.Tensor):
-        """Per-track X-Pool operands: kz [N*96,768] fp16, gram [N*96,96] fp16, maskbits [N,4] int32."""
+    def gallery_prepare(self, seg16: torch.Tensor, seg_masks: torch.Tensor, out=None):
+        """Per-track X-Pool operands: kz [N*96,768] fp16, gram [N*96,96] fp16, maskbits [N,4] int32.
+        `out=(kz, gram, bits)` writes into caller-provided (contiguous slices of) tensors."""
         N = seg16.shape[0]
         dev = seg16.device
         if seg16.dtype != torch.float16:
             raise ValueError("gallery_prepare takes the fp16 encoded segments")
-        kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev)
-        gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev)
-        bits = torch.empty((N, 4), dtype=torch.int32, device=dev)
+        if out is not None:
+            kz, gram, bits = out
+        else:
+            kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev)
+            gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev)
+            bits = torch.empty((N, 4), dtype=torch.int32, device=dev)
         masks = seg_masks.to(torch.float32).contiguous()
         _lib.check(self._lib.made_gallery_prepare(self._h, _lib.ptr(seg16.contiguous()), _lib.ptr(masks), N,
                                                   _lib.ptr(kz), _lib.ptr(gram), _lib.ptr(bits), _lib.stream_ptr()))

@@ -72,8 +72,8 @@ class ShardedEvaluator:
         q0, q1 = shard_bounds(n_queries, R, W)
         m0, m1 = shard_bounds(n_tracks, R, W)
         q_sizes = [shard_bounds(n_queries, r, W)[1] - shard_bounds(n_queries, r, W)[0] for r in range(W)]
-        frame_seq, vf_local, frame_mask = ev.encode_queries(videos["frame_feats"], videos["frame_mask"], on_host)
-        gal = ev.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_host)
+        frame_seq, vf_local, frame_mask = ev.encode_queries(videos["frame_feats"], videos["frame_mask"])
+        gal = ev.encode_gallery(tracks["segment_feats"], tracks["segment_mask"])
         video_feats = self._all_gather_cat(vf_local, q_sizes)                      # exchange 1
         single, dual = ev.score(video_feats, gal)
         gt = gt_col.to(dev).to(torch.int32)

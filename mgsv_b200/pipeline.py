@@ -3,15 +3,23 @@
 This is the B200 replacement of the body of test-MaDe.py:eval_epoch (243-447): encode queries and
 gallery, fused full-gallery X-Pool scoring (never materialising [N_m,N_v,256]), dual-tower cosine,
 fp64-sum ranking/top-k, DETR moment detection for the paired track, IoU — all as C-ABI kernel
-launches on one stream; host<->device copies of the e2e path run on a second stream and overlap
-the kernels chunk by chunk.  Multi-GPU: the gallery is sharded by track, queries are replicated
-for scoring and sharded for detection (`shard=(rank, world)`), see `parallel.py`.
+launches.
+
+Stream plan.  Features enter through `Engine.ingest` on a second ("ingest") stream, one chunk
+ahead of the compute stream: the ingest kernel reads the raw features — device memory, or PINNED
+HOST memory in place over PCIe, valid rows only — and writes the masked fp16 operand buffer
+(double-buffered).  The compute stream then runs, per gallery chunk, encode -> X-Pool operands ->
+fused scoring of every query against the chunk, so that host->device traffic of chunk i+1 hides
+behind the kernels of chunk i.  Moment detection starts as soon as every paired track is encoded;
+ranking/top-k runs once all columns are scored.
+
+Multi-GPU: the gallery is sharded by track, queries are replicated for scoring and sharded for
+detection (`parallel.py`).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional
 
-import numpy as np
 import torch
 
 from . import _lib, ops
@@ -21,78 +29,144 @@ from .engine import Engine
 
 class GalleryEvaluator:
     def __init__(self, engine: Engine, k: int = 100, music_chunk: int = 1024, video_chunk: int = 1024,
-                 detr_chunk: int = 500):
+                 detr_chunk: int = 4096):
         self.eng = engine
         self.dev = engine.device
         self.k = k
         self.music_chunk = music_chunk
         self.video_chunk = video_chunk
         self.detr_chunk = detr_chunk
-        self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.launches = 0   # kernels launched by the last run (counted per C-ABI op, see _count)
-        self.xpool_events = None   # bench.py: list that receives (start, end) CUDA events per xpool launch
+        self.ingest_stream = torch.cuda.Stream(device=self.dev)
+        self._stage = {}            # (modality, slot) -> fp16 staging buffer of one chunk
+        self._stage_free = {}       # (modality, slot) -> event: compute stream is done with the buffer
+        self.launches = 0           # kernels launched by the last run (counted per C-ABI op, see _count)
+        self.xpool_events = None    # bench.py: list that receives (start, end, n_pairs) per xpool launch
 
     # ---- launch accounting (bench.py reports gpu_launches) --------------------------------------
-    # kernels per C-ABI call: encode = cast + 6 GEMM + attn + pool = 9; gallery_prepare = LN + GEMM +
-    # Gram GEMM + maskbits = 4; query_prepare = LN + GEMM + vhat = 3; xpool_score = 1; cosine = 1;
-    # rank_topk = 1; detr_detect = prep 1 + enc 2*6 + KV 2 + cast 1 + dec 6*6 (5 GEMM + CA) + 6 D2D copies
-    # (not kernels) + LN 1 + heads 3 = 56; moment_postproc = 1.
-    _K = dict(encode=9, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=56, postproc=1)
+    # kernels per C-ABI call: ingest = 1; encode (ingested input) = 6 GEMM + attn + pool = 8;
+    # gallery_prepare = LN + GEMM + Gram GEMM + maskbits = 4; query_prepare = LN + GEMM + vhat = 3;
+    # xpool_score = 1; cosine = 1; rank_topk = 1; detr_detect = per 512-sequence encoder chunk
+    # (prep 1 + enc 2*6 = 13) + cast 1 + dec 6*(5 GEMM + attention) + LN 1 + heads 3 = 41 (the 6 D2D
+    # copies are not kernels); moment_postproc = 1.
+    _K = dict(ingest=1, encode=8, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=41,
+              detr_chunk=13, postproc=1)
 
     def _count(self, what: str, n: int = 1):
         self.launches += self._K[what] * n
 
+    # ---- feature ingest, one chunk ahead on the ingest stream ---------------------------------------
+    def _ingest_iter(self, modality: int, feats: torch.Tensor, mask_d: torch.Tensor, chunk: int):
+        """Yield (start, end, x16, release) per chunk: x16 = fp16 masked features of rows start:end,
+        ready on the compute stream; call release() after the last kernel that reads x16 has been
+        enqueued so the ingest stream may refill the buffer."""
+        n = feats.shape[0]
+        L, din = feats.shape[1], feats.shape[2]
+        bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+        cur = torch.cuda.current_stream(self.dev)
+        start_ev = torch.cuda.Event()
+        start_ev.record(cur)            # mask_d (and anything else enqueued so far) is ready
+        ready = {}
+
+        def issue(i):
+            s, e = bounds[i]
+            slot = i & 1
+            key = (modality, slot)
+            buf = self._stage.get(key)
+            if buf is None or buf.shape[0] < e - s:
+                buf = torch.empty((max(chunk, e - s), L, din), dtype=torch.float16, device=self.dev)
+                self._stage[key] = buf
+            with torch.cuda.stream(self.ingest_stream):
+                self.ingest_stream.wait_event(start_ev)
+                free = self._stage_free.get(key)
+                if free is not None:
+                    self.ingest_stream.wait_event(free)
+                self.eng.ingest(modality, feats[s:e], mask_d[s:e], out=buf[:e - s])
+                ev = torch.cuda.Event()
+                ev.record(self.ingest_stream)
+            ready[i] = (buf[:e - s], ev, key)
+            self._count("ingest")
+
+        if bounds:
+            issue(0)
+        for i, (s, e) in enumerate(bounds):
+            if i + 1 < len(bounds):
+                issue(i + 1)
+            x16, ev, key = ready.pop(i)
+            cur.wait_event(ev)
+
+            def release(key=key):
+                done = torch.cuda.Event()
+                done.record(cur)
+                self._stage_free[key] = done
+
+            yield s, e, x16, release
+
     # ---- stages -----------------------------------------------------------------------------------
-    def encode_queries(self, frame_feats, frame_mask, on_host: bool):
+    def encode_queries(self, frame_feats, frame_mask):
         n = frame_feats.shape[0]
         seq = torch.empty((n, cfg.L_V, cfg.D_MODEL), dtype=torch.float16, device=self.dev)
         pooled = torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=self.dev)
-        mask_d = self._to_dev(frame_mask, on_host)
-        for s, e, feats_d in self._chunks(frame_feats, self.video_chunk, on_host):
-            sq, _, pl = self.eng.encode(_lib.VIDEO, feats_d, mask_d[s:e], want_f32=False)
-            seq[s:e] = sq
-            pooled[s:e] = pl
+        mask_d = self._to_dev(frame_mask).to(torch.float32)
+        for s, e, x16, release in self._ingest_iter(_lib.VIDEO, frame_feats, mask_d, self.video_chunk):
+            self.eng.encode(_lib.VIDEO, x16, mask_d[s:e], want_f32=False, ingested=True, out=(seq[s:e], pooled[s:e]))
+            release()
             self._count("encode")
         return seq, pooled, mask_d
 
-    def encode_gallery(self, segment_feats, segment_mask, on_host: bool):
+    def new_gallery(self, n: int):
+        dev = self.dev
+        return dict(seq=torch.empty((n, cfg.L_M, cfg.D_MODEL), dtype=torch.float16, device=dev),
+                    pooled=torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=dev),
+                    kz=torch.empty((n * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev),
+                    gram=torch.empty((n * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev),
+                    bits=torch.empty((n, 4), dtype=torch.int32, device=dev))
+
+    def encode_gallery(self, segment_feats, segment_mask, on_chunk=None):
+        """Encode the gallery chunk by chunk; `on_chunk(gal, s, e)` runs right after chunk [s,e) has
+        its encoded segments and X-Pool operands enqueued (used to score / detect while later chunks
+        are still being ingested)."""
         n = segment_feats.shape[0]
-        seq = torch.empty((n, cfg.L_M, cfg.D_MODEL), dtype=torch.float16, device=self.dev)
-        pooled = torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=self.dev)
-        kz = torch.empty((n * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=self.dev)
-        gram = torch.empty((n * cfg.L_M, cfg.L_M), dtype=torch.float16, device=self.dev)
-        bits = torch.empty((n, 4), dtype=torch.int32, device=self.dev)
-        mask_d = self._to_dev(segment_mask, on_host)
-        for s, e, feats_d in self._chunks(segment_feats, self.music_chunk, on_host):
-            sq, _, pl = self.eng.encode(_lib.MUSIC, feats_d, mask_d[s:e], want_f32=False)
-            seq[s:e] = sq
-            pooled[s:e] = pl
-            k_, g_, b_ = self.eng.gallery_prepare(sq, mask_d[s:e])
-            kz[s * cfg.L_M:e * cfg.L_M] = k_
-            gram[s * cfg.L_M:e * cfg.L_M] = g_
-            bits[s:e] = b_
-            self._count("encode")
-            self._count("gallery_prepare")
-        return dict(seq=seq, pooled=pooled, kz=kz, gram=gram, bits=bits, mask=mask_d)
+        L = cfg.L_M
+        gal = self.new_gallery(n)
+        mask_d = self._to_dev(segment_mask).to(torch.float32)
+        gal["mask"] = mask_d
+        for s, e, x16, release in self._ingest_iter(_lib.MUSIC, segment_feats, mask_d, self.music_chunk):
+            self.eng.encode(_lib.MUSIC, x16, mask_d[s:e], want_f32=False, ingested=True,
+                            out=(gal["seq"][s:e], gal["pooled"][s:e]))
+            release()
+            self.eng.gallery_prepare(gal["seq"][s:e], mask_d[s:e],
+                                     out=(gal["kz"][s * L:e * L], gal["gram"][s * L:e * L], gal["bits"][s:e]))
+            self._count("encode"), self._count("gallery_prepare")
+            if on_chunk is not None:
+                on_chunk(gal, s, e)
+        return gal
+
+    def score_chunk(self, qprep, video_feats, gal, s: int, e: int, single, dual, col_offset: int = 0):
+        """single/dual similarity of every query against gallery tracks [s, e) -> columns col_offset+s..."""
+        q, vhat = qprep
+        L = cfg.L_M
+        if self.xpool_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.eng.xpool_score(q, vhat, gal["kz"][s * L:e * L], gal["gram"][s * L:e * L], gal["bits"][s:e], out=single,
+                             col_offset=col_offset + s)
+        if self.xpool_events is not None:
+            e1.record()
+            self.xpool_events.append((e0, e1, q.shape[0] * (e - s)))
+        ops.cal_distance(video_feats, gal["pooled"][s:e], out=dual, col_offset=col_offset + s)
+        self._count("xpool"), self._count("cosine")
 
     def score(self, video_feats, gal, out=None, col_offset: int = 0):
-        """single/dual similarity of every query against this gallery (shard)."""
+        """single/dual similarity of every query against a whole (already encoded) gallery shard."""
         n_q, n_m = video_feats.shape[0], gal["bits"].shape[0]
         if out is None:
             single = torch.empty((n_q, n_m), dtype=torch.float32, device=self.dev)
             dual = torch.empty((n_q, n_m), dtype=torch.float32, device=self.dev)
         else:
             single, dual = out
-        q, vhat = self.eng.query_prepare(video_feats)
-        if self.xpool_events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        self.eng.xpool_score(q, vhat, gal["kz"], gal["gram"], gal["bits"], out=single, col_offset=col_offset)
-        if self.xpool_events is not None:
-            e1.record()
-            self.xpool_events.append((e0, e1))
-        ops.cal_distance(video_feats, gal["pooled"], out=dual, col_offset=col_offset)
-        self._count("query_prepare"), self._count("xpool"), self._count("cosine")
+        qprep = self.eng.query_prepare(video_feats)
+        self._count("query_prepare")
+        self.score_chunk(qprep, video_feats, gal, 0, n_m, single, dual, col_offset)
         return single, dual
 
     def detect(self, frame_seq, frame_mask, gal, video_feats, track_idx, gt_moment, m_duration):
@@ -108,70 +182,57 @@ class GalleryEvaluator:
             spans[s:e] = r["pred_spans"][-1]
             a, b, c, d = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1], gt_moment[s:e], m_duration[s:e])
             st[s:e], ed[s:e], sc[s:e], iou[s:e] = a, b, c, d
-            self._count("detr"), self._count("postproc")
+            self._count("detr"), self._count("detr_chunk", -(-(e - s) // 512)), self._count("postproc")
         return dict(pred_st=st, pred_ed=ed, score=sc, iou=iou, pred_spans=spans)
 
     # ---- whole job --------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, videos: Dict[str, torch.Tensor], tracks: Dict[str, torch.Tensor], gt_col: torch.Tensor,
             prev_same: Optional[torch.Tensor] = None, on_host: bool = False, want_sims: bool = False):
-        """One step of the hot path.  `videos`/`tracks` are the dicts of `synth.make_*` (device
-        resident, or pinned host tensors with on_host=True).  Query i is paired with track gt_col[i]
-        for both the rank and the moment detection (test-MaDe.py:280 evaluates the paired track)."""
+        """One step of the hot path.  `videos`/`tracks` are the dicts of `synth.make_*`: device
+        resident, or PINNED host tensors (`on_host=True`; the features are then read in place over
+        PCIe by the ingest kernel).  Query i is paired with track gt_col[i] for both the rank and the
+        moment detection (test-MaDe.py:280 evaluates the paired track)."""
         self.launches = 0
-        frame_seq, video_feats, frame_mask = self.encode_queries(videos["frame_feats"], videos["frame_mask"], on_host)
-        gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_host)
-        single, dual = self.score(video_feats, gal)
-        gt_col_d = self._to_dev(gt_col, on_host).to(torch.int32)
-        prev_d = None if prev_same is None else self._to_dev(prev_same, on_host).to(torch.int32)
+        n_q = videos["frame_feats"].shape[0]
+        n_m = tracks["segment_feats"].shape[0]
+        # the pairing decides when detection may start: after the chunk that encodes its last track
+        last_needed = int(gt_col.max()) if gt_col.numel() else -1
+        if last_needed >= n_m or (gt_col.numel() and int(gt_col.min()) < 0):
+            raise ValueError("gt_col must index tracks of the gallery")
+        gt_col_d = self._to_dev(gt_col).to(torch.int32)
+        prev_d = None if prev_same is None else self._to_dev(prev_same).to(torch.int32)
+        gt_moment = self._to_dev(tracks["gt_moment"])
+        m_dur = self._to_dev(tracks["m_duration"])
+        idx64 = gt_col_d.long()
+        frame_seq, video_feats, frame_mask = self.encode_queries(videos["frame_feats"], videos["frame_mask"])
+        qprep = self.eng.query_prepare(video_feats)
+        self._count("query_prepare")
+        single = torch.empty((n_q, n_m), dtype=torch.float32, device=self.dev)
+        dual = torch.empty((n_q, n_m), dtype=torch.float32, device=self.dev)
+        state = {}
+
+        def on_chunk(gal, s, e):
+            self.score_chunk(qprep, video_feats, gal, s, e, single, dual)
+            if "det" not in state and last_needed < e:
+                state["det"] = self.detect(frame_seq, frame_mask, gal, video_feats, gt_col_d, gt_moment[idx64],
+                                           m_dur[idx64])
+
+        gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_chunk)
         rk = ops.rank_topk(single, dual, gt_col_d, prev_d, k=self.k)
         self._count("rank")
-        gt_moment = self._to_dev(tracks["gt_moment"], on_host)
-        m_dur = self._to_dev(tracks["m_duration"], on_host)
-        idx64 = gt_col_d.long()
-        det = self.detect(frame_seq, frame_mask, gal, video_feats, gt_col_d, gt_moment[idx64], m_dur[idx64])
         out = dict(rank=rk["rank"], topk_idx=rk["topk_idx"], topk_score=rk["topk_score"], gt_score=rk["gt_score"],
-                   video_feats=video_feats, music_feats=gal["pooled"], **det)
+                   video_feats=video_feats, music_feats=gal["pooled"], **state["det"])
         if want_sims:
             out.update(single=single, dual=dual)
         return out
 
     def to_host(self, out: Dict[str, torch.Tensor], keys=("rank", "topk_idx", "iou", "pred_st", "pred_ed", "score")):
         """Device→host read of the step's result (what eval_epoch consumes on the CPU)."""
-        host = {k: out[k].cpu() for k in keys}
-        return host
+        return {k: out[k].cpu() for k in keys}
 
     # ---- helpers ----------------------------------------------------------------------------------
-    def _to_dev(self, t: torch.Tensor, on_host: bool):
+    def _to_dev(self, t: torch.Tensor):
         if t.device == self.dev:
             return t
         return t.to(self.dev, non_blocking=True)
-
-    def _chunks(self, feats: torch.Tensor, chunk: int, on_host: bool):
-        """Yield (start, end, device chunk).  Host inputs are copied on the copy stream one chunk
-        ahead of the kernels that consume them."""
-        n = feats.shape[0]
-        bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
-        if not on_host:
-            for s, e in bounds:
-                yield s, e, feats[s:e]
-            return
-        cur = torch.cuda.current_stream(self.dev)
-        pending = []
-
-        def issue(i):
-            s, e = bounds[i]
-            with torch.cuda.stream(self.copy_stream):
-                d = feats[s:e].to(self.dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-            pending.append((d, ev))
-
-        issue(0)
-        for i, (s, e) in enumerate(bounds):
-            if i + 1 < len(bounds):
-                issue(i + 1)
-            d, ev = pending.pop(0)
-            cur.wait_event(ev)
-            d.record_stream(cur)
-            yield s, e, d

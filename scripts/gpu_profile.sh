@@ -1,12 +1,23 @@
 #!/bin/bash
-# ncu --set full captures of the hot kernels (one GPU).  Reports land in gpurun_out/*.ncu-rep.
+# ncu --set full captures of the hot kernels (one GPU).  The .ncu-rep files stay small (few
+# launches) and the raw/source pages are exported to CSV on the box; gpurun_out/ is capped at 64 MiB.
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-# launches per step ~304; skip the first step
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:xpool_score -s 1 -c 1 \
-  -o gpurun_out/prof_xpool -f $B > gpurun_out/prof_xpool.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 253 -c 40 \
-  -o gpurun_out/prof_gemm -f $B > gpurun_out/prof_gemm.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mha_core -s 17 -c 3 \
-  -o gpurun_out/prof_mha -f $B > gpurun_out/prof_mha.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+WHAT="${@:-xpool gemm mha}"
+for w in $WHAT; do
+  case $w in
+    xpool) K="regex:xpool_score"; S=4; C=1;;
+    gemm)  K="regex:gemm_tc_kernel"; S=${GEMM_SKIP:-150}; C=${GEMM_COUNT:-8};;
+    mha)   K="regex:mha_core"; S=10; C=2;;
+    dec)   K="regex:dec_attn_folded"; S=6; C=1;;
+    *) echo "unknown $w"; continue;;
+  esac
+  timeout 900 ncu --set full --clock-control none --import-source on -k $K -s $S -c $C \
+    -o gpurun_out/prof_$w -f $B > gpurun_out/prof_$w.log 2>&1
+  ncu -i gpurun_out/prof_$w.ncu-rep --page raw --csv > gpurun_out/prof_${w}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_$w.ncu-rep --page source --csv > gpurun_out/prof_${w}_source.csv 2>/dev/null
+  ls -la gpurun_out/prof_$w*
+  # keep the transfer small: drop reports above 20 MB (the CSV pages carry what is read here)
+  find gpurun_out -name "prof_$w.ncu-rep" -size +20M -delete
+done
+du -sh gpurun_out

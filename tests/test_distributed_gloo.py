@@ -63,11 +63,11 @@ class _CpuEvaluator:
     def _count(self, *a, **k):
         pass
 
-    def encode_queries(self, feats, mask, on_host):
+    def encode_queries(self, feats, mask):
         seq, pooled = O.encode_video(self.sd, feats, mask)
         return seq, pooled, mask
 
-    def encode_gallery(self, feats, mask, on_host):
+    def encode_gallery(self, feats, mask, on_chunk=None):
         seq, pooled = O.encode_music(self.sd, feats, mask)
         return dict(seq=seq, pooled=pooled, mask=mask)
 
