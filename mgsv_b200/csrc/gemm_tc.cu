@@ -5,42 +5,54 @@ namespace made {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;
+constexpr int kStagePitch = 36;                       // fp32 words per row of an epilogue transpose tile
+constexpr int kStageWords = 32 * kStagePitch;         // one 32 x 32 tile per epilogue warp
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 
-template <int BN>
+// WS = weight-stationary: the whole [BN x K<=256] slice of W stays in shared memory while the CTA
+// walks a contiguous range of M tiles (n-major tile order), so only A tiles stream through the ring.
+constexpr int kWsKBlocks = 4;                       // K <= 256
+template <int BN, bool WS = false>
 struct GemmCfg {
   static constexpr int kBTileBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStageBytes = WS ? kATileBytes : kATileBytes + kBTileBytes;
+  static constexpr int kResidentBytes = WS ? kWsKBlocks * kBTileBytes : 0;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;      // TMEM columns per acc stage
   static constexpr uint32_t kTmemCols = kAccStride * kAccStages;  // 256 or 512
   static constexpr int kChunks = BN / 32;
   // dynamic smem: tiles + barriers + tmem slot + LN partials
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 + 4 * 128 * 4;
+  static constexpr int kSmemBytes = kResidentBytes + kStages * kStageBytes + 1024 /*align slack*/ + 256 +
+                                    4 * 128 * 4 + kEpiWarps * kStageWords * 4;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int BN>
+template <int BN, bool WS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, WS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* resident = smem;                           // WS: W slice, kWsKBlocks tiles of [BN x 64]
+  uint8_t* tiles = smem + Cfg::kResidentBytes;
+  uint8_t* after = tiles + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
-  float* ln_part = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [2 halves][2][128]
+  uint64_t* w_full = tmem_empty + kAccStages;         // WS: resident W slice landed
+  uint64_t* w_empty = w_full + 1;                     // WS: every MMA that reads the slice has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
+  float* ln_part = reinterpret_cast<float*>(after + 256);   // [2 halves][2][128]
+  float* stage_all = ln_part + 4 * 128;                     // [8 warps][32][36]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -49,6 +61,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * n_blocks;
   const int k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  // tile schedule: streaming = round-robin, m-major; WS = one contiguous n-major range per CTA
+  const int64_t ws_per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t ws_t0 = static_cast<int64_t>(blockIdx.x) * ws_per;
+  const int64_t my_tiles = WS ? (ws_t0 >= n_tiles ? 0 : (n_tiles - ws_t0 < ws_per ? n_tiles - ws_t0 : ws_per))
+                              : (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto decode = [&](int64_t i, int64_t& m_blk, int& n_blk) {
+    if constexpr (WS) {
+      const int64_t t = ws_t0 + i;
+      n_blk = static_cast<int>(t / m_tiles);
+      m_blk = t % m_tiles;
+    } else {
+      const int64_t t = blockIdx.x + i * gridDim.x;
+      m_blk = t / n_blocks;
+      n_blk = static_cast<int>(t % n_blocks);
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -63,6 +91,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kEpiWarps);
     }
+    mbar_init(w_full, 1);
+    mbar_init(w_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -76,18 +106,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t m_blk = tile / n_blocks;
-        const int n_blk = static_cast<int>(tile % n_blocks);
+      int cur_n = -1;
+      uint32_t groups = 0;
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        int64_t m_blk;
+        int n_blk;
+        decode(i, m_blk, n_blk);
         const int32_t row_a = static_cast<int32_t>(m_blk * p.m_stride);
         const int32_t row_b = p.b_batched ? row_a : n_blk * BN;
+        if constexpr (WS) {
+          if (n_blk != cur_n) {     // (re)load the resident W slice once the MMAs of the old one are done
+            if (groups > 0) mbar_wait(w_empty, (groups - 1) & 1);
+            mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(k_blocks) * Cfg::kBTileBytes);
+            for (int kb = 0; kb < k_blocks; ++kb)
+              tma_load_2d(resident + kb * Cfg::kBTileBytes, &tmap_b, w_full, kb * kBlockK, row_b);
+            cur_n = n_blk;
+            ++groups;
+          }
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kATileBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row_a);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
+          if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -98,18 +140,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      int cur_n = -1;
+      uint32_t groups = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        int64_t m_blk;
+        int n_blk, n_next = -1;
+        decode(it, m_blk, n_blk);
+        if (it + 1 < my_tiles) {
+          int64_t m2;
+          decode(it + 1, m2, n_next);
+        }
         const int as = static_cast<int>(it & 1);
         const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
+        if constexpr (WS) {
+          if (n_blk != cur_n) {
+            mbar_wait(w_full, groups & 1);
+            cur_n = n_blk;
+            ++groups;
+          }
+        }
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t sb = WS ? smem_u32(resident + kb * Cfg::kBTileBytes) : sa + kATileBytes;
           const uint64_t adesc = umma_smem_desc(sa, 0, 1024);
           const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
 #pragma unroll
@@ -118,13 +175,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) tc_commit(&tmem_full[as]);
+          if (kb == k_blocks - 1) {
+            tc_commit(&tmem_full[as]);
+            if constexpr (WS) {
+              if (n_next != n_blk) tc_commit(w_empty);   // last tile that reads this W slice
+            }
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
+    // Thread = accumulator row (TMEM lane), 32 columns per chunk in registers.  All global traffic
+    // of the epilogue goes through a per-warp shared-memory transpose tile so that every warp-wide
+    // load/store instruction touches whole 64/128-byte row segments (4-8 rows per instruction)
+    // instead of 32 different rows.
     const GemmEpilogue& e = p.epi;
     const int ew = warp - 4;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -132,20 +198,122 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int r_in_tile = q * 32 + lane;
     const bool do_ln = e.ln_gamma != nullptr;
     const bool two_pass = do_ln || e.l2norm;
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    float* stg = stage_all + ew * kStageWords;           // [32 rows][kStagePitch] fp32
+    const int l8r = lane >> 3, l8c = (lane & 7) * 4;      // fp32 pattern: 4 rows x 32 cols per instruction
+    const int l4r = lane >> 2, l4c = (lane & 3) * 8;      // fp16 pattern: 8 rows x 32 cols per instruction
+
+    // x[32] += residual / row_table for this thread's row, loaded coalesced through the tile
+    auto add_row_inputs = [&](float (&v)[32], int64_t row0, int col0) {
+      if (e.residual == nullptr && e.row_table == nullptr) return;
+      if (e.residual != nullptr && !e.residual_f32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rl = 8 * j + l4r;
+          const int rt = q * 32 + rl;
+          const int64_t gr = row0 + rt;
+          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (rt < p.m_valid && gr < p.M) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(
+                static_cast<const op_t*>(e.residual) + gr * e.res_ld + col0 + l4c));
+            const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const float2 x = op2_to_f2(h[u]); f[2 * u] = x.x; f[2 * u + 1] = x.y; }
+            if (e.row_table) {
+              const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (gr % e.row_mod) * p.N + col0 + l4c);
+              const float4 a = __ldg(t4), b = __ldg(t4 + 1);
+              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+            }
+          }
+          float4* d = reinterpret_cast<float4*>(stg + rl * kStagePitch + l4c);
+          d[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rl = 4 * j + l8r;
+          const int rt = q * 32 + rl;
+          const int64_t gr = row0 + rt;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rt < p.m_valid && gr < p.M) {
+            if (e.residual)
+              acc = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(e.residual) + gr * e.res_ld +
+                                                          col0 + l8c));
+            if (e.row_table) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(e.row_table + (gr % e.row_mod) * p.N + col0 + l8c));
+              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+          }
+          *reinterpret_cast<float4*>(stg + rl * kStagePitch + l8c) = acc;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(stg + lane * kStagePitch + 4 * i);
+        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+      }
+      __syncwarp();
+    };
+
+    // final values of this thread's row -> all requested outputs, coalesced through the tile
+    auto store_chunk = [&](const float (&v)[32], int64_t row0, int col0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * i) =
+            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      __syncwarp();
+      if (e.out_f32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rl = 4 * j + l8r;
+          const int rt = q * 32 + rl;
+          const int64_t gr = row0 + rt;
+          if (rt < p.m_valid && gr < p.M)
+            *reinterpret_cast<float4*>(e.out_f32 + gr * e.ld_f32 + col0 + l8c) =
+                *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l8c);
+        }
+      }
+      if (e.out_h || e.out2_h) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rl = 8 * j + l4r;
+          const int rt = q * 32 + rl;
+          const int64_t gr = row0 + rt;
+          if (rt < p.m_valid && gr < p.M) {
+            const float4 a = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l4c);
+            const float4 b = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l4c + 4);
+            if (e.out_h)
+              *reinterpret_cast<uint4*>(e.out_h + gr * e.ld_h + col0 + l4c) =
+                  make_uint4(pack_op2(a.x, a.y), pack_op2(a.z, a.w), pack_op2(b.x, b.y), pack_op2(b.z, b.w));
+            if (e.out2_h) {
+              const uint4 t = __ldg(reinterpret_cast<const uint4*>(e.add2 + gr * e.add2_ld + col0 + l4c));
+              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+              const float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]), f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+              *reinterpret_cast<uint4*>(e.out2_h + gr * e.ld_out2 + col0 + l4c) =
+                  make_uint4(pack_op2(a.x + f0.x, a.y + f0.y), pack_op2(a.z + f1.x, a.w + f1.y),
+                             pack_op2(b.x + f2.x, b.y + f2.y), pack_op2(b.z + f3.x, b.w + f3.y));
+            }
+          }
+        }
+      }
+      __syncwarp();
+    };
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-      const int64_t m_blk = tile / n_blocks;
-      const int n_blk = static_cast<int>(tile % n_blocks);
-      const int64_t grow = m_blk * p.m_stride + r_in_tile;
+      int64_t m_blk;
+      int n_blk;
+      decode(it, m_blk, n_blk);
+      const int64_t row0 = m_blk * p.m_stride;
+      const int64_t grow = row0 + r_in_tile;
       const bool row_ok = r_in_tile < p.m_valid && grow < p.M;
-      const int64_t srow = row_ok ? grow : 0;   // safe row for loads
+      float keep = 1.f;
+      if (e.row_mask) keep = (row_ok && __ldg(e.row_mask + grow) != 0.f) ? 1.f : 0.f;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-      float keep = 1.f;
-      if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
 
       float psum = 0.f;
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
@@ -165,39 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
           }
         }
-        if (e.row_table) {
-          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (srow % e.row_mod) * p.N + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 t = __ldg(t4 + i);
-            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-          }
-        }
-        if (e.residual) {
-          if (e.residual_f32) {
-            const float4* r4 = reinterpret_cast<const float4*>(
-                static_cast<const float*>(e.residual) + srow * e.res_ld + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = __ldg(r4 + i);
-              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-            }
-          } else {
-            const uint4* r4 = reinterpret_cast<const uint4*>(
-                static_cast<const op_t*>(e.residual) + srow * e.res_ld + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 t = __ldg(r4 + i);
-              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = op2_to_f2(h[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-              }
-            }
-          }
-        }
+        add_row_inputs(v, row0, col0);
         if (e.act == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
@@ -214,38 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tmem_st_x32(t_acc + c * 32, st);
         } else {
-          // ---------- direct store ----------
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
-          if (row_ok) {
-            if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
-            }
-            if (e.out_f32) {
-              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (e.out2_h) {
-              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 t = __ldg(a4 + i);
-                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
-                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
-                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
-              }
-            }
-          }
+          store_chunk(v, row0, col0);
         }
       }
       if (two_pass) {
@@ -301,35 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
-          if (row_ok) {
-            if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
-            }
-            if (e.out_f32) {
-              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (e.out2_h) {
-              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 t = __ldg(a4 + i);
-                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
-                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
-                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
-              }
-            }
-          }
+          store_chunk(v, row0, col0);
         }
         // the partial-sum slots are reused by the next tile: all readers must be done
         named_bar_sync(1, kEpiThreads);
@@ -349,20 +428,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, bool WS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, WS>;
+  static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget of an sm_100 CTA");
   static bool attr_set = false;
   if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MADE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     attr_set = true;
   }
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * (p.N / BN);
   int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  gemm_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -390,8 +470,13 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                                static_cast<uint64_t>(lda) * 2, kBlockK, kBlockM));
   MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
-  if (block_n == 256) return launch_gemm<256>(ta, tb, p, stream);
-  return launch_gemm<96>(ta, tb, p, stream);
+  if (block_n == 256) {
+    // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles
+    const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
+    const bool ws = p.K <= kWsKBlocks * kBlockK && !p.b_batched && m_tiles * (p.N / 256) >= 2 * sm_count();
+    return ws ? launch_gemm<256, true>(ta, tb, p, stream) : launch_gemm<256, false>(ta, tb, p, stream);
+  }
+  return launch_gemm<96, false>(ta, tb, p, stream);
 }
 
 }  // namespace made
