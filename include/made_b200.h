@@ -113,6 +113,16 @@ int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const 
 int made_ingest_features(const void* feats, int feats_dtype, const float* masks, int64_t rows, int dim,
                          void* out16, void* stream);
 
+/* Host -> device transfer of a zero-padded feature tensor, valid rows only (the reference copies the
+ * whole padded tensor per batch, test-MaDe.py:268-271).  host_feats [B, L, dim] and host_masks
+ * [B, L] are HOST pointers (host_feats pinned for the copies to be asynchronous); for every
+ * sequence the rows [0, last row with mask != 0] are copied to the same offsets of dev_staging
+ * [B, L, dim] by the copy engines (one batched cudaMemcpyBatchAsync, no SM involved); the other
+ * rows of dev_staging are left untouched and must be treated as garbage (made_encode /
+ * made_ingest_features never read rows whose mask is 0).  bytes_copied (nullable) = bytes queued. */
+int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
+                        int dim, void* dev_staging, int64_t* bytes_copied, void* stream);
+
 /* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16, fp16 — rows with mask 0 are
  * never read — or MADE_DTYPE_F16_MASKED = the output of made_ingest_features, used in place),
  * masks [B,L] float {0,1}; L,Din = 50,512 (MADE_VIDEO) or 96,768 (MADE_MUSIC).

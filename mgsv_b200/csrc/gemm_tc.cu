@@ -5,9 +5,7 @@ namespace made {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int kStages = 3;
-constexpr int kStagePitch = 36;                       // fp32 words per row of an epilogue transpose tile
-constexpr int kStageWords = 32 * kStagePitch;         // one 32 x 32 tile per epilogue warp
+constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -27,7 +25,7 @@ struct GemmCfg {
   static constexpr int kChunks = BN / 32;
   // dynamic smem: tiles + barriers + tmem slot + LN partials
   static constexpr int kSmemBytes = kResidentBytes + kStages * kStageBytes + 1024 /*align slack*/ + 256 +
-                                    4 * 128 * 4 + kEpiWarps * kStageWords * 4;
+                                    4 * 128 * 4;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -52,7 +50,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* w_empty = w_full + 1;                     // WS: every MMA that reads the slice has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
   float* ln_part = reinterpret_cast<float*>(after + 256);   // [2 halves][2][128]
-  float* stage_all = ln_part + 4 * 128;                     // [8 warps][32][36]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,10 +184,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    // Thread = accumulator row (TMEM lane), 32 columns per chunk in registers.  All global traffic
-    // of the epilogue goes through a per-warp shared-memory transpose tile so that every warp-wide
-    // load/store instruction touches whole 64/128-byte row segments (4-8 rows per instruction)
-    // instead of 32 different rows.
     const GemmEpilogue& e = p.epi;
     const int ew = warp - 4;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -198,122 +191,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int r_in_tile = q * 32 + lane;
     const bool do_ln = e.ln_gamma != nullptr;
     const bool two_pass = do_ln || e.l2norm;
-    float* stg = stage_all + ew * kStageWords;           // [32 rows][kStagePitch] fp32
-    const int l8r = lane >> 3, l8c = (lane & 7) * 4;      // fp32 pattern: 4 rows x 32 cols per instruction
-    const int l4r = lane >> 2, l4c = (lane & 3) * 8;      // fp16 pattern: 8 rows x 32 cols per instruction
-
-    // x[32] += residual / row_table for this thread's row, loaded coalesced through the tile
-    auto add_row_inputs = [&](float (&v)[32], int64_t row0, int col0) {
-      if (e.residual == nullptr && e.row_table == nullptr) return;
-      if (e.residual != nullptr && !e.residual_f32) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rl = 8 * j + l4r;
-          const int rt = q * 32 + rl;
-          const int64_t gr = row0 + rt;
-          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (rt < p.m_valid && gr < p.M) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(
-                static_cast<const op_t*>(e.residual) + gr * e.res_ld + col0 + l4c));
-            const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const float2 x = op2_to_f2(h[u]); f[2 * u] = x.x; f[2 * u + 1] = x.y; }
-            if (e.row_table) {
-              const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (gr % e.row_mod) * p.N + col0 + l4c);
-              const float4 a = __ldg(t4), b = __ldg(t4 + 1);
-              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
-            }
-          }
-          float4* d = reinterpret_cast<float4*>(stg + rl * kStagePitch + l4c);
-          d[0] = make_float4(f[0], f[1], f[2], f[3]);
-          d[1] = make_float4(f[4], f[5], f[6], f[7]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rl = 4 * j + l8r;
-          const int rt = q * 32 + rl;
-          const int64_t gr = row0 + rt;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rt < p.m_valid && gr < p.M) {
-            if (e.residual)
-              acc = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(e.residual) + gr * e.res_ld +
-                                                          col0 + l8c));
-            if (e.row_table) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(e.row_table + (gr % e.row_mod) * p.N + col0 + l8c));
-              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-          }
-          *reinterpret_cast<float4*>(stg + rl * kStagePitch + l8c) = acc;
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(stg + lane * kStagePitch + 4 * i);
-        v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-      }
-      __syncwarp();
-    };
-
-    // final values of this thread's row -> all requested outputs, coalesced through the tile
-    auto store_chunk = [&](const float (&v)[32], int64_t row0, int col0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * i) =
-            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      __syncwarp();
-      if (e.out_f32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rl = 4 * j + l8r;
-          const int rt = q * 32 + rl;
-          const int64_t gr = row0 + rt;
-          if (rt < p.m_valid && gr < p.M)
-            *reinterpret_cast<float4*>(e.out_f32 + gr * e.ld_f32 + col0 + l8c) =
-                *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l8c);
-        }
-      }
-      if (e.out_h || e.out2_h) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rl = 8 * j + l4r;
-          const int rt = q * 32 + rl;
-          const int64_t gr = row0 + rt;
-          if (rt < p.m_valid && gr < p.M) {
-            const float4 a = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l4c);
-            const float4 b = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + l4c + 4);
-            if (e.out_h)
-              *reinterpret_cast<uint4*>(e.out_h + gr * e.ld_h + col0 + l4c) =
-                  make_uint4(pack_op2(a.x, a.y), pack_op2(a.z, a.w), pack_op2(b.x, b.y), pack_op2(b.z, b.w));
-            if (e.out2_h) {
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(e.add2 + gr * e.add2_ld + col0 + l4c));
-              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-              const float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]), f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
-              *reinterpret_cast<uint4*>(e.out2_h + gr * e.ld_out2 + col0 + l4c) =
-                  make_uint4(pack_op2(a.x + f0.x, a.y + f0.y), pack_op2(a.z + f1.x, a.w + f1.y),
-                             pack_op2(b.x + f2.x, b.y + f2.y), pack_op2(b.z + f3.x, b.w + f3.y));
-            }
-          }
-        }
-      }
-      __syncwarp();
-    };
-
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
       int64_t m_blk;
       int n_blk;
       decode(it, m_blk, n_blk);
-      const int64_t row0 = m_blk * p.m_stride;
-      const int64_t grow = row0 + r_in_tile;
+      const int64_t grow = m_blk * p.m_stride + r_in_tile;
       const bool row_ok = r_in_tile < p.m_valid && grow < p.M;
-      float keep = 1.f;
-      if (e.row_mask) keep = (row_ok && __ldg(e.row_mask + grow) != 0.f) ? 1.f : 0.f;
+      const int64_t srow = row_ok ? grow : 0;   // safe row for loads
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      float keep = 1.f;
+      if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
 
       float psum = 0.f;
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
@@ -333,7 +224,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
           }
         }
-        add_row_inputs(v, row0, col0);
+        if (e.row_table) {
+          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (srow % e.row_mod) * p.N + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 t = __ldg(t4 + i);
+            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+          }
+        }
+        if (e.residual) {
+          if (e.residual_f32) {
+            const float4* r4 = reinterpret_cast<const float4*>(
+                static_cast<const float*>(e.residual) + srow * e.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(r4 + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          } else {
+            const uint4* r4 = reinterpret_cast<const uint4*>(
+                static_cast<const op_t*>(e.residual) + srow * e.res_ld + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 t = __ldg(r4 + i);
+              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = op2_to_f2(h[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+        }
         if (e.act == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
@@ -350,9 +273,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tmem_st_x32(t_acc + c * 32, st);
         } else {
+          // ---------- direct store ----------
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
-          store_chunk(v, row0, col0);
+          if (row_ok) {
+            if (e.out_h) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            if (e.out_f32) {
+              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (e.out2_h) {
+              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t = __ldg(a4 + i);
+                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
+                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+              }
+            }
+          }
         }
       }
       if (two_pass) {
@@ -408,7 +360,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= keep;
-          store_chunk(v, row0, col0);
+          if (row_ok) {
+            if (e.out_h) {
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+            }
+            if (e.out_f32) {
+              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (e.out2_h) {
+              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t = __ldg(a4 + i);
+                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
+                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+              }
+            }
+          }
         }
         // the partial-sum slots are reused by the next tile: all readers must be done
         named_bar_sync(1, kEpiThreads);

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -52,7 +53,7 @@ int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint6
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -81,6 +82,60 @@ extern "C" {
 const char* made_last_error_string(void) { return made::g_err; }
 
 int made_abi_version(void) { return MADE_ABI_VERSION; }
+
+int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
+                        int dim, void* dev_staging, int64_t* bytes_copied, void* stream) {
+  using namespace made;
+  if (bytes_copied) *bytes_copied = 0;
+  if (B == 0) return MADE_OK;
+  MADE_REQUIRE(host_feats && host_masks && dev_staging, "h2d_valid_rows: null pointer");
+  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "h2d_valid_rows: bad dtype %d",
+               feats_dtype);
+  MADE_REQUIRE(L > 0 && dim > 0, "h2d_valid_rows: bad shape");
+  const size_t esz = feats_dtype == MADE_DTYPE_F32 ? 4 : 2;
+  const size_t row = static_cast<size_t>(dim) * esz, seq = row * static_cast<size_t>(L);
+  // one copy per sequence: rows [0, last valid row]; runs of fully valid sequences are merged
+  static thread_local std::vector<void*> dsts, srcs;
+  static thread_local std::vector<size_t> sizes;
+  dsts.clear(); srcs.clear(); sizes.clear();
+  const char* hsrc = static_cast<const char*>(host_feats);
+  char* ddst = static_cast<char*>(dev_staging);
+  size_t total = 0;
+  bool open = false;   // the previous copy ends exactly at the start of this sequence
+  for (int64_t b = 0; b < B; ++b) {
+    const float* m = host_masks + b * L;
+    int n = L;
+    while (n > 0 && m[n - 1] == 0.f) --n;
+    if (n == 0) { open = false; continue; }
+    const size_t bytes = row * static_cast<size_t>(n);
+    if (open) {
+      sizes.back() += bytes;
+    } else {
+      dsts.push_back(ddst + b * seq);
+      srcs.push_back(const_cast<char*>(hsrc + b * seq));
+      sizes.push_back(bytes);
+    }
+    total += bytes;
+    open = (n == L);
+  }
+  if (bytes_copied) *bytes_copied = static_cast<int64_t>(total);
+  if (dsts.empty()) return MADE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaMemcpyAttributes attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+  attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+  size_t attr_idx = 0, fail = 0;
+  cudaError_t e = st == nullptr ? cudaErrorNotSupported   // the batch API rejects the legacy default stream
+                                : cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr,
+                                                       &attr_idx, 1, &fail, st);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    for (size_t i = 0; i < dsts.size(); ++i)
+      MADE_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, st));
+  }
+  return MADE_OK;
+}
 
 int made_device_check(int device) {
   cudaDeviceProp prop;

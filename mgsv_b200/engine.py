@@ -58,6 +58,24 @@ class Engine:
         self.loaded = True
 
     # -----------------------------------------------------------------------------------------
+    def h2d_valid_rows(self, feats_host: torch.Tensor, masks_host: torch.Tensor, out: torch.Tensor) -> int:
+        """Copy-engine transfer of the valid rows of a zero-padded host feature tensor [B,L,dim]
+        (pinned) into the device staging tensor `out` of the same shape/dtype; rows whose mask is 0
+        are not transferred (and are garbage in `out`).  Returns the bytes queued."""
+        if feats_host.is_cuda or masks_host.is_cuda or not out.is_cuda:
+            raise ValueError("h2d_valid_rows: host features + host masks -> device staging")
+        if feats_host.shape != out.shape or feats_host.dtype != out.dtype:
+            raise ValueError("h2d_valid_rows: staging must match the host tensor's shape and dtype")
+        dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}.get(feats_host.dtype)
+        if dt is None:
+            raise ValueError(f"unsupported feature dtype {feats_host.dtype}")
+        B, L, dim = feats_host.shape
+        m = masks_host.to(torch.float32).contiguous()
+        n = C.c_int64(0)
+        _lib.check(self._lib.made_h2d_valid_rows(feats_host.contiguous().data_ptr(), dt, m.data_ptr(), B, L, dim,
+                                                 _lib.ptr(out), C.byref(n), _lib.stream_ptr()))
+        return int(n.value)
+
     def ingest(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, out: Optional[torch.Tensor] = None):
         """Masked cast of raw features (device tensor or PINNED host tensor, fp32/bf16/fp16) into the
         fp16 operand buffer consumed by `encode(..., ingested=True)`.  Padded rows are never read, so
