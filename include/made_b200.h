@@ -35,7 +35,6 @@ extern "C" {
 #define MADE_DTYPE_F32 0
 #define MADE_DTYPE_BF16 1
 #define MADE_DTYPE_F16 2
-#define MADE_DTYPE_F16_MASKED 3 /* fp16 written by made_ingest_features: consumed in place */
 
 #define MADE_VIDEO 0
 #define MADE_MUSIC 1
@@ -104,14 +103,34 @@ int made_ctx_destroy(made_ctx* ctx);
 int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const float* const* host_ptrs,
                           const int64_t* numels, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ragged (token-packed) batches.  The reference computes every zero-padded position and masks it
+ * afterwards (model_Base.py:533-541); padded keys never reach a softmax and padded query rows never
+ * reach an output, so this path only materialises the VALID tokens of a batch: the rows with
+ * mask != 0, packed in order into a dense [total, features] matrix.
+ *   seq_len[b] = valid tokens of sequence b      seq_off[b] = exclusive prefix sum of seq_len
+ *   total[0]   = sum(seq_len), a DEVICE scalar   tok_src[i] = b * L + t of packed row i
+ * All pointers are device memory inside the caller's idx_workspace of made_ragged_index_words(B, L)
+ * int32 words; the host never learns `total` (no sync) — kernels read it from the device.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct made_ragged {
+  const int32_t* seq_len;
+  const int32_t* seq_off;
+  const int32_t* total;
+  const int32_t* tok_src;
+  int64_t B;
+  int32_t L;
+} made_ragged;
+int64_t made_ragged_index_words(int64_t B, int L);
+/* masks [B, L] float {0,1} (device) -> descriptor (3 small kernels on `stream`). */
+int made_ragged_build(const float* masks, int64_t B, int L, int32_t* idx_workspace, made_ragged* out, void* stream);
 /* Feature ingest = the masked_fill + cast at the top of forward_{video,audio}_encoder_feature
- * (model_Base.py:556 / :595) on its own: feats [rows, dim] (fp32 / bf16 / fp16) -> out16 [rows, dim]
- * fp16 with rows of mask == 0 written as zero and NEVER READ.  `feats` may be device memory or
- * pinned host memory (unified addressing): in the latter case the kernel pulls only the valid rows
- * over PCIe, which replaces the reference's per-batch H2D copy of the zero-padded tensors
- * (test-MaDe.py:268-277).  masks and out16 are device memory.  dim % 8 == 0. */
-int made_ingest_features(const void* feats, int feats_dtype, const float* masks, int64_t rows, int dim,
-                         void* out16, void* stream);
+ * (model_Base.py:556 / :595): feats [B, L, dim] (fp32 / bf16 / fp16) -> out16_packed [<= B*L, dim] fp16
+ * holding the valid rows only; rows with mask == 0 are NEVER READ.  `feats` may be device memory or
+ * pinned host memory (unified addressing: the kernel then pulls just the valid rows over PCIe).
+ * dim % 8 == 0. */
+int made_ingest_ragged(const void* feats, int feats_dtype, const made_ragged* rb, int dim, void* out16_packed,
+                       void* stream);
 
 /* Host -> device transfer of a zero-padded feature tensor, valid rows only (the reference copies the
  * whole padded tensor per batch, test-MaDe.py:268-271).  host_feats [B, L, dim] and host_masks
@@ -119,16 +138,21 @@ int made_ingest_features(const void* feats, int feats_dtype, const float* masks,
  * sequence the rows [0, last row with mask != 0] are copied to the same offsets of dev_staging
  * [B, L, dim] by the copy engines (one batched cudaMemcpyBatchAsync, no SM involved); the other
  * rows of dev_staging are left untouched and must be treated as garbage (made_encode /
- * made_ingest_features never read rows whose mask is 0).  bytes_copied (nullable) = bytes queued. */
+ * made_ingest_ragged never read rows whose mask is 0).  bytes_copied (nullable) = bytes queued. */
 int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
                         int dim, void* dev_staging, int64_t* bytes_copied, void* stream);
 
-/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16, fp16 — rows with mask 0 are
- * never read — or MADE_DTYPE_F16_MASKED = the output of made_ingest_features, used in place),
+/* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16 or fp16; rows with mask 0 are
+ * never read),
  * masks [B,L] float {0,1}; L,Din = 50,512 (MADE_VIDEO) or 96,768 (MADE_MUSIC).
  * -> seq16 [B,L,256] fp16, seq_f32 [B,L,256] (nullable), pooled [B,256] fp32 (L2-normalised). */
 int made_encode(made_ctx* ctx, int modality, const void* feats, int feats_dtype, const float* masks,
                 int64_t B, void* seq16, float* seq_f32, float* pooled, void* stream);
+/* Same on a batch that was already ingested: x16_packed = output of made_ingest_ragged for `rb`
+ * (lets the caller run the ingest of the next chunk on another stream).  Outputs keep the padded
+ * [B,L,256] layout with zero rows at the padded positions (model_Base.py:541). */
+int made_encode_ragged(made_ctx* ctx, int modality, const void* x16_packed, const made_ragged* rb, void* seq16,
+                       float* seq_f32, float* pooled, void* stream);
 
 /* Per-track X-Pool operands from encoded segments (modules/transformer.py:165, 102-106 folded):
  * seg16 [N,96,256], seg_masks [N,96] -> kz [N*96,768] fp16 (K | V'' | Z''),

@@ -13,13 +13,18 @@ from . import build as _build
 _LIB: Optional[C.CDLL] = None
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
-F32, BF16, F16, F16_MASKED = 0, 1, 2, 3
+F32, BF16, F16 = 0, 1, 2
 VIDEO, MUSIC = 0, 1
 
 _p = C.c_void_p
 _i64 = C.c_int64
 _i32 = C.c_int
 _f = C.c_float
+
+class Ragged(C.Structure):
+    """include/made_b200.h: made_ragged (device pointers into the caller's int32 index workspace)."""
+    _fields_ = [("seq_len", _p), ("seq_off", _p), ("total", _p), ("tok_src", _p), ("B", _i64), ("L", C.c_int32)]
+
 
 # name -> argtypes, in the order of include/made_b200.h
 SIGNATURES = {
@@ -37,8 +42,10 @@ SIGNATURES = {
     "made_ctx_destroy": [_p],
     "made_ctx_load_weights": [_p, _i32, C.POINTER(C.c_char_p), C.POINTER(_p), C.POINTER(_i64), _p],
     "made_h2d_valid_rows": [_p, _i32, _p, _i64, _i32, _i32, _p, C.POINTER(_i64), _p],
-    "made_ingest_features": [_p, _i32, _p, _i64, _i32, _p, _p],
+    "made_ragged_build": [_p, _i64, _i32, _p, C.POINTER(Ragged), _p],
+    "made_ingest_ragged": [_p, _i32, C.POINTER(Ragged), _i32, _p, _p],
     "made_encode": [_p, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p],
+    "made_encode_ragged": [_p, _i32, _p, C.POINTER(Ragged), _p, _p, _p, _p],
     "made_gallery_prepare": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
     "made_xpool_score": [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _p],
@@ -67,6 +74,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.made_ragged_index_words.argtypes = [_i64, _i32]
+    lib.made_ragged_index_words.restype = C.c_int64
     _LIB = lib
     return lib
 
@@ -93,7 +102,7 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def ptr_any(t: Optional[torch.Tensor]) -> Optional[int]:
-    """Device tensor or PINNED host tensor (read in place over PCIe by made_ingest_features)."""
+    """Device tensor or PINNED host tensor (read in place over PCIe by made_ingest_ragged)."""
     if t is not None and not t.is_cuda:
         if not t.is_pinned():
             raise RuntimeError("host tensors handed to made_b200 must be pinned (tensor.pin_memory())")

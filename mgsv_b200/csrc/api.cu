@@ -455,34 +455,52 @@ int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const fl
   return MADE_OK;
 }
 
-int made_ingest_features(const void* feats, int feats_dtype, const float* masks, int64_t rows, int dim,
-                         void* out16, void* stream) {
-  if (rows == 0) return MADE_OK;
-  MADE_REQUIRE(feats && masks && out16, "ingest_features: null pointer");
-  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "ingest_features: bad dtype %d",
-               feats_dtype);
-  MADE_REQUIRE(dim > 0 && dim % 8 == 0, "ingest_features: dim=%d must be a positive multiple of 8", dim);
-  return cast_mask_rows(feats, feats_dtype, masks, rows, dim, static_cast<op_t*>(out16),
-                        static_cast<cudaStream_t>(stream));
+static Ragged to_ragged(const made_ragged* rb) {
+  Ragged r;
+  r.seq_len = rb->seq_len;
+  r.seq_off = rb->seq_off;
+  r.total = rb->total;
+  r.tok_src = rb->tok_src;
+  r.B = rb->B;
+  r.L = rb->L;
+  return r;
 }
 
-int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, const float* masks, int64_t B,
-                void* seq16, float* seq_f32, float* pooled, void* stream) {
-  CTX_READY(c);
-  MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode: bad modality %d", modality);
-  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16_MASKED,
-               "encode: bad feature dtype %d", feats_dtype);
-  if (B == 0) return MADE_OK;
-  MADE_REQUIRE(feats && masks && seq16 && pooled, "encode: null pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+int64_t made_ragged_index_words(int64_t B, int L) {
+  if (B <= 0 || L <= 0) return 0;
+  return static_cast<int64_t>(ragged_index_words(B, L));
+}
+
+int made_ragged_build(const float* masks, int64_t B, int L, int32_t* idx_workspace, made_ragged* out, void* stream) {
+  MADE_REQUIRE(out, "ragged_build: null descriptor");
+  Ragged r;
+  MADE_TRY(ragged_build(masks, B, L, idx_workspace, &r, static_cast<cudaStream_t>(stream)));
+  out->seq_len = r.seq_len;
+  out->seq_off = r.seq_off;
+  out->total = r.total;
+  out->tok_src = r.tok_src;
+  out->B = r.B;
+  out->L = r.L;
+  return MADE_OK;
+}
+
+int made_ingest_ragged(const void* feats, int feats_dtype, const made_ragged* rb, int dim, void* out16_packed,
+                       void* stream) {
+  MADE_REQUIRE(feats && rb && out16_packed, "ingest_ragged: null pointer");
+  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "ingest_ragged: bad dtype %d",
+               feats_dtype);
+  MADE_REQUIRE(dim > 0 && dim % 8 == 0, "ingest_ragged: dim=%d must be a positive multiple of 8", dim);
+  if (rb->B == 0) return MADE_OK;
+  return ingest_gather(feats, feats_dtype, to_ragged(rb), dim, static_cast<op_t*>(out16_packed),
+                       static_cast<cudaStream_t>(stream));
+}
+
+// forward_{video,audio}_encoder_feature on a token-packed batch (valid tokens only).
+static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged& rb, void* seq16, float* seq_f32,
+                         float* pooled, cudaStream_t st) {
   const EncW& e = c->enc[modality];
-  const int64_t T = B * e.L;
-  MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
-  size_t need = padded(T * e.din, 2) + padded(T * D, 2) * 4 + padded(T * D, 4) * 3 + padded(T * 3 * D, 2) +
-                padded(T * DFF, 2);
-  MADE_TRY(c->reserve(need));
-  op_t* x0 = c->take<op_t>(T * e.din);
-  if (feats_dtype == MADE_DTYPE_F16_MASKED) x0 = const_cast<op_t*>(static_cast<const op_t*>(feats));
+  const int64_t B = rb.B;
+  const int64_t T = B * e.L;   // upper bound of the packed row count (the real count lives on the device)
   op_t* x1 = c->take<op_t>(T * D);
   float* x1f = c->take<float>(T * D);
   op_t* qkv = c->take<op_t>(T * 3 * D);
@@ -491,29 +509,39 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   float* x2f = c->take<float>(T * D);
   op_t* h = c->take<op_t>(T * DFF);
   op_t* x3 = c->take<op_t>(T * D);
-  float* seqf = seq_f32 ? seq_f32 : c->take<float>(T * D);
+  float* seqf = c->take<float>(T * D);
 
-  // model_Base.py:556/595 masked_fill, cast to the GEMM operand type
-  if (feats_dtype != MADE_DTYPE_F16_MASKED) MADE_TRY(cast_mask_rows(feats, feats_dtype, masks, T, e.din, x0, st));
-  {  // :559/598 projection, :533 += pe[:L], Transformer_enhancement norm1 (:86)
+  auto lin = [&](const op_t* A, int64_t lda, const Lin& w, int N, int K, GemmEpilogue ep) {
+    GemmParams p;
+    p.M = T;
+    p.N = N;
+    p.K = K;
+    p.m_dev = rb.total;
+    ep.bias = w.b;
+    p.epi = ep;
+    return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
+  };
+  {  // :559/598 projection, :533 += pe[position], Transformer_enhancement norm1 (:86)
     GemmEpilogue ep;
     ep.row_table = e.pe;
     ep.row_mod = e.L;
+    ep.row_src = rb.tok_src;
     ep.ln_gamma = e.ln1.g;
     ep.ln_beta = e.ln1.b;
     ep.out_h = x1;
     ep.ld_h = D;
     ep.out_f32 = x1f;
     ep.ld_f32 = D;
-    MADE_TRY(linear(x0, e.din, e.proj, T, D, e.din, ep, st));
+    MADE_TRY(lin(x0, e.din, e.proj, D, e.din, ep));
   }
   {  // packed in_proj (nn.MultiheadAttention)
     GemmEpilogue ep;
     ep.out_h = qkv;
     ep.ld_h = 3 * D;
-    MADE_TRY(linear(x1, D, e.in_proj, T, 3 * D, D, ep, st));
+    MADE_TRY(lin(x1, D, e.in_proj, 3 * D, D, ep));
   }
-  MADE_TRY(mha_core(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, masks, B, e.L, att, D, st));
+  MADE_TRY(mha_core(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, nullptr, B, e.L, att, D, st, rb.seq_off,
+                    rb.seq_len));
   {  // out_proj + residual (from the normed tensor, Q2) + norm2 (:87-88)
     GemmEpilogue ep;
     ep.residual = x1f;
@@ -525,14 +553,14 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
     ep.ld_h = D;
     ep.out_f32 = x2f;
     ep.ld_f32 = D;
-    MADE_TRY(linear(att, D, e.out_proj, T, D, D, ep, st));
+    MADE_TRY(lin(att, D, e.out_proj, D, D, ep));
   }
   {  // FF: Linear -> GELU(erf)
     GemmEpilogue ep;
     ep.act = 1;
     ep.out_h = h;
     ep.ld_h = DFF;
-    MADE_TRY(linear(x2, D, e.ff1, T, DFF, D, ep, st));
+    MADE_TRY(lin(x2, D, e.ff1, DFF, D, ep));
   }
   {  // FF: Linear + residual (:89)
     GemmEpilogue ep;
@@ -541,20 +569,64 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
     ep.res_ld = D;
     ep.out_h = x3;
     ep.ld_h = D;
-    MADE_TRY(linear(h, DFF, e.ff2, T, D, DFF, ep, st));
+    MADE_TRY(lin(h, DFF, e.ff2, D, DFF, ep));
   }
-  {  // final_linear (:91) + masked_fill (:541)
+  {  // final_linear (:91); masked_fill (:541) = padded rows of the output stay zero
+    MADE_CUDA(cudaMemsetAsync(seq16, 0, static_cast<size_t>(T) * D * 2, st));
     GemmEpilogue ep;
-    ep.row_mask = masks;
     ep.out_h = static_cast<op_t*>(seq16);
     ep.ld_h = D;
+    ep.h_row_idx = rb.tok_src;      // scatter packed rows back to [B, L, 256]
     ep.out_f32 = seqf;
     ep.ld_f32 = D;
-    MADE_TRY(linear(x3, D, e.fin, T, D, D, ep, st));
+    MADE_TRY(lin(x3, D, e.fin, D, D, ep));
   }
+  if (seq_f32) MADE_TRY(scatter_rows_f32(seqf, rb, seq_f32, st));
   // masked mean + F.normalize (:579-580 / :615-616)
-  MADE_TRY(pool_norm(seqf, masks, B, e.L, pooled, st));
+  MADE_TRY(pool_norm_ragged(seqf, rb, pooled, st));
   return MADE_OK;
+}
+
+static size_t encode_scratch_bytes(int64_t T) {
+  return padded(T * D, 2) * 4 + padded(T * D, 4) * 3 + padded(T * 3 * D, 2) + padded(T * DFF, 2);
+}
+
+int made_encode_ragged(made_ctx* c, int modality, const void* x16_packed, const made_ragged* rb, void* seq16,
+                       float* seq_f32, float* pooled, void* stream) {
+  CTX_READY(c);
+  MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode_ragged: bad modality %d", modality);
+  MADE_REQUIRE(rb, "encode_ragged: null descriptor");
+  if (rb->B == 0) return MADE_OK;
+  MADE_REQUIRE(x16_packed && seq16 && pooled, "encode_ragged: null pointer");
+  const EncW& e = c->enc[modality];
+  MADE_REQUIRE(rb->L == e.L, "encode_ragged: descriptor built for L=%d, modality needs L=%d", rb->L, e.L);
+  const int64_t T = rb->B * e.L;
+  MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
+  MADE_TRY(c->reserve(encode_scratch_bytes(T)));
+  return encode_packed(c, modality, static_cast<const op_t*>(x16_packed), to_ragged(rb), seq16, seq_f32, pooled,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, const float* masks, int64_t B,
+                void* seq16, float* seq_f32, float* pooled, void* stream) {
+  CTX_READY(c);
+  MADE_REQUIRE(modality == MADE_VIDEO || modality == MADE_MUSIC, "encode: bad modality %d", modality);
+  MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "encode: bad feature dtype %d",
+               feats_dtype);
+  if (B == 0) return MADE_OK;
+  MADE_REQUIRE(feats && masks && seq16 && pooled, "encode: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const EncW& e = c->enc[modality];
+  const int64_t T = B * e.L;
+  MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
+  MADE_TRY(c->reserve(padded(ragged_index_words(B, e.L), 4) + padded(T * e.din, 2) + encode_scratch_bytes(T)));
+  int32_t* idx = c->take<int32_t>(ragged_index_words(B, e.L));
+  op_t* x0 = c->take<op_t>(T * e.din);
+  Ragged rb;
+  MADE_TRY(ragged_build(masks, B, e.L, idx, &rb, st));
+  // model_Base.py:556/595 masked_fill + cast: only the valid rows are read and packed
+  MADE_TRY(ingest_gather(feats, feats_dtype, rb, e.din, x0, st));
+  return encode_packed(c, modality, x0, rb, seq16, seq_f32, pooled, st);
 }
 
 int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks, int64_t N, void* kz,
@@ -635,14 +707,21 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   const int64_t Bc = B < kEncChunk ? B : kEncChunk;
   const int64_t Tc = Bc * LD, Tall = B * LD;
   const int64_t R = NDEC * B;
-  size_t need = padded(Tall * D, 2) * 2 + padded(Tall, 4) +                                  // mem, mp, mask
+  const int64_t n_chunks = (B + Bc - 1) / Bc;
+  const size_t idx_words = ragged_index_words(Bc, LD);
+  size_t need = padded(Tall * D, 2) * 2 + padded(Tall, 4) + padded(B, 4) * 2 +                  // mem, mp, mask, off, len
+                padded(idx_words, 4) * n_chunks +
                 padded(Tc * D, 2) * 7 + padded(Tc * 2 * D, 2) + padded(Tc * D, 4) * 2 + padded(Tc * DFF, 2) +
                 padded(B * D, 2) * 4 + padded(B * D, 4) * 2 + padded(B * 8 * D, 4) + padded(B * 8 * D, 2) +
                 padded(B * DFF, 2) + padded(R * D, 4) + padded(R * D, 2) * 3;
   MADE_TRY(c->reserve(need));
-  op_t* mem_all = c->take<op_t>(Tall * D);     // encoder output (memory), fp16
+  // Encoder output of every sequence, token-packed per encoder chunk: chunk k owns rows
+  // [k * Tc, ...) of mem_all / mp_all, sequence b its chunk's rows [seq_off[b], + seq_len[b]).
+  op_t* mem_all = c->take<op_t>(Tall * D);     // memory, fp16
   op_t* mp_all = c->take<op_t>(Tall * D);      // memory + pos
-  float* mask = c->take<float>(Tall);
+  float* mask = c->take<float>(Tall);          // concatenated key mask [B, 146]
+  int32_t* row_off = c->take<int32_t>(B);      // first row of sequence b inside mem_all / mp_all
+  int32_t* row_len = c->take<int32_t>(B);
   op_t* src = c->take<op_t>(Tc * D);
   op_t* pos = c->take<op_t>(Tc * D);
   op_t* srcpos = c->take<op_t>(Tc * D);
@@ -671,13 +750,29 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
 
   const op_t* fr = static_cast<const op_t*>(frame16);
   static_assert(NENC % 2 == 0, "the encoder ping-pong below ends in the (src, srcpos) buffers");
-  // ---------------- encoder (forward_post, music_detr/transformer.py:191-210), chunked ----------------
-  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+  if (memory) MADE_CUDA(cudaMemsetAsync(memory, 0, static_cast<size_t>(Tall) * D * 4, st));
+  // ---------------- encoder (forward_post, music_detr/transformer.py:191-210), chunked, valid tokens only ----
+  for (int64_t b0 = 0, ck = 0; b0 < B; b0 += Bc, ++ck) {
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
-    const int64_t T = nb * LD;
+    const int64_t T = nb * LD;          // upper bound of this chunk's packed rows
     float* mask_c = mask + b0 * LD;
-    MADE_TRY(detr_prep(fr + b0 * LV * D, frame_masks + b0 * LV, static_cast<const op_t*>(seg16), seg_masks,
-                       track_idx ? track_idx + b0 : nullptr, b0, c->inv_dim_t, nb, src, pos, srcpos, mask_c, st));
+    int32_t* idx = c->take<int32_t>(idx_words);
+    Ragged rb;
+    MADE_TRY(detr_mask(frame_masks + b0 * LV, seg_masks, track_idx ? track_idx + b0 : nullptr, b0, nb, mask_c, st));
+    MADE_TRY(ragged_build(mask_c, nb, LD, idx, &rb, st));
+    MADE_TRY(detr_prep_ragged(fr + b0 * LV * D, static_cast<const op_t*>(seg16), track_idx ? track_idx + b0 : nullptr,
+                              b0, rb, c->inv_dim_t, src, pos, srcpos, st));
+    MADE_TRY(offset_rows(rb, static_cast<int32_t>(b0 * LD), row_off + b0, row_len + b0, st));
+    auto lin = [&](const op_t* A, int64_t lda, const Lin& w, int N, int K, GemmEpilogue ep) {
+      GemmParams p;
+      p.M = T;
+      p.N = N;
+      p.K = K;
+      p.m_dev = rb.total;
+      ep.bias = w.b;
+      p.epi = ep;
+      return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
+    };
     op_t *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
     for (int l = 0; l < NENC; ++l) {
       const DetrEncW& w = c->denc[l];
@@ -689,15 +784,15 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
         GemmEpilogue ep;
         ep.out_h = qk;
         ep.ld_h = 2 * D;
-        MADE_TRY(linear(curpos, D, w.qk, T, 2 * D, D, ep, st));   // q = k = src + pos
+        MADE_TRY(lin(curpos, D, w.qk, 2 * D, D, ep));   // q = k = src + pos
       }
       {
         GemmEpilogue ep;
         ep.out_h = v;
         ep.ld_h = D;
-        MADE_TRY(linear(cur, D, w.v, T, D, D, ep, st));           // value = src
+        MADE_TRY(lin(cur, D, w.v, D, D, ep));           // value = src
       }
-      MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, mask_c, nb, LD, att, D, st));
+      MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, nullptr, nb, LD, att, D, st, rb.seq_off, rb.seq_len));
       {
         GemmEpilogue ep;
         if (l == 0) {
@@ -714,14 +809,14 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
         ep.ld_h = D;
         ep.out_f32 = s1f;
         ep.ld_f32 = D;
-        MADE_TRY(linear(att, D, w.out, T, D, D, ep, st));
+        MADE_TRY(lin(att, D, w.out, D, D, ep));
       }
       {
         GemmEpilogue ep;
         ep.act = 2;
         ep.out_h = hbuf;
         ep.ld_h = DFF;
-        MADE_TRY(linear(s1, D, w.ff1, T, DFF, D, ep, st));
+        MADE_TRY(lin(s1, D, w.ff1, DFF, D, ep));
       }
       {
         GemmEpilogue ep;
@@ -733,18 +828,19 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
         ep.out_h = nxt;
         ep.ld_h = D;
         if (l < NENC - 1 || memory) {
-          ep.out_f32 = (l == NENC - 1) ? memory + b0 * LD * D : srcf;
+          ep.out_f32 = srcf;
           ep.ld_f32 = D;
         }
         ep.add2 = pos;
         ep.add2_ld = D;
         ep.out2_h = nxtpos;
         ep.ld_out2 = D;
-        MADE_TRY(linear(hbuf, DFF, w.ff2, T, D, DFF, ep, st));
+        MADE_TRY(lin(hbuf, DFF, w.ff2, D, DFF, ep));
       }
       op_t* t = cur; cur = nxt; nxt = t;
       t = curpos; curpos = nxtpos; nxtpos = t;
     }
+    if (memory) MADE_TRY(scatter_rows_f32_nozero(srcf, rb, memory + b0 * LD * D, st));
   }
   // ---------------- decoder (forward_post :273-307), one moment query per sequence ----------------
   cast_f32_op_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
@@ -773,7 +869,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       ep.ld_f32 = 8 * D;
       MADE_TRY(linear(t1, D, w.qfold, B, 8 * D, D, ep, st));
     }
-    MADE_TRY(dec_attn_folded(qt, mp_all, mem_all, mask, B, LD, mbar, st));
+    MADE_TRY(dec_attn_folded(qt, mp_all, mem_all, nullptr, B, LD, mbar, st, row_off, row_len));
     {
       GemmEpilogue ep;   // out_proj o v_proj folded, + residual + norm2
       ep.residual = t1f;

@@ -36,8 +36,10 @@ template <int LP>
 __global__ void __launch_bounds__(kHeadsPerCta * 32)
 mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict__ K,
                 int64_t ldk, const op_t* __restrict__ V, int64_t ldv,
-                const float* __restrict__ key_mask, int L, float scale,
-                op_t* __restrict__ O, int64_t ldo) {
+                const float* __restrict__ key_mask, int L_in, const int32_t* __restrict__ seq_off,
+                const int32_t* __restrict__ seq_len, float scale, op_t* __restrict__ O, int64_t ldo) {
+  // Dense batches: sequence b occupies rows [b*L, (b+1)*L) and key_mask marks the valid keys.
+  // Ragged batches (seq_off != null): rows [seq_off[b], +seq_len[b]) and every key is valid.
   using S = AttnSmem<LP>;
   constexpr int NT = LP / 8, KK = LP / 16;
   extern __shared__ __align__(16) uint8_t attn_smem[];
@@ -48,13 +50,17 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   op_t* Ks = reinterpret_cast<op_t*>(attn_smem) + warp * S::kPerWarp;
   op_t* Vt = Ks + LP * kKStride;
   float* smask = reinterpret_cast<float*>(attn_smem + kHeadsPerCta * S::kPerWarp * 2);
+  const int L = seq_off ? min(seq_len[b], LP) : L_in;
+  const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L_in;
+  if (L <= 0) return;
 
   for (int i = threadIdx.x; i < LP; i += blockDim.x)
-    smask[i] = (i < L && key_mask[b * L + i] != 0.f) ? 0.f : -INFINITY;
+    smask[i] = (i < L && (seq_off != nullptr || key_mask[row0 + i] != 0.f)) ? 0.f : -INFINITY;
 
   // ---- stage K (row-major) and V (transposed) head slices; rows >= L are zero ----
-  const op_t* Kg = K + (b * L) * ldk + h * kHeadDim;
-  const op_t* Vg = V + (b * L) * ldv + h * kHeadDim;
+  const op_t* Kg = K + row0 * ldk + h * kHeadDim;
+  const op_t* Vg = V + row0 * ldv + h * kHeadDim;
+  const int n_nt = (L + 7) >> 3, n_kk = (L + 15) >> 4;   // key tiles that hold at least one real key
   for (int idx = lane; idx < LP * 4; idx += 32) {
     const int key = idx >> 2, ch = idx & 3;
     uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -69,7 +75,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   }
   __syncthreads();
 
-  const op_t* Qg = Q + (b * L) * ldq + h * kHeadDim;
+  const op_t* Qg = Q + row0 * ldq + h * kHeadDim;
   for (int rt = 0; rt < KK; ++rt) {
     const int r0 = rt * 16 + g, r1 = r0 + 8;
     if (rt * 16 >= L) break;
@@ -88,6 +94,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt >= n_nt) continue;       // keys beyond the sequence: masked to -inf below
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t kb[2];
@@ -138,6 +145,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
       o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < KK; ++kk) {
+        if (kk >= n_kk) continue;     // all-zero probabilities
         uint32_t vb[2];
         const op_t* vp = Vt + (nd * 8 + g) * S::kVStride + kk * 16 + 2 * t;
         vb[0] = *reinterpret_cast<const uint32_t*>(vp);
@@ -146,7 +154,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
       }
     }
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
-    op_t* Og = O + (b * L) * ldo + h * kHeadDim;
+    op_t* Og = O + row0 * ldo + h * kHeadDim;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
       const int c = nd * 8 + 2 * t;
@@ -166,13 +174,19 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 __global__ void __launch_bounds__(256)
 dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp,
                        const op_t* __restrict__ mem, const float* __restrict__ key_mask, int L,
+                       const int32_t* __restrict__ seq_off, const int32_t* __restrict__ seq_len,
                        op_t* __restrict__ out) {
   __shared__ float sp[8][160];
   __shared__ short vidx[160];
   __shared__ int s_nvalid;
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 0) {   // ordered compaction of the valid key positions
+  const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L;
+  if (seq_off) {     // ragged batch: the sequence's rows are exactly its valid keys
+    const int n = min(seq_len[b], 160);
+    for (int i = tid; i < n; i += 256) vidx[i] = static_cast<short>(i);
+    if (tid == 0) s_nvalid = n;
+  } else if (warp == 0) {   // ordered compaction of the valid key positions
     int base = 0;
     for (int t0 = 0; t0 < L; t0 += 32) {
       const int t = t0 + lane;
@@ -191,8 +205,8 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
   }
   __syncthreads();
   const int nv = s_nvalid;
-  const op_t* mpb = mp + b * L * 256 + lane * 8;
-  const op_t* memb = mem + b * L * 256 + lane * 8;
+  const op_t* mpb = mp + row0 * 256 + lane * 8;
+  const op_t* memb = mem + row0 * 256 + lane * 8;
   float mx = -INFINITY;
   for (int i = 0; i < nv; ++i) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mpb + vidx[i] * 256));
@@ -241,8 +255,8 @@ using namespace made;
 
 template <int LP>
 static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
-                      const op_t* V, int64_t ldv, const float* mask, int64_t B, int L,
-                      op_t* O, int64_t ldo, cudaStream_t st) {
+                      const op_t* V, int64_t ldv, const float* mask, int64_t B, int L, const int32_t* seq_off,
+                      const int32_t* seq_len, op_t* O, int64_t ldo, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     MADE_CUDA(cudaFuncSetAttribute(mha_core_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -251,7 +265,7 @@ static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
   }
   dim3 grid(static_cast<unsigned>(B), 8 / kHeadsPerCta);
   mha_core_kernel<LP><<<grid, kHeadsPerCta * 32, AttnSmem<LP>::kBytes, st>>>(
-      Q, ldq, K, ldk, V, ldv, mask, L, 0.17677669529663687f /* 1/sqrt(32) */, O, ldo);
+      Q, ldq, K, ldk, V, ldv, mask, L, seq_off, seq_len, 0.17677669529663687f /* 1/sqrt(32) */, O, ldo);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -259,21 +273,22 @@ static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
 namespace made {
 int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
              const op_t* V, int64_t ldv, const float* key_mask, int64_t B, int L,
-             op_t* O, int64_t ldo, cudaStream_t st) {
+             op_t* O, int64_t ldo, cudaStream_t st, const int32_t* seq_off, const int32_t* seq_len) {
   if (B == 0) return MADE_OK;
-  MADE_REQUIRE(Q && K && V && key_mask && O, "mha_core: null pointer");
+  MADE_REQUIRE(Q && K && V && O && (key_mask || (seq_off && seq_len)), "mha_core: null pointer");
   MADE_REQUIRE(L > 0 && L <= 160, "mha_core: L=%d unsupported (max 160)", L);
   MADE_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "mha_core: bad strides");
-  if (L <= 64) return launch_mha<64>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, O, ldo, st);
-  if (L <= 96) return launch_mha<96>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, O, ldo, st);
-  return launch_mha<160>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, O, ldo, st);
+  if (L <= 64) return launch_mha<64>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, seq_off, seq_len, O, ldo, st);
+  if (L <= 96) return launch_mha<96>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, seq_off, seq_len, O, ldo, st);
+  return launch_mha<160>(Q, ldq, K, ldk, V, ldv, key_mask, B, L, seq_off, seq_len, O, ldo, st);
 }
 
 int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const float* key_mask, int64_t B,
-                    int L, op_t* out, cudaStream_t st) {
+                    int L, op_t* out, cudaStream_t st, const int32_t* seq_off, const int32_t* seq_len) {
   if (B == 0) return MADE_OK;
-  MADE_REQUIRE(qt && mp && mem && key_mask && out && L > 0 && L <= 160, "dec_attn_folded: bad arguments");
-  dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(qt, mp, mem, key_mask, L, out);
+  MADE_REQUIRE(qt && mp && mem && (key_mask || (seq_off && seq_len)) && out && L > 0 && L <= 160,
+               "dec_attn_folded: bad arguments");
+  dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(qt, mp, mem, key_mask, L, seq_off, seq_len, out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

@@ -55,7 +55,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   const int n_blocks = p.N / BN;
-  const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
+  const int64_t M = p.m_dev ? static_cast<int64_t>(__ldg(p.m_dev)) : p.M;   // ragged batches: rows actually present
+  const int64_t m_tiles = (M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * n_blocks;
   const int k_blocks = (p.K + kBlockK - 1) / kBlockK;
   // tile schedule: streaming = round-robin, m-major; WS = one contiguous n-major range per CTA
@@ -198,13 +199,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int n_blk;
       decode(it, m_blk, n_blk);
       const int64_t grow = m_blk * p.m_stride + r_in_tile;
-      const bool row_ok = r_in_tile < p.m_valid && grow < p.M;
+      const bool row_ok = r_in_tile < p.m_valid && grow < M;
       const int64_t srow = row_ok ? grow : 0;   // safe row for loads
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       float keep = 1.f;
       if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
+      const int64_t hrow = e.h_row_idx ? static_cast<int64_t>(__ldg(e.h_row_idx + srow)) : grow;
 
       float psum = 0.f;
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
@@ -225,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (e.row_table) {
-          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + (srow % e.row_mod) * p.N + col0);
+          const int64_t trow = (e.row_src ? static_cast<int64_t>(__ldg(e.row_src + srow)) : srow) % e.row_mod;
+          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + trow * p.N + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 t = __ldg(t4 + i);
@@ -278,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 32; ++i) v[i] *= keep;
           if (row_ok) {
             if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
@@ -362,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 32; ++i) v[i] *= keep;
           if (row_ok) {
             if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + grow * e.ld_h + col0);
+              uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),

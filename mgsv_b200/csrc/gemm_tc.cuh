@@ -11,8 +11,10 @@ namespace made {
 
 struct GemmEpilogue {
   const float* bias = nullptr;          // [N]
-  const float* row_table = nullptr;     // [row_mod, N] fp32, added by (row % row_mod)
+  const float* row_table = nullptr;     // [row_mod, N] fp32, added by ((row_src ? row_src[row] : row) % row_mod)
   int row_mod = 1;
+  const int32_t* row_src = nullptr;     // ragged batches: tok_src (position of a packed row = tok_src % L)
+  const int32_t* h_row_idx = nullptr;   // ragged batches: out_h row r is written to row h_row_idx[r] (scatter)
   const void* residual = nullptr;       // [M, N], row stride res_ld elements
   int residual_f32 = 0;
   int64_t res_ld = 0;
@@ -38,6 +40,7 @@ struct GemmParams {
   int m_stride = 128;   // rows between consecutive M tiles (96 for per-track batched tiles)
   int m_valid = 128;    // rows of each tile that are stored
   int b_batched = 0;    // 1: B rows start at tile_m * m_stride (per-tile B, e.g. Gram matrix)
+  const int32_t* m_dev = nullptr;   // device scalar: actual row count (<= M); M then only sizes the grid / TMA map
   GemmEpilogue epi;
 };
 

@@ -4,16 +4,31 @@
 
 namespace made {
 
+// ragged.cu — token-packed batches (see the header comment there)
+struct Ragged {
+  const int32_t* seq_len = nullptr;   // [B]
+  const int32_t* seq_off = nullptr;   // [B]
+  const int32_t* total = nullptr;     // [1] device scalar
+  const int32_t* tok_src = nullptr;   // [total] = b * L + t
+  int64_t B = 0;
+  int L = 0;
+};
+size_t ragged_index_words(int64_t B, int L);
+int ragged_build(const float* mask, int64_t B, int L, int32_t* idx, Ragged* out, cudaStream_t st);
+int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t* out, cudaStream_t st);
+int pool_norm_ragged(const float* seq_packed, const Ragged& rb, float* pooled, cudaStream_t st);
+int scatter_rows_f32(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
+int scatter_rows_f32_nozero(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
+int offset_rows(const Ragged& rb, int32_t base, int32_t* row_off, int32_t* row_len, cudaStream_t st);
+int detr_mask(const float* frame_mask, const float* seg_mask, const int32_t* track_idx, int64_t seq_offset,
+              int64_t B, float* mask_out, cudaStream_t st);
+int detr_prep_ragged(const op_t* frame_out, const op_t* seg_out, const int32_t* track_idx, int64_t seq_offset,
+                     const Ragged& rb, const float* inv_dim_t, op_t* src, op_t* pos, op_t* srcpos,
+                     cudaStream_t st);
+
 // prep.cu
-int cast_mask_rows(const void* in, int in_dtype, const float* mask, int64_t rows, int dim,
-                   op_t* out, cudaStream_t st);
 int layernorm_rows(const void* in, int in_is_op, int64_t ld_in, int64_t rows, const float* gamma,
                    const float* beta, op_t* out_h, float* out_f32, cudaStream_t st);
-int pool_norm(const float* seq, const float* mask, int64_t B, int L, float* pooled, cudaStream_t st);
-int detr_prep(const op_t* frame_out, const float* frame_mask, const op_t* seg_out,
-              const float* seg_mask, const int32_t* track_idx, int64_t seq_offset, const float* inv_dim_t,
-              int64_t B, op_t* src, op_t* pos, op_t* srcpos, float* mask_out,
-              cudaStream_t st);
 int heads_final(const float* hs, const op_t* h2, int64_t rows, const float* w_cls,
                 const float* b_cls, const float* w_sp, const float* b_sp, float* logits, float* spans,
                 cudaStream_t st);
@@ -23,9 +38,11 @@ int vhat_rows(const float* v, int64_t rows, __half* out, cudaStream_t st);
 // attn.cu
 int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
              const op_t* V, int64_t ldv, const float* key_mask, int64_t B, int L,
-             op_t* O, int64_t ldo, cudaStream_t st);
+             op_t* O, int64_t ldo, cudaStream_t st, const int32_t* seq_off = nullptr,
+             const int32_t* seq_len = nullptr);
 int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const float* key_mask, int64_t B,
-                    int L, op_t* out, cudaStream_t st);
+                    int L, op_t* out, cudaStream_t st, const int32_t* seq_off = nullptr,
+                    const int32_t* seq_len = nullptr);
 
 // xpool.cu
 int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st);

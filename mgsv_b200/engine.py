@@ -76,57 +76,68 @@ class Engine:
                                                  _lib.ptr(out), C.byref(n), _lib.stream_ptr()))
         return int(n.value)
 
-    def ingest(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, out: Optional[torch.Tensor] = None):
+    def ragged(self, masks: torch.Tensor):
+        """Token-packing descriptor of a batch of masks [B, L] (device, float): → (made_ragged struct,
+        index tensor that owns its memory — keep both alive while kernels that use it are pending)."""
+        if not masks.is_cuda or masks.dim() != 2:
+            raise ValueError("ragged: expected a device mask of shape [B, L]")
+        masks = masks.to(torch.float32).contiguous()
+        B, L = masks.shape
+        words = int(self._lib.made_ragged_index_words(B, L))
+        idx = torch.empty(max(words, 1), dtype=torch.int32, device=masks.device)
+        rb = _lib.Ragged()
+        if B:
+            _lib.check(self._lib.made_ragged_build(_lib.ptr(masks), B, L, _lib.ptr(idx), C.byref(rb), _lib.stream_ptr()))
+        else:
+            rb.B, rb.L = 0, L
+        return rb, (idx, masks)
+
+    def ingest(self, modality: int, feats: torch.Tensor, rb, out: Optional[torch.Tensor] = None):
         """Masked cast of raw features (device tensor or PINNED host tensor, fp32/bf16/fp16) into the
-        fp16 operand buffer consumed by `encode(..., ingested=True)`.  Padded rows are never read, so
-        a pinned host tensor costs only its valid rows of PCIe traffic.  `masks` is a device tensor."""
+        token-packed fp16 operand buffer consumed by `encode(..., ragged=rb)`.  Padded rows are never
+        read, so a pinned host tensor costs only its valid rows of PCIe traffic."""
         L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
-        if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
-            raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
-        if tuple(masks.shape) != (feats.shape[0], L) or masks.dtype != torch.float32 or not masks.is_cuda:
-            raise ValueError(f"expected a float32 device mask of shape [B,{L}]")
+        if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din or feats.shape[0] != rb.B or rb.L != L:
+            raise ValueError(f"expected features of shape [{rb.B},{L},{din}], got {tuple(feats.shape)}")
         dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}.get(feats.dtype)
         if dt is None:
             raise ValueError(f"unsupported feature dtype {feats.dtype}")
         B = feats.shape[0]
         if out is None:
-            out = torch.empty((B, L, din), dtype=torch.float16, device=masks.device)
-        _lib.check(self._lib.made_ingest_features(_lib.ptr_any(feats), dt, _lib.ptr(masks.contiguous()), B * L, din,
-                                                  _lib.ptr(out), _lib.stream_ptr()))
+            out = torch.empty((B * L, din), dtype=torch.float16, device=self.device)
+        _lib.check(self._lib.made_ingest_ragged(_lib.ptr_any(feats), dt, C.byref(rb), din, _lib.ptr(out),
+                                                _lib.stream_ptr()))
         return out
 
     def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True,
-               ingested: bool = False, out=None):
+               ragged=None, out=None):
         """forward_{video,audio}_encoder_feature → (seq16 [B,L,256], seq_f32 or None, pooled [B,256]).
-        `ingested=True`: feats is the fp16 buffer written by `ingest` (used in place).
+        `ragged=rb`: feats is the packed fp16 buffer written by `ingest(..., rb)` (used in place).
         `out=(seq16, pooled)` writes into caller-provided (contiguous slices of) tensors."""
         L, din = (cfg.L_V, cfg.D_VIT) if modality == _lib.VIDEO else (cfg.L_M, cfg.D_AST)
-        if feats.dim() != 3 or feats.shape[1] != L or feats.shape[2] != din:
-            raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
-        if tuple(masks.shape) != (feats.shape[0], L):
+        B = masks.shape[0]
+        if tuple(masks.shape) != (B, L):
             raise ValueError(f"expected masks of shape [B,{L}], got {tuple(masks.shape)}")
-        if ingested:
-            if feats.dtype != torch.float16:
-                raise ValueError("ingested features must be the fp16 output of Engine.ingest")
-            dt = _lib.F16_MASKED
-        elif feats.dtype == torch.float32:
-            dt = _lib.F32
-        elif feats.dtype == torch.bfloat16:
-            dt = _lib.BF16
-        elif feats.dtype == torch.float16:
-            dt = _lib.F16
-        else:
-            raise ValueError(f"unsupported feature dtype {feats.dtype}")
-        feats = feats.contiguous()
-        masks = masks.to(torch.float32).contiguous()
-        B = feats.shape[0]
-        dev = feats.device
+        dev = masks.device if masks.is_cuda else feats.device
         if out is not None:
             seq, pooled = out
         else:
             seq = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float16, device=dev)
             pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
         seq32 = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
+        if ragged is not None:
+            if feats.dtype != torch.float16 or feats.dim() != 2 or feats.shape[1] != din or ragged.B != B:
+                raise ValueError("ragged encode takes the packed fp16 output of Engine.ingest")
+            _lib.check(self._lib.made_encode_ragged(self._h, modality, _lib.ptr(feats), C.byref(ragged), _lib.ptr(seq),
+                                                    _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
+            return seq, seq32, pooled
+        if feats.dim() != 3 or feats.shape[0] != B or feats.shape[1] != L or feats.shape[2] != din:
+            raise ValueError(f"expected features of shape [B,{L},{din}], got {tuple(feats.shape)}")
+        dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}.get(feats.dtype)
+        if dt is None:
+            raise ValueError(f"unsupported feature dtype {feats.dtype}")
+        feats = feats.contiguous()
+        masks = masks.to(torch.float32).contiguous()
         _lib.check(self._lib.made_encode(self._h, modality, _lib.ptr(feats), dt, _lib.ptr(masks), B, _lib.ptr(seq),
                                          _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
         return seq, seq32, pooled

@@ -45,26 +45,29 @@ class GalleryEvaluator:
         self._raw = {}              # (modality, slot) -> raw-dtype device staging buffer of one chunk (dma mode)
         self._stage = {}            # (modality, slot) -> fp16 staging buffer of one chunk
         self._stage_free = {}       # (modality, slot) -> event: compute stream is done with the buffer
+        self._keep = []             # ragged index tensors of the current step
         self.launches = 0           # kernels launched by the last run (counted per C-ABI op, see _count)
         self.xpool_events = None    # bench.py: list that receives (start, end, n_pairs) per xpool launch
 
     # ---- launch accounting (bench.py reports gpu_launches) --------------------------------------
-    # kernels per C-ABI call: ingest = 1; encode (ingested input) = 6 GEMM + attn + pool = 8;
+    # kernels per C-ABI call: ingest = 3 (ragged index) + 1 (gather/cast); encode (ragged input) = 6 GEMM +
+    # attn + pool = 8 (+ 1 memset, not a kernel of ours);
     # gallery_prepare = LN + GEMM + Gram GEMM + maskbits = 4; query_prepare = LN + GEMM + vhat = 3;
     # xpool_score = 1; cosine = 1; rank_topk = 1; detr_detect = per 512-sequence encoder chunk
-    # (prep 1 + enc 2*6 = 13) + cast 1 + dec 6*(5 GEMM + attention) + LN 1 + heads 3 = 41 (the 6 D2D
-    # copies are not kernels); moment_postproc = 1.
-    _K = dict(ingest=1, encode=8, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=41,
-              detr_chunk=13, postproc=1)
+    # (mask 1 + ragged index 3 + prep 1 + row offsets 1 + enc 2*6 = 18) + cast 1 + dec 6*(5 GEMM +
+    # attention) + LN 1 + heads 3 = 41 (the 6 D2D copies are not kernels); moment_postproc = 1.
+    _K = dict(ingest=4, encode=8, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=41,
+              detr_chunk=18, postproc=1)
 
     def _count(self, what: str, n: int = 1):
         self.launches += self._K[what] * n
 
     # ---- feature ingest, one chunk ahead on the ingest stream ---------------------------------------
     def _ingest_iter(self, modality: int, feats: torch.Tensor, mask_d: torch.Tensor, chunk: int, mask_h=None):
-        """Yield (start, end, x16, release) per chunk: x16 = fp16 masked features of rows start:end,
-        ready on the compute stream; call release() after the last kernel that reads x16 has been
-        enqueued so the ingest stream may refill the buffer."""
+        """Yield (start, end, x16, rb, release) per chunk: x16 = token-packed fp16 features of rows
+        start:end (valid tokens only) with their ragged descriptor rb, ready on the compute stream;
+        call release() after the last kernel that reads x16 has been enqueued so the ingest stream
+        may refill the buffer."""
         n = feats.shape[0]
         L, din = feats.shape[1], feats.shape[2]
         bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
@@ -78,14 +81,15 @@ class GalleryEvaluator:
             slot = i & 1
             key = (modality, slot)
             buf = self._stage.get(key)
-            if buf is None or buf.shape[0] < e - s:
-                buf = torch.empty((max(chunk, e - s), L, din), dtype=torch.float16, device=self.dev)
+            if buf is None or buf.shape[0] < (e - s) * L:
+                buf = torch.empty((max(chunk, e - s) * L, din), dtype=torch.float16, device=self.dev)
                 self._stage[key] = buf
             with torch.cuda.stream(self.ingest_stream):
                 self.ingest_stream.wait_event(start_ev)
                 free = self._stage_free.get(key)
                 if free is not None:
                     self.ingest_stream.wait_event(free)
+                rb, keep = self.eng.ragged(mask_d[s:e])
                 src = feats[s:e]
                 if not feats.is_cuda and self.h2d_mode == "dma":
                     raw = self._raw.get(key)
@@ -94,10 +98,11 @@ class GalleryEvaluator:
                         self._raw[key] = raw
                     self.h2d_bytes += self.eng.h2d_valid_rows(src, mask_h[s:e], raw[:e - s])
                     src = raw[:e - s]
-                self.eng.ingest(modality, src, mask_d[s:e], out=buf[:e - s])
+                x16 = buf[:(e - s) * L]
+                self.eng.ingest(modality, src, rb, out=x16)
                 ev = torch.cuda.Event()
                 ev.record(self.ingest_stream)
-            ready[i] = (buf[:e - s], ev, key)
+            ready[i] = (x16, rb, keep, ev, key)
             self._count("ingest")
 
         if bounds:
@@ -105,15 +110,16 @@ class GalleryEvaluator:
         for i, (s, e) in enumerate(bounds):
             if i + 1 < len(bounds):
                 issue(i + 1)
-            x16, ev, key = ready.pop(i)
+            x16, rb, keep, ev, key = ready.pop(i)
             cur.wait_event(ev)
 
-            def release(key=key):
+            def release(key=key, keep=keep):
                 done = torch.cuda.Event()
                 done.record(cur)
                 self._stage_free[key] = done
+                self._keep.append(keep)     # index tensors stay alive until the step's kernels are enqueued
 
-            yield s, e, x16, release
+            yield s, e, x16, rb, release
 
     # ---- stages -----------------------------------------------------------------------------------
     def encode_queries(self, frame_feats, frame_mask):
@@ -121,8 +127,8 @@ class GalleryEvaluator:
         seq = torch.empty((n, cfg.L_V, cfg.D_MODEL), dtype=torch.float16, device=self.dev)
         pooled = torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=self.dev)
         mask_d = self._to_dev(frame_mask).to(torch.float32)
-        for s, e, x16, release in self._ingest_iter(_lib.VIDEO, frame_feats, mask_d, self.video_chunk, frame_mask):
-            self.eng.encode(_lib.VIDEO, x16, mask_d[s:e], want_f32=False, ingested=True, out=(seq[s:e], pooled[s:e]))
+        for s, e, x16, rb, release in self._ingest_iter(_lib.VIDEO, frame_feats, mask_d, self.video_chunk, frame_mask):
+            self.eng.encode(_lib.VIDEO, x16, mask_d[s:e], want_f32=False, ragged=rb, out=(seq[s:e], pooled[s:e]))
             release()
             self._count("encode")
         return seq, pooled, mask_d
@@ -144,9 +150,9 @@ class GalleryEvaluator:
         gal = self.new_gallery(n)
         mask_d = self._to_dev(segment_mask).to(torch.float32)
         gal["mask"] = mask_d
-        for s, e, x16, release in self._ingest_iter(_lib.MUSIC, segment_feats, mask_d, self.music_chunk,
-                                                    segment_mask):
-            self.eng.encode(_lib.MUSIC, x16, mask_d[s:e], want_f32=False, ingested=True,
+        for s, e, x16, rb, release in self._ingest_iter(_lib.MUSIC, segment_feats, mask_d, self.music_chunk,
+                                                        segment_mask):
+            self.eng.encode(_lib.MUSIC, x16, mask_d[s:e], want_f32=False, ragged=rb,
                             out=(gal["seq"][s:e], gal["pooled"][s:e]))
             release()
             self.eng.gallery_prepare(gal["seq"][s:e], mask_d[s:e],
@@ -210,6 +216,7 @@ class GalleryEvaluator:
         moment detection (test-MaDe.py:280 evaluates the paired track)."""
         self.launches = 0
         self.h2d_bytes = 0
+        self._keep = []
         n_q = videos["frame_feats"].shape[0]
         n_m = tracks["segment_feats"].shape[0]
         # the pairing decides when detection may start: after the chunk that encodes its last track

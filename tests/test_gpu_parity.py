@@ -433,3 +433,80 @@ def test_whole_job_from_pinned_host_buffers_matches_device_resident(dev, engine)
     assert ev.launches > 0
     for k in ("rank", "topk_idx", "iou", "pred_st", "pred_ed", "score"):
         assert torch.equal(a[k].cpu(), b[k]), k
+
+
+# ---------------------------------------------------------------------------------------------
+# ragged (token-packed) batches, host->device ingest
+# ---------------------------------------------------------------------------------------------
+def test_ragged_batches_with_mask_holes_and_poisoned_padding(dev, engine, sd_fp32):
+    """Masks need not be prefixes; rows with mask 0 are never read (NaN-poisoned here) and come out
+    as exact zeros, like the reference's masked_fill (model_Base.py:556, :541)."""
+    B = 37
+    v, m, ids = synth.make_eval_set(B, B, synth.BASE_SEED + 31)
+    g = torch.Generator().manual_seed(5)
+    for mod, feats, mask, fn in ((_lib.VIDEO, v["frame_feats"], v["frame_mask"], O.encode_video),
+                                 (_lib.MUSIC, m["segment_feats"], m["segment_mask"], O.encode_music)):
+        mask = mask.clone()
+        holes = torch.rand(mask.shape, generator=g) < 0.2
+        holes[:, 0] = False                       # keep at least one valid token
+        mask[holes] = 0
+        mask[3] = 0
+        mask[3, 7] = 1                            # a sequence with one valid token in the middle
+        mask[4] = 1                               # a full-length sequence
+        clean = feats * mask.unsqueeze(-1)
+        poisoned = clean.clone()
+        poisoned[mask == 0] = float("nan")
+        seq, seq32, pooled = engine.encode(mod, poisoned.to(dev), mask.to(dev))
+        rs, rp = fn(sd_fp32, clean, mask)
+        assert not torch.isnan(seq32).any() and not torch.isnan(pooled).any()
+        assert _rel(seq32, rs) < ACT_RTOL
+        assert bool((seq32[mask.to(dev) == 0] == 0).all()) and bool((seq[mask.to(dev) == 0] == 0).all())
+        np.testing.assert_allclose(pooled.cpu().numpy(), rp.numpy(), atol=VEC_ATOL, rtol=0)
+        # the pipelined path (explicit descriptor + packed ingest) is the same computation
+        rb, keep = engine.ragged(mask.to(dev))
+        x16 = engine.ingest(mod, poisoned.to(dev), rb)
+        seq_b, _, pooled_b = engine.encode(mod, x16, mask.to(dev), want_f32=False, ragged=rb)
+        assert torch.equal(seq_b, seq) and torch.equal(pooled_b, pooled)
+        total = int(mask.sum().item())
+        assert int(keep[0][2 * ((B + 3) // 4 * 4)].item()) == total      # device-side row count
+
+
+def test_detr_with_mask_holes(dev, engine, sd_fp32):
+    B = 21
+    v, m, ids = synth.make_eval_set(B, B, synth.BASE_SEED + 32)
+    g = torch.Generator().manual_seed(6)
+    fmask, smask = v["frame_mask"].clone(), m["segment_mask"].clone()
+    fmask[torch.rand(fmask.shape, generator=g) < 0.15] = 0
+    smask[torch.rand(smask.shape, generator=g) < 0.15] = 0
+    fmask[:, 0] = 1
+    fo, vf = O.encode_video(sd_fp32, v["frame_feats"] * fmask.unsqueeze(-1), fmask)
+    so, mf = O.encode_music(sd_fp32, m["segment_feats"] * smask.unsqueeze(-1), smask)
+    src = torch.cat([fo, so], 1)
+    mask = torch.cat([fmask, smask], 1)
+    hs, memory = O.detr_forward(sd_fp32, src, mask, O.position_embedding_sine(mask), vf.unsqueeze(1))
+    om = O.calc_output(sd_fp32, hs, fo)
+    r = engine.detr_detect(fo.to(torch.float16).to(dev), fmask.to(dev), so.to(torch.float16).to(dev), smask.to(dev),
+                           vf.to(dev), want_memory=True)
+    valid = mask.to(dev) != 0
+    assert _rel(r["memory"][valid], memory[mask != 0]) < ACT_RTOL
+    assert bool((r["memory"][~valid] == 0).all())          # padded memory rows are not materialised
+    np.testing.assert_allclose(r["pred_spans"][-1].cpu().numpy(), om["pred_spans"][:, 0].numpy(), atol=4e-4)
+    np.testing.assert_allclose(r["pred_logits"][-1].cpu().numpy(), om["pred_logits"][:, 0].numpy(), atol=3e-3)
+
+
+def test_h2d_valid_rows_copies_exactly_the_valid_prefixes(dev, engine):
+    B, L, dim = 19, 96, 768
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(B, L, dim, generator=g).pin_memory()
+    n = torch.randint(1, L + 1, (B,), generator=g)
+    n[2], n[3], n[4] = L, L, 0
+    mask = (torch.arange(L)[None] < n[:, None]).float()
+    mask[7, 5] = 0                                       # a hole inside the valid prefix is still copied
+    stage = torch.full((B, L, dim), -1.0, device=dev)
+    nbytes = engine.h2d_valid_rows(feats, mask, stage)
+    torch.cuda.synchronize()
+    last = [int(torch.nonzero(mask[b]).max()) + 1 if mask[b].any() else 0 for b in range(B)]
+    assert nbytes == sum(last) * dim * 4
+    for b in range(B):
+        assert torch.equal(stage[b, :last[b]].cpu(), feats[b, :last[b]])
+        assert bool((stage[b, last[b]:] == -1).all())

@@ -70,7 +70,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/made_b200.h but not exported"
-    assert set(_lib.SIGNATURES) | {"made_last_error_string"} == declared
+    assert set(_lib.SIGNATURES) | {"made_last_error_string", "made_ragged_index_words"} == declared
     assert lib.made_abi_version() == 1
 
 
