@@ -311,7 +311,7 @@ def main():
                     "kernel_ms": t_s * 1e3, "launches_per_step": launches_per_step,
                     "share_of_step": t_s * 1e3 * launches_per_step / ms_dev,
                     "algorithmic_flops_per_launch": F_XPOOL_PAIR * pairs,
-                    "executed_flops_per_launch": 2.0 * (96 * 256 + 96 * 352) * pairs,
+                    "executed_flops_per_launch": 2.0 * (96 * 256 + 96 * 112 + 96 * 256) * pairs,
                     "whole_step_tflops": F_TOTAL_JOB * (nq / N_QUERIES) / (ms_dev / 1e3) / 1e12 if nm == N_TRACKS else None}
 
     cpu_baseline = None

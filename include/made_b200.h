@@ -156,7 +156,8 @@ int made_encode_ragged(made_ctx* ctx, int modality, const void* x16_packed, cons
 
 /* Per-track X-Pool operands from encoded segments (modules/transformer.py:165, 102-106 folded):
  * seg16 [N,96,256], seg_masks [N,96] -> kz [N*96,768] fp16 (K | V'' | Z''),
- * gram [N*96,96] fp16, maskbits [N,4] u32. */
+ * gram [N*96,112] fp16 = [G = V''V''^T (96) | W5 = Z''.{1,b',g3^2,g3^2 b',g3 beta3} (5) | 0],
+ * maskbits [N,4] u32. */
 int made_gallery_prepare(made_ctx* ctx, const void* seg16, const float* seg_masks, int64_t N,
                          void* kz, void* gram, uint32_t* maskbits, void* stream);
 /* Per-query X-Pool operands (modules/transformer.py:164, 98; metrics.py:19):

@@ -26,6 +26,7 @@ MAX_M_DURATION = 240.0
 STRIDE = 2.5
 TEMPERATURE_INIT = 0.03
 LN_EPS = 1e-5
+XPOOL_G_COLS = 112     # per-track X-Pool operand [G (96) | W5 (5) | 0]: csrc/xpool.cu
 
 SHIPPED = dict(
     dim_input=256, hidden_dim=256, detr_hidden_dim=256,

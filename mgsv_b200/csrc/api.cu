@@ -648,7 +648,7 @@ int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks,
     ep.ld_h = 3 * D;
     MADE_TRY(linear(sp, D, c->xp_kvz, T, 3 * D, D, ep, st));
   }
-  {  // per-track Gram matrix G = V'' V''^T (96 x 96), batched over tracks
+  {  // per-track Gram matrix G = V'' V''^T (96 x 96), batched over tracks -> columns 0..95 of [G | W5 | 0]
     GemmParams p;
     p.M = T;
     p.N = LM;
@@ -657,9 +657,11 @@ int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks,
     p.m_valid = LM;
     p.b_batched = 1;
     p.epi.out_h = static_cast<op_t*>(gram);
-    p.epi.ld_h = LM;
+    p.epi.ld_h = 112;
     MADE_TRY(gemm_f16_tc(kzb + D, 3 * D, kzb + D, 3 * D, T, p, 96, st));
   }
+  // W5 = Z'' . {1, b', g3^2, g3^2 b', g3 beta3} -> columns 96..100 (xpool.cu)
+  MADE_TRY(xpool_w5(kzb + 2 * D, 3 * D, T, static_cast<op_t*>(gram), st));
   MADE_TRY(mask_bits(seg_masks, N, maskbits, st));
   return MADE_OK;
 }

@@ -46,6 +46,7 @@ int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const floa
 
 // xpool.cu
 int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st);
+int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, op_t* gw, cudaStream_t st);
 int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t* kz,
                 int64_t ldkz, int z_col, const op_t* gram, const uint32_t* maskbits,
                 int64_t n_tracks, float* sim, int64_t ld, int64_t col_offset, cudaStream_t st);

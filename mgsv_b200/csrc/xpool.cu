@@ -4,26 +4,36 @@
 // sim_matrix_music_pooling (modules/metrics.py:10-24), WITHOUT materialising the reference's
 // [N_m, N_v, 256] pooled tensor (8.2 GB fp32 at 2k x 4k).
 //
-// Algebra (all exact in real arithmetic; DESIGN.md "X-Pool folding"):
-//   o - mean(o)          = sum_t a_t V''_t            V'' = centred (Wo Wv) LN1(x) + centred biases
-//   |o - mean(o)|^2      = a^T G a                    G   = V'' V''^T   (per track, 96x96)
-//   LN2 -> (I+Wl) + bl   = (1/sigma) sum_t a_t Z''_t + b'     Z'' = V'' W'^T,  W' = (I+Wl) diag(g2)
-// so per pair only three products remain:  S = q K^T (96),  T = e G (96),  Y = e Z'' (256), with
-// e = exp(S - max) kept unnormalised in fp16 and divided by the sum of the rounded weights.
+// Algebra (all exact in real arithmetic; DESIGN.md "X-Pool folding").  With e = exp(S - max) the
+// un-normalised attention weights of a pair, l = sum(e):
+//   o - mean(o)          = (1/l) sum_t e_t V''_t      V'' = centred (Wo Wv) LN1(x) + centred biases
+//   |o - mean(o)|^2      = e^T G e / l^2              G   = V'' V''^T   (per track, 96x96)
+//   LN2 -> (I+Wl) + bl   = alpha Y + b',  Y = e Z'',  alpha = 1 / (l sigma2),  Z'' = V'' W'^T
+// and LN3 + the cosine with v_hat only need SUMS over the 256 features of alpha*Y + b':
+//   linear in Y with constant weights  (sum Y, sum b'Y, sum g^2 Y, sum g^2 b'Y, sum g*beta Y)
+//        = e . w_c with w_c = Z'' c per track  ->  five extra columns "W5" next to G, so the
+//          tensor core produces them in the same MMA as T = e G;
+//   quadratic / per-query terms        (sum Y^2, sum g^2 Y^2, sum u Y with u = v_hat*g)
+//        = one sweep over the Y accumulator, 4 flops per element.
+// Per pair the MMAs are S = q K^T (96), [T | L] = e [G | W5] (112) and Y = e Z'' (256):
+// 119 808 executed flops instead of the reference's 360 960.
 //
-// One CTA owns a 128-query tile (Q resident in shared memory, v_hat resident in TMEM as fp16) and
-// streams tracks: TMA brings K/Z''/G of a track into 128B-swizzled shared memory, one thread issues
-// tcgen05.mma (S: K-major B; T,Y: MN-major B straight from the row-major [token, feature]
-// matrices), and 4 epilogue warps (thread == query row) do softmax -> P (swizzled smem A operand)
-// and the LN2/LN3/cosine sweep out of TMEM.  GEMM1 of track i+1 overlaps the Y sweep of track i.
+// One CTA owns a 128-query tile (Q resident in shared memory, u resident in TMEM as fp16) and
+// streams tracks: TMA brings K / Z'' / [G|W5] of a track into 128B-swizzled shared memory, one thread
+// issues tcgen05.mma (S: K-major B; T, Y: MN-major B straight from the row-major [token, feature]
+// matrices), and 8 epilogue warps (two per TMEM lane quarter, each owning half of the columns of a
+// query row) do softmax -> P (swizzled smem A operand), the quadratic form, the Y sweep and the
+// closed-form LN2/LN3/cosine.  GEMM1 of track i+1 overlaps the Y sweep of track i.
 #include "common.cuh"
+#include "prep.cuh"
 
 namespace made {
 
 constexpr int kXQ = 128;     // queries per tile
 constexpr int kXL = 96;      // segments per track
 constexpr int kXD = 256;
-constexpr int kXThreads = 256;
+constexpr int kXG = 112;     // columns of the per-track [G | W5 | 0] operand
+constexpr int kXThreads = 384;
 constexpr uint32_t kQBytes = kXQ * kXD * 2;          // 64 KB: 4 k-slabs of [128 x 128B]
 constexpr uint32_t kKBytes = kXL * kXD * 2;          // 48 KB: 4 k-slabs of [96 x 128B]
 constexpr uint32_t kZBytes = kXL * kXD * 2;          // 48 KB: 4 n-slabs of [96 x 128B]
@@ -31,16 +41,26 @@ constexpr uint32_t kGBytes = 2 * kXL * 128;          // 24 KB: 2 n-slabs of [96 
 constexpr uint32_t kPBytes = 2 * kXQ * 128;          // 32 KB: 2 k-slabs of [128 x 128B]
 constexpr uint32_t kSlabQ = kXQ * 128;               // 16 KB
 constexpr uint32_t kSlabT = kXL * 128;               // 12 KB
-constexpr uint32_t kXSmem = kQBytes + kKBytes + kZBytes + kGBytes + kPBytes + 1024 + 256;
+constexpr uint32_t kXchgBytes = 2 * kXQ * 4 + 2 * kXQ * 5 * 4;   // max + 5 partial sums per (half, row)
+constexpr uint32_t kXSmem = kQBytes + kKBytes + kZBytes + kGBytes + kPBytes + 1024 + 256 + kXchgBytes;
+static_assert(kXSmem <= 232448, "shared memory budget of an sm_100 CTA");
 
 // TMEM columns
 constexpr uint32_t kColY = 0;      // 256 fp32 columns
-constexpr uint32_t kColT = 256;    // 96 fp32 columns; also holds S before the softmax
-constexpr uint32_t kColV = 384;    // 128 columns: v_hat as packed fp16 pairs
+constexpr uint32_t kColT = 256;    // 112 fp32 columns [T | L]; also holds S before the softmax
+constexpr uint32_t kColV = 384;    // 128 columns: u = v_hat * gamma3 as packed fp16 pairs
 
-__constant__ float c_xp_bias[kXD];    // b' = (I + Wl) beta2 + bl
-__constant__ float c_xp_gamma3[kXD];
-__constant__ float c_xp_beta3[kXD];
+struct XpoolConsts {
+  float bias[kXD];      // b' = (I + Wl) beta2 + bl
+  float gamma[kXD];     // gamma3
+  float gamma2[kXD];    // gamma3^2
+  float beta[kXD];      // beta3
+  // sums over the 256 features
+  float B1, B2;         // sum b', sum b'^2
+  float G2, G2b2, G2b;  // sum g^2, sum g^2 b'^2, sum g^2 b'
+  float Gbb, Gb, Bb;    // sum g beta b', sum g beta, sum beta^2
+};
+__constant__ XpoolConsts c_xp;
 
 struct XpoolParams {
   int64_t n_queries, n_tracks;
@@ -52,6 +72,30 @@ struct XpoolParams {
   int64_t col_offset;
   float ln2_eps, ln3_eps;
 };
+
+// One sweep over half H of the Y accumulator of this thread's row: sum Y^2, sum g^2 Y^2, sum u Y.
+// H is a template parameter so that the gamma^2 constants are immediate constant-bank operands.
+template <int H>
+__device__ __forceinline__ void y_sweep(uint32_t lane_addr, float& s2, float& sg2, float& su) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t y[32], uh[16];
+    tmem_ld_x32(lane_addr + kColY + H * 128 + c * 32, y);
+    tmem_ld_x16(lane_addr + kColV + H * 64 + c * 16, uh);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 uu = __half22float2(*reinterpret_cast<const __half2*>(&uh[i]));
+      const float y0 = __uint_as_float(y[2 * i]), y1 = __uint_as_float(y[2 * i + 1]);
+      const float a0 = y0 * y0, a1 = y1 * y1;
+      s2 += a0 + a1;
+      sg2 = fmaf(a0, c_xp.gamma2[H * 128 + c * 32 + 2 * i], sg2);
+      sg2 = fmaf(a1, c_xp.gamma2[H * 128 + c * 32 + 2 * i + 1], sg2);
+      su = fmaf(uu.x, y0, su);
+      su = fmaf(uu.y, y1, su);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kXThreads, 1)
 xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -76,6 +120,8 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint64_t* t_free = bars + 8;
   uint64_t* y_free = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][128]
+  float* xpart = xmax + 2 * kXQ;                                                     // [2][128][5]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.q_tiles;
@@ -95,10 +141,10 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     mbar_init(zg_full, 1);
     mbar_init(zg_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(y_full, 1);
-    mbar_init(t_free, 128);
-    mbar_init(y_free, 128);
+    mbar_init(t_free, 256);
+    mbar_init(y_free, 256);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -121,15 +167,15 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(zg_empty, (u & 1) ^ 1);
         mbar_arrive_expect_tx(zg_full, kZBytes + kGBytes);
         for (int j = 0; j < 4; ++j) tma_load_2d(sZ + j * kSlabT, &tm_z, zg_full, j * 64, row);
-        for (int j = 0; j < 2; ++j) tma_load_2d(sG + j * kSlabT, &tm_g, zg_full, j * 64, row);
+        for (int j = 0; j < 2; ++j) tma_load_2d(sG + j * kSlabT, &tm_g, zg_full, j * 64, row);   // cols >= 112: zero fill
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, 0, 0);    // S = Q K^T   (B K-major)
-      constexpr uint32_t idesc_y = umma_idesc_f16(128, 256, 0, 1);   // Y = P Z''   (B MN-major)
-      constexpr uint32_t idesc_t = umma_idesc_f16(128, 96, 0, 1);    // T = P G     (B MN-major)
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, 96, 0, 0);     // S = Q K^T        (B K-major)
+      constexpr uint32_t idesc_y = umma_idesc_f16(128, 256, 0, 1);    // Y = P Z''        (B MN-major)
+      constexpr uint32_t idesc_t = umma_idesc_f16(128, kXG, 0, 1);    // [T|L] = P [G|W5] (B MN-major)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aZ = smem_u32(sZ), aG = smem_u32(sG),
                      aP = smem_u32(sP);
       mbar_wait(q_full, 0);
@@ -157,150 +203,183 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const uint32_t offp = (ks >> 2) * kSlabQ + (ks & 3) * 32;      // P: K-major A, 16 k = 32 B
           const uint64_t adesc = umma_smem_desc(aP + offp, 0, 1024);
           const uint32_t offb = ks * 16 * 128;                            // 16 t-rows of 128 B
-          umma_ss(tmem_base + kColY, adesc, umma_smem_desc(aZ + offb, kSlabT, 1024), idesc_y, ks != 0);
           umma_ss(tmem_base + kColT, adesc, umma_smem_desc(aG + offb, kSlabT, 1024), idesc_t, ks != 0);
+          umma_ss(tmem_base + kColY, adesc, umma_smem_desc(aZ + offb, kSlabT, 1024), idesc_y, ks != 0);
         }
         tc_commit(zg_empty);
         tc_commit(y_full);
       }
     }
   } else if (warp >= 4) {
-    // ============================ epilogue: thread == query row ============================
+    // ============================ epilogue ============================
+    // thread = (query row r, column half h): h = 0 owns segments 0..47 / features 0..127,
+    // h = 1 owns segments 48..95 / features 128..255.  Partner threads (same row, other half)
+    // exchange their partial max / sums through shared memory with a 64-thread named barrier.
     const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const int64_t grow = q0 + r;
     const bool row_ok = grow < p.n_queries;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // v_hat row -> TMEM (fp16 pairs), once
+    const uint32_t bar_id = 1 + q;
+    // ---- per-query constants and u = v_hat * gamma3 (fp16) -> TMEM, once ----
+    float Cu1 = 0.f, Cu0 = 0.f, Cvb = 0.f;
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.vhat + (row_ok ? grow : 0) * kXD);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t w[32];
+      for (int c = 0; c < 8; ++c) {          // 32 features per step
+        uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 t = row_ok ? __ldg(src + c * 8 + i) : make_uint4(0, 0, 0, 0);
-          w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t = row_ok ? __ldg(src + c * 4 + i) : make_uint4(0, 0, 0, 0);
+          const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int f = c * 32 + i * 8 + j * 2;
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&tt[j]));
+            const __half2 uh = __floats2half2_rn(v.x * c_xp.gamma[f], v.y * c_xp.gamma[f + 1]);
+            const float2 uf = __half22float2(uh);
+            Cu1 = fmaf(uf.x, c_xp.bias[f], Cu1);
+            Cu1 = fmaf(uf.y, c_xp.bias[f + 1], Cu1);
+            Cu0 += uf.x + uf.y;
+            Cvb = fmaf(v.x, c_xp.beta[f], Cvb);
+            Cvb = fmaf(v.y, c_xp.beta[f + 1], Cvb);
+            w[i * 4 + j] = *reinterpret_cast<const uint32_t*>(&uh);
+          }
         }
-        tmem_st_x32(lane_addr + kColV + c * 32, w);
+        if ((c >> 2) == h) tmem_st_x16(lane_addr + kColV + c * 16, w);   // own half of the columns
       }
       tmem_wait_st();
     }
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
+    float* my_max = xmax + h * kXQ + r;
+    const float* peer_max = xmax + (h ^ 1) * kXQ + r;
+    float* my_part = xpart + (h * kXQ + r) * 5;
+    const float* peer_part = xpart + ((h ^ 1) * kXQ + r) * 5;
     uint32_t u = 0;
     for (int64_t m = slice; m < p.n_tracks; m += p.slices, ++u) {
-      // ---------------- softmax over the 96 segments ----------------
+      // ---------------- A. softmax over this half's 48 segments ----------------
       const uint4 mb = __ldg(reinterpret_cast<const uint4*>(p.maskbits + m * 4));
-      const uint32_t mw[3] = {mb.x, mb.y, mb.z};
+      const uint64_t lo64 = (static_cast<uint64_t>(mb.y) << 32) | mb.x;
+      const uint64_t bits = h == 0 ? lo64 : ((lo64 >> 48) | (static_cast<uint64_t>(mb.z) << 16));   // 48 valid bits
       mbar_wait(s_full, u & 1);
       tc_fence_after_sync();
-      uint32_t pk[48];
+      uint32_t pk[24];
       float lsum = 0.f;
       {
-        uint32_t s0[32], s1[32], s2[32];
-        tmem_ld_x32(lane_addr + kColT + 0, s0);
-        tmem_ld_x32(lane_addr + kColT + 32, s1);
-        tmem_ld_x32(lane_addr + kColT + 64, s2);
+        uint32_t s0[32], s1[16];
+        tmem_ld_x32(lane_addr + kColT + h * 48, s0);
+        tmem_ld_x16(lane_addr + kColT + h * 48 + 32, s1);
         tmem_wait_ld();
         float mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float a = ((mw[0] >> i) & 1u) ? __uint_as_float(s0[i]) : -INFINITY;
-          float b = ((mw[1] >> i) & 1u) ? __uint_as_float(s1[i]) : -INFINITY;
-          float c = ((mw[2] >> i) & 1u) ? __uint_as_float(s2[i]) : -INFINITY;
-          s0[i] = __float_as_uint(a); s1[i] = __float_as_uint(b); s2[i] = __float_as_uint(c);
-          mx = fmaxf(mx, fmaxf(a, fmaxf(b, c)));
+          const float a = ((bits >> i) & 1ull) ? __uint_as_float(s0[i]) : -INFINITY;
+          s0[i] = __float_as_uint(a);
+          mx = fmaxf(mx, a);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          op2_t e0 = floats2op2(__expf(__uint_as_float(s0[2 * i]) - mx),
-                                                    __expf(__uint_as_float(s0[2 * i + 1]) - mx));
-          op2_t e1 = floats2op2(__expf(__uint_as_float(s1[2 * i]) - mx),
-                                                    __expf(__uint_as_float(s1[2 * i + 1]) - mx));
-          op2_t e2 = floats2op2(__expf(__uint_as_float(s2[2 * i]) - mx),
-                                                    __expf(__uint_as_float(s2[2 * i + 1]) - mx));
-          float2 f0 = op2_to_f2(e0), f1 = op2_to_f2(e1), f2 = op2_to_f2(e2);
-          lsum += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y);
-          pk[i] = *reinterpret_cast<uint32_t*>(&e0);
-          pk[16 + i] = *reinterpret_cast<uint32_t*>(&e1);
-          pk[32 + i] = *reinterpret_cast<uint32_t*>(&e2);
+          const float a = ((bits >> (32 + i)) & 1ull) ? __uint_as_float(s1[i]) : -INFINITY;
+          s1[i] = __float_as_uint(a);
+          mx = fmaxf(mx, a);
+        }
+        *my_max = mx;
+        named_bar_sync(bar_id, 64);
+        mx = fmaxf(mx, *peer_max);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __half2 e = __floats2half2_rn(__expf(__uint_as_float(s0[2 * i]) - mx),
+                                              __expf(__uint_as_float(s0[2 * i + 1]) - mx));
+          const float2 f = __half22float2(e);
+          lsum += f.x + f.y;
+          pk[i] = *reinterpret_cast<const uint32_t*>(&e);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 e = __floats2half2_rn(__expf(__uint_as_float(s1[2 * i]) - mx),
+                                              __expf(__uint_as_float(s1[2 * i + 1]) - mx));
+          const float2 f = __half22float2(e);
+          lsum += f.x + f.y;
+          pk[16 + i] = *reinterpret_cast<const uint32_t*>(&e);
         }
       }
       // P -> shared memory, 128B-swizzled K-major: logical 16-byte chunk c of row r sits at c ^ (r & 7)
 #pragma unroll
-      for (int c = 0; c < 12; ++c) {
+      for (int k = 0; k < 6; ++k) {
+        const int c = h * 6 + k;
         const int slab = c >> 3, cc = c & 7;
         *reinterpret_cast<uint4*>(prow + slab * kSlabQ + ((cc ^ sw) << 4)) =
-            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_full);
 
-      // ---------------- sigma of LN2 from the quadratic form e^T G e ----------------
+      // ---------------- B. quadratic form e^T G e and the five linear sums ----------------
       mbar_wait(y_full, u & 1);
       tc_fence_after_sync();
       float qf = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t tt[32];
-        tmem_ld_x32(lane_addr + kColT + c * 32, tt);
+      float lin[5];
+      {
+        uint32_t t0[32], t1[16], t2[16];
+        tmem_ld_x32(lane_addr + kColT + h * 48, t0);
+        tmem_ld_x16(lane_addr + kColT + h * 48 + 32, t1);
+        tmem_ld_x16(lane_addr + kColT + 96, t2);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float2 e = op2_to_f2(*reinterpret_cast<const op2_t*>(&pk[c * 16 + i]));
-          qf = fmaf(e.x, __uint_as_float(tt[2 * i]), qf);
-          qf = fmaf(e.y, __uint_as_float(tt[2 * i + 1]), qf);
+          const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&pk[i]));
+          qf = fmaf(e.x, __uint_as_float(t0[2 * i]), qf);
+          qf = fmaf(e.y, __uint_as_float(t0[2 * i + 1]), qf);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&pk[16 + i]));
+          qf = fmaf(e.x, __uint_as_float(t1[2 * i]), qf);
+          qf = fmaf(e.y, __uint_as_float(t1[2 * i + 1]), qf);
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) lin[i] = __uint_as_float(t2[i]);
       }
       tc_fence_before_sync();
       mbar_arrive(t_free);
-      const float inv_l = 1.0f / lsum;
-      const float var2 = qf * inv_l * inv_l * (1.0f / kXD);
-      const float alpha = rsqrtf(fmaxf(var2, 0.f) + p.ln2_eps) * inv_l;   // 1 / (l * sigma)
 
-      // ---------------- LN3 statistics (pass 1) ----------------
-      float sum = 0.f, sq = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t y[32];
-        tmem_ld_x32(lane_addr + kColY + c * 32, y);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float o = fmaf(alpha, __uint_as_float(y[i]), c_xp_bias[c * 32 + i]);
-          sum += o;
-          sq = fmaf(o, o, sq);
-        }
-      }
-      const float mean = sum * (1.0f / kXD);
-      const float var3 = fmaxf(sq * (1.0f / kXD) - mean * mean, 0.f);
-      const float rs3 = rsqrtf(var3 + p.ln3_eps);
-      // ---------------- LN3 output norm and cosine with v_hat (pass 2) ----------------
-      float n2 = 0.f, dot = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t y[32], vh[16];
-        tmem_ld_x32(lane_addr + kColY + c * 32, y);
-        tmem_ld_x16(lane_addr + kColV + c * 16, vh);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float2 v = __half22float2(*reinterpret_cast<const __half2*>(&vh[i]));
-          float o0 = fmaf(alpha, __uint_as_float(y[2 * i]), c_xp_bias[c * 32 + 2 * i]);
-          float o1 = fmaf(alpha, __uint_as_float(y[2 * i + 1]), c_xp_bias[c * 32 + 2 * i + 1]);
-          float t0 = fmaf((o0 - mean) * rs3, c_xp_gamma3[c * 32 + 2 * i], c_xp_beta3[c * 32 + 2 * i]);
-          float t1 = fmaf((o1 - mean) * rs3, c_xp_gamma3[c * 32 + 2 * i + 1], c_xp_beta3[c * 32 + 2 * i + 1]);
-          n2 = fmaf(t0, t0, n2);
-          n2 = fmaf(t1, t1, n2);
-          dot = fmaf(v.x, t0, dot);
-          dot = fmaf(v.y, t1, dot);
-        }
-      }
+      // ---------------- C. one sweep over this half of Y ----------------
+      float s2 = 0.f, sg2 = 0.f, su = 0.f;
+      if (h == 0) y_sweep<0>(lane_addr, s2, sg2, su);
+      else y_sweep<1>(lane_addr, s2, sg2, su);
       tc_fence_before_sync();
       mbar_arrive(y_free);
-      if (row_ok) p.sim[grow * p.ld + p.col_offset + m] = dot / sqrtf(n2);
+
+      // ---------------- D. combine the halves, closed-form LN2 / LN3 / cosine ----------------
+      my_part[0] = lsum; my_part[1] = qf; my_part[2] = s2; my_part[3] = sg2; my_part[4] = su;
+      named_bar_sync(bar_id, 64);
+      if (h == 0) {
+        const float l = lsum + peer_part[0];
+        qf += peer_part[1];
+        s2 += peer_part[2];
+        sg2 += peer_part[3];
+        su += peer_part[4];
+        const float inv_l = 1.0f / l;
+        const float var2 = qf * inv_l * inv_l * (1.0f / kXD);
+        const float alpha = rsqrtf(fmaxf(var2, 0.f) + p.ln2_eps) * inv_l;   // 1 / (l * sigma2)
+        const float a2 = alpha * alpha;
+        // lin = {sum Y, sum b'Y, sum g^2 Y, sum g^2 b' Y, sum g beta Y}
+        const float So = fmaf(alpha, lin[0], c_xp.B1);
+        const float So2 = fmaf(a2, s2, fmaf(2.f * alpha, lin[1], c_xp.B2));
+        const float mean = So * (1.0f / kXD);
+        const float var3 = fmaxf(So2 * (1.0f / kXD) - mean * mean, 0.f);
+        const float rs = rsqrtf(var3 + p.ln3_eps);
+        const float dot = fmaf(rs, fmaf(alpha, su, Cu1) - mean * Cu0, Cvb);
+        const float Sg2o = fmaf(a2, sg2, fmaf(2.f * alpha, lin[3], c_xp.G2b2));
+        const float Sg1o = fmaf(alpha, lin[2], c_xp.G2b);
+        const float A2 = Sg2o - 2.f * mean * Sg1o + mean * mean * c_xp.G2;
+        const float A1 = fmaf(alpha, lin[4], c_xp.Gbb) - mean * c_xp.Gb;
+        const float n2 = fmaf(rs * rs, A2, fmaf(2.f * rs, A1, c_xp.Bb));
+        if (row_ok) p.sim[grow * p.ld + p.col_offset + m] = dot / sqrtf(n2);
+      }
     }
   }
 
@@ -312,20 +391,73 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
+// W5[t, :] = Z''[t, :] . {1, b', g^2, g^2 b', g beta}  -> columns 96..100 of the [G | W5 | 0] operand
+// (columns 101..111 are zeroed).  Warp per row.
+__global__ void xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __restrict__ gw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4 raw = *reinterpret_cast<const uint4*>(z + row * ldz + lane * 8);
+  const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
+  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = op2_to_f2(hh[j]);
+    const float zz[2] = {f.x, f.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = lane * 8 + 2 * j + k;
+      const float g2 = c_xp.gamma2[i], b = c_xp.bias[i];
+      a[0] += zz[k];
+      a[1] = fmaf(zz[k], b, a[1]);
+      a[2] = fmaf(zz[k], g2, a[2]);
+      a[3] = fmaf(zz[k], g2 * b, a[3]);
+      a[4] = fmaf(zz[k], c_xp.gamma[i] * c_xp.beta[i], a[4]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) a[k] = warp_sum(a[k]);
+  if (lane == 0) {
+    uint4* o = reinterpret_cast<uint4*>(gw + row * kXG + kXL);
+    o[0] = make_uint4(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]), pack_op2(a[4], 0.f), 0u);
+    o[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st) {
-  MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp_bias, bias_prime, kXD * 4, 0, cudaMemcpyHostToDevice, st));
-  MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp_gamma3, gamma3, kXD * 4, 0, cudaMemcpyHostToDevice, st));
-  MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp_beta3, beta3, kXD * 4, 0, cudaMemcpyHostToDevice, st));
+  static XpoolConsts h;   // host staging must outlive the async copy
+  double B1 = 0, B2 = 0, G2 = 0, G2b2 = 0, G2b = 0, Gbb = 0, Gb = 0, Bb = 0;
+  for (int i = 0; i < kXD; ++i) {
+    const double b = bias_prime[i], g = gamma3[i], be = beta3[i];
+    h.bias[i] = bias_prime[i];
+    h.gamma[i] = gamma3[i];
+    h.gamma2[i] = static_cast<float>(g * g);
+    h.beta[i] = beta3[i];
+    B1 += b; B2 += b * b; G2 += g * g; G2b2 += g * g * b * b; G2b += g * g * b;
+    Gbb += g * be * b; Gb += g * be; Bb += be * be;
+  }
+  h.B1 = static_cast<float>(B1); h.B2 = static_cast<float>(B2); h.G2 = static_cast<float>(G2);
+  h.G2b2 = static_cast<float>(G2b2); h.G2b = static_cast<float>(G2b); h.Gbb = static_cast<float>(Gbb);
+  h.Gb = static_cast<float>(Gb); h.Bb = static_cast<float>(Bb);
+  MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
+  MADE_CUDA(cudaStreamSynchronize(st));
+  return MADE_OK;
+}
+
+int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, op_t* gw, cudaStream_t st) {
+  if (rows == 0) return MADE_OK;
+  xpool_w5_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, st>>>(z, ldz, rows, gw);
+  MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
 
 // q [n_queries,256] fp16 (pre-scaled by 1/16), vhat fp16, kz [n_tracks*96, ldkz] fp16 with the K block
-// at column 0 and the Z'' block at column z_col, gram [n_tracks*96, 96] fp16.
+// at column 0 and the Z'' block at column z_col, gw [n_tracks*96, 112] fp16 = [G | W5 | 0].
 int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t* kz,
-                int64_t ldkz, int z_col, const op_t* gram, const uint32_t* maskbits,
+                int64_t ldkz, int z_col, const op_t* gw, const uint32_t* maskbits,
                 int64_t n_tracks, float* sim, int64_t ld, int64_t col_offset, cudaStream_t st) {
   if (n_queries == 0 || n_tracks == 0) return MADE_OK;
-  MADE_REQUIRE(q && vhat && kz && gram && maskbits && sim, "xpool_score: null pointer");
+  MADE_REQUIRE(q && vhat && kz && gw && maskbits && sim, "xpool_score: null pointer");
   MADE_REQUIRE(n_tracks * kXL < (1LL << 31), "xpool_score: too many tracks for one launch");
   static bool attr_set = false;
   if (!attr_set) {
@@ -337,7 +469,7 @@ int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t
   MADE_TRY(encode_tmap_2d_16b(&tq, q, kXD, static_cast<uint64_t>(n_queries), kXD * 2, 64, kXQ));
   MADE_TRY(encode_tmap_2d_16b(&tk, kz, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
   MADE_TRY(encode_tmap_2d_16b(&tz, kz + z_col, kXD, T, static_cast<uint64_t>(ldkz) * 2, 64, kXL));
-  MADE_TRY(encode_tmap_2d_16b(&tg, gram, kXL, T, kXL * 2, 64, kXL));
+  MADE_TRY(encode_tmap_2d_16b(&tg, gw, kXG, T, kXG * 2, 64, kXL));
   XpoolParams p;
   p.n_queries = n_queries;
   p.n_tracks = n_tracks;

@@ -143,7 +143,7 @@ class Engine:
         return seq, seq32, pooled
 
     def gallery_prepare(self, seg16: torch.Tensor, seg_masks: torch.Tensor, out=None):
-        """Per-track X-Pool operands: kz [N*96,768] fp16, gram [N*96,96] fp16, maskbits [N,4] int32.
+        """Per-track X-Pool operands: kz [N*96,768] fp16, gram [N*96,112] fp16 (= [G | W5 | 0]), maskbits [N,4] int32.
         `out=(kz, gram, bits)` writes into caller-provided (contiguous slices of) tensors."""
         N = seg16.shape[0]
         dev = seg16.device
@@ -153,7 +153,7 @@ class Engine:
             kz, gram, bits = out
         else:
             kz = torch.empty((N * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev)
-            gram = torch.empty((N * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev)
+            gram = torch.empty((N * cfg.L_M, cfg.XPOOL_G_COLS), dtype=torch.float16, device=dev)
             bits = torch.empty((N, 4), dtype=torch.int32, device=dev)
         masks = seg_masks.to(torch.float32).contiguous()
         _lib.check(self._lib.made_gallery_prepare(self._h, _lib.ptr(seg16.contiguous()), _lib.ptr(masks), N,

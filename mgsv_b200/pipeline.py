@@ -138,7 +138,7 @@ class GalleryEvaluator:
         return dict(seq=torch.empty((n, cfg.L_M, cfg.D_MODEL), dtype=torch.float16, device=dev),
                     pooled=torch.empty((n, cfg.D_MODEL), dtype=torch.float32, device=dev),
                     kz=torch.empty((n * cfg.L_M, 3 * cfg.D_MODEL), dtype=torch.float16, device=dev),
-                    gram=torch.empty((n * cfg.L_M, cfg.L_M), dtype=torch.float16, device=dev),
+                    gram=torch.empty((n * cfg.L_M, cfg.XPOOL_G_COLS), dtype=torch.float16, device=dev),
                     bits=torch.empty((n, 4), dtype=torch.int32, device=dev))
 
     def encode_gallery(self, segment_feats, segment_mask, on_chunk=None):

@@ -326,7 +326,8 @@ def test_detr_detection_vs_oracle(dev, engine, sd_fp32):
     om = O.calc_output(sd_fp32, hs, fo)
     r = engine.detr_detect(fo.to(torch.float16).to(dev), v["frame_mask"].to(dev), so.to(torch.float16).to(dev),
                            m["segment_mask"].to(dev), vf.to(dev), want_proj=True, want_memory=True)
-    assert _rel(r["memory"], memory) < ACT_RTOL
+    valid = mask.to(dev) != 0        # padded memory rows are never read by the decoder: not materialised here
+    assert _rel(r["memory"][valid], memory[mask != 0]) < ACT_RTOL
     assert _rel(r["hs"], hs[:, :, 0]) < ACT_RTOL
     np.testing.assert_allclose(r["pred_spans"][-1].cpu().numpy(), om["pred_spans"][:, 0].numpy(), atol=4e-4)
     np.testing.assert_allclose(r["pred_logits"][-1].cpu().numpy(), om["pred_logits"][:, 0].numpy(), atol=3e-3)
