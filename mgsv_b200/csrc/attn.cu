@@ -207,20 +207,40 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
   const int nv = s_nvalid;
   const op_t* mpb = mp + row0 * 256 + lane * 8;
   const op_t* memb = mem + row0 * 256 + lane * 8;
+  // 4 keys per step: four independent 16-byte loads and four interleaved butterflies in flight
   float mx = -INFINITY;
-  for (int i = 0; i < nv; ++i) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(mpb + vidx[i] * 256));
-    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
-    float acc = 0.f;
+  for (int i0 = 0; i0 < nv; i0 += 4) {
+    uint4 raw[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = op2_to_f2(hh[j]);
-      acc = fmaf(f.x, q[2 * j], acc);
-      acc = fmaf(f.y, q[2 * j + 1], acc);
+    for (int k = 0; k < 4; ++k) {
+      const int i = min(i0 + k, nv - 1);
+      raw[k] = __ldg(reinterpret_cast<const uint4*>(mpb + vidx[i] * 256));
     }
-    acc = warp_sum(acc);
-    if (lane == 0) sp[warp][i] = acc;
-    mx = fmaxf(mx, acc);
+    float acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw[k]);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = op2_to_f2(hh[j]);
+        a = fmaf(f.x, q[2 * j], a);
+        a = fmaf(f.y, q[2 * j + 1], a);
+      }
+      acc[k] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < nv) {
+        if (lane == 0) sp[warp][i0 + k] = acc[k];
+        mx = fmaxf(mx, acc[k]);
+      }
+    }
   }
   __syncwarp();
   float sum = 0.f;
@@ -232,15 +252,24 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
   sum = warp_sum(sum);
   __syncwarp();
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = 0; i < nv; ++i) {
-    const float a = sp[warp][i];
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(memb + vidx[i] * 256));
-    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
+  for (int i0 = 0; i0 < nv; i0 += 4) {
+    uint4 raw[4];
+    float a[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = op2_to_f2(hh[j]);
-      o[2 * j] = fmaf(a, f.x, o[2 * j]);
-      o[2 * j + 1] = fmaf(a, f.y, o[2 * j + 1]);
+    for (int k = 0; k < 4; ++k) {
+      const int i = min(i0 + k, nv - 1);
+      raw[k] = __ldg(reinterpret_cast<const uint4*>(memb + vidx[i] * 256));
+      a[k] = i0 + k < nv ? sp[warp][i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = op2_to_f2(hh[j]);
+        o[2 * j] = fmaf(a[k], f.x, o[2 * j]);
+        o[2 * j + 1] = fmaf(a[k], f.y, o[2 * j + 1]);
+      }
     }
   }
   const float inv = 1.f / sum;

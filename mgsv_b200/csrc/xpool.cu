@@ -11,8 +11,8 @@
 //   LN2 -> (I+Wl) + bl   = alpha Y + b',  Y = e Z'',  alpha = 1 / (l sigma2),  Z'' = V'' W'^T
 // and LN3 + the cosine with v_hat only need SUMS over the 256 features of alpha*Y + b':
 //   linear in Y with constant weights  (sum Y, sum b'Y, sum g^2 Y, sum g^2 b'Y, sum g*beta Y)
-//        = e . w_c with w_c = Z'' c per track  ->  five extra columns "W5" next to G, so the
-//          tensor core produces them in the same MMA as T = e G;
+//        = e . w_c with w_c = Z'' c per track  ->  extra columns "W5" next to G (each w_c as an fp16
+//          hi/lo pair), so the tensor core produces them in the same MMA as T = e G;
 //   quadratic / per-query terms        (sum Y^2, sum g^2 Y^2, sum u Y with u = v_hat*g)
 //        = one sweep over the Y accumulator, 4 flops per element.
 // Per pair the MMAs are S = q K^T (96), [T | L] = e [G | W5] (112) and Y = e Z'' (256):
@@ -341,7 +341,7 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           qf = fmaf(e.y, __uint_as_float(t1[2 * i + 1]), qf);
         }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) lin[i] = __uint_as_float(t2[i]);
+        for (int i = 0; i < 5; ++i) lin[i] = __uint_as_float(t2[i]) + __uint_as_float(t2[5 + i]);   // hi + lo
       }
       tc_fence_before_sync();
       mbar_arrive(t_free);
@@ -391,36 +391,42 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   }
 }
 
-// W5[t, :] = Z''[t, :] . {1, b', g^2, g^2 b', g beta}  -> columns 96..100 of the [G | W5 | 0] operand
-// (columns 101..111 are zeroed).  Warp per row.
+// W5[t, :] = Z''[t, :] . {1, b', g^2, g^2 b', g beta}, stored as an fp16 (hi, lo) pair per sum so that
+// the tensor core reproduces the five linear sums to fp32 accuracy: columns 96..100 = hi,
+// 101..105 = lo of the [G | W5 | 0] operand (106..111 zero).  Warp per row; the weight vectors live
+// in global memory (lane-indexed reads of __constant__ memory would serialise).
+__device__ float g_xp_c5[5][kXD];
+
 __global__ void xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __restrict__ gw) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const uint4 raw = *reinterpret_cast<const uint4*>(z + row * ldz + lane * 8);
   const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
-  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float zz[8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = op2_to_f2(hh[j]);
-    const float zz[2] = {f.x, f.y};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = lane * 8 + 2 * j + k;
-      const float g2 = c_xp.gamma2[i], b = c_xp.bias[i];
-      a[0] += zz[k];
-      a[1] = fmaf(zz[k], b, a[1]);
-      a[2] = fmaf(zz[k], g2, a[2]);
-      a[3] = fmaf(zz[k], g2 * b, a[3]);
-      a[4] = fmaf(zz[k], c_xp.gamma[i] * c_xp.beta[i], a[4]);
-    }
+    zz[2 * j] = f.x;
+    zz[2 * j + 1] = f.y;
   }
+  float a[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) a[k] = warp_sum(a[k]);
+  for (int k = 0; k < 5; ++k) {
+    const float4 c0 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8]);
+    const float4 c1 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8 + 4]);
+    float t = zz[0] * c0.x;
+    t = fmaf(zz[1], c0.y, t); t = fmaf(zz[2], c0.z, t); t = fmaf(zz[3], c0.w, t);
+    t = fmaf(zz[4], c1.x, t); t = fmaf(zz[5], c1.y, t); t = fmaf(zz[6], c1.z, t); t = fmaf(zz[7], c1.w, t);
+    a[k] = warp_sum(t);
+  }
   if (lane == 0) {
+    float lo[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lo[k] = a[k] - op2f(f2op(a[k]));
     uint4* o = reinterpret_cast<uint4*>(gw + row * kXG + kXL);
-    o[0] = make_uint4(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]), pack_op2(a[4], 0.f), 0u);
-    o[1] = make_uint4(0u, 0u, 0u, 0u);
+    o[0] = make_uint4(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]), pack_op2(a[4], lo[0]), pack_op2(lo[1], lo[2]));
+    o[1] = make_uint4(pack_op2(lo[3], lo[4]), 0u, 0u, 0u);
   }
 }
 
@@ -439,7 +445,17 @@ int xpool_set_constants(const float* bias_prime, const float* gamma3, const floa
   h.B1 = static_cast<float>(B1); h.B2 = static_cast<float>(B2); h.G2 = static_cast<float>(G2);
   h.G2b2 = static_cast<float>(G2b2); h.G2b = static_cast<float>(G2b); h.Gbb = static_cast<float>(Gbb);
   h.Gb = static_cast<float>(Gb); h.Bb = static_cast<float>(Bb);
+  static float c5[5][kXD];
+  for (int i = 0; i < kXD; ++i) {
+    const double b = bias_prime[i], g = gamma3[i], be = beta3[i];
+    c5[0][i] = 1.0f;
+    c5[1][i] = bias_prime[i];
+    c5[2][i] = static_cast<float>(g * g);
+    c5[3][i] = static_cast<float>(g * g * b);
+    c5[4][i] = static_cast<float>(g * be);
+  }
   MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
+  MADE_CUDA(cudaMemcpyToSymbolAsync(g_xp_c5, c5, sizeof(c5), 0, cudaMemcpyHostToDevice, st));
   MADE_CUDA(cudaStreamSynchronize(st));
   return MADE_OK;
 }
