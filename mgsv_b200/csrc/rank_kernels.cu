@@ -12,6 +12,7 @@
 // The row is staged once in shared memory (up to kMaxSmemCols columns; beyond that the passes
 // re-read global memory), so HBM traffic is the algorithmic 8 B per (query, track).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace made {
 
@@ -323,6 +324,38 @@ cosine_sim_kernel(const float* __restrict__ a, int64_t n, const float* __restric
     }
 }
 
+// Tensor-core route of the dual-tower cosine for 256-d embeddings: each L2-normalised fp32 row is
+// split into an fp16 (hi, lo) pair, x = hi + lo to ~2^-22, and  <x, y> ~= hi.hi' + hi.lo' + lo.hi'
+// is ONE K = 768 GEMM of [hi | hi | lo] against [hi' | lo' | hi'] with fp32 accumulation
+// (error ~1e-7, the dropped lo.lo' term is ~2^-24).  Warp per row.
+__global__ void cos_split_kernel(const float* __restrict__ x, int64_t rows, int is_track, op_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[8];
+  const float4* p = reinterpret_cast<const float4*>(x + row * 256 + lane * 8);
+  const float4 a = p[0], b = p[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s = fmaf(v[j], v[j], s);
+  const float nrm = sqrtf(warp_sum(s));
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = __fdiv_rn(v[2 * j], nrm), x1 = __fdiv_rn(v[2 * j + 1], nrm);
+    const op2_t h = floats2op2(x0, x1);
+    const float2 hf = op2_to_f2(h);
+    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[j] = pack_op2(x0 - hf.x, x1 - hf.y);
+  }
+  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]), L = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  uint4* o = reinterpret_cast<uint4*>(out + row * 768 + lane * 8);
+  o[0] = H;                          // columns   0..255
+  o[32] = is_track ? L : H;          // columns 256..511
+  o[64] = is_track ? H : L;          // columns 512..767
+}
+
 }  // namespace made
 
 using namespace made;
@@ -382,10 +415,34 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
                     int64_t ld, void* stream) {
   if (n == 0 || m == 0) return MADE_OK;
   MADE_REQUIRE(a && b && out && d > 0 && ld >= m, "cosine_sim: bad arguments");
-  dim3 grid(static_cast<unsigned>(ceil_div64(m, kCosTile)),
-            static_cast<unsigned>(ceil_div64(n, kCosTile)));
-  cosine_sim_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, n, b, m, d, out, ld);
-  MADE_CHECK_LAUNCH();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t m_tc = 0;
+  if (d == 256 && m >= 256 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // tcgen05 route for the columns that fill whole 256-wide tiles
+    m_tc = (m / 256) * 256;
+    op_t *a16 = nullptr, *b16 = nullptr;
+    MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&a16), static_cast<size_t>(n) * 768 * 2, st));
+    MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&b16), static_cast<size_t>(m_tc) * 768 * 2, st));
+    cos_split_kernel<<<static_cast<unsigned>(ceil_div64(n, 8)), 256, 0, st>>>(a, n, 0, a16);
+    MADE_CHECK_LAUNCH();
+    cos_split_kernel<<<static_cast<unsigned>(ceil_div64(m_tc, 8)), 256, 0, st>>>(b, m_tc, 1, b16);
+    MADE_CHECK_LAUNCH();
+    GemmParams p;
+    p.M = n;
+    p.N = static_cast<int>(m_tc);
+    p.K = 768;
+    p.epi.out_f32 = out;
+    p.epi.ld_f32 = ld;
+    int rc = gemm_f16_tc(a16, 768, b16, 768, m_tc, p, 256, st);
+    MADE_CUDA(cudaFreeAsync(a16, st));
+    MADE_CUDA(cudaFreeAsync(b16, st));
+    MADE_TRY(rc);
+  }
+  if (m_tc < m) {   // remaining columns (and every non-256-d call): fp32 SIMT tiles
+    dim3 grid(static_cast<unsigned>(ceil_div64(m - m_tc, kCosTile)), static_cast<unsigned>(ceil_div64(n, kCosTile)));
+    cosine_sim_kernel<<<grid, 256, 0, st>>>(a, n, b + m_tc * d, m - m_tc, d, out + m_tc, ld);
+    MADE_CHECK_LAUNCH();
+  }
   return MADE_OK;
 }
 

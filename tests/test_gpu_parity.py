@@ -209,6 +209,12 @@ def test_topk_merge_and_cosine(dev):
     np.testing.assert_allclose(got.cpu().numpy(), O.cal_distance_cos(x, y).numpy(), atol=1e-5, rtol=0)
     with pytest.raises(ValueError):
         ops.cal_distance(x.to(dev), y.to(dev), "L2")
+    # >= 256 gallery rows: tcgen05 route (fp16 hi/lo split, K = 768) + SIMT tail, still fp32-accurate
+    x, y = torch.randn(333, 256), torch.randn(600, 256)
+    got = ops.cal_distance(x.to(dev), y.to(dev))
+    ref = torch.nn.functional.normalize(x.double(), dim=1) @ torch.nn.functional.normalize(y.double(), dim=1).t()
+    np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), atol=2e-6, rtol=0)
+    np.testing.assert_allclose(got.cpu().numpy(), O.cal_distance_cos(x, y).numpy(), atol=2e-6, rtol=0)
 
 
 # ---------------------------------------------------------------------------------------------
