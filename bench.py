@@ -218,7 +218,11 @@ def main():
 
     def step(on_host: bool):
         if sharded is not None:
-            out = sharded.run(host_v if on_host else dev_v, host_m if on_host else dev_m, gt_col_d, nq, nm, on_host=on_host)
+            out = sharded.run(host_v if on_host else dev_v, host_m if on_host else dev_m, gt_col, nq, nm, on_host=on_host)
+            if not on_host:
+                # a step ends when its results exist: without this the host runs several steps ahead of
+                # the NCCL stream and the caching allocator starts growing instead of reusing blocks
+                torch.cuda.current_stream().synchronize()
         else:
             out = ev.run(host_v if on_host else dev_v, host_m if on_host else dev_m, gt_col, on_host=on_host)
         if on_host:
@@ -238,8 +242,13 @@ def main():
         ev.xpool_events = xp_events
         t_wall = time.perf_counter()
         e0.record()
+        trace = os.environ.get("MADE_BENCH_TRACE")
         for _ in range(steps):
+            ts = time.perf_counter()
             step(on_host)
+            if trace:
+                torch.cuda.synchronize()
+                sys.stderr.write(f"[trace rank {rank}] on_host={on_host} step wall {1e3 * (time.perf_counter() - ts):.2f} ms\n")
         e1.record()
         barrier()
         wall = time.perf_counter() - t_wall

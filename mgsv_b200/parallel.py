@@ -5,9 +5,11 @@ gallery is split into contiguous shards; the only exchange steps are tiny:
   1. all_gather of the query embeddings [N_v/G, 256] (each rank encodes its slice of the queries),
   2. all_reduce(MAX) of the ground-truth scores [N_v] f64 (the GT track lives on one shard),
   3. all_reduce(SUM) of the "ids ahead of the GT" counts [N_v] i32,
-  4. all_gather of the local top-k candidates [N_v, k] (score f64, global index i32) + merge kernel.
+  4. all_gather of the local top-k candidates [N_v, k] (score f64, global index i32) + merge kernel,
+  5. all_to_all of the paired tracks' encoded segments (planned on the host, no device sync).
 Moment detection shards by query; a query's paired track may live on another shard, so the encoded
-segments of the paired tracks are exchanged with one all_gather of [N_v/G, 96, 256] fp16 slices.
+segments of the paired tracks travel in one all_to_all of [*, 96, 256] fp16 rows (+ one of their
+masks / ground-truth moments) whose split sizes are planned on the host from the pairing.
 """
 from __future__ import annotations
 
@@ -35,22 +37,6 @@ def owner_of(col: torch.Tensor, n: int, world: int) -> torch.Tensor:
     return torch.where(col < big, col // max(base + 1, 1), rem + (col - big) // max(base, 1))
 
 
-def deliver_rows(send: torch.Tensor, sizes, rank: int, group=None) -> torch.Tensor:
-    """Each row of `send` [sum(sizes), ...] is non-zero on exactly one rank (its owner) and zero
-    elsewhere; rank r must end up with rows offs[r]:offs[r+1].  A SUM reduce-scatter does that in
-    one collective (NCCL); backends without reduce_scatter (gloo, CPU tests) all_reduce and slice."""
-    offs = [0]
-    for s_ in sizes:
-        offs.append(offs[-1] + s_)
-    if dist.get_backend(group) == "nccl":
-        recv = torch.empty((sizes[rank],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
-        dist.reduce_scatter(recv, [send[offs[r]:offs[r + 1]] for r in range(len(sizes))], group=group)
-        return recv
-    buf = send.clone()
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf[offs[rank]:offs[rank + 1]].contiguous()
-
-
 class ShardedEvaluator:
     """Strong-scaling evaluation of one (N_v queries x N_m tracks) job on `world` GPUs."""
 
@@ -62,21 +48,65 @@ class ShardedEvaluator:
         dist.all_gather(outs, t.contiguous(), group=self.group)
         return torch.cat(outs, 0)
 
+    def exchange_plan(self, gt_col, n_queries: int, n_tracks: int):
+        """Host-side plan of the paired-track exchange (no device sync): detection of query q runs on
+        the rank that owns q, its paired track gt_col[q] lives on the rank that owns that gallery
+        column.  Returns (send_loc [sum], in_splits [W], out_splits [W], perm [q1-q0]) where
+        send_loc are local track indices grouped by destination rank (query order inside a group),
+        and perm[i] is the position of my i-th query's row in the received buffer."""
+        import numpy as np
+        W, R = self.world, self.rank
+        gt = np.asarray(gt_col.cpu() if isinstance(gt_col, torch.Tensor) else gt_col, dtype=np.int64)
+        q_b = [shard_bounds(n_queries, r, W) for r in range(W)]
+        m_b = [shard_bounds(n_tracks, r, W) for r in range(W)]
+        m0, m1 = m_b[R]
+        send_loc, in_splits = [], []
+        for d in range(W):
+            g = gt[q_b[d][0]:q_b[d][1]]
+            mine = g[(g >= m0) & (g < m1)] - m0
+            send_loc.append(mine)
+            in_splits.append(int(mine.shape[0]))
+        g = gt[q_b[R][0]:q_b[R][1]]
+        starts = np.array([b[0] for b in m_b] + [n_tracks])
+        owner = np.searchsorted(starts, g, side="right") - 1
+        out_splits = [int((owner == s_).sum()) for s_ in range(W)]
+        # received rows are grouped by source rank, query order inside a group
+        order = np.argsort(owner, kind="stable")          # received position j holds query order[j]
+        perm = np.empty_like(order)
+        perm[order] = np.arange(order.shape[0])
+        return np.concatenate(send_loc) if send_loc else np.zeros(0, np.int64), in_splits, out_splits, perm
+
+    def _all_to_all_rows(self, send: torch.Tensor, in_splits, out_splits) -> torch.Tensor:
+        recv = torch.empty((sum(out_splits),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send.contiguous(), out_splits, in_splits, group=self.group)
+        return recv
+
     @torch.no_grad()
     def run(self, videos: Dict[str, torch.Tensor], tracks: Dict[str, torch.Tensor], gt_col: torch.Tensor,
             n_queries: int, n_tracks: int, on_host: bool = False):
         """`videos` holds THIS rank's slice of the queries, `tracks` THIS rank's gallery shard
-        (features, masks, gt_moment, m_duration); gt_col [n_queries] are GLOBAL column indices."""
+        (features, masks, gt_moment, m_duration); gt_col [n_queries] are GLOBAL column indices
+        (pass a CPU tensor: the exchange plan is made on the host without a device sync)."""
         ev, dev, W, R = self.ev, self.ev.dev, self.world, self.rank
         ev.launches = 0
+        ev._keep = []
         q0, q1 = shard_bounds(n_queries, R, W)
         m0, m1 = shard_bounds(n_tracks, R, W)
         q_sizes = [shard_bounds(n_queries, r, W)[1] - shard_bounds(n_queries, r, W)[0] for r in range(W)]
+        send_loc, in_splits, out_splits, perm = self.exchange_plan(gt_col, n_queries, n_tracks)
+        send_loc_d = torch.from_numpy(send_loc).to(dev, non_blocking=True)
+        perm_d = torch.from_numpy(perm).to(dev, non_blocking=True)
         frame_seq, vf_local, frame_mask = ev.encode_queries(videos["frame_feats"], videos["frame_mask"])
         gal = ev.encode_gallery(tracks["segment_feats"], tracks["segment_mask"])
+        # ---- exchange 5 (issued early): every query's paired track -> the rank that detects it ----
+        gtm = tracks["gt_moment"].to(dev, non_blocking=True).reshape(-1, 2).to(torch.float32)
+        mdur = tracks["m_duration"].to(dev, non_blocking=True).to(torch.float32)
+        aux = torch.cat([gal["mask"], gtm, mdur.unsqueeze(1)], 1)                  # [n_local, 96 + 3]
+        recv_seq = self._all_to_all_rows(gal["seq"][send_loc_d], in_splits, out_splits)[perm_d]
+        recv_aux = self._all_to_all_rows(aux[send_loc_d], in_splits, out_splits)[perm_d]
         video_feats = self._all_gather_cat(vf_local, q_sizes)                      # exchange 1
         single, dual = ev.score(video_feats, gal)
-        gt = gt_col.to(dev).to(torch.int32)
+        gt = (gt_col if gt_col.device == dev else gt_col.to(dev, non_blocking=True)).to(torch.int32)
         local_gt = torch.where((gt >= m0) & (gt < m1), gt - m0, torch.full_like(gt, -1))
         r1 = ops.rank_topk(single, dual, local_gt, None, k=0)
         ev._count("rank")
@@ -92,22 +122,9 @@ class ShardedEvaluator:
         dist.all_gather(cand_i, r2["topk_idx"], group=self.group)
         topk_idx, topk_score = ops.topk_merge(torch.cat(cand_s, 1), torch.cat(cand_i, 1), ev.k)
         ev.launches += 1
-        # ---- detection for this rank's queries; fetch the paired tracks' encoded segments ----
-        all_need = gt.long()                       # every rank knows the global pairing
-        sel = (all_need >= m0) & (all_need < m1)
-        loc = all_need[sel] - m0
-        send = torch.zeros((n_queries, cfg.L_M, cfg.D_MODEL), dtype=gal["seq"].dtype, device=dev)
-        send_mask = torch.zeros((n_queries, cfg.L_M), dtype=torch.float32, device=dev)
-        send_meta = torch.zeros((n_queries, 3), dtype=torch.float32, device=dev)
-        send[sel] = gal["seq"][loc]
-        send_mask[sel] = gal["mask"][loc]
-        gtm = tracks["gt_moment"].to(dev).reshape(-1, 2)
-        send_meta[sel] = torch.cat([gtm[loc], tracks["m_duration"].to(dev)[loc].unsqueeze(1)], 1)
-        recv = deliver_rows(send, q_sizes, R, self.group)                          # exchange 5
-        recv_mask = deliver_rows(send_mask, q_sizes, R, self.group)
-        recv_meta = deliver_rows(send_meta, q_sizes, R, self.group)
-        pair = dict(seq=recv, mask=recv_mask)
+        # ---- detection for this rank's queries on the received tracks ----
+        pair = dict(seq=recv_seq, mask=recv_aux[:, :cfg.L_M].contiguous())
         det = ev.detect(frame_seq, frame_mask, pair, vf_local,
                         torch.arange(q1 - q0, dtype=torch.int32, device=dev),
-                        recv_meta[:, :2].contiguous(), recv_meta[:, 2].contiguous())
+                        recv_aux[:, cfg.L_M:cfg.L_M + 2].contiguous(), recv_aux[:, cfg.L_M + 2].contiguous())
         return dict(rank=rank_cnt, topk_idx=topk_idx, topk_score=topk_score, q_range=(q0, q1), **det)
