@@ -214,15 +214,18 @@ def main():
     eng = Engine(dev)
     eng.load_state_dict(synth.make_state_dict(0))
     ev = GalleryEvaluator(eng, k=TOPK, music_chunk=args.chunk, video_chunk=args.chunk)
+    if "MADE_H2D" not in os.environ:
+        # one process per box: spend the idle host cores on rounding the features to fp16 before they
+        # cross PCIe; with several ranks sharing the host the plain fp32 DMA is the better trade
+        ev.h2d_mode = "dma16" if world == 1 else "dma"
     sharded = ShardedEvaluator(ev, rank, world) if world > 1 else None
 
     def step(on_host: bool):
         if sharded is not None:
             out = sharded.run(host_v if on_host else dev_v, host_m if on_host else dev_m, gt_col, nq, nm, on_host=on_host)
-            if not on_host:
-                # a step ends when its results exist: without this the host runs several steps ahead of
-                # the NCCL stream and the caching allocator starts growing instead of reusing blocks
-                torch.cuda.current_stream().synchronize()
+            # a step ends when its results exist on every stream: without this the host runs ahead of the
+            # NCCL / ingest streams and steps start to interleave pathologically (measured: 3x slower)
+            torch.cuda.synchronize()
         else:
             out = ev.run(host_v if on_host else dev_v, host_m if on_host else dev_m, gt_col, on_host=on_host)
         if on_host:
@@ -288,15 +291,18 @@ def main():
         # bytes that actually cross PCIe: the ingest kernel reads only the rows whose mask is 1
         small = sum(host_v[k].numel() * 4 for k in ("frame_mask",)) + \
             sum(host_m[k].numel() * host_m[k].element_size() for k in ("segment_mask", "gt_moment", "m_duration")) + gt_col.numel() * 4
-        h2d = int(host_v["frame_mask"].sum().item()) * 512 * 4 + int(host_m["segment_mask"].sum().item()) * 768 * 4 + small
+        esz = 2 if ev.h2d_mode == "dma16" else 4
+        h2d = int(host_v["frame_mask"].sum().item()) * 512 * esz + int(host_m["segment_mask"].sum().item()) * 768 * esz + small
         d2h = nq * (4 + TOPK * 4 + 4 * 4)
         e2e = {"value": nq / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h),
                "h2d_bytes_if_padded_rows_were_copied": int(h2d_padded * world),
                "h2d_link_gbs_measured": link_gbs, "h2d_mode": ev.h2d_mode,
                "h2d_bound_ms": (h2d / (link_gbs * 1e9) * 1e3) if link_gbs else None,
-               "host_dtype": "f32 features (reference-facing dtype) in pinned host memory; only the valid rows "
-                             "cross PCIe (copy engines, one batched copy per chunk)"}
+               "host_dtype": "f32 features (reference-facing dtype) in pinned host memory; only the valid rows cross "
+                             "PCIe (copy engines, one batched copy per chunk)" +
+                             ("; rounded to fp16 by host threads first" if ev.h2d_mode == "dma16" else ""),
+               "host_threads": ev.host_threads if ev.h2d_mode == "dma16" else 0}
 
     # roofline of the dominant kernel: fused X-Pool scoring (tensor bound), timed with CUDA events on
     # the launching stream inside the timed region

@@ -138,9 +138,15 @@ int made_ingest_ragged(const void* feats, int feats_dtype, const made_ragged* rb
  * sequence the rows [0, last row with mask != 0] are copied to the same offsets of dev_staging
  * [B, L, dim] by the copy engines (one batched cudaMemcpyBatchAsync, no SM involved); the other
  * rows of dev_staging are left untouched and must be treated as garbage (made_encode /
- * made_ingest_ragged never read rows whose mask is 0).  bytes_copied (nullable) = bytes queued. */
+ * made_ingest_ragged never read rows whose mask is 0).  bytes_copied (nullable) = bytes queued.
+ * host_stage16 (nullable): a pinned host fp16 tensor of the same [B, L, dim] shape.  When given
+ * (fp32 features only) n_threads host threads first round the valid rows to fp16 into it — the
+ * same rounding the ingest kernel would apply on the device — and the fp16 rows are what crosses
+ * PCIe; dev_staging is then an fp16 [B, L, dim] tensor.  The caller must not reuse host_stage16
+ * before the copies queued here have completed. */
 int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
-                        int dim, void* dev_staging, int64_t* bytes_copied, void* stream);
+                        int dim, void* host_stage16, int n_threads, void* dev_staging, int64_t* bytes_copied,
+                        void* stream);
 
 /* forward_{video,audio}_encoder_feature (model_Base.py:544-617): feats [B,L,Din] (fp32, bf16 or fp16; rows with mask 0 are
  * never read),

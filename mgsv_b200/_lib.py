@@ -41,7 +41,7 @@ SIGNATURES = {
     "made_ctx_create": [C.POINTER(_p), _i32],
     "made_ctx_destroy": [_p],
     "made_ctx_load_weights": [_p, _i32, C.POINTER(C.c_char_p), C.POINTER(_p), C.POINTER(_i64), _p],
-    "made_h2d_valid_rows": [_p, _i32, _p, _i64, _i32, _i32, _p, C.POINTER(_i64), _p],
+    "made_h2d_valid_rows": [_p, _i32, _p, _i64, _i32, _i32, _p, _i32, _p, C.POINTER(_i64), _p],
     "made_ragged_build": [_p, _i64, _i32, _p, C.POINTER(Ragged), _p],
     "made_ingest_ragged": [_p, _i32, C.POINTER(Ragged), _i32, _p, _p],
     "made_encode": [_p, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p],

@@ -2,8 +2,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
+
+#include <immintrin.h>
 
 #include "common.cuh"
 
@@ -75,6 +80,95 @@ int sm_count() {
   return n;
 }
 
+// ---- small persistent host thread pool (fp32 -> fp16 conversion of host features) -----------------
+class HostPool {
+ public:
+  explicit HostPool(int n) : n_(n < 1 ? 1 : n) {
+    for (int i = 1; i < n_; ++i) workers_.emplace_back([this, i] { loop(i); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return n_; }
+  // runs fn(worker_index) on every worker (the caller is worker 0) and waits for all of them
+  void run(const std::function<void(int)>& fn) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &fn;
+      pending_ = n_ - 1;
+      ++gen_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int idx) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(idx);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+static HostPool* host_pool(int n_threads) {
+  static std::mutex m;
+  static HostPool* pool = nullptr;
+  std::lock_guard<std::mutex> g(m);
+  if (!pool || pool->size() != n_threads) {
+    delete pool;
+    pool = new HostPool(n_threads);
+  }
+  return pool;
+}
+
+// fp32 -> IEEE fp16, round to nearest even, saturating at +-65504 (same as the device's cvt.rn.satfinite)
+__attribute__((target("avx2,f16c"))) static void cvt_f32_f16(const float* src, uint16_t* dst, size_t n) {
+  const __m256 lim = _mm256_set1_ps(65504.0f), nlim = _mm256_set1_ps(-65504.0f);
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    __m256 a = _mm256_loadu_ps(src + i), b = _mm256_loadu_ps(src + i + 8);
+    a = _mm256_max_ps(_mm256_min_ps(a, lim), nlim);
+    b = _mm256_max_ps(_mm256_min_ps(b, lim), nlim);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm256_cvtps_ph(a, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i + 8), _mm256_cvtps_ph(b, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+  }
+  for (; i < n; ++i) {
+    float f = src[i];
+    f = f > 65504.0f ? 65504.0f : (f < -65504.0f ? -65504.0f : f);
+    dst[i] = _cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+  }
+}
+
 }  // namespace made
 
 extern "C" {
@@ -84,7 +178,8 @@ const char* made_last_error_string(void) { return made::g_err; }
 int made_abi_version(void) { return MADE_ABI_VERSION; }
 
 int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
-                        int dim, void* dev_staging, int64_t* bytes_copied, void* stream) {
+                        int dim, void* host_stage16, int n_threads, void* dev_staging, int64_t* bytes_copied,
+                        void* stream) {
   using namespace made;
   if (bytes_copied) *bytes_copied = 0;
   if (B == 0) return MADE_OK;
@@ -92,6 +187,8 @@ int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* ho
   MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "h2d_valid_rows: bad dtype %d",
                feats_dtype);
   MADE_REQUIRE(L > 0 && dim > 0, "h2d_valid_rows: bad shape");
+  const bool convert = host_stage16 != nullptr;
+  MADE_REQUIRE(!convert || feats_dtype == MADE_DTYPE_F32, "h2d_valid_rows: host fp16 conversion needs fp32 features");
   const size_t esz = feats_dtype == MADE_DTYPE_F32 ? 4 : 2;
   const size_t row = static_cast<size_t>(dim) * esz, seq = row * static_cast<size_t>(L);
   // one copy per sequence: rows [0, last valid row]; runs of fully valid sequences are merged
@@ -118,8 +215,41 @@ int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* ho
     total += bytes;
     open = (n == L);
   }
-  if (bytes_copied) *bytes_copied = static_cast<int64_t>(total);
   if (dsts.empty()) return MADE_OK;
+  if (convert) {
+    // The host threads round the valid rows to fp16 into the pinned staging tensor (same [B, L, dim]
+    // layout), which halves the bytes that cross PCIe; the copy list is rewritten to move the fp16 rows.
+    const size_t n_el = total / 4;
+    HostPool* pool = host_pool(n_threads < 1 ? 1 : n_threads);
+    const int W = pool->size();
+    const size_t per = ((n_el + W - 1) / W + 15) & ~size_t(15);
+    char* stage = static_cast<char*>(host_stage16);
+    const std::vector<void*>& srcs_c = srcs;
+    const std::vector<size_t>& sizes_c = sizes;
+    pool->run([&](int w) {
+      size_t lo = static_cast<size_t>(w) * per, hi = lo + per;
+      if (hi > n_el) hi = n_el;
+      size_t pos = 0;   // element offset of copy i inside the concatenation of all copies
+      for (size_t i = 0; i < srcs_c.size() && pos < hi; ++i) {
+        const size_t cnt = sizes_c[i] / 4;
+        if (pos + cnt > lo) {
+          const size_t a = lo > pos ? lo - pos : 0, b = (hi - pos < cnt) ? hi - pos : cnt;
+          const float* s0 = static_cast<const float*>(srcs_c[i]);
+          const size_t off_el = static_cast<size_t>(static_cast<const char*>(srcs_c[i]) - hsrc) / 4;
+          cvt_f32_f16(s0 + a, reinterpret_cast<uint16_t*>(stage) + off_el + a, b - a);
+        }
+        pos += cnt;
+      }
+    });
+    for (size_t i = 0; i < srcs.size(); ++i) {
+      const size_t off = static_cast<size_t>(static_cast<char*>(srcs[i]) - hsrc);
+      srcs[i] = stage + off / 2;
+      dsts[i] = ddst + off / 2;
+      sizes[i] /= 2;
+    }
+    total /= 2;
+  }
+  if (bytes_copied) *bytes_copied = static_cast<int64_t>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaMemcpyAttributes attr;
   memset(&attr, 0, sizeof(attr));

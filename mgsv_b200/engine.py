@@ -58,22 +58,31 @@ class Engine:
         self.loaded = True
 
     # -----------------------------------------------------------------------------------------
-    def h2d_valid_rows(self, feats_host: torch.Tensor, masks_host: torch.Tensor, out: torch.Tensor) -> int:
+    def h2d_valid_rows(self, feats_host: torch.Tensor, masks_host: torch.Tensor, out: torch.Tensor,
+                       host_stage16: Optional[torch.Tensor] = None, n_threads: int = 1) -> int:
         """Copy-engine transfer of the valid rows of a zero-padded host feature tensor [B,L,dim]
-        (pinned) into the device staging tensor `out` of the same shape/dtype; rows whose mask is 0
-        are not transferred (and are garbage in `out`).  Returns the bytes queued."""
+        (pinned) into the device staging tensor `out`; rows whose mask is 0 are not transferred (and
+        are garbage in `out`).  With `host_stage16` (pinned fp16 [B,L,dim]) the host threads round the
+        valid rows to fp16 first and `out` is an fp16 tensor: half the PCIe bytes.  Returns the bytes
+        queued."""
         if feats_host.is_cuda or masks_host.is_cuda or not out.is_cuda:
             raise ValueError("h2d_valid_rows: host features + host masks -> device staging")
-        if feats_host.shape != out.shape or feats_host.dtype != out.dtype:
-            raise ValueError("h2d_valid_rows: staging must match the host tensor's shape and dtype")
+        want = torch.float16 if host_stage16 is not None else feats_host.dtype
+        if feats_host.shape != out.shape or out.dtype != want:
+            raise ValueError("h2d_valid_rows: staging must match the host tensor's shape (and dtype)")
+        if host_stage16 is not None and (host_stage16.shape != feats_host.shape or host_stage16.dtype != torch.float16
+                                         or not host_stage16.is_pinned() or feats_host.dtype != torch.float32):
+            raise ValueError("h2d_valid_rows: host_stage16 must be a pinned fp16 tensor shaped like the fp32 features")
         dt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}.get(feats_host.dtype)
         if dt is None:
             raise ValueError(f"unsupported feature dtype {feats_host.dtype}")
         B, L, dim = feats_host.shape
         m = masks_host.to(torch.float32).contiguous()
         n = C.c_int64(0)
-        _lib.check(self._lib.made_h2d_valid_rows(feats_host.contiguous().data_ptr(), dt, m.data_ptr(), B, L, dim,
-                                                 _lib.ptr(out), C.byref(n), _lib.stream_ptr()))
+        _lib.check(self._lib.made_h2d_valid_rows(
+            feats_host.contiguous().data_ptr(), dt, m.data_ptr(), B, L, dim,
+            None if host_stage16 is None else host_stage16.data_ptr(), int(n_threads), _lib.ptr(out), C.byref(n),
+            _lib.stream_ptr()))
         return int(n.value)
 
     def ragged(self, masks: torch.Tensor):

@@ -39,8 +39,12 @@ class GalleryEvaluator:
         self.detr_chunk = detr_chunk
         self.ingest_stream = torch.cuda.Stream(device=self.dev)
         # host inputs: "dma" = copy engines move the valid rows into a device staging buffer (no SM
-        # involved, overlaps any kernel); "zerocopy" = the ingest kernel reads pinned host memory in place
+        # involved, overlaps any kernel); "dma16" = host threads round the valid rows to fp16 first (half
+        # the PCIe bytes; worth it when one process has the host cores to itself); "zerocopy" = the
+        # ingest kernel reads pinned host memory in place
         self.h2d_mode = os.environ.get("MADE_H2D", "dma")
+        self.host_threads = max(1, min(16, (os.cpu_count() or 1)))
+        self._hstage = {}           # (modality, slot) -> (pinned fp16 host staging, event of its last DMA)
         self.h2d_bytes = 0          # bytes queued for host->device transfer by the last run (dma mode)
         self._raw = {}              # (modality, slot) -> raw-dtype device staging buffer of one chunk (dma mode)
         self._stage = {}            # (modality, slot) -> fp16 staging buffer of one chunk
@@ -91,12 +95,26 @@ class GalleryEvaluator:
                     self.ingest_stream.wait_event(free)
                 rb, keep = self.eng.ragged(mask_d[s:e])
                 src = feats[s:e]
-                if not feats.is_cuda and self.h2d_mode == "dma":
+                if not feats.is_cuda and self.h2d_mode in ("dma", "dma16"):
+                    to16 = self.h2d_mode == "dma16" and feats.dtype == torch.float32
+                    raw_dt = torch.float16 if to16 else feats.dtype
                     raw = self._raw.get(key)
-                    if raw is None or raw.shape[0] < e - s or raw.dtype != feats.dtype:
-                        raw = torch.empty((max(chunk, e - s), L, din), dtype=feats.dtype, device=self.dev)
+                    if raw is None or raw.shape[0] < e - s or raw.dtype != raw_dt:
+                        raw = torch.empty((max(chunk, e - s), L, din), dtype=raw_dt, device=self.dev)
                         self._raw[key] = raw
-                    self.h2d_bytes += self.eng.h2d_valid_rows(src, mask_h[s:e], raw[:e - s])
+                    hs = None
+                    if to16:
+                        hs, hs_ev = self._hstage.get(key, (None, None))
+                        if hs is None or hs.shape[0] < e - s:
+                            hs = torch.empty((max(chunk, e - s), L, din), dtype=torch.float16).pin_memory()
+                        elif hs_ev is not None:
+                            hs_ev.synchronize()      # the previous DMA out of this staging tensor is done
+                    self.h2d_bytes += self.eng.h2d_valid_rows(src, mask_h[s:e], raw[:e - s],
+                                                              None if hs is None else hs[:e - s], self.host_threads)
+                    if to16:
+                        hs_ev = torch.cuda.Event()
+                        hs_ev.record(self.ingest_stream)
+                        self._hstage[key] = (hs, hs_ev)
                     src = raw[:e - s]
                 x16 = buf[:(e - s) * L]
                 self.eng.ingest(modality, src, rb, out=x16)

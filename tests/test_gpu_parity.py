@@ -524,3 +524,36 @@ def test_h2d_valid_rows_copies_exactly_the_valid_prefixes(dev, engine):
     for b in range(B):
         assert torch.equal(stage[b, :last[b]].cpu(), feats[b, :last[b]])
         assert bool((stage[b, last[b]:] == -1).all())
+
+
+def test_h2d_valid_rows_with_host_fp16_rounding(dev, engine):
+    B, L, dim = 23, 50, 512
+    g = torch.Generator().manual_seed(10)
+    feats = (torch.randn(B, L, dim, generator=g) * 3).pin_memory()
+    feats[0, 0, :4] = torch.tensor([1e6, -1e6, 65504.0, 6e-8])          # saturation + subnormal
+    n = torch.randint(1, L + 1, (B,), generator=g)
+    n[1], n[2] = L, L
+    mask = (torch.arange(L)[None] < n[:, None]).float()
+    hs = torch.zeros((B, L, dim), dtype=torch.float16).pin_memory()
+    stage = torch.full((B, L, dim), -1.0, dtype=torch.float16, device=dev)
+    for threads in (1, 5, 16):
+        nbytes = engine.h2d_valid_rows(feats, mask, stage, hs, threads)
+        torch.cuda.synchronize()
+        assert nbytes == int(n.sum()) * dim * 2
+        ref = feats.clamp(-65504.0, 65504.0).to(torch.float16)           # RNE, saturating like cvt.rn.satfinite
+        for b in range(B):
+            assert torch.equal(stage[b, :n[b]].cpu(), ref[b, :n[b]]), (threads, b)
+            assert bool((stage[b, n[b]:] == -1).all())
+    # and the whole job gives bit-identical results through either host path
+    from mgsv_b200.pipeline import GalleryEvaluator
+    v, m, ids = synth.make_eval_set(40, 70, synth.BASE_SEED + 11)
+    hv = {k: t.pin_memory() for k, t in v.items()}
+    hm = {k: t.pin_memory() for k, t in m.items()}
+    gt = torch.arange(40, dtype=torch.int32)
+    outs = []
+    for mode in ("dma", "dma16", "zerocopy"):
+        ev = GalleryEvaluator(engine, k=10, music_chunk=32, video_chunk=16)
+        ev.h2d_mode = mode
+        outs.append(ev.to_host(ev.run(hv, hm, gt, on_host=True)))
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k]), k
