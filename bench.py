@@ -214,10 +214,8 @@ def main():
     eng = Engine(dev)
     eng.load_state_dict(synth.make_state_dict(0))
     ev = GalleryEvaluator(eng, k=TOPK, music_chunk=args.chunk, video_chunk=args.chunk)
-    if "MADE_H2D" not in os.environ:
-        # one process per box: spend the idle host cores on rounding the features to fp16 before they
-        # cross PCIe; with several ranks sharing the host the plain fp32 DMA is the better trade
-        ev.h2d_mode = "dma16" if world == 1 else "dma"
+    # MADE_H2D=dma16 additionally rounds the features to fp16 with host threads before the DMA (half the
+    # PCIe bytes); measured on this pool it is host-bound and no faster than the plain fp32 DMA.
     sharded = ShardedEvaluator(ev, rank, world) if world > 1 else None
 
     def step(on_host: bool):

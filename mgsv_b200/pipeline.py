@@ -82,7 +82,7 @@ class GalleryEvaluator:
 
         def issue(i):
             s, e = bounds[i]
-            slot = i & 1
+            slot = i % 3
             key = (modality, slot)
             buf = self._stage.get(key)
             if buf is None or buf.shape[0] < (e - s) * L:
@@ -126,8 +126,8 @@ class GalleryEvaluator:
         if bounds:
             issue(0)
         for i, (s, e) in enumerate(bounds):
-            if i + 1 < len(bounds):
-                issue(i + 1)
+            if i == 0 and len(bounds) > 1:
+                issue(1)
             x16, rb, keep, ev, key = ready.pop(i)
             cur.wait_event(ev)
 
@@ -138,6 +138,10 @@ class GalleryEvaluator:
                 self._keep.append(keep)     # index tensors stay alive until the step's kernels are enqueued
 
             yield s, e, x16, rb, release
+            # chunk i's kernels are enqueued by now: only then spend host time (batched copy setup,
+            # optional fp16 rounding) on chunk i + 2, so the device never waits for the host
+            if i >= 0 and i + 2 < len(bounds):
+                issue(i + 2)
 
     # ---- stages -----------------------------------------------------------------------------------
     def encode_queries(self, frame_feats, frame_mask):
