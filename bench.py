@@ -41,7 +41,7 @@ F_TOTAL_JOB = 5.54e12
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="made_b200", choices=["made_b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES)
@@ -138,7 +138,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -267,7 +267,6 @@ def main():
     xp_events = []
     ms_dev, _ = timed(False, args.steps, max(args.warmup, 3), xp_events)
     launches = ev.launches
-    clocks = sampler.stop()
     e2e = None
     link_gbs = None
     if not args.no_e2e:
@@ -302,6 +301,7 @@ def main():
                              ("; rounded to fp16 by host threads first" if ev.h2d_mode == "dma16" else ""),
                "host_threads": ev.host_threads if ev.h2d_mode == "dma16" else 0}
 
+    clocks = sampler.stop()      # sampled over both timed regions (device-resident and e2e)
     # roofline of the dominant kernel: fused X-Pool scoring (tensor bound), timed with CUDA events on
     # the launching stream inside the timed region
     torch.cuda.synchronize()
@@ -312,6 +312,20 @@ def main():
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    # DRAM traffic of the same launch shape from the committed `ncu --set full` capture (profiles/)
+    traffic, traffic_src = None, None
+    cap = os.path.join(REPO, "profiles", "r01_g_xpool_v2_ncu_full_raw.csv")
+    if os.path.exists(cap) and xp_pairs:
+        import csv
+        rows = list(csv.reader(open(cap)))
+        col = {h: i for i, h in enumerate(rows[0])}
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(rows[2][col[key]].replace(",", "")) * unit[rows[1][col[key]]]
+        cap_pairs = 2000 * 512          # the capture's launch: 2000 queries x 512 tracks
+        traffic = tot * float(np.mean(xp_pairs)) / cap_pairs
+        traffic_src = "profiles/r01_g_xpool_v2_ncu_full_raw.csv (2000 x 512 launch), scaled by pairs per launch"
     roofline = None
     if xp_ms:
         t_s = float(np.mean(xp_ms)) / 1e3                  # average launch duration
@@ -319,7 +333,7 @@ def main():
         launches_per_step = len(xp_ms) / args.steps
         ach = F_XPOOL_PAIR * pairs / t_s / 1e12
         roofline = {"kernel": "xpool_score_kernel", "bound": "tensor", "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                     "kernel_ms": t_s * 1e3, "launches_per_step": launches_per_step,
                     "share_of_step": t_s * 1e3 * launches_per_step / ms_dev,

@@ -3,9 +3,10 @@
 // model_Base.py:87 and music_detr/transformer.py:196.
 //
 // These are ~5-9 % of the path's FLOPs in 32-wide heads, too small for a 128-row tcgen05 tile, so
-// one warp owns one (sequence, head): K and V^T head slices live in padded shared memory
-// (conflict-free fragment loads), scores stay in registers (whole row, no online softmax), and the
-// two products run on mma.sync m16n8k16 fp16 with fp32 accumulation.
+// one warp owns one (sequence, head): the K and V head slices live row-major in padded shared memory
+// (80-byte rows: conflict-free 16-byte stores, fragment loads and ldmatrix.trans), scores stay in
+// registers (whole row, no online softmax), and the two products run on mma.sync m16n8k16 fp16 with
+// fp32 accumulation.
 // The decoder's single-query cross-attention (1 x 146 per head) is a separate SIMT kernel that
 // works on the memory itself (K/V projections folded into the query side).
 #include "common.cuh"
@@ -27,10 +28,17 @@ constexpr int kKStride = 40;  // fp16 elements per K row in smem (80 B: conflict
 
 template <int LP>  // padded length, multiple of 16
 struct AttnSmem {
-  static constexpr int kVStride = LP + 8;  // (LP+8)/2 words == 4 or 20 (mod 32): conflict-free
-  static constexpr int kPerWarp = LP * kKStride + kHeadDim * kVStride;  // fp16 elements
+  static constexpr int kPerWarp = 2 * LP * kKStride;  // K and V head slices, both [key][32 (+8 pad)] fp16
   static constexpr int kBytes = kHeadsPerCta * kPerWarp * 2 + LP * 4;
 };
+
+// B fragments of P.V straight from the row-major V slice: two transposed 8x8 tiles (keys 0-7 / 8-15
+// of the k-step, 8 head dims) -> {b0, b1} of mma.m16n8k16.  Lanes 0-15 supply the row addresses.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&b)[2], const op_t* row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(b[0]), "=r"(b[1])
+               : "r"(smem_u32(row_ptr)));
+}
 
 template <int LP>
 __global__ void __launch_bounds__(kHeadsPerCta * 32)
@@ -48,7 +56,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   const int64_t b = blockIdx.x;
   const int h = blockIdx.y * kHeadsPerCta + warp;
   op_t* Ks = reinterpret_cast<op_t*>(attn_smem) + warp * S::kPerWarp;
-  op_t* Vt = Ks + LP * kKStride;
+  op_t* Vs = Ks + LP * kKStride;
   float* smask = reinterpret_cast<float*>(attn_smem + kHeadsPerCta * S::kPerWarp * 2);
   const int L = seq_off ? min(seq_len[b], LP) : L_in;
   const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L_in;
@@ -57,7 +65,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   for (int i = threadIdx.x; i < LP; i += blockDim.x)
     smask[i] = (i < L && (seq_off != nullptr || key_mask[row0 + i] != 0.f)) ? 0.f : -INFINITY;
 
-  // ---- stage K (row-major) and V (transposed) head slices; rows >= L are zero ----
+  // ---- stage the K and V head slices (row-major); rows >= L are zero ----
   const op_t* Kg = K + row0 * ldk + h * kHeadDim;
   const op_t* Vg = V + row0 * ldv + h * kHeadDim;
   const int n_nt = (L + 7) >> 3, n_kk = (L + 15) >> 4;   // key tiles that hold at least one real key
@@ -69,9 +77,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
       vv = __ldg(reinterpret_cast<const uint4*>(Vg + key * ldv + ch * 8));
     }
     *reinterpret_cast<uint4*>(Ks + key * kKStride + ch * 8) = kv;
-    const op_t* ve = reinterpret_cast<const op_t*>(&vv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) Vt[(ch * 8 + j) * S::kVStride + key] = ve[j];
+    *reinterpret_cast<uint4*>(Vs + key * kKStride + ch * 8) = vv;
   }
   __syncthreads();
 
@@ -147,9 +153,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
       for (int kk = 0; kk < KK; ++kk) {
         if (kk >= n_kk) continue;     // all-zero probabilities
         uint32_t vb[2];
-        const op_t* vp = Vt + (nd * 8 + g) * S::kVStride + kk * 16 + 2 * t;
-        vb[0] = *reinterpret_cast<const uint32_t*>(vp);
-        vb[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
+        ldmatrix_x2_trans(vb, Vs + (kk * 16 + (lane & 15)) * kKStride + nd * 8);
         mma_f16_16816(o[nd], pa[kk], vb);
       }
     }
@@ -168,22 +172,35 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 // per-layer K/V projections of the memory folded into the query side (api.cu load_detr):
 //   scores_h[t] = q~_h . (memory + pos)_t          q~ [B, 8*256] fp32 (includes 1/sqrt(32))
 //   mbar_h      = sum_t softmax_t(scores_h)[t] * memory_t   -> out [B, 8*256] fp16
-// so every layer reads the SAME two [146,256] fp16 matrices of a sequence (L1/L2 resident across
-// the 8 heads) and the [B*146, 6*512] K/V tensors of the reference are never formed.
-// One CTA per sequence, warp = head, lane = 8 consecutive features; only valid keys are visited.
+// so every layer reads the SAME two [len,256] fp16 matrices of a sequence and the [B*146, 6*512] K/V
+// tensors of the reference are never formed.
+// One CTA per sequence: all 256 threads stage the valid rows of (memory + pos) in shared memory with
+// cp.async (every row crosses L2 once, all loads in flight together), warp = head computes the
+// scores and the softmax, then the same buffer is refilled with the memory rows for the weighted sum.
+constexpr int kDecMaxRows = 160;
+constexpr int kDecSmemBytes = kDecMaxRows * 512;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256)
 dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp,
                        const op_t* __restrict__ mem, const float* __restrict__ key_mask, int L,
                        const int32_t* __restrict__ seq_off, const int32_t* __restrict__ seq_len,
                        op_t* __restrict__ out) {
-  __shared__ float sp[8][160];
-  __shared__ short vidx[160];
+  extern __shared__ __align__(16) uint8_t dec_rows[];     // [nv][256] fp16
+  __shared__ float sp[8][kDecMaxRows];
+  __shared__ short vidx[kDecMaxRows];
   __shared__ int s_nvalid;
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L;
   if (seq_off) {     // ragged batch: the sequence's rows are exactly its valid keys
-    const int n = min(seq_len[b], 160);
+    const int n = min(seq_len[b], kDecMaxRows);
     for (int i = tid; i < n; i += 256) vidx[i] = static_cast<short>(i);
     if (tid == 0) s_nvalid = n;
   } else if (warp == 0) {   // ordered compaction of the valid key positions
@@ -205,21 +222,19 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
   }
   __syncthreads();
   const int nv = s_nvalid;
-  const op_t* mpb = mp + row0 * 256 + lane * 8;
-  const op_t* memb = mem + row0 * 256 + lane * 8;
-  // 4 keys per step: four independent 16-byte loads and four interleaved butterflies in flight
+  // ---- stage (memory + pos) rows: thread = (row tid/32 + 8k, 16-byte chunk tid%32) ----
+  for (int i = warp; i < nv; i += 8)
+    cp_async_16(dec_rows + i * 512 + lane * 16, mp + (row0 + vidx[i]) * 256 + lane * 8);
+  cp_async_wait_all();
+  __syncthreads();
   float mx = -INFINITY;
   for (int i0 = 0; i0 < nv; i0 += 4) {
-    uint4 raw[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = min(i0 + k, nv - 1);
-      raw[k] = __ldg(reinterpret_cast<const uint4*>(mpb + vidx[i] * 256));
-    }
     float acc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw[k]);
+      const int i = min(i0 + k, nv - 1);
+      const uint4 raw = *reinterpret_cast<const uint4*>(dec_rows + i * 512 + lane * 16);
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
       float a = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -242,34 +257,28 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
       }
     }
   }
-  __syncwarp();
-  float sum = 0.f;
+  __syncthreads();                 // every warp is done with the (memory + pos) rows
+  for (int i = warp; i < nv; i += 8)
+    cp_async_16(dec_rows + i * 512 + lane * 16, mem + (row0 + vidx[i]) * 256 + lane * 8);
+  float sum = 0.f;                 // the softmax overlaps the refill
   for (int i = lane; i < nv; i += 32) {
     const float e = __expf(sp[warp][i] - mx);
     sp[warp][i] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  __syncwarp();
+  cp_async_wait_all();
+  __syncthreads();
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i0 = 0; i0 < nv; i0 += 4) {
-    uint4 raw[4];
-    float a[4];
+  for (int i = 0; i < nv; ++i) {
+    const float a = sp[warp][i];
+    const uint4 raw = *reinterpret_cast<const uint4*>(dec_rows + i * 512 + lane * 16);
+    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = min(i0 + k, nv - 1);
-      raw[k] = __ldg(reinterpret_cast<const uint4*>(memb + vidx[i] * 256));
-      a[k] = i0 + k < nv ? sp[warp][i] : 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw[k]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = op2_to_f2(hh[j]);
-        o[2 * j] = fmaf(a[k], f.x, o[2 * j]);
-        o[2 * j + 1] = fmaf(a[k], f.y, o[2 * j + 1]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = op2_to_f2(hh[j]);
+      o[2 * j] = fmaf(a, f.x, o[2 * j]);
+      o[2 * j + 1] = fmaf(a, f.y, o[2 * j + 1]);
     }
   }
   const float inv = 1.f / sum;
@@ -317,7 +326,13 @@ int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const floa
   if (B == 0) return MADE_OK;
   MADE_REQUIRE(qt && mp && mem && (key_mask || (seq_off && seq_len)) && out && L > 0 && L <= 160,
                "dec_attn_folded: bad arguments");
-  dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, 0, st>>>(qt, mp, mem, key_mask, L, seq_off, seq_len, out);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MADE_CUDA(cudaFuncSetAttribute(dec_attn_folded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
+    attr_set = true;
+  }
+  dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, kDecSmemBytes, st>>>(qt, mp, mem, key_mask, L, seq_off,
+                                                                              seq_len, out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
