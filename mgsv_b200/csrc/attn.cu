@@ -22,6 +22,19 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// 16-byte cp.async that writes zeros when !valid (src-size 0)
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+
 constexpr int kHeadDim = 32;
 constexpr int kHeadsPerCta = 4;
 constexpr int kKStride = 40;  // fp16 elements per K row in smem (80 B: conflict-free 4-byte frags)
@@ -69,24 +82,20 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   const op_t* Kg = K + row0 * ldk + h * kHeadDim;
   const op_t* Vg = V + row0 * ldv + h * kHeadDim;
   const int n_nt = (L + 7) >> 3, n_kk = (L + 15) >> 4;   // key tiles that hold at least one real key
-  for (int idx = lane; idx < LP * 4; idx += 32) {
+  for (int idx = lane; idx < n_kk * 64; idx += 32) {  // rows the MMAs touch; all copies in flight, one wait
     const int key = idx >> 2, ch = idx & 3;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (key < L) {
-      kv = __ldg(reinterpret_cast<const uint4*>(Kg + key * ldk + ch * 8));
-      vv = __ldg(reinterpret_cast<const uint4*>(Vg + key * ldv + ch * 8));
-    }
-    *reinterpret_cast<uint4*>(Ks + key * kKStride + ch * 8) = kv;
-    *reinterpret_cast<uint4*>(Vs + key * kKStride + ch * 8) = vv;
+    const bool ok = key < L;
+    const int kr = ok ? key : 0;
+    cp_async_16_zfill(Ks + key * kKStride + ch * 8, Kg + kr * ldk + ch * 8, ok);
+    cp_async_16_zfill(Vs + key * kKStride + ch * 8, Vg + kr * ldv + ch * 8, ok);
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const op_t* Qg = Q + row0 * ldq + h * kHeadDim;
-  for (int rt = 0; rt < KK; ++rt) {
+  // Q fragments straight from global (each element is read exactly once), one row tile ahead
+  auto load_q = [&](int rt, uint32_t (&qa)[2][4]) {
     const int r0 = rt * 16 + g, r1 = r0 + 8;
-    if (rt * 16 >= L) break;
-    // ---- Q fragments straight from global (each element is read exactly once) ----
-    uint32_t qa[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int c = ks * 16 + 2 * t;
@@ -95,6 +104,18 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
       qa[ks][2] = r0 < L ? __ldg(reinterpret_cast<const uint32_t*>(Qg + r0 * ldq + c + 8)) : 0u;
       qa[ks][3] = r1 < L ? __ldg(reinterpret_cast<const uint32_t*>(Qg + r1 * ldq + c + 8)) : 0u;
     }
+  };
+  uint32_t qn[2][4];
+  load_q(0, qn);
+  for (int rt = 0; rt < KK; ++rt) {
+    const int r0 = rt * 16 + g, r1 = r0 + 8;
+    if (rt * 16 >= L) break;
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[ks][i] = qn[ks][i];
+    if ((rt + 1) * 16 < L) load_q(rt + 1, qn);
     // ---- S = Q K^T ----
     float s[NT][4];
 #pragma unroll
@@ -132,8 +153,8 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
     for (int nt = 0; nt < NT; ++nt) {
       // unnormalised weights, rounded to fp16 for the MMA; the divisor is the sum of the ROUNDED
       // weights so that the weights used sum to one exactly
-      op2_t p01 = floats2op2(__expf(s[nt][0] - mx0), __expf(s[nt][1] - mx0));
-      op2_t p23 = floats2op2(__expf(s[nt][2] - mx1), __expf(s[nt][3] - mx1));
+      op2_t p01 = floats2op2(fast_exp(s[nt][0] - mx0), fast_exp(s[nt][1] - mx0));
+      op2_t p23 = floats2op2(fast_exp(s[nt][2] - mx1), fast_exp(s[nt][3] - mx1));
       float2 f01 = op2_to_f2(p01), f23 = op2_to_f2(p23);
       sum0 += f01.x + f01.y;
       sum1 += f23.x + f23.y;
@@ -180,12 +201,6 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 constexpr int kDecMaxRows = 160;
 constexpr int kDecSmemBytes = kDecMaxRows * 512;
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(256)
 dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp,
@@ -262,7 +277,7 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
     cp_async_16(dec_rows + i * 512 + lane * 16, mem + (row0 + vidx[i]) * 256 + lane * 8);
   float sum = 0.f;                 // the softmax overlaps the refill
   for (int i = lane; i < nv; i += 32) {
-    const float e = __expf(sp[warp][i] - mx);
+    const float e = fast_exp(sp[warp][i] - mx);
     sp[warp][i] = e;
     sum += e;
   }

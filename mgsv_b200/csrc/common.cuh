@@ -282,6 +282,13 @@ __device__ __forceinline__ op_t f2op(float x) {
 }
 __device__ __forceinline__ float op2f(op_t x) { return __half2float(x); }
 __device__ __forceinline__ float2 op2_to_f2(op2_t x) { return __half22float2(x); }
+// exp(x) for softmax arguments (x <= 0): one FMUL + MUFU.EX2 with flush-to-zero (the plain __expf
+// adds a denormal-range rescale: FSETP + 2 FMUL per call).
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

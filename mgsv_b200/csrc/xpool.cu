@@ -290,16 +290,16 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mx = fmaxf(mx, *peer_max);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const __half2 e = __floats2half2_rn(__expf(__uint_as_float(s0[2 * i]) - mx),
-                                              __expf(__uint_as_float(s0[2 * i + 1]) - mx));
+          const __half2 e = __floats2half2_rn(fast_exp(__uint_as_float(s0[2 * i]) - mx),
+                                              fast_exp(__uint_as_float(s0[2 * i + 1]) - mx));
           const float2 f = __half22float2(e);
           lsum += f.x + f.y;
           pk[i] = *reinterpret_cast<const uint32_t*>(&e);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const __half2 e = __floats2half2_rn(__expf(__uint_as_float(s1[2 * i]) - mx),
-                                              __expf(__uint_as_float(s1[2 * i + 1]) - mx));
+          const __half2 e = __floats2half2_rn(fast_exp(__uint_as_float(s1[2 * i]) - mx),
+                                              fast_exp(__uint_as_float(s1[2 * i + 1]) - mx));
           const float2 f = __half22float2(e);
           lsum += f.x + f.y;
           pk[16 + i] = *reinterpret_cast<const uint32_t*>(&e);
