@@ -218,9 +218,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
       const int64_t hrow = e.h_row_idx ? static_cast<int64_t>(__ldg(e.h_row_idx + srow)) : grow;
 
-      float psum = 0.f;
+      float psum = 0.f, psq = 0.f;
+      // fp32 residual rows are fetched one 32-column chunk ahead of the chunk being processed, so their
+      // L2 latency overlaps the TMEM read / math / store of the previous chunk
+      const bool res32 = e.residual != nullptr && e.residual_f32;
+      const float* res_row = res32 ? static_cast<const float*>(e.residual) + srow * e.res_ld + n_blk * BN : nullptr;
+      float4 rnext[8];
+      if (res32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + half * 32) + i);
+      }
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
       for (int c = half; c < Cfg::kChunks; c += 2) {
+        float4 rcur[8];
+        if (res32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+          if (c + 2 < Cfg::kChunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + (c + 2) * 32) + i);
+          }
+        }
         uint32_t acc[32];
         tmem_ld_x32(t_acc + c * 32, acc);
         tmem_wait_ld();
@@ -247,11 +265,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (e.residual) {
           if (e.residual_f32) {
-            const float4* r4 = reinterpret_cast<const float4*>(
-                static_cast<const float*>(e.residual) + srow * e.res_ld + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 t = __ldg(r4 + i);
+              const float4 t = rcur[i];
               v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
             }
           } else {
@@ -281,7 +297,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t st[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            psum += do_ln ? v[i] : v[i] * v[i];
+            psum += v[i];
+            psq = fmaf(v[i], v[i], psq);
             st[i] = __float_as_uint(v[i]);
           }
           tmem_st_x32(t_acc + c * 32, st);
@@ -322,32 +339,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       if (two_pass) {
         tmem_wait_st();
-        // ---------- row statistics across the two column halves ----------
+        // ---------- row statistics across the two column halves (sum and sum of squares) ----------
         float mean = 0.f, scale;
-        float* slot_a = ln_part + (0 * 2 + half) * 128 + r_in_tile;
-        float* slot_b = ln_part + (1 * 2 + half) * 128 + r_in_tile;
-        *slot_a = psum;
+        ln_part[(0 * 2 + half) * 128 + r_in_tile] = psum;
+        ln_part[(1 * 2 + half) * 128 + r_in_tile] = psq;
         named_bar_sync(1, kEpiThreads);
-        float tot = ln_part[(0 * 2 + 0) * 128 + r_in_tile] + ln_part[(0 * 2 + 1) * 128 + r_in_tile];
+        const float tot = ln_part[(0 * 2 + 0) * 128 + r_in_tile] + ln_part[(0 * 2 + 1) * 128 + r_in_tile];
+        const float totsq = ln_part[(1 * 2 + 0) * 128 + r_in_tile] + ln_part[(1 * 2 + 1) * 128 + r_in_tile];
         if (do_ln) {
           mean = tot * (1.0f / BN);
-          float psq = 0.f;
-          for (int c = half; c < Cfg::kChunks; c += 2) {
-            uint32_t acc[32];
-            tmem_ld_x32(t_acc + c * 32, acc);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float d = __uint_as_float(acc[i]) - mean;
-              psq = fmaf(d, d, psq);
-            }
-          }
-          *slot_b = psq;
-          named_bar_sync(1, kEpiThreads);
-          float var = (ln_part[(1 * 2 + 0) * 128 + r_in_tile] + ln_part[(1 * 2 + 1) * 128 + r_in_tile]) * (1.0f / BN);
+          const float var = fmaxf(totsq * (1.0f / BN) - mean * mean, 0.f);
           scale = rsqrtf(var + e.ln_eps);
         } else {
-          scale = 1.0f / fmaxf(sqrtf(tot), 1e-12f);   // F.normalize
+          scale = 1.0f / fmaxf(sqrtf(totsq), 1e-12f);   // F.normalize
         }
         // ---------- pass 3: normalise + store ----------
         for (int c = half; c < Cfg::kChunks; c += 2) {
