@@ -55,6 +55,10 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// generic 2-D tiled map (elem_bytes 2 = fp16, 4 = fp32), 128-byte swizzle
+int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
 int sm_count();
 
 #ifdef __CUDACC__
@@ -146,6 +150,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
         "r"(c_inner), "r"(c_outer)
       : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c_inner,
+                                             int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
+               : "memory");
 }
 
 // ---- TMEM ----------------------------------------------------------------------------------

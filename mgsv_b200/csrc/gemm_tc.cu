@@ -1,11 +1,15 @@
 // tcgen05 / TMA / TMEM GEMM with fused epilogues (see gemm_tc.cuh).
 #include "gemm_tc.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace made {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;
+constexpr int kStageBoxBytes = 128 * 128;            // one TMA store box: 128 rows x 128 bytes (swizzled)
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -24,8 +28,11 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = kAccStride * kAccStages;  // 256 or 512
   static constexpr int kChunks = BN / 32;
   // dynamic smem: tiles + barriers + tmem slot + LN partials
-  static constexpr int kSmemBytes = kResidentBytes + kStages * kStageBytes + 1024 /*align slack*/ + 256 +
-                                    4 * 128 * 4;
+  static constexpr int kMiscBytes = 256 + 4 * 128 * 4;      // barriers + TMEM slot, LN partial sums
+  static constexpr int kStageOutOffset = ((kResidentBytes + kStages * kStageBytes + kMiscBytes + 1023) / 1024) * 1024;
+  // the weight-stationary variant has room for the fp16 boxes only (fp32 outputs go to the streaming variant)
+  static constexpr int kStageOutBytes = (WS ? 2 : 4) * kStageBoxBytes;
+  static constexpr int kSmemBytes = kStageOutOffset + kStageOutBytes + 1024 /*align slack*/;
 };
 
 // GELU(erf) (nn.GELU default, model_Base.py:77).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
@@ -45,6 +52,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, bool WS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_oh, const __grid_constant__ CUtensorMap tmap_of,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, WS>;
   extern __shared__ uint8_t smem_raw[];
@@ -60,6 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* w_empty = w_full + 1;                     // WS: every MMA that reads the slice has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
   float* ln_part = reinterpret_cast<float*>(after + 256);   // [2 halves][2][128]
+  uint8_t* stage_out = smem + Cfg::kStageOutOffset;         // 4 boxes of 16 KB: fp16 x 2 halves, fp32 x 2 halves
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +98,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) {
+      if (p.epi.out_h) tma_prefetch_desc(&tmap_oh);
+      if (p.epi.out_f32) tma_prefetch_desc(&tmap_of);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -195,20 +208,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
+    // Thread = accumulator row (TMEM lane); warps 4-7 own the left half of the tile's columns, warps
+    // 8-11 the right half, 32 columns per chunk in registers.  Outputs leave through shared-memory
+    // staging boxes and TMA bulk stores (p.tma_store): a thread=row epilogue that stores straight to
+    // global memory touches 32 different 128-byte lines per instruction and saturates the LSU.
     const GemmEpilogue& e = p.epi;
     const int ew = warp - 4;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;        // which column chunks (even/odd) this warp owns
+    const int half = ew >> 2;        // column half this warp owns
     const int r_in_tile = q * 32 + lane;
     const bool do_ln = e.ln_gamma != nullptr;
     const bool two_pass = do_ln || e.l2norm;
+    constexpr bool kContig = (Cfg::kChunks % 2) == 0;                 // BN = 256: chunks [4*half, 4*half + 4)
+    const int n_my = kContig ? Cfg::kChunks / 2 : (Cfg::kChunks - half + 1) / 2;
+    auto chunk_of = [&](int j) { return kContig ? half * (Cfg::kChunks / 2) + j : half + 2 * j; };
+    const bool tma_out = p.tma_store != 0;
+    const bool issuer = (ew & 3) == 0 && lane == 0;                   // one thread per half issues the bulk stores
+    const uint32_t bar_half = 2 + half;                               // named barrier of this half's 128 threads
+    uint8_t* stg_h = stage_out + half * kStageBoxBytes;               // [128 rows][128 B] fp16 box (64 columns)
+    uint8_t* stg_f = stage_out + (2 + half) * kStageBoxBytes;         // [128 rows][128 B] fp32 box (32 columns)
+    const int swz = r_in_tile & 7;
+
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
       int64_t m_blk;
       int n_blk;
       decode(it, m_blk, n_blk);
-      const int64_t grow = m_blk * p.m_stride + r_in_tile;
+      const int64_t row0 = m_blk * p.m_stride;
+      const int64_t grow = row0 + r_in_tile;
       const bool row_ok = r_in_tile < p.m_valid && grow < M;
       const int64_t srow = row_ok ? grow : 0;   // safe row for loads
       mbar_wait(&tmem_full[as], aphase);
@@ -218,6 +246,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (e.row_mask) keep = (row_ok && e.row_mask[srow] != 0.f) ? 1.f : 0.f;
       const int64_t hrow = e.h_row_idx ? static_cast<int64_t>(__ldg(e.h_row_idx + srow)) : grow;
 
+      // final values of chunk j (columns col0..col0+31 of this thread's row) -> every requested output
+      auto emit = [&](int j, int col0, float (&v)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= keep;
+        if (tma_out) {
+          const bool h_first = (j & 1) == 0;     // an fp16 box holds two chunks
+          // the previous bulk stores of this half have finished READING the staging boxes
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          named_bar_sync(bar_half, 128);
+          if (e.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(stg_f + r_in_tile * 128 + ((i ^ swz) << 4)) =
+                  make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (e.out_h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(stg_h + r_in_tile * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) =
+                  make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_half, 128);
+          if (issuer) {
+            if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, static_cast<int32_t>(row0));
+            if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, static_cast<int32_t>(row0));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (row_ok) {
+          if (e.out_h) {
+            uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+          }
+          if (e.out_f32) {
+            float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+        if (e.out2_h && row_ok) {     // second output out + add2 (DETR src + pos): direct stores
+          const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
+          uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t = __ldg(a4 + i);
+            const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+            float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
+            float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+            o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
+                              pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
+                              pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
+                              pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
+          }
+        }
+      };
+
       float psum = 0.f, psq = 0.f;
       // fp32 residual rows are fetched one 32-column chunk ahead of the chunk being processed, so their
       // L2 latency overlaps the TMEM read / math / store of the previous chunk
@@ -226,17 +314,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float4 rnext[8];
       if (res32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + half * 32) + i);
+        for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + chunk_of(0) * 32) + i);
       }
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
-      for (int c = half; c < Cfg::kChunks; c += 2) {
+      for (int j = 0; j < n_my; ++j) {
+        const int c = chunk_of(j);
         float4 rcur[8];
         if (res32) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          if (c + 2 < Cfg::kChunks) {
+          if (j + 1 < n_my) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + (c + 2) * 32) + i);
+            for (int i = 0; i < 8; ++i)
+              rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + chunk_of(j + 1) * 32) + i);
           }
         }
         uint32_t acc[32];
@@ -278,10 +368,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint4 t = __ldg(r4 + i);
               const op2_t* h = reinterpret_cast<const op2_t*>(&t);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = op2_to_f2(h[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
+              for (int jj = 0; jj < 4; ++jj) {
+                float2 f = op2_to_f2(h[jj]);
+                v[8 * i + 2 * jj] += f.x;
+                v[8 * i + 2 * jj + 1] += f.y;
               }
             }
           }
@@ -303,38 +393,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tmem_st_x32(t_acc + c * 32, st);
         } else {
-          // ---------- direct store ----------
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= keep;
-          if (row_ok) {
-            if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
-            }
-            if (e.out_f32) {
-              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (e.out2_h) {
-              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 t = __ldg(a4 + i);
-                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
-                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
-                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
-              }
-            }
-          }
+          emit(j, col0, v);
         }
       }
       if (two_pass) {
@@ -353,8 +412,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else {
           scale = 1.0f / fmaxf(sqrtf(totsq), 1e-12f);   // F.normalize
         }
-        // ---------- pass 3: normalise + store ----------
-        for (int c = half; c < Cfg::kChunks; c += 2) {
+        // ---------- pass 2: normalise + store ----------
+        for (int j = 0; j < n_my; ++j) {
+          const int c = chunk_of(j);
           uint32_t acc[32];
           tmem_ld_x32(t_acc + c * 32, acc);
           tmem_wait_ld();
@@ -365,47 +425,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float4* b4 = reinterpret_cast<const float4*>(e.ln_beta + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
-              v[4 * i] = (__uint_as_float(acc[4 * i]) - mean) * scale * g.x + b.x;
-              v[4 * i + 1] = (__uint_as_float(acc[4 * i + 1]) - mean) * scale * g.y + b.y;
-              v[4 * i + 2] = (__uint_as_float(acc[4 * i + 2]) - mean) * scale * g.z + b.z;
-              v[4 * i + 3] = (__uint_as_float(acc[4 * i + 3]) - mean) * scale * g.w + b.w;
+              float4 g = __ldg(g4 + i), bb = __ldg(b4 + i);
+              v[4 * i] = (__uint_as_float(acc[4 * i]) - mean) * scale * g.x + bb.x;
+              v[4 * i + 1] = (__uint_as_float(acc[4 * i + 1]) - mean) * scale * g.y + bb.y;
+              v[4 * i + 2] = (__uint_as_float(acc[4 * i + 2]) - mean) * scale * g.z + bb.z;
+              v[4 * i + 3] = (__uint_as_float(acc[4 * i + 3]) - mean) * scale * g.w + bb.w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * scale;
           }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= keep;
-          if (row_ok) {
-            if (e.out_h) {
-              uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
-            }
-            if (e.out_f32) {
-              float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (e.out2_h) {
-              const uint4* a4 = reinterpret_cast<const uint4*>(e.add2 + grow * e.add2_ld + col0);
-              uint4* o = reinterpret_cast<uint4*>(e.out2_h + grow * e.ld_out2 + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 t = __ldg(a4 + i);
-                const op2_t* h = reinterpret_cast<const op2_t*>(&t);
-                float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]);
-                float2 f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
-                o[i] = make_uint4(pack_op2(v[8 * i] + f0.x, v[8 * i + 1] + f0.y),
-                                  pack_op2(v[8 * i + 2] + f1.x, v[8 * i + 3] + f1.y),
-                                  pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y),
-                                  pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
-              }
-            }
-          }
+          emit(j, col0, v);
         }
         // the partial-sum slots are reused by the next tile: all readers must be done
         named_bar_sync(1, kEpiThreads);
@@ -415,6 +445,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    // the staging boxes must outlive the bulk stores that read them
+    if (tma_out && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before_sync();
@@ -426,8 +458,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 template <int BN, bool WS>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& toh, const CUtensorMap& tof,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, WS>;
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget of an sm_100 CTA");
   static bool attr_set = false;
@@ -439,7 +471,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * (p.N / BN);
   int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -462,18 +494,43 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
   MADE_REQUIRE(e.out_h || e.out_f32 || e.out2_h, "gemm: no output");
   MADE_REQUIRE(p.m_valid >= 1 && p.m_valid <= 128 && p.m_stride >= 1 && p.m_stride <= 128,
                "gemm: bad tile geometry");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, toh, tof;
+  memset(&toh, 0, sizeof(toh));
+  memset(&tof, 0, sizeof(tof));
   MADE_TRY(encode_tmap_2d_16b(&ta, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M),
                                static_cast<uint64_t>(lda) * 2, kBlockK, kBlockM));
   MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
-  if (block_n == 256) {
-    // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles
-    const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
-    const bool ws = p.K <= kWsKBlocks * kBlockK && !p.b_batched && m_tiles * (p.N / 256) >= 2 * sm_count();
-    return ws ? launch_gemm<256, true>(ta, tb, p, stream) : launch_gemm<256, false>(ta, tb, p, stream);
+  GemmParams pp = p;
+  // outputs through TMA bulk stores whenever the tile is a plain [128 x 256] block of the output matrices
+  static const bool tma_store_enabled = [] {
+    const char* v = getenv("MADE_GEMM_TMA_STORE");
+    return !(v && v[0] == '0');
+  }();
+  auto aligned16 = [](const void* ptr, int64_t ld, int esz) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0;
+  };
+  pp.tma_store = tma_store_enabled && block_n == 256 && p.m_valid == 128 && p.m_stride == 128 && !e.h_row_idx &&
+                 (e.out_h || e.out_f32) && (!e.out_h || aligned16(e.out_h, e.ld_h, 2)) &&
+                 (!e.out_f32 || aligned16(e.out_f32, e.ld_f32, 4));
+  if (pp.tma_store) {
+    if (e.out_h)
+      MADE_TRY(encode_tmap_2d(&toh, e.out_h, 2, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
+                              static_cast<uint64_t>(e.ld_h) * 2, 64, 128));
+    if (e.out_f32)
+      MADE_TRY(encode_tmap_2d(&tof, e.out_f32, 4, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
+                              static_cast<uint64_t>(e.ld_f32) * 4, 32, 128));
   }
-  return launch_gemm<96, false>(ta, tb, p, stream);
+  if (block_n == 256) {
+    // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles;
+    // its shared memory has no room for fp32 staging boxes, so fp32 outputs take the streaming variant
+    const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
+    const bool ws = p.K <= kWsKBlocks * kBlockK && !p.b_batched && m_tiles * (p.N / 256) >= 2 * sm_count() &&
+                    !(pp.tma_store && e.out_f32);
+    return ws ? launch_gemm<256, true>(ta, tb, toh, tof, pp, stream)
+              : launch_gemm<256, false>(ta, tb, toh, tof, pp, stream);
+  }
+  return launch_gemm<96, false>(ta, tb, toh, tof, pp, stream);
 }
 
 }  // namespace made

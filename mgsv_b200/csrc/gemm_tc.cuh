@@ -41,6 +41,7 @@ struct GemmParams {
   int m_valid = 128;    // rows of each tile that are stored
   int b_batched = 0;    // 1: B rows start at tile_m * m_stride (per-tile B, e.g. Gram matrix)
   const int32_t* m_dev = nullptr;   // device scalar: actual row count (<= M); M then only sizes the grid / TMA map
+  int tma_store = 0;                // set by the launcher: out_h / out_f32 leave through TMA bulk stores
   GemmEpilogue epi;
 };
 
