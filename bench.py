@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="made_b200", choices=["made_b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES)
     ap.add_argument("--tracks", type=int, default=N_TRACKS)
-    ap.add_argument("--chunk", type=int, default=512, help="tracks / videos per ingest+encode chunk")
+    ap.add_argument("--chunk", type=int, default=1000, help="tracks / videos per ingest+encode chunk")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

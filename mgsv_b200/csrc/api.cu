@@ -705,7 +705,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   // The encoder (token-wise GEMMs over B*146 rows) runs in chunks of kEncChunk sequences so that its
   // scratch stays small and L2-friendly; the decoder (one query per sequence: tiny, latency-bound
   // GEMMs) runs once over all B sequences.
-  constexpr int64_t kEncChunk = 1024;
+  constexpr int64_t kEncChunk = 2048;
   const int64_t Bc = B < kEncChunk ? B : kEncChunk;
   const int64_t Tc = Bc * LD, Tall = B * LD;
   const int64_t R = NDEC * B;

@@ -57,7 +57,7 @@ class GalleryEvaluator:
     # kernels per C-ABI call: ingest = 3 (ragged index) + 1 (gather/cast); encode (ragged input) = 6 GEMM +
     # attn + pool = 8 (+ 1 memset, not a kernel of ours);
     # gallery_prepare = LN + GEMM + Gram GEMM + maskbits = 4; query_prepare = LN + GEMM + vhat = 3;
-    # xpool_score = 1; cosine = 1; rank_topk = 1; detr_detect = per 1024-sequence encoder chunk
+    # xpool_score = 1; cosine = 1; rank_topk = 1; detr_detect = per 2048-sequence encoder chunk
     # (mask 1 + ragged index 3 + prep 1 + row offsets 1 + enc 2*6 = 18) + cast 1 + dec 6*(5 GEMM +
     # attention) + LN 1 + heads 3 = 41 (the 6 D2D copies are not kernels); moment_postproc = 1.
     _K = dict(ingest=4, encode=8, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=41,
@@ -225,7 +225,7 @@ class GalleryEvaluator:
             spans[s:e] = r["pred_spans"][-1]
             a, b, c, d = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1], gt_moment[s:e], m_duration[s:e])
             st[s:e], ed[s:e], sc[s:e], iou[s:e] = a, b, c, d
-            self._count("detr"), self._count("detr_chunk", -(-(e - s) // 1024)), self._count("postproc")
+            self._count("detr"), self._count("detr_chunk", -(-(e - s) // 2048)), self._count("postproc")
         return dict(pred_st=st, pred_ed=ed, score=sc, iou=iou, pred_spans=spans)
 
     # ---- whole job --------------------------------------------------------------------------------
