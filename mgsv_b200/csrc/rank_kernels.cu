@@ -420,6 +420,19 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
   if (d == 256 && m >= 256 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     // tcgen05 route for the columns that fill whole 256-wide tiles
     m_tc = (m / 256) * 256;
+    // stream-ordered scratch: keep freed blocks in the pool across synchronisations (the default
+    // release threshold of 0 hands them back to the OS at every sync, which turned the next
+    // cudaMallocAsync into a multi-millisecond allocation whenever a step ended with a sync)
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    MADE_CUDA(cudaGetDevice(&dev));
+    if (pool_ready_dev != dev) {
+      cudaMemPool_t pool;
+      MADE_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = UINT64_MAX;
+      MADE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      pool_ready_dev = dev;
+    }
     op_t *a16 = nullptr, *b16 = nullptr;
     MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&a16), static_cast<size_t>(n) * 768 * 2, st));
     MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&b16), static_cast<size_t>(m_tc) * 768 * 2, st));

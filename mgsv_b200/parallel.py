@@ -13,6 +13,8 @@ masks / ground-truth moments) whose split sizes are planned on the host from the
 """
 from __future__ import annotations
 
+import os
+import time
 from typing import Dict, Optional
 
 import torch
@@ -90,6 +92,15 @@ class ShardedEvaluator:
         ev, dev, W, R = self.ev, self.ev.dev, self.world, self.rank
         ev.launches = 0
         ev._keep = []
+        trace = os.environ.get("MADE_TRACE_PHASES")     # diagnostics: per-phase wall times (adds syncs)
+        marks = []
+
+        def mark(name):
+            if trace:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
         q0, q1 = shard_bounds(n_queries, R, W)
         m0, m1 = shard_bounds(n_tracks, R, W)
         q_sizes = [shard_bounds(n_queries, r, W)[1] - shard_bounds(n_queries, r, W)[0] for r in range(W)]
@@ -97,15 +108,20 @@ class ShardedEvaluator:
         send_loc_d = torch.from_numpy(send_loc).to(dev, non_blocking=True)
         perm_d = torch.from_numpy(perm).to(dev, non_blocking=True)
         frame_seq, vf_local, frame_mask = ev.encode_queries(videos["frame_feats"], videos["frame_mask"])
+        mark("plan+encode_queries")
         gal = ev.encode_gallery(tracks["segment_feats"], tracks["segment_mask"])
+        mark("encode_gallery")
         # ---- exchange 5 (issued early): every query's paired track -> the rank that detects it ----
         gtm = tracks["gt_moment"].to(dev, non_blocking=True).reshape(-1, 2).to(torch.float32)
         mdur = tracks["m_duration"].to(dev, non_blocking=True).to(torch.float32)
         aux = torch.cat([gal["mask"], gtm, mdur.unsqueeze(1)], 1)                  # [n_local, 96 + 3]
         recv_seq = self._all_to_all_rows(gal["seq"][send_loc_d], in_splits, out_splits)[perm_d]
         recv_aux = self._all_to_all_rows(aux[send_loc_d], in_splits, out_splits)[perm_d]
+        mark("all_to_all")
         video_feats = self._all_gather_cat(vf_local, q_sizes)                      # exchange 1
+        mark("all_gather_q")
         single, dual = ev.score(video_feats, gal)
+        mark("score")
         gt = (gt_col if gt_col.device == dev else gt_col.to(dev, non_blocking=True)).to(torch.int32)
         local_gt = torch.where((gt >= m0) & (gt < m1), gt - m0, torch.full_like(gt, -1))
         r1 = ops.rank_topk(single, dual, local_gt, None, k=0)
@@ -122,9 +138,14 @@ class ShardedEvaluator:
         dist.all_gather(cand_i, r2["topk_idx"], group=self.group)
         topk_idx, topk_score = ops.topk_merge(torch.cat(cand_s, 1), torch.cat(cand_i, 1), ev.k)
         ev.launches += 1
+        mark("rank+topk+collectives")
         # ---- detection for this rank's queries on the received tracks ----
         pair = dict(seq=recv_seq, mask=recv_aux[:, :cfg.L_M].contiguous())
         det = ev.detect(frame_seq, frame_mask, pair, vf_local,
                         torch.arange(q1 - q0, dtype=torch.int32, device=dev),
                         recv_aux[:, cfg.L_M:cfg.L_M + 2].contiguous(), recv_aux[:, cfg.L_M + 2].contiguous())
+        mark("detect")
+        if trace and R == 0:
+            print("[phases rank 0] " + " ".join(f"{n}={1e3 * (t - marks[i][1]):.2f}" for i, (n, t) in
+                                                 enumerate(marks[1:])), flush=True)
         return dict(rank=rank_cnt, topk_idx=topk_idx, topk_score=topk_score, q_range=(q0, q1), **det)
