@@ -196,6 +196,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     nq, nm = args.queries, args.tracks

@@ -228,10 +228,33 @@ class GalleryEvaluator:
             self._count("detr"), self._count("detr_chunk", -(-(e - s) // 2048)), self._count("postproc")
         return dict(pred_st=st, pred_ed=ed, score=sc, iou=iou, pred_spans=spans)
 
+    def detect_topk(self, frame_seq, frame_mask, gal, video_feats, topk_idx, k_det: int):
+        """Retrieve-then-detect: one moment per (query, retrieved track) for the
+        k_det best-ranked tracks of every query.  The reference only detects on the ground-truth
+        pair (test-MaDe.py:280); serving has no ground truth, so the span of each candidate track is
+        what the product returns.  → dict(spans_se [n,k_det,2] seconds, score [n,k_det])."""
+        n = video_feats.shape[0]
+        if k_det < 1 or k_det > topk_idx.shape[1]:
+            raise ValueError(f"k_det={k_det} must be in [1, {topk_idx.shape[1]}]")
+        idx = topk_idx[:, :k_det].reshape(-1).to(torch.int32).clamp_min(0)
+        fs = frame_seq.repeat_interleave(k_det, 0)
+        fm = frame_mask.repeat_interleave(k_det, 0)
+        vf = video_feats.repeat_interleave(k_det, 0)
+        st = torch.empty(n * k_det, dtype=torch.float32, device=self.dev)
+        ed, sc = torch.empty_like(st), torch.empty_like(st)
+        for s in range(0, n * k_det, self.detr_chunk):
+            e = min(n * k_det, s + self.detr_chunk)
+            r = self.eng.detr_detect(fs[s:e], fm[s:e], gal["seq"], gal["mask"], vf[s:e], track_idx=idx[s:e])
+            a, b, c, _ = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1])
+            st[s:e], ed[s:e], sc[s:e] = a, b, c
+            self._count("detr"), self._count("detr_chunk", -(-(e - s) // 2048)), self._count("postproc")
+        return dict(spans_se=torch.stack([st, ed], 1).reshape(n, k_det, 2), score=sc.reshape(n, k_det))
+
     # ---- whole job --------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, videos: Dict[str, torch.Tensor], tracks: Dict[str, torch.Tensor], gt_col: torch.Tensor,
-            prev_same: Optional[torch.Tensor] = None, on_host: bool = False, want_sims: bool = False):
+            prev_same: Optional[torch.Tensor] = None, on_host: bool = False, want_sims: bool = False,
+            detect_topk: int = 0):
         """One step of the hot path.  `videos`/`tracks` are the dicts of `synth.make_*`: device
         resident, or PINNED host tensors (`on_host=True`; the features are then read in place over
         PCIe by the ingest kernel).  Query i is paired with track gt_col[i] for both the rank and the
@@ -247,9 +270,13 @@ class GalleryEvaluator:
             raise ValueError("gt_col must index tracks of the gallery")
         gt_col_d = self._to_dev(gt_col).to(torch.int32)
         prev_d = None if prev_same is None else self._to_dev(prev_same).to(torch.int32)
-        gt_moment = self._to_dev(tracks["gt_moment"])
-        m_dur = self._to_dev(tracks["m_duration"])
         idx64 = gt_col_d.long()
+        if "gt_moment" in videos:     # per-query ground truth (FeatureStore: the moment belongs to the CSV row)
+            gt_moment_q = self._to_dev(videos["gt_moment"])
+            m_dur_q = self._to_dev(videos["m_duration"])
+        else:                         # per-track ground truth (synthetic sets): query i <-> track gt_col[i]
+            gt_moment_q = self._to_dev(tracks["gt_moment"])[idx64]
+            m_dur_q = self._to_dev(tracks["m_duration"])[idx64]
         frame_seq, video_feats, frame_mask = self.encode_queries(videos["frame_feats"], videos["frame_mask"])
         qprep = self.eng.query_prepare(video_feats)
         self._count("query_prepare")
@@ -260,14 +287,16 @@ class GalleryEvaluator:
         def on_chunk(gal, s, e):
             self.score_chunk(qprep, video_feats, gal, s, e, single, dual)
             if "det" not in state and last_needed < e:
-                state["det"] = self.detect(frame_seq, frame_mask, gal, video_feats, gt_col_d, gt_moment[idx64],
-                                           m_dur[idx64])
+                state["det"] = self.detect(frame_seq, frame_mask, gal, video_feats, gt_col_d, gt_moment_q, m_dur_q)
 
         gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_chunk)
         rk = ops.rank_topk(single, dual, gt_col_d, prev_d, k=self.k)
         self._count("rank")
         out = dict(rank=rk["rank"], topk_idx=rk["topk_idx"], topk_score=rk["topk_score"], gt_score=rk["gt_score"],
                    video_feats=video_feats, music_feats=gal["pooled"], **state["det"])
+        if detect_topk:
+            t = self.detect_topk(frame_seq, frame_mask, gal, video_feats, rk["topk_idx"], detect_topk)
+            out.update(topk_spans=t["spans_se"], topk_span_score=t["score"])
         if want_sims:
             out.update(single=single, dual=dual)
         return out

@@ -557,3 +557,22 @@ def test_h2d_valid_rows_with_host_fp16_rounding(dev, engine):
         outs.append(ev.to_host(ev.run(hv, hm, gt, on_host=True)))
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k]), k
+
+
+def test_retrieve_then_detect_matches_paired_detection(dev, engine):
+    """DETR on the top-k retrieved tracks.  Where a retrieved track is the paired
+    one, the span equals the paired detection bit for bit (GEMM rows are independent of the batch)."""
+    from mgsv_b200.pipeline import GalleryEvaluator
+    nq, nm, kd = 60, 90, 4
+    v, m, ids = synth.make_eval_set(nq, nm, synth.BASE_SEED + 12)
+    ev = GalleryEvaluator(engine, k=10, music_chunk=50, video_chunk=64)
+    gt = torch.arange(nq, dtype=torch.int32)
+    out = ev.run({k: t.to(dev) for k, t in v.items()}, {k: t.to(dev) for k, t in m.items()}, gt, detect_topk=kd)
+    assert tuple(out["topk_spans"].shape) == (nq, kd, 2) and tuple(out["topk_span_score"].shape) == (nq, kd)
+    hit = out["topk_idx"][:, :kd].cpu() == gt[:, None]
+    assert int(hit.sum()) > 0
+    rows, cols = torch.nonzero(hit, as_tuple=True)
+    spans = out["topk_spans"].cpu()
+    assert torch.equal(spans[rows, cols, 0], out["pred_st"].cpu()[rows])
+    assert torch.equal(spans[rows, cols, 1], out["pred_ed"].cpu()[rows])
+    assert bool((spans[..., 0] >= 0).all()) and bool((spans[..., 1] <= 240).all())

@@ -128,3 +128,60 @@ def test_shard_bounds_partition():
             own = owner_of(cols, n, w)
             for r in range(w):
                 assert (own[b[r][0]:b[r][1]] == r).all()
+
+
+def test_feature_store_reads_reference_file_layout(tmp_path):
+    """dataloaders/dataloader_MGSV_EC_feature.py:46-75: {id}.pt files + CSV -> one batch schema."""
+    import pandas as pd
+    from mgsv_b200.ingest import FeatureStore, get_cw_proportion
+    g = torch.Generator().manual_seed(3)
+    fr, mu = tmp_path / "frames", tmp_path / "music"
+    for d in (fr / "vit_feature", fr / "vit_mask", mu / "ast_feature", mu / "ast_mask"):
+        d.mkdir(parents=True)
+    vids, mids = ["v1", "v2", "v3", "v4"], ["m1", "m2", "m1", "m3"]       # m1 is used by two videos
+    vfeat, mfeat = {}, {}
+    for i, v in enumerate(vids):
+        n = 5 + 3 * i
+        f = torch.zeros(50, 512); f[:n] = torch.randn(n, 512, generator=g)
+        m = torch.zeros(50); m[:n] = 1
+        torch.save(f, fr / "vit_feature" / f"{v}.pt"); torch.save(m, fr / "vit_mask" / f"{v}.pt")
+        vfeat[v] = (f, m)
+    for i, mname in enumerate(sorted(set(mids))):
+        n = 20 + 10 * i
+        f = torch.zeros(96, 768); f[:n] = torch.randn(n, 768, generator=g)
+        m = torch.zeros(96); m[:n] = 1
+        torch.save(f, mu / "ast_feature" / f"{mname}.pt"); torch.save(m, mu / "ast_mask" / f"{mname}.pt")
+        mfeat[mname] = (f, m)
+    df = pd.DataFrame(dict(video_id=vids, music_id=mids, video_start=[0, 1, 2, 3], video_end=[10, 12, 14, 16],
+                           music_start=[5.0, 30.0, 50.0, 100.0], music_end=[15.0, 41.0, 62.0, 250.0],
+                           music_total_duration=[120.0, 200.0, 120.0, 260.0]))
+    csv = tmp_path / "test.csv"
+    df.to_csv(csv, index=False)
+    st = FeatureStore.from_csv(str(csv), str(fr), str(mu), pin=False)
+    assert st.videos["frame_feats"].shape == (4, 50, 512) and st.tracks["segment_feats"].shape == (4, 96, 768)
+    for i, v in enumerate(vids):
+        assert torch.equal(st.videos["frame_feats"][i], vfeat[v][0]) and torch.equal(st.videos["frame_mask"][i], vfeat[v][1])
+    for i, mname in enumerate(mids):
+        assert torch.equal(st.tracks["segment_feats"][i], mfeat[mname][0])
+    # reference gallery = one column per row; the repeated track is marked for the dedup-aware rank
+    assert list(st.gt_col) == [2, 1, 2, 3] and list(st.prev_same) == [-1, -1, 0, -1]
+    assert torch.allclose(st.meta["spans_target"][3, 0], torch.tensor([(100 + 240) / 2 / 240, (240 - 100) / 240]))
+    assert torch.equal(st.meta["spans_target"][:, 0], get_cw_proportion(st.videos["gt_moment"][:, 0]))
+    assert torch.allclose(st.videos["v_duration"], torch.tensor([10., 11., 12., 13.]))
+    st2 = FeatureStore.from_csv(str(csv), str(fr), str(mu), pin=False, dedup_tracks=True)
+    assert st2.tracks["segment_feats"].shape[0] == 3 and list(st2.gt_col) == [0, 1, 0, 2] and st2.prev_same is None
+    with pytest.raises(FileNotFoundError):
+        FeatureStore.from_csv(str(csv), str(fr), str(tmp_path / "nowhere"), pin=False)
+
+
+def test_save_results_json_schema(tmp_path):
+    """utils/util_test.py:202-226."""
+    import json
+    from mgsv_b200.ingest import save_results_json
+    ret = [dict(music_id="m1", rank=3, topk_music_ids=["m9"])]
+    loc = [dict(video_id="v1", music_id="m1", m_duration=120.0, gt_moment=[[5.04321, 15.98765]], pred_st=-2.0, pred_ed=250.123456)]
+    path = tmp_path / "r.json"
+    save_results_json(ret, loc, [torch.tensor(0.123456)], str(path))
+    got = json.load(open(path))
+    assert got == [dict(video_id="v1", music_id="m1", topk_mids=["m9"], gt_mid_rank=3, iou=0.1235, m_duration=120.0,
+                        gt_st=5.043, gt_ed=15.988, pred_st=0, pred_ed=240)]
