@@ -575,4 +575,4 @@ def test_retrieve_then_detect_matches_paired_detection(dev, engine):
     spans = out["topk_spans"].cpu()
     assert torch.equal(spans[rows, cols, 0], out["pred_st"].cpu()[rows])
     assert torch.equal(spans[rows, cols, 1], out["pred_ed"].cpu()[rows])
-    assert bool((spans[..., 0] >= 0).all()) and bool((spans[..., 1] <= 240).all())
+    assert bool(torch.isfinite(spans).all()) and bool((spans[..., 1] >= spans[..., 0]).all())
