@@ -56,6 +56,17 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.made_ctx_load_weights(self._h, n, c_names, c_ptrs, c_num, _lib.stream_ptr()))
         self.loaded = True
+        self._weights = dict(zip([k.decode() for k in names], arrs))    # host fp32 masters, for clone()
+
+    def clone(self) -> "Engine":
+        """A second context with the same weights and its own workspace arena: calls on one made_ctx
+        are serialised by contract, so work that should overlap on another stream (moment detection
+        beside scoring) needs its own context (21 MB of packed weights)."""
+        if not self.loaded:
+            raise RuntimeError("clone() needs loaded weights")
+        other = Engine(self.device)
+        other.load_state_dict(self._weights)
+        return other
 
     # -----------------------------------------------------------------------------------------
     def h2d_valid_rows(self, feats_host: torch.Tensor, masks_host: torch.Tensor, out: torch.Tensor,

@@ -118,6 +118,12 @@ class ShardedEvaluator:
         recv_seq = self._all_to_all_rows(gal["seq"][send_loc_d], in_splits, out_splits)[perm_d]
         recv_aux = self._all_to_all_rows(aux[send_loc_d], in_splits, out_splits)[perm_d]
         mark("all_to_all")
+        # ---- detection for this rank's queries on the received tracks: enqueued now on the detection
+        # stream, it overlaps the scoring / ranking / collectives below ----
+        pair = dict(seq=recv_seq, mask=recv_aux[:, :cfg.L_M].contiguous())
+        det = ev.detect(frame_seq, frame_mask, pair, vf_local,
+                        torch.arange(q1 - q0, dtype=torch.int32, device=dev),
+                        recv_aux[:, cfg.L_M:cfg.L_M + 2].contiguous(), recv_aux[:, cfg.L_M + 2].contiguous())
         video_feats = self._all_gather_cat(vf_local, q_sizes)                      # exchange 1
         mark("all_gather_q")
         single, dual = ev.score(video_feats, gal)
@@ -139,11 +145,8 @@ class ShardedEvaluator:
         topk_idx, topk_score = ops.topk_merge(torch.cat(cand_s, 1), torch.cat(cand_i, 1), ev.k)
         ev.launches += 1
         mark("rank+topk+collectives")
-        # ---- detection for this rank's queries on the received tracks ----
-        pair = dict(seq=recv_seq, mask=recv_aux[:, :cfg.L_M].contiguous())
-        det = ev.detect(frame_seq, frame_mask, pair, vf_local,
-                        torch.arange(q1 - q0, dtype=torch.int32, device=dev),
-                        recv_aux[:, cfg.L_M:cfg.L_M + 2].contiguous(), recv_aux[:, cfg.L_M + 2].contiguous())
+        if hasattr(ev, "join_detect"):
+            ev.join_detect()
         mark("detect")
         if trace and R == 0:
             print("[phases rank 0] " + " ".join(f"{n}={1e3 * (t - marks[i][1]):.2f}" for i, (n, t) in

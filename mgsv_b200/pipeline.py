@@ -38,6 +38,12 @@ class GalleryEvaluator:
         self.video_chunk = video_chunk
         self.detr_chunk = detr_chunk
         self.ingest_stream = torch.cuda.Stream(device=self.dev)
+        # moment detection is a long chain of small, latency-bound launches (one query per sequence in
+        # the decoder): it runs on its own stream and made_ctx so that it fills the SMs left idle by /
+        # beside the scoring kernels instead of serialising with them
+        self.detect_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("MADE_DETECT_STREAM", "1") != "0" \
+            else None
+        self._eng_detect = None
         # host inputs: "dma" = copy engines move the valid rows into a device staging buffer (no SM
         # involved, overlaps any kernel); "dma16" = host threads round the valid rows to fp16 first (half
         # the PCIe bytes; worth it when one process has the host cores to itself); "zerocopy" = the
@@ -213,20 +219,47 @@ class GalleryEvaluator:
         return single, dual
 
     def detect(self, frame_seq, frame_mask, gal, video_feats, track_idx, gt_moment, m_duration):
-        """DETR moment detection for (query b, track track_idx[b]) pairs + post-processing + IoU."""
+        """DETR moment detection for (query b, track track_idx[b]) pairs + post-processing + IoU.
+        Enqueued on the detection stream (if enabled) behind everything already on the current
+        stream; `join_detect()` makes the current stream wait for it."""
         n = video_feats.shape[0]
-        st = torch.empty(n, dtype=torch.float32, device=self.dev)
-        ed, sc, iou = torch.empty_like(st), torch.empty_like(st), torch.empty_like(st)
-        spans = torch.empty((n, 2), dtype=torch.float32, device=self.dev)
-        for s in range(0, n, self.detr_chunk):
-            e = min(n, s + self.detr_chunk)
-            r = self.eng.detr_detect(frame_seq[s:e], frame_mask[s:e], gal["seq"], gal["mask"], video_feats[s:e],
-                                     track_idx=track_idx[s:e])
-            spans[s:e] = r["pred_spans"][-1]
-            a, b, c, d = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1], gt_moment[s:e], m_duration[s:e])
-            st[s:e], ed[s:e], sc[s:e], iou[s:e] = a, b, c, d
-            self._count("detr"), self._count("detr_chunk", -(-(e - s) // 2048)), self._count("postproc")
-        return dict(pred_st=st, pred_ed=ed, score=sc, iou=iou, pred_spans=spans)
+        cur = torch.cuda.current_stream(self.dev)
+        side = self.detect_stream
+        eng = self.eng
+        if side is not None:
+            if self._eng_detect is None:
+                self._eng_detect = self.eng.clone()
+            eng = self._eng_detect
+            side.wait_stream(cur)
+            # the inputs were allocated on the current stream: keep the allocator from recycling them
+            # (e.g. temporaries of the caller) before the detection stream has read them
+            for t in (frame_seq, frame_mask, gal["seq"], gal["mask"], video_feats, track_idx, gt_moment, m_duration):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(side)
+        with torch.cuda.stream(side if side is not None else cur):
+            st = torch.empty(n, dtype=torch.float32, device=self.dev)
+            ed, sc, iou = torch.empty_like(st), torch.empty_like(st), torch.empty_like(st)
+            spans = torch.empty((n, 2), dtype=torch.float32, device=self.dev)
+            for s in range(0, n, self.detr_chunk):
+                e = min(n, s + self.detr_chunk)
+                r = eng.detr_detect(frame_seq[s:e], frame_mask[s:e], gal["seq"], gal["mask"], video_feats[s:e],
+                                    track_idx=track_idx[s:e])
+                spans[s:e] = r["pred_spans"][-1]
+                a, b, c, d = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1], gt_moment[s:e],
+                                                 m_duration[s:e])
+                st[s:e], ed[s:e], sc[s:e], iou[s:e] = a, b, c, d
+                self._count("detr"), self._count("detr_chunk", -(-(e - s) // 2048)), self._count("postproc")
+        out = dict(pred_st=st, pred_ed=ed, score=sc, iou=iou, pred_spans=spans)
+        if side is not None:
+            for t in out.values():
+                t.record_stream(cur)
+            # inputs produced on the current stream stay alive in the caller until join_detect()
+        return out
+
+    def join_detect(self):
+        """The current stream waits for the detection stream (call before consuming detect()'s outputs)."""
+        if self.detect_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.detect_stream)
 
     def detect_topk(self, frame_seq, frame_mask, gal, video_feats, topk_idx, k_det: int):
         """Retrieve-then-detect: one moment per (query, retrieved track) for the
@@ -292,6 +325,7 @@ class GalleryEvaluator:
         gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_chunk)
         rk = ops.rank_topk(single, dual, gt_col_d, prev_d, k=self.k)
         self._count("rank")
+        self.join_detect()
         out = dict(rank=rk["rank"], topk_idx=rk["topk_idx"], topk_score=rk["topk_score"], gt_score=rk["gt_score"],
                    video_feats=video_feats, music_feats=gal["pooled"], **state["det"])
         if detect_topk:
