@@ -576,3 +576,27 @@ def test_retrieve_then_detect_matches_paired_detection(dev, engine):
     assert torch.equal(spans[rows, cols, 0], out["pred_st"].cpu()[rows])
     assert torch.equal(spans[rows, cols, 1], out["pred_ed"].cpu()[rows])
     assert bool(torch.isfinite(spans).all()) and bool((spans[..., 1] >= spans[..., 0]).all())
+
+
+def test_hungarian_matcher_mirror(dev):
+    """music_detr/matcher.py:36-92 with Q > 1 queries and a variable number of targets per sample."""
+    from mgsv_b200.matcher import build_matcher
+    g = torch.Generator().manual_seed(21)
+    bs, nq, nt = 9, 5, 3
+    logits = torch.randn(bs, nq, 2, generator=g)
+    spans = torch.stack([torch.rand(bs, nq, generator=g), torch.rand(bs, nq, generator=g) * 0.3 + 0.01], -1)
+    targets = torch.stack([torch.rand(bs, nt, generator=g), torch.rand(bs, nt, generator=g) * 0.3 + 0.01], -1)
+    targets[0, 1:, 1] = 0            # one target only
+    targets[3, 2, 1] = 0
+    matcher = build_matcher(config.default_args())
+    got = matcher({"pred_logits": logits.to(dev), "pred_spans": spans.to(dev)}, targets.to(dev))
+    ref = O.hungarian_indices(logits, spans, targets)
+    assert len(got) == bs
+    for (gi, gj), (ri, rj) in zip(got, ref):
+        assert torch.equal(gi, ri) and torch.equal(gj, rj)
+    C, sizes = matcher.cost_matrix({"pred_logits": logits.to(dev), "pred_spans": spans.to(dev)}, targets.to(dev))
+    mask = targets[:, :, 1] != 0
+    refC = O.matcher_cost(logits.flatten(0, 1).softmax(-1)[:, 0], spans.flatten(0, 1), targets[mask]).view(bs, nq, -1)
+    np.testing.assert_allclose(C.cpu().numpy(), refC.numpy(), atol=2e-6, rtol=0)     # device exp in the softmax
+    with pytest.raises(ValueError):
+        build_matcher(config.default_args(span_loss_type="ce"))
