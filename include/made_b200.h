@@ -51,6 +51,13 @@ int made_device_check(int device);
  * ------------------------------------------------------------------------------------------- */
 /* span_cw_to_se (span_utils.py:15-24): cw [n,2] -> se [n,2] */
 int made_span_cw_to_se(const float* cw, float* se, int64_t n, void* stream);
+/* span_se_to_cw (span_utils.py:4-13): se [n,2] -> cw [n,2] */
+int made_span_se_to_cw(const float* se, float* cw, int64_t n, void* stream);
+/* detr_iou + individual_IoU_tensor (span_utils.py:119-170) for n predicted spans in seconds:
+ * clamp start >= 0, end <= max_m_duration then <= m_duration[i]; 0 when the ground truth is
+ * degenerate or the union is <= 0.  gt_moment [n,2]. */
+int made_span_iou(const float* pred_st, const float* pred_ed, const float* gt_moment, const float* m_duration,
+                  float max_m_duration, int64_t n, float* iou, void* stream);
 /* generalized_temporal_iou (span_utils.py:86-115): spans1_se [n,2], spans2_se [m,2] -> giou [n,m] */
 int made_giou(const float* spans1_se, int64_t n, const float* spans2_se, int64_t m, float* giou,
               void* stream);

@@ -31,6 +31,8 @@ SIGNATURES = {
     "made_abi_version": [],
     "made_device_check": [_i32],
     "made_span_cw_to_se": [_p, _p, _i64, _p],
+    "made_span_se_to_cw": [_p, _p, _i64, _p],
+    "made_span_iou": [_p, _p, _p, _p, _f, _i64, _p, _p],
     "made_giou": [_p, _i64, _p, _i64, _p, _p],
     "made_temporal_iou": [_p, _i64, _p, _i64, _p, _p, _p],
     "made_matcher_cost": [_p, _p, _i64, _p, _i64, _f, _f, _f, _p, _p],

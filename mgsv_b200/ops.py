@@ -28,6 +28,42 @@ def span_cw_to_se(cw_spans: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def span_se_to_cw(se_spans: torch.Tensor) -> torch.Tensor:
+    """span_utils.py:4-13."""
+    se = _f32c(se_spans)
+    out = torch.empty_like(se)
+    _lib.check(_lib.load().made_span_se_to_cw(_lib.ptr(se), _lib.ptr(out), se.shape[0], _lib.stream_ptr()))
+    return out
+
+
+def span_iou(pred_st: torch.Tensor, pred_ed: torch.Tensor, gt_moment: torch.Tensor, m_duration: torch.Tensor,
+             max_m_duration: float = MAX_M_DURATION) -> torch.Tensor:
+    """detr_iou + individual_IoU_tensor (span_utils.py:119-170), batched: spans in seconds → IoU [n]."""
+    st, ed = _f32c(pred_st.reshape(-1)), _f32c(pred_ed.reshape(-1))
+    gt, md = _f32c(gt_moment.reshape(-1, 2)), _f32c(m_duration.reshape(-1))
+    if not (st.shape[0] == ed.shape[0] == gt.shape[0] == md.shape[0]):
+        raise ValueError("span_iou: inputs disagree on the number of spans")
+    out = torch.empty_like(st)
+    _lib.check(_lib.load().made_span_iou(_lib.ptr(st), _lib.ptr(ed), _lib.ptr(gt), _lib.ptr(md), max_m_duration,
+                                         st.shape[0], _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def detr_iou(args, mr_results_list, device=None) -> List[torch.Tensor]:
+    """span_utils.py:147-170 with the reference's argument (list of dicts with "gt_moment" [1,2],
+    "m_duration", "ranked_preds" [#preds,3]); one kernel launch for the whole list.  Returns the
+    reference's list of 0-d tensors (on the host)."""
+    if not mr_results_list:
+        return []
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    st = torch.tensor([float(d["ranked_preds"][0][0]) for d in mr_results_list], dtype=torch.float32)
+    ed = torch.tensor([float(d["ranked_preds"][0][1]) for d in mr_results_list], dtype=torch.float32)
+    gt = torch.stack([torch.as_tensor(d["gt_moment"], dtype=torch.float32).reshape(-1, 2)[0] for d in mr_results_list])
+    md = torch.tensor([float(d["m_duration"]) for d in mr_results_list], dtype=torch.float32)
+    iou = span_iou(st.to(dev), ed.to(dev), gt.to(dev), md.to(dev), float(getattr(args, "max_m_duration", MAX_M_DURATION)))
+    return list(iou.cpu().unbind(0))
+
+
 def _check_spans(s: torch.Tensor, name: str) -> torch.Tensor:
     if s.dim() != 2 or s.shape[1] != 2:
         raise ValueError(f"{name} must be [n,2], got {tuple(s.shape)}")

@@ -600,3 +600,25 @@ def test_hungarian_matcher_mirror(dev):
     np.testing.assert_allclose(C.cpu().numpy(), refC.numpy(), atol=2e-6, rtol=0)     # device exp in the softmax
     with pytest.raises(ValueError):
         build_matcher(config.default_args(span_loss_type="ce"))
+
+
+def test_span_se_to_cw_and_detr_iou_mirror(dev):
+    """span_utils.py:4-13 and :147-170 through the reference's own call shapes."""
+    rng = np.random.default_rng(17)
+    se = torch.sort(torch.from_numpy(rng.uniform(0, 1, (513, 2)).astype(np.float32)), dim=-1)[0]
+    cw = ops.span_se_to_cw(se.to(dev)).cpu()
+    ref_cw = torch.stack([se.sum(-1) * 0.5, se[:, 1] - se[:, 0]], -1)
+    assert torch.equal(cw, ref_cw)
+    assert torch.equal(ops.span_cw_to_se(cw.to(dev)).cpu(), O.span_cw_to_se(cw))
+    n = 300
+    st = torch.from_numpy(rng.uniform(-20, 200, n).astype(np.float32))
+    ed = st + torch.from_numpy(rng.uniform(0, 120, n).astype(np.float32))
+    gt = torch.sort(torch.from_numpy(rng.uniform(0, 240, (n, 1, 2)).astype(np.float32)), dim=-1)[0]
+    gt[5, 0, 1] = gt[5, 0, 0]
+    md = torch.from_numpy(rng.uniform(30, 240, n).astype(np.float32))
+    items = [dict(gt_moment=gt[i], m_duration=float(md[i]),
+                  ranked_preds=torch.tensor([[float(st[i]), float(ed[i]), 0.5]])) for i in range(n)]
+    got = ops.detr_iou(config.default_args(), items, device=dev)
+    ref = O.detr_iou(st, ed, gt, md)
+    assert len(got) == n and got[0].dim() == 0
+    assert np.array_equal(torch.stack(got).numpy(), ref.numpy())
