@@ -9,7 +9,7 @@ namespace made {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
 constexpr int kStages = 3;
-constexpr int kStageBoxBytes = 128 * 128;            // one TMA store box: 128 rows x 128 bytes (swizzled)
+constexpr int kWarpBoxBytes = 32 * 128;              // one TMA store box: a warp's 32 rows x 128 bytes (swizzled)
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -31,7 +31,7 @@ struct GemmCfg {
   static constexpr int kMiscBytes = 256 + 4 * 128 * 4;      // barriers + TMEM slot, LN partial sums
   static constexpr int kStageOutOffset = ((kResidentBytes + kStages * kStageBytes + kMiscBytes + 1023) / 1024) * 1024;
   // the weight-stationary variant has room for the fp16 boxes only (fp32 outputs go to the streaming variant)
-  static constexpr int kStageOutBytes = (WS ? 2 : 4) * kStageBoxBytes;
+  static constexpr int kStageOutBytes = (WS ? 1 : 2) * kEpiWarps * kWarpBoxBytes;
   static constexpr int kSmemBytes = kStageOutOffset + kStageOutBytes + 1024 /*align slack*/;
 };
 
@@ -68,7 +68,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* w_empty = w_full + 1;                     // WS: every MMA that reads the slice has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
   float* ln_part = reinterpret_cast<float*>(after + 256);   // [2 halves][2][128]
-  uint8_t* stage_out = smem + Cfg::kStageOutOffset;         // 4 boxes of 16 KB: fp16 x 2 halves, fp32 x 2 halves
+  uint8_t* stage_out = smem + Cfg::kStageOutOffset;         // per epilogue warp: one fp16 box, then one fp32 box
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,11 +223,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int n_my = kContig ? Cfg::kChunks / 2 : (Cfg::kChunks - half + 1) / 2;
     auto chunk_of = [&](int j) { return kContig ? half * (Cfg::kChunks / 2) + j : half + 2 * j; };
     const bool tma_out = p.tma_store != 0;
-    const bool issuer = (ew & 3) == 0 && lane == 0;                   // one thread per half issues the bulk stores
-    const uint32_t bar_half = 2 + half;                               // named barrier of this half's 128 threads
-    uint8_t* stg_h = stage_out + half * kStageBoxBytes;               // [128 rows][128 B] fp16 box (64 columns)
-    uint8_t* stg_f = stage_out + (2 + half) * kStageBoxBytes;         // [128 rows][128 B] fp32 box (32 columns)
-    const int swz = r_in_tile & 7;
+    // every warp owns its 32 rows of the staging boxes and issues its own bulk stores: no barrier wider
+    // than the warp on the store path
+    const bool issuer = lane == 0;
+    uint8_t* stg_h = stage_out + ew * kWarpBoxBytes;                        // [32 rows][128 B] fp16 box (64 columns)
+    uint8_t* stg_f = stage_out + (kEpiWarps + ew) * kWarpBoxBytes;          // [32 rows][128 B] fp32 box (32 columns)
+    const int swz = lane & 7;
 
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int as = static_cast<int>(it & 1);
@@ -254,25 +255,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const bool h_first = (j & 1) == 0;     // an fp16 box holds two chunks
           // the previous bulk stores of this half have finished READING the staging boxes
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          named_bar_sync(bar_half, 128);
+          __syncwarp();
           if (e.out_f32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(stg_f + r_in_tile * 128 + ((i ^ swz) << 4)) =
+              *reinterpret_cast<float4*>(stg_f + lane * 128 + ((i ^ swz) << 4)) =
                   make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           if (e.out_h) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(stg_h + r_in_tile * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) =
+              *reinterpret_cast<uint4*>(stg_h + lane * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) =
                   make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
                              pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
           }
           fence_proxy_async_smem();
-          named_bar_sync(bar_half, 128);
+          __syncwarp();
           if (issuer) {
-            if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, static_cast<int32_t>(row0));
-            if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, static_cast<int32_t>(row0));
+            const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
+            if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, wrow);
+            if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, wrow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else if (row_ok) {
@@ -516,10 +518,10 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
   if (pp.tma_store) {
     if (e.out_h)
       MADE_TRY(encode_tmap_2d(&toh, e.out_h, 2, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
-                              static_cast<uint64_t>(e.ld_h) * 2, 64, 128));
+                              static_cast<uint64_t>(e.ld_h) * 2, 64, 32));
     if (e.out_f32)
       MADE_TRY(encode_tmap_2d(&tof, e.out_f32, 4, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
-                              static_cast<uint64_t>(e.ld_f32) * 4, 32, 128));
+                              static_cast<uint64_t>(e.ld_f32) * 4, 32, 32));
   }
   if (block_n == 256) {
     // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles;
