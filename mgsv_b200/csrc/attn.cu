@@ -195,24 +195,35 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 //   mbar_h      = sum_t softmax_t(scores_h)[t] * memory_t   -> out [B, 8*256] fp16
 // so every layer reads the SAME two [len,256] fp16 matrices of a sequence and the [B*146, 6*512] K/V
 // tensors of the reference are never formed.
-// One CTA per sequence: all 256 threads stage the valid rows of (memory + pos) in shared memory with
-// cp.async (every row crosses L2 once, all loads in flight together), warp = head computes the
-// scores and the softmax, then the same buffer is refilled with the memory rows for the weighted sum.
+// One CTA per sequence.  All 256 threads stage the valid rows of (memory + pos) in shared memory with
+// cp.async; the 8 heads form the 8 real rows of an m16n8k16 A tile (rows 8-15 are zero), so
+//   S[8 x len]  = Q~[8 x 256] . MP^T      (q~ as an fp16 hi + lo pair: two MMAs per k-step)
+//   O[8 x 256]  = P[8 x len]  . MEM       (P = un-normalised exps in fp16, B via ldmatrix.trans)
+// run on mma.sync; the same row buffer is refilled with the memory rows while the softmax runs.
 constexpr int kDecMaxRows = 160;
-constexpr int kDecSmemBytes = kDecMaxRows * 512;
-
+constexpr int kDecPitch = 264;                          // fp16 elements per staged row (528 B: conflict-free)
+constexpr int kDecRowsBytes = kDecMaxRows * kDecPitch * 2;
+constexpr int kDecQBytes = 2 * 8 * kDecPitch * 2;       // q~ hi / lo, 8 heads
+constexpr int kDecPPitch = kDecMaxRows + 8;             // fp16 elements per P row
+constexpr int kDecSmemBytes = kDecRowsBytes + kDecQBytes + 8 * kDecPPitch * 2;
 
 __global__ void __launch_bounds__(256)
 dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp,
                        const op_t* __restrict__ mem, const float* __restrict__ key_mask, int L,
                        const int32_t* __restrict__ seq_off, const int32_t* __restrict__ seq_len,
                        op_t* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t dec_rows[];     // [nv][256] fp16
-  __shared__ float sp[8][kDecMaxRows];
+  extern __shared__ __align__(16) uint8_t dec_smem[];
+  op_t* rows = reinterpret_cast<op_t*>(dec_smem);                               // [nvp][264]
+  op_t* qhi = reinterpret_cast<op_t*>(dec_smem + kDecRowsBytes);                // [8][264]
+  op_t* qlo = qhi + 8 * kDecPitch;                                              // [8][264]
+  op_t* ps = reinterpret_cast<op_t*>(dec_smem + kDecRowsBytes + kDecQBytes);    // [8][168] exps (fp16)
+  __shared__ float sc[8][kDecMaxRows];
+  __shared__ float ssum[8];
   __shared__ short vidx[kDecMaxRows];
   __shared__ int s_nvalid;
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L;
   if (seq_off) {     // ragged batch: the sequence's rows are exactly its valid keys
     const int n = min(seq_len[b], kDecMaxRows);
@@ -221,85 +232,97 @@ dec_attn_folded_kernel(const float* __restrict__ qt, const op_t* __restrict__ mp
   } else if (warp == 0) {   // ordered compaction of the valid key positions
     int base = 0;
     for (int t0 = 0; t0 < L; t0 += 32) {
-      const int t = t0 + lane;
-      const bool ok = t < L && key_mask[b * L + t] != 0.f;
+      const int tt = t0 + lane;
+      const bool ok = tt < L && key_mask[b * L + tt] != 0.f;
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) vidx[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<short>(t);
+      if (ok) vidx[base + __popc(bal & ((1u << lane) - 1u))] = static_cast<short>(tt);
       base += __popc(bal);
     }
     if (lane == 0) s_nvalid = base;
   }
-  float q[8];
+  // q~ -> fp16 hi + lo in shared memory (warp = head, lane = 8 features)
   {
     const float4* qp = reinterpret_cast<const float4*>(qt + b * 2048 + warp * 256 + lane * 8);
     const float4 a = __ldg(qp), c = __ldg(qp + 1);
-    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = c.x; q[5] = c.y; q[6] = c.z; q[7] = c.w;
+    const float q[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const op2_t h = floats2op2(q[2 * j], q[2 * j + 1]);
+      const float2 hf = op2_to_f2(h);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = pack_op2(q[2 * j] - hf.x, q[2 * j + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(qhi + warp * kDecPitch + lane * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(qlo + warp * kDecPitch + lane * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
   __syncthreads();
   const int nv = s_nvalid;
-  // ---- stage (memory + pos) rows: thread = (row tid/32 + 8k, 16-byte chunk tid%32) ----
-  for (int i = warp; i < nv; i += 8)
-    cp_async_16(dec_rows + i * 512 + lane * 16, mp + (row0 + vidx[i]) * 256 + lane * 8);
+  const int nvp = (nv + 15) & ~15;                       // keys padded to the MMA k-step
+  // ---- stage (memory + pos) rows; rows [nv, nvp) are zero-filled ----
+  for (int i = warp; i < nvp; i += 8)
+    cp_async_16_zfill(rows + i * kDecPitch + lane * 8, mp + (row0 + (i < nv ? vidx[i] : 0)) * 256 + lane * 8, i < nv);
   cp_async_wait_all();
   __syncthreads();
-  float mx = -INFINITY;
-  for (int i0 = 0; i0 < nv; i0 += 4) {
-    float acc[4];
+  // ---- S = Q~ MP^T: warp w takes key tiles w, w+8, ... (8 keys each) ----
+  for (int nt = warp; nt * 8 < nv; nt += 8) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const op_t* krow = rows + (nt * 8 + g) * kDecPitch + 2 * t;
+    const op_t* qh = qhi + g * kDecPitch + 2 * t;
+    const op_t* ql = qlo + g * kDecPitch + 2 * t;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = min(i0 + k, nv - 1);
-      const uint4 raw = *reinterpret_cast<const uint4*>(dec_rows + i * 512 + lane * 16);
-      const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = op2_to_f2(hh[j]);
-        a = fmaf(f.x, q[2 * j], a);
-        a = fmaf(f.y, q[2 * j + 1], a);
-      }
-      acc[k] = a;
+    for (int ks = 0; ks < 16; ++ks) {
+      uint32_t kb[2], ah[4], al[4];
+      kb[0] = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+      kb[1] = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+      ah[0] = *reinterpret_cast<const uint32_t*>(qh + ks * 16);
+      ah[2] = *reinterpret_cast<const uint32_t*>(qh + ks * 16 + 8);
+      al[0] = *reinterpret_cast<const uint32_t*>(ql + ks * 16);
+      al[2] = *reinterpret_cast<const uint32_t*>(ql + ks * 16 + 8);
+      ah[1] = ah[3] = al[1] = al[3] = 0u;                 // rows 8..15 of the A tile are zero
+      mma_f16_16816(c, ah, kb);
+      mma_f16_16816(c, al, kb);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i0 + k < nv) {
-        if (lane == 0) sp[warp][i0 + k] = acc[k];
-        mx = fmaxf(mx, acc[k]);
-      }
-    }
+    const int key = nt * 8 + 2 * t;                       // c[0], c[1]: head g, keys key, key + 1
+    if (key < nv) sc[g][key] = c[0];
+    if (key + 1 < nv) sc[g][key + 1] = c[1];
   }
-  __syncthreads();                 // every warp is done with the (memory + pos) rows
-  for (int i = warp; i < nv; i += 8)
-    cp_async_16(dec_rows + i * 512 + lane * 16, mem + (row0 + vidx[i]) * 256 + lane * 8);
-  float sum = 0.f;                 // the softmax overlaps the refill
-  for (int i = lane; i < nv; i += 32) {
-    const float e = fast_exp(sp[warp][i] - mx);
-    sp[warp][i] = e;
-    sum += e;
+  __syncthreads();                 // scores complete; every warp is done with the (memory + pos) rows
+  for (int i = warp; i < nvp; i += 8)
+    cp_async_16_zfill(rows + i * kDecPitch + lane * 8, mem + (row0 + (i < nv ? vidx[i] : 0)) * 256 + lane * 8, i < nv);
+  // ---- softmax of head `warp` (overlaps the refill): un-normalised exps -> fp16 ----
+  {
+    float mx = -INFINITY;
+    for (int i = lane; i < nv; i += 32) mx = fmaxf(mx, sc[warp][i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int i = lane; i < nvp; i += 32) {
+      const op_t e = i < nv ? f2op(fast_exp(sc[warp][i] - mx)) : f2op(0.f);
+      ps[warp * kDecPPitch + i] = e;
+      sum += op2f(e);                                      // divisor = sum of the ROUNDED weights
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) ssum[warp] = sum;
   }
-  sum = warp_sum(sum);
   cp_async_wait_all();
   __syncthreads();
-  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = 0; i < nv; ++i) {
-    const float a = sp[warp][i];
-    const uint4 raw = *reinterpret_cast<const uint4*>(dec_rows + i * 512 + lane * 16);
-    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
+  // ---- O = P MEM: warp w takes feature tiles 4w .. 4w+3 (8 features each) ----
+  const op_t* prow = ps + g * kDecPPitch + 2 * t;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = op2_to_f2(hh[j]);
-      o[2 * j] = fmaf(a, f.x, o[2 * j]);
-      o[2 * j + 1] = fmaf(a, f.y, o[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) {
+    const int nd = warp * 4 + j;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kk = 0; kk * 16 < nvp; ++kk) {
+      uint32_t a[4], vb[2];
+      a[0] = *reinterpret_cast<const uint32_t*>(prow + kk * 16);
+      a[2] = *reinterpret_cast<const uint32_t*>(prow + kk * 16 + 8);
+      a[1] = a[3] = 0u;
+      ldmatrix_x2_trans(vb, rows + (kk * 16 + (lane & 15)) * kDecPitch + nd * 8);
+      mma_f16_16816(c, a, vb);
     }
+    const float inv = 1.f / ssum[g];                       // c[0], c[1]: head g, features nd*8 + 2t, +1
+    *reinterpret_cast<uint32_t*>(out + b * 2048 + g * 256 + nd * 8 + 2 * t) = pack_op2(c[0] * inv, c[1] * inv);
   }
-  const float inv = 1.f / sum;
-  *reinterpret_cast<uint4*>(out + b * 2048 + warp * 256 + lane * 8) =
-      make_uint4(pack_op2(o[0] * inv, o[1] * inv), pack_op2(o[2] * inv, o[3] * inv),
-                 pack_op2(o[4] * inv, o[5] * inv), pack_op2(o[6] * inv, o[7] * inv));
 }
 
 }  // namespace made

@@ -254,8 +254,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (tma_out) {
           const bool h_first = (j & 1) == 0;     // an fp16 box holds two chunks
           // the previous bulk stores of this half have finished READING the staging boxes
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
+          if (e.out_f32 || h_first) {      // a box is about to be overwritten
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
           if (e.out_f32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
