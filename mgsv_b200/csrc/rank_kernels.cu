@@ -172,14 +172,39 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
       if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int rem = sh_krem, b = 255, acc = 0;
-      for (; b > 0; --b) {
-        if (acc + hist[b] >= rem) break;
-        acc += hist[b];
+    // find the bucket that holds the k-th largest key: warp 0 scans the 256 buckets from the top,
+    // 8 buckets per lane + a shuffle scan (a single thread walking 256 buckets cost ~1.3 us per pass)
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int rem = sh_krem;
+      int loc[8], tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {          // lane 0 owns buckets 255..248, lane 1 247..240, ...
+        loc[i] = hist[255 - (lane * 8 + i)];
+        tot += loc[i];
       }
-      sh_krem = rem - acc;  // still needed inside bucket b
-      sh_prefix = prefix | (static_cast<unsigned long long>(b) << shift);
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      int acc = incl - tot;                   // keys in buckets above this lane's range
+      const bool here = acc < rem && incl >= rem;      // the k-th largest falls inside this lane's 8 buckets
+      const bool none = __ballot_sync(0xffffffffu, here) == 0u;   // fewer than `rem` keys in total: bucket 0
+      if (here) {
+        int b = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (acc + loc[i] >= rem) { b = 255 - (lane * 8 + i); break; }
+          acc += loc[i];
+        }
+        sh_krem = rem - acc;  // still needed inside bucket b
+        sh_prefix = prefix | (static_cast<unsigned long long>(b) << shift);
+      } else if (none && lane == 31) {
+        sh_krem = rem - (incl - loc[7]);
+        sh_prefix = prefix;                   // bucket 0
+      }
     }
     __syncthreads();
   }
