@@ -480,6 +480,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return MADE_OK;
 }
 
+bool gemm_tma_store_enabled() {
+  static const bool enabled = [] {
+    const char* v = getenv("MADE_GEMM_TMA_STORE");
+    return !(v && v[0] == '0');
+  }();
+  return enabled;
+}
+
 int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                  int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream) {
   if (p.M == 0) return MADE_OK;
@@ -507,22 +515,24 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
   GemmParams pp = p;
   // outputs through TMA bulk stores whenever the tile is a plain [128 x 256] block of the output matrices
-  static const bool tma_store_enabled = [] {
-    const char* v = getenv("MADE_GEMM_TMA_STORE");
-    return !(v && v[0] == '0');
-  }();
+  const bool tma_store_enabled = gemm_tma_store_enabled();
   auto aligned16 = [](const void* ptr, int64_t ld, int esz) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0;
   };
   pp.tma_store = tma_store_enabled && block_n == 256 && p.m_valid == 128 && p.m_stride == 128 && !e.h_row_idx &&
                  (e.out_h || e.out_f32) && (!e.out_h || aligned16(e.out_h, e.ld_h, 2)) &&
                  (!e.out_f32 || aligned16(e.out_f32, e.ld_f32, 4));
+  if (p.n_store > 0 && p.n_store < p.N && !(pp.tma_store && !e.out2_h && !e.ln_gamma && !e.l2norm)) {
+    set_error("gemm: a clipped output width needs the plain TMA-store epilogue");
+    return MADE_EUNSUPPORTED;
+  }
   if (pp.tma_store) {
+    const uint64_t n_ext = static_cast<uint64_t>(p.n_store > 0 && p.n_store < p.N ? p.n_store : p.N);
     if (e.out_h)
-      MADE_TRY(encode_tmap_2d(&toh, e.out_h, 2, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
+      MADE_TRY(encode_tmap_2d(&toh, e.out_h, 2, n_ext, static_cast<uint64_t>(p.M),
                               static_cast<uint64_t>(e.ld_h) * 2, 64, 32));
     if (e.out_f32)
-      MADE_TRY(encode_tmap_2d(&tof, e.out_f32, 4, static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M),
+      MADE_TRY(encode_tmap_2d(&tof, e.out_f32, 4, n_ext, static_cast<uint64_t>(p.M),
                               static_cast<uint64_t>(e.ld_f32) * 4, 32, 32));
   }
   if (block_n == 256) {

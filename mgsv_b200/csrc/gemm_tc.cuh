@@ -42,11 +42,15 @@ struct GemmParams {
   int b_batched = 0;    // 1: B rows start at tile_m * m_stride (per-tile B, e.g. Gram matrix)
   const int32_t* m_dev = nullptr;   // device scalar: actual row count (<= M); M then only sizes the grid / TMA map
   int tma_store = 0;                // set by the launcher: out_h / out_f32 leave through TMA bulk stores
+  int n_store = 0;                  // > 0: only the first n_store (< N) output columns exist; W rows >= w_rows read as
+                                    // zero and the TMA store clips the rest (needs the TMA-store path, else EUNSUPPORTED)
   GemmEpilogue epi;
 };
 
 // Host launcher. A: [M, K] fp16 with row stride lda; W: [N(or M for batched), K] fp16, stride ldb.
 int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                  int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream);
+// whether outputs may leave through TMA bulk stores (MADE_GEMM_TMA_STORE=0 turns them off)
+bool gemm_tma_store_enabled();
 
 }  // namespace made

@@ -7,8 +7,12 @@
 //   1. s* = max score over the ground-truth id's columns (chain walk over prev_same),
 //   2. rank = number of DISTINCT music ids whose best column beats s* (strictly) — a column counts
 //      iff s > s* and no earlier column of the same id also has s > s* (prev_same chain),
-//   3. exact top-k by an 8-pass MSB radix select on order-preserving 64-bit keys, ties broken by
-//      the lower column index, then a bitonic sort of the k winners.
+//   3. exact top-k on order-preserving 64-bit keys, ties broken by the lower column index.  Fast path
+//      (row staged in shared memory): a 1024-bin histogram over the row's key RANGE locates the bin
+//      of the k-th largest key (refined 10 bits at a time while more than 512 keys sit at or above
+//      it), those keys are gathered and ordered by counting — three sweeps of shared memory for a
+//      typical score row.  Rows where one key repeats > 512 times around rank k (or rows too long to
+//      stage) take the exact 8-pass MSB radix select + bitonic sort instead.
 // The row is staged once in shared memory (up to kMaxSmemCols columns; beyond that the passes
 // re-read global memory), so HBM traffic is the algorithmic 8 B per (query, track).
 #include "common.cuh"
@@ -18,6 +22,10 @@ namespace made {
 
 constexpr int kRankThreads = 256;
 constexpr int kMaxK = 256;
+constexpr int kValueBinBits = 10;
+constexpr int kValueBins = 1 << kValueBinBits;   // value-histogram bins of the fast top-k path
+constexpr int kMaxCand = 512;                    // candidates the fast path orders (>= kMaxK + kCandSlack)
+constexpr int kCandSlack = 32;                   // refine the threshold while more than k + 32 keys pass it
 constexpr int kMaxSmemCols = 24576;  // 24576 * 8 B = 192 KB of keys
 
 __device__ __forceinline__ unsigned long long f64_key(double x) {
@@ -88,50 +96,115 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
                  double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
                  double* __restrict__ gt_score_out) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ int hist[256];
+  __shared__ int hist[kValueBins];           // value histogram (fast path) / 256 radix buckets
   __shared__ int red[kRankThreads / 32];
-  __shared__ unsigned long long sel_keys[kMaxK];
-  __shared__ int sel_idx[kMaxK];
+  __shared__ unsigned long long red64[2][kRankThreads / 32];
+  __shared__ unsigned long long sel_keys[kMaxCand];
+  __shared__ int sel_idx[kMaxCand];
   __shared__ unsigned long long sh_prefix;
-  __shared__ int sh_krem, sh_count, sh_eq_taken;
+  __shared__ int sh_krem, sh_count, sh_eq_taken, sh_bin, sh_ncand;
   __shared__ unsigned long long sh_gt_key;
 
   const int64_t row = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowView rv;
   rv.a = single + row * ld;
   rv.b = dual ? dual + row * ld : nullptr;
   rv.cache = nullptr;
+  const bool want_rank = rank_out != nullptr;
+
+  // ---- 1. ground-truth score (thread 0 walks the id's columns while the others stage the row) --
+  if (want_rank && threadIdx.x == 0) {
+    unsigned long long best = 0;  // smaller than any real key
+    if (gt_score_in) {
+      best = f64_key(gt_score_in[row]);
+    } else {
+      int32_t g = gt_col ? gt_col[row] : -1;
+      int32_t guard = 0;
+      while (g >= 0 && g < n_cols && guard++ < (1 << 20)) {
+        unsigned long long kk = rv.key(g);
+        best = kk > best ? kk : best;
+        g = prev_same ? prev_same[g] : -1;
+      }
+    }
+    sh_gt_key = best;
+  }
+  unsigned long long kmin = ~0ull, kmax = 0ull;
   if (use_cache) {
+    // stage the row once as 64-bit keys, tracking the key range for the value histogram
     unsigned long long* cache = reinterpret_cast<unsigned long long*>(dyn_smem);
-    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) cache[j] = rv.key(j);
-    __syncthreads();
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
+                     (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
+    if (vec) {
+      const int64_t n4 = n_cols / 4;
+      const float4* a4 = reinterpret_cast<const float4*>(rv.a);
+      const float4* b4 = reinterpret_cast<const float4*>(rv.b);
+#pragma unroll 2
+      for (int64_t q = threadIdx.x; q < n4; q += kRankThreads) {
+        const float4 x = __ldg(a4 + q);
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rv.b) y = __ldg(b4 + q);
+        unsigned long long k0 = f64_key(rv.b ? double(x.x) + double(y.x) : double(x.x));
+        unsigned long long k1 = f64_key(rv.b ? double(x.y) + double(y.y) : double(x.y));
+        unsigned long long k2 = f64_key(rv.b ? double(x.z) + double(y.z) : double(x.z));
+        unsigned long long k3 = f64_key(rv.b ? double(x.w) + double(y.w) : double(x.w));
+        *reinterpret_cast<ulonglong2*>(cache + q * 4) = make_ulonglong2(k0, k1);
+        *reinterpret_cast<ulonglong2*>(cache + q * 4 + 2) = make_ulonglong2(k2, k3);
+        unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+        unsigned long long lo2 = k2 < k3 ? k2 : k3, hi2 = k2 < k3 ? k3 : k2;
+        lo = lo < lo2 ? lo : lo2; hi = hi > hi2 ? hi : hi2;
+        kmin = lo < kmin ? lo : kmin; kmax = hi > kmax ? hi : kmax;
+      }
+      for (int64_t j = n4 * 4 + threadIdx.x; j < n_cols; j += kRankThreads) {
+        unsigned long long key = rv.key(j);
+        cache[j] = key;
+        kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+      }
+    } else {
+      for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+        unsigned long long key = rv.key(j);
+        cache[j] = key;
+        kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long u = __shfl_xor_sync(0xffffffffu, kmin, o);
+      unsigned long long v = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmin = u < kmin ? u : kmin; kmax = v > kmax ? v : kmax;
+    }
+    if (lane == 0) { red64[0][warp] = kmin; red64[1][warp] = kmax; }
     rv.cache = cache;
   }
-
-  // ---- 1. ground-truth score ------------------------------------------------------------
-  const bool want_rank = rank_out != nullptr;
-  if (want_rank) {
-    if (threadIdx.x == 0) {
-      unsigned long long best = 0;  // smaller than any real key
-      if (gt_score_in) {
-        best = f64_key(gt_score_in[row]);
-      } else {
-        int32_t g = gt_col ? gt_col[row] : -1;
-        int32_t guard = 0;
-        while (g >= 0 && g < n_cols && guard++ < (1 << 20)) {
-          unsigned long long kk = rv.key(g);
-          best = kk > best ? kk : best;
-          g = prev_same ? prev_same[g] : -1;
-        }
-      }
-      sh_gt_key = best;
+  for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) hist[t] = 0;
+  if (threadIdx.x == 0) { sh_count = 0; sh_ncand = 0; }
+  __syncthreads();
+  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
+  const bool want_topk = k > 0 && topk_idx != nullptr;
+  // fast path (row staged in shared memory): one sweep feeds both the rank count and a 1024-bin
+  // histogram over the row's VALUE range; the bin holding the k-th largest key gives a threshold
+  // with at most a few keys more than k above it, and those candidates are ordered by counting.
+  bool fast = use_cache && want_topk && kk > 0;
+  int vshift = 0;
+  if (use_cache) {
+#pragma unroll
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+      kmin = red64[0][w] < kmin ? red64[0][w] : kmin;
+      kmax = red64[1][w] > kmax ? red64[1][w] : kmax;
     }
-    __syncthreads();
-    // ---- 2. distinct ids ahead of the ground truth --------------------------------------
-    const unsigned long long gk = sh_gt_key;
+    const unsigned long long range = kmax - kmin;
+    const int bits = range ? 64 - __clzll(static_cast<long long>(range)) : 0;
+    vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
+  }
+
+  // ---- 2. distinct ids ahead of the ground truth (+ value histogram on the fast path) --------
+  if (want_rank || fast) {
+    const unsigned long long gk = want_rank ? sh_gt_key : ~0ull;
     int cnt = 0;
     for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-      if (rv.key(j) > gk) {
+      const unsigned long long key = rv.key(j);
+      if (fast) atomicAdd(&hist[static_cast<int>((key - kmin) >> vshift)], 1);
+      if (want_rank && key > gk) {
         bool first = true;
         if (prev_same) {
           int32_t p = prev_same[j];
@@ -144,16 +217,106 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
         cnt += first ? 1 : 0;
       }
     }
-    cnt = block_sum_int(cnt, red);
-    if (threadIdx.x == 0) {
-      rank_out[row] = cnt;
-      if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
+    if (want_rank) {
+      cnt = block_sum_int(cnt, red);   // contains the barriers that publish hist
+      if (threadIdx.x == 0) {
+        rank_out[row] = cnt;
+        if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
+      }
+    } else {
+      __syncthreads();
     }
   }
-  if (k <= 0 || topk_idx == nullptr) return;
+  if (!want_topk) return;
+
+  if (fast) {
+    // Locate the k-th largest key by value: 10 bits of the row's key range per level (level 0 was
+    // histogrammed in the sweep above).  Stop as soon as at most kMaxCand keys sit at or above the
+    // chosen bin; real score rows need one level, rows with outliers two.
+    unsigned long long base = kmin, thr = 0ull;
+    int shift = vshift, need = kk, above = 0, n_cand = 0;
+    bool ok = false;
+    for (int level = 0; level < 8; ++level) {
+      if (level > 0) {
+        for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) hist[t] = 0;
+        __syncthreads();
+        for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+          const unsigned long long key = rv.key(j);
+          const unsigned long long d = (key - base) >> shift;
+          if (key >= base && d < kValueBins) atomicAdd(&hist[static_cast<int>(d)], 1);
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {   // scan the bins from the top, 32 bins per lane
+        constexpr int kPer = kValueBins / 32;
+        int tot = 0;
+        const int top = kValueBins - 1 - lane * kPer;   // this lane owns bins top, top-1, ..., top-kPer+1
+#pragma unroll 8
+        for (int i = 0; i < kPer; ++i) tot += hist[top - ((i + lane) & (kPer - 1))];   // rotated: no bank conflicts
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        int acc = incl - tot;
+        if (acc < need && incl >= need) {
+          for (int i = 0; i < kPer; ++i) {
+            const int c = hist[top - i];
+            if (acc + c >= need) { sh_bin = top - i; sh_krem = acc; sh_ncand = c; break; }
+            acc += c;
+          }
+        }
+      }
+      __syncthreads();
+      const int bin = sh_bin, acc = sh_krem, c = sh_ncand;
+      n_cand = above + acc + c;
+      // accept once the candidate set is close to k (ordering it costs n_cand^2 / 256 steps per
+      // thread); at shift 0 the bin is a single key value and cannot be split further
+      if (n_cand <= kk + kCandSlack || (shift == 0 && n_cand <= kMaxCand)) {
+        thr = base + (static_cast<unsigned long long>(bin) << shift);
+        ok = true;
+        break;
+      }
+      if (shift == 0) break;   // more than kMaxCand copies of one key: the radix path orders the ties
+      above += acc;
+      need -= acc;
+      base += static_cast<unsigned long long>(bin) << shift;
+      shift = shift > kValueBinBits ? shift - kValueBinBits : 0;
+    }
+    if (ok) {
+      for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+        const unsigned long long key = rv.key(j);
+        if (key >= thr) {
+          const int slot = atomicAdd(&sh_count, 1);
+          if (slot < kMaxCand) { sel_keys[slot] = key; sel_idx[slot] = static_cast<int>(j); }
+        }
+      }
+      __syncthreads();
+      // order by counting: position = number of candidates that come first (key desc, column asc)
+      for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
+        const unsigned long long key = sel_keys[t];
+        const int idx = sel_idx[t];
+        int pos = 0;
+        for (int u = 0; u < n_cand; ++u) {
+          const unsigned long long ku = sel_keys[u];
+          pos += (ku > key || (ku == key && sel_idx[u] < idx)) ? 1 : 0;
+        }
+        if (pos < kk) {
+          topk_idx[row * k + pos] = idx + col_offset;
+          if (topk_score) topk_score[row * k + pos] = key_f64(key);
+        }
+      }
+      for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
+        topk_idx[row * k + t] = -1;
+        if (topk_score) topk_score[row * k + t] = -INFINITY;
+      }
+      return;
+    }
+    __syncthreads();   // a key repeated > kMaxCand times: fall through to the exact radix select
+  }
 
   // ---- 3. top-k: radix select of the k-th largest key -----------------------------------
-  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
   if (threadIdx.x == 0) {
     sh_prefix = 0ull;
     sh_krem = kk;
@@ -175,7 +338,6 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
     // find the bucket that holds the k-th largest key: warp 0 scans the 256 buckets from the top,
     // 8 buckets per lane + a shuffle scan (a single thread walking 256 buckets cost ~1.3 us per pass)
     if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
       const int rem = sh_krem;
       int loc[8], tot = 0;
 #pragma unroll
@@ -226,7 +388,6 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
     int64_t j = base + threadIdx.x;
     bool eq = j < n_cols && rv.key(j) == thr;
     unsigned ballot = __ballot_sync(0xffffffffu, eq);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) red[warp] = __popc(ballot);
     __syncthreads();
     int before = 0, total = 0;
@@ -443,8 +604,9 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int64_t m_tc = 0;
   if (d == 256 && m >= 256 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    // tcgen05 route for the columns that fill whole 256-wide tiles
-    m_tc = (m / 256) * 256;
+    // tcgen05 route: every column when outputs leave through TMA stores (the last 256-wide tile reads
+    // zero rows past the gallery and its store is clipped at column m), else the whole tiles only
+    m_tc = gemm_tma_store_enabled() ? m : (m / 256) * 256;
     // stream-ordered scratch: keep freed blocks in the pool across synchronisations (the default
     // release threshold of 0 hands them back to the OS at every sync, which turned the next
     // cudaMallocAsync into a multi-millisecond allocation whenever a step ended with a sync)
@@ -467,7 +629,8 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
     MADE_CHECK_LAUNCH();
     GemmParams p;
     p.M = n;
-    p.N = static_cast<int>(m_tc);
+    p.N = static_cast<int>(ceil_div64(m_tc, 256) * 256);
+    p.n_store = static_cast<int>(m_tc);
     p.K = 768;
     p.epi.out_f32 = out;
     p.epi.ld_f32 = ld;

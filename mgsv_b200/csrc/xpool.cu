@@ -397,36 +397,53 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // in global memory (lane-indexed reads of __constant__ memory would serialise).
 __device__ float g_xp_c5[5][kXD];
 
-__global__ void xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __restrict__ gw) {
+__global__ void __launch_bounds__(256)
+xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __restrict__ gw) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const uint4 raw = *reinterpret_cast<const uint4*>(z + row * ldz + lane * 8);
-  const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
-  float zz[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = op2_to_f2(hh[j]);
-    zz[2 * j] = f.x;
-    zz[2 * j + 1] = f.y;
-  }
-  float a[5];
+  // this lane's 8-column slice of the five weight vectors stays in registers for all its rows
+  float c[5][8];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const float4 c0 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8]);
     const float4 c1 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8 + 4]);
-    float t = zz[0] * c0.x;
-    t = fmaf(zz[1], c0.y, t); t = fmaf(zz[2], c0.z, t); t = fmaf(zz[3], c0.w, t);
-    t = fmaf(zz[4], c1.x, t); t = fmaf(zz[5], c1.y, t); t = fmaf(zz[6], c1.z, t); t = fmaf(zz[7], c1.w, t);
-    a[k] = warp_sum(t);
+    c[k][0] = c0.x; c[k][1] = c0.y; c[k][2] = c0.z; c[k][3] = c0.w;
+    c[k][4] = c1.x; c[k][5] = c1.y; c[k][6] = c1.z; c[k][7] = c1.w;
   }
-  if (lane == 0) {
-    float lo[5];
+  // rows are strided over the warps; the next two rows are in flight while this one is reduced
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  auto load = [&](int64_t r) { return r < rows ? __ldg(reinterpret_cast<const uint4*>(z + r * ldz + lane * 8)) : zero4; };
+  uint4 r0 = load(row), r1 = load(row + n_warps);
+  for (; row < rows; row += n_warps) {
+    const uint4 raw = r0;
+    r0 = r1;
+    r1 = load(row + 2 * n_warps);
+    const op2_t* hh = reinterpret_cast<const op2_t*>(&raw);
+    float zz[8];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) lo[k] = a[k] - op2f(f2op(a[k]));
-    uint4* o = reinterpret_cast<uint4*>(gw + row * kXG + kXL);
-    o[0] = make_uint4(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]), pack_op2(a[4], lo[0]), pack_op2(lo[1], lo[2]));
-    o[1] = make_uint4(pack_op2(lo[3], lo[4]), 0u, 0u, 0u);
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = op2_to_f2(hh[j]);
+      zz[2 * j] = f.x;
+      zz[2 * j + 1] = f.y;
+    }
+    float a[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float t = zz[0] * c[k][0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t = fmaf(zz[j], c[k][j], t);
+      a[k] = warp_sum(t);
+    }
+    if (lane == 0) {
+      float lo[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) lo[k] = a[k] - op2f(f2op(a[k]));
+      uint4* o = reinterpret_cast<uint4*>(gw + row * kXG + kXL);
+      o[0] = make_uint4(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]), pack_op2(a[4], lo[0]), pack_op2(lo[1], lo[2]));
+      o[1] = make_uint4(pack_op2(lo[3], lo[4]), 0u, 0u, 0u);
+    }
   }
 }
 
@@ -462,7 +479,8 @@ int xpool_set_constants(const float* bias_prime, const float* gamma3, const floa
 
 int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, op_t* gw, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
-  xpool_w5_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, st>>>(z, ldz, rows, gw);
+  const int64_t want = ceil_div64(rows, 8), cap = static_cast<int64_t>(sm_count()) * 3;   // persistent: 3 resident CTAs per SM (78 registers)
+  xpool_w5_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, st>>>(z, ldz, rows, gw);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

@@ -10,6 +10,7 @@ for w in $WHAT; do
     gemm)  K="regex:gemm_tc_kernel"; S=${GEMM_SKIP:-150}; C=${GEMM_COUNT:-8};;
     mha)   K="regex:mha_core"; S=10; C=2;;
     dec)   K="regex:dec_attn_folded"; S=6; C=1;;
+    rank)  K="regex:rank_topk"; S=2; C=1;;
     *) echo "unknown $w"; continue;;
   esac
   timeout 900 ncu --set full --clock-control none --import-source on -k $K -s $S -c $C \

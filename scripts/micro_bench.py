@@ -42,9 +42,9 @@ def main():
         rows.append(dict(kernel=name, ms=ms, algorithmic_bytes=nbytes, gbs=gbs, frac_of_hbm_peak=gbs / peak, note=note))
 
     for n in (1000, 16384):
-        a, b, logits = synth.make_span_pairs(n, n, 3)
+        a, b, logits = synth.make_span_pairs(n, n + 8, 3)
         a, b = a.to(dev), b.to(dev)
-        b = b[b[:, 1] != 0]
+        b = b[b[:, 1] != 0][:n].contiguous()      # matcher.py:59 drops zero-width targets; keep n of them
         se_a, se_b = ops.span_cw_to_se(a), ops.span_cw_to_se(b)
         prob = logits.softmax(-1)[:, 0].contiguous().to(dev)
         m = b.shape[0]

@@ -197,6 +197,42 @@ def test_rank_and_topk_exact(dev, n, n_dup, k):
     assert [x["topk_music_ids"][0] for x in res] == top1 or n_dup > 0
 
 
+@pytest.mark.parametrize("kind", ["clustered", "all_equal", "inf", "quantised", "similarity", "single_only", "long"])
+def test_topk_value_distributions(dev, kind):
+    """The value-histogram fast path and the radix fallback must both give the exact top-k:
+    score descending, lower column first on exact ties, for any distribution of a row's values."""
+    g = torch.Generator().manual_seed(11)
+    n, m, k = 37, 4000, 100
+    dual = torch.zeros(n, m)
+    if kind == "clustered":          # 3 outliers stretch the range, everything else in one bin
+        single = 0.5 + 1e-6 * torch.randn(n, m, generator=g)
+        single[:, 5], single[:, 77], single[:, 1234] = 1e6, -1e6, 3e5
+    elif kind == "all_equal":
+        single = torch.full((n, m), 0.25)
+    elif kind == "inf":
+        single = torch.randn(n, m, generator=g)
+        single[:, ::7] = float("-inf")
+        single[:, 3] = float("inf")
+    elif kind == "quantised":        # heavy exact ties around the k-th value
+        single = torch.randint(0, 20, (n, m), generator=g).float()
+    elif kind == "similarity":       # the shape of real scores: cosine-like in [-1, 1], unaligned ld
+        m = 4001
+        single = torch.tanh(torch.randn(n, m, generator=g))
+        dual = torch.tanh(torch.randn(n, m, generator=g))
+    elif kind == "single_only":
+        single, dual = torch.rand(n, m, generator=g), None
+    else:                            # longer than the shared-memory stage: global-memory radix path
+        m, k = 30000, 64
+        single, dual = torch.randn(n, m, generator=g), torch.randn(n, m, generator=g)
+    total = single.double() + (dual.double() if dual is not None else 0.0)
+    r = ops.rank_topk(single.to(dev), None if dual is None else dual.to(dev), k=k)
+    got_s, got_i = r["topk_score"].cpu(), r["topk_idx"].cpu().long()
+    # reference order: stable sort of the negated scores = score descending, lower column first
+    order = torch.sort(-total, dim=1, stable=True).indices[:, :k]
+    assert torch.equal(got_i, order)
+    assert torch.equal(got_s, torch.gather(total, 1, order))
+
+
 def test_topk_merge_and_cosine(dev):
     cs = torch.randn(50, 300, dtype=torch.float64)
     ci = torch.arange(300, dtype=torch.int32).repeat(50, 1)
