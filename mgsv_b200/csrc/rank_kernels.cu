@@ -7,14 +7,18 @@
 //   1. s* = max score over the ground-truth id's columns (chain walk over prev_same),
 //   2. rank = number of DISTINCT music ids whose best column beats s* (strictly) — a column counts
 //      iff s > s* and no earlier column of the same id also has s > s* (prev_same chain),
-//   3. exact top-k on order-preserving 64-bit keys, ties broken by the lower column index.  Fast path
-//      (row staged in shared memory): a 1024-bin histogram over the row's key RANGE locates the bin
-//      of the k-th largest key (refined 10 bits at a time while more than 512 keys sit at or above
-//      it), those keys are gathered and ordered by counting — three sweeps of shared memory for a
-//      typical score row.  Rows where one key repeats > 512 times around rank k (or rows too long to
-//      stage) take the exact 8-pass MSB radix select + bitonic sort instead.
-// The row is staged once in shared memory (up to kMaxSmemCols columns; beyond that the passes
-// re-read global memory), so HBM traffic is the algorithmic 8 B per (query, track).
+//   3. exact top-k, score descending, ties broken by the lower column index.
+//
+// Staged kernel (rows up to 49 152 columns): the row is read ONCE from HBM and kept in shared memory
+// as order-preserving 32-bit keys of fl32(single + dual).  Rounding is monotone, so a column that
+// beats another in fp64 never has the smaller fp32 key: the fp32 keys select a SUPERSET of the true
+// top-k and decide every rank comparison that is more than two fp32 steps away from s*; only the
+// <= k + 32 selected columns and the near-ties of s* are re-read (L2) and compared in fp64.  The
+// k-th largest key is located by value: a 1024-bin histogram over the row's key range, refined 10
+// bits at a time while more than k + 32 keys sit at or above the chosen bin; the candidates are then
+// ordered by counting.  A typical score row costs three sweeps of shared memory.
+// Rows where more than 512 columns tie around rank k, and rows too long to stage, take the exact
+// 8-pass MSB radix select on the 64-bit keys (re-reading global memory) + a bitonic sort instead.
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -22,11 +26,11 @@ namespace made {
 
 constexpr int kRankThreads = 256;
 constexpr int kMaxK = 256;
+constexpr int kMaxSmemCols = 49152;              // 49152 * 4 B = 192 KB of 32-bit keys
 constexpr int kValueBinBits = 10;
-constexpr int kValueBins = 1 << kValueBinBits;   // value-histogram bins of the fast top-k path
-constexpr int kMaxCand = 512;                    // candidates the fast path orders (>= kMaxK + kCandSlack)
+constexpr int kValueBins = 1 << kValueBinBits;   // value-histogram bins of the staged path
+constexpr int kMaxCand = 512;                    // candidates the staged path orders (>= kMaxK + kCandSlack)
 constexpr int kCandSlack = 32;                   // refine the threshold while more than k + 32 keys pass it
-constexpr int kMaxSmemCols = 24576;  // 24576 * 8 B = 192 KB of keys
 
 __device__ __forceinline__ unsigned long long f64_key(double x) {
   unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
@@ -36,17 +40,34 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
   unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
   return __longlong_as_double(static_cast<long long>(b));
 }
+__device__ __forceinline__ unsigned int f32_key(float x) {
+  const unsigned int b = __float_as_uint(x);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
 
+// exact 64-bit keys of one row, read from global memory
 struct RowView {
   const float* a;
   const float* b;  // may be null
-  const unsigned long long* cache;  // smem keys or null
   __device__ __forceinline__ unsigned long long key(int64_t j) const {
-    if (cache) return cache[j];
     double s = static_cast<double>(a[j]);
     if (b) s += static_cast<double>(b[j]);
     return f64_key(s);
   }
+  __device__ __forceinline__ unsigned int key32(int64_t j) const {
+    return f32_key(b ? __fadd_rn(a[j], b[j]) : a[j]);
+  }
+};
+
+struct RankSmem {
+  int hist[kValueBins];                     // value histogram / the 256 radix buckets
+  int red[kRankThreads / 32];
+  unsigned int red32[2][kRankThreads / 32];
+  unsigned long long sel_keys[kMaxCand];
+  int sel_idx[kMaxCand];
+  unsigned long long prefix, gt_key;
+  unsigned int gt_key32;
+  int krem, count, eq_taken, bin, ncand;
 };
 
 __device__ __forceinline__ int block_sum_int(int v, int* red) {
@@ -88,261 +109,58 @@ __device__ void bitonic_sort_desc(unsigned long long* keys, int* idx, int n) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRankThreads)
-rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
-                 int64_t n_cols, const int32_t* __restrict__ gt_col,
-                 const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
-                 int32_t col_offset, int k, int use_cache, int32_t* __restrict__ topk_idx,
-                 double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
-                 double* __restrict__ gt_score_out) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ int hist[kValueBins];           // value histogram (fast path) / 256 radix buckets
-  __shared__ int red[kRankThreads / 32];
-  __shared__ unsigned long long red64[2][kRankThreads / 32];
-  __shared__ unsigned long long sel_keys[kMaxCand];
-  __shared__ int sel_idx[kMaxCand];
-  __shared__ unsigned long long sh_prefix;
-  __shared__ int sh_krem, sh_count, sh_eq_taken, sh_bin, sh_ncand;
-  __shared__ unsigned long long sh_gt_key;
+// ground-truth score of the row: thread 0 walks the id's columns (exact fp64 keys)
+__device__ __forceinline__ void gt_walk(const RowView& rv, int64_t row, int64_t n_cols, const int32_t* gt_col,
+                                        const double* gt_score_in, const int32_t* prev_same, RankSmem& sm) {
+  unsigned long long best = 0;  // smaller than any real key
+  unsigned int best32 = 0;
+  if (gt_score_in) {
+    best = f64_key(gt_score_in[row]);
+    best32 = f32_key(__double2float_rn(gt_score_in[row]));
+  } else {
+    int32_t g = gt_col ? gt_col[row] : -1;
+    int32_t guard = 0;
+    while (g >= 0 && g < n_cols && guard++ < (1 << 20)) {
+      const unsigned long long kk = rv.key(g);
+      if (kk > best) { best = kk; best32 = rv.key32(g); }
+      g = prev_same ? prev_same[g] : -1;
+    }
+  }
+  sm.gt_key = best;
+  sm.gt_key32 = best32;
+}
 
-  const int64_t row = blockIdx.x;
+// Exact top-k of one row by an 8-pass MSB radix select on the 64-bit keys (global memory), ordered
+// append of the ties at the k-th key, bitonic sort of the winners.  Called by the whole CTA.
+__device__ void radix_topk_row(const RowView& rv, int64_t n_cols, int kk, int k, int64_t row, int32_t col_offset,
+                               int32_t* __restrict__ topk_idx, double* __restrict__ topk_score, RankSmem& sm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RowView rv;
-  rv.a = single + row * ld;
-  rv.b = dual ? dual + row * ld : nullptr;
-  rv.cache = nullptr;
-  const bool want_rank = rank_out != nullptr;
-
-  // ---- 1. ground-truth score (thread 0 walks the id's columns while the others stage the row) --
-  if (want_rank && threadIdx.x == 0) {
-    unsigned long long best = 0;  // smaller than any real key
-    if (gt_score_in) {
-      best = f64_key(gt_score_in[row]);
-    } else {
-      int32_t g = gt_col ? gt_col[row] : -1;
-      int32_t guard = 0;
-      while (g >= 0 && g < n_cols && guard++ < (1 << 20)) {
-        unsigned long long kk = rv.key(g);
-        best = kk > best ? kk : best;
-        g = prev_same ? prev_same[g] : -1;
-      }
-    }
-    sh_gt_key = best;
-  }
-  unsigned long long kmin = ~0ull, kmax = 0ull;
-  if (use_cache) {
-    // stage the row once as 64-bit keys, tracking the key range for the value histogram
-    unsigned long long* cache = reinterpret_cast<unsigned long long*>(dyn_smem);
-    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
-                     (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
-    if (vec) {
-      const int64_t n4 = n_cols / 4;
-      const float4* a4 = reinterpret_cast<const float4*>(rv.a);
-      const float4* b4 = reinterpret_cast<const float4*>(rv.b);
-#pragma unroll 2
-      for (int64_t q = threadIdx.x; q < n4; q += kRankThreads) {
-        const float4 x = __ldg(a4 + q);
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rv.b) y = __ldg(b4 + q);
-        unsigned long long k0 = f64_key(rv.b ? double(x.x) + double(y.x) : double(x.x));
-        unsigned long long k1 = f64_key(rv.b ? double(x.y) + double(y.y) : double(x.y));
-        unsigned long long k2 = f64_key(rv.b ? double(x.z) + double(y.z) : double(x.z));
-        unsigned long long k3 = f64_key(rv.b ? double(x.w) + double(y.w) : double(x.w));
-        *reinterpret_cast<ulonglong2*>(cache + q * 4) = make_ulonglong2(k0, k1);
-        *reinterpret_cast<ulonglong2*>(cache + q * 4 + 2) = make_ulonglong2(k2, k3);
-        unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
-        unsigned long long lo2 = k2 < k3 ? k2 : k3, hi2 = k2 < k3 ? k3 : k2;
-        lo = lo < lo2 ? lo : lo2; hi = hi > hi2 ? hi : hi2;
-        kmin = lo < kmin ? lo : kmin; kmax = hi > kmax ? hi : kmax;
-      }
-      for (int64_t j = n4 * 4 + threadIdx.x; j < n_cols; j += kRankThreads) {
-        unsigned long long key = rv.key(j);
-        cache[j] = key;
-        kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
-      }
-    } else {
-      for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-        unsigned long long key = rv.key(j);
-        cache[j] = key;
-        kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long u = __shfl_xor_sync(0xffffffffu, kmin, o);
-      unsigned long long v = __shfl_xor_sync(0xffffffffu, kmax, o);
-      kmin = u < kmin ? u : kmin; kmax = v > kmax ? v : kmax;
-    }
-    if (lane == 0) { red64[0][warp] = kmin; red64[1][warp] = kmax; }
-    rv.cache = cache;
-  }
-  for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) hist[t] = 0;
-  if (threadIdx.x == 0) { sh_count = 0; sh_ncand = 0; }
-  __syncthreads();
-  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
-  const bool want_topk = k > 0 && topk_idx != nullptr;
-  // fast path (row staged in shared memory): one sweep feeds both the rank count and a 1024-bin
-  // histogram over the row's VALUE range; the bin holding the k-th largest key gives a threshold
-  // with at most a few keys more than k above it, and those candidates are ordered by counting.
-  bool fast = use_cache && want_topk && kk > 0;
-  int vshift = 0;
-  if (use_cache) {
-#pragma unroll
-    for (int w = 0; w < kRankThreads / 32; ++w) {
-      kmin = red64[0][w] < kmin ? red64[0][w] : kmin;
-      kmax = red64[1][w] > kmax ? red64[1][w] : kmax;
-    }
-    const unsigned long long range = kmax - kmin;
-    const int bits = range ? 64 - __clzll(static_cast<long long>(range)) : 0;
-    vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
-  }
-
-  // ---- 2. distinct ids ahead of the ground truth (+ value histogram on the fast path) --------
-  if (want_rank || fast) {
-    const unsigned long long gk = want_rank ? sh_gt_key : ~0ull;
-    int cnt = 0;
-    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-      const unsigned long long key = rv.key(j);
-      if (fast) atomicAdd(&hist[static_cast<int>((key - kmin) >> vshift)], 1);
-      if (want_rank && key > gk) {
-        bool first = true;
-        if (prev_same) {
-          int32_t p = prev_same[j];
-          int32_t guard = 0;
-          while (p >= 0 && guard++ < (1 << 20)) {
-            if (rv.key(p) > gk) { first = false; break; }
-            p = prev_same[p];
-          }
-        }
-        cnt += first ? 1 : 0;
-      }
-    }
-    if (want_rank) {
-      cnt = block_sum_int(cnt, red);   // contains the barriers that publish hist
-      if (threadIdx.x == 0) {
-        rank_out[row] = cnt;
-        if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
-      }
-    } else {
-      __syncthreads();
-    }
-  }
-  if (!want_topk) return;
-
-  if (fast) {
-    // Locate the k-th largest key by value: 10 bits of the row's key range per level (level 0 was
-    // histogrammed in the sweep above).  Stop as soon as at most kMaxCand keys sit at or above the
-    // chosen bin; real score rows need one level, rows with outliers two.
-    unsigned long long base = kmin, thr = 0ull;
-    int shift = vshift, need = kk, above = 0, n_cand = 0;
-    bool ok = false;
-    for (int level = 0; level < 8; ++level) {
-      if (level > 0) {
-        for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) hist[t] = 0;
-        __syncthreads();
-        for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-          const unsigned long long key = rv.key(j);
-          const unsigned long long d = (key - base) >> shift;
-          if (key >= base && d < kValueBins) atomicAdd(&hist[static_cast<int>(d)], 1);
-        }
-        __syncthreads();
-      }
-      if (warp == 0) {   // scan the bins from the top, 32 bins per lane
-        constexpr int kPer = kValueBins / 32;
-        int tot = 0;
-        const int top = kValueBins - 1 - lane * kPer;   // this lane owns bins top, top-1, ..., top-kPer+1
-#pragma unroll 8
-        for (int i = 0; i < kPer; ++i) tot += hist[top - ((i + lane) & (kPer - 1))];   // rotated: no bank conflicts
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        int acc = incl - tot;
-        if (acc < need && incl >= need) {
-          for (int i = 0; i < kPer; ++i) {
-            const int c = hist[top - i];
-            if (acc + c >= need) { sh_bin = top - i; sh_krem = acc; sh_ncand = c; break; }
-            acc += c;
-          }
-        }
-      }
-      __syncthreads();
-      const int bin = sh_bin, acc = sh_krem, c = sh_ncand;
-      n_cand = above + acc + c;
-      // accept once the candidate set is close to k (ordering it costs n_cand^2 / 256 steps per
-      // thread); at shift 0 the bin is a single key value and cannot be split further
-      if (n_cand <= kk + kCandSlack || (shift == 0 && n_cand <= kMaxCand)) {
-        thr = base + (static_cast<unsigned long long>(bin) << shift);
-        ok = true;
-        break;
-      }
-      if (shift == 0) break;   // more than kMaxCand copies of one key: the radix path orders the ties
-      above += acc;
-      need -= acc;
-      base += static_cast<unsigned long long>(bin) << shift;
-      shift = shift > kValueBinBits ? shift - kValueBinBits : 0;
-    }
-    if (ok) {
-      for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-        const unsigned long long key = rv.key(j);
-        if (key >= thr) {
-          const int slot = atomicAdd(&sh_count, 1);
-          if (slot < kMaxCand) { sel_keys[slot] = key; sel_idx[slot] = static_cast<int>(j); }
-        }
-      }
-      __syncthreads();
-      // order by counting: position = number of candidates that come first (key desc, column asc)
-      for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
-        const unsigned long long key = sel_keys[t];
-        const int idx = sel_idx[t];
-        int pos = 0;
-        for (int u = 0; u < n_cand; ++u) {
-          const unsigned long long ku = sel_keys[u];
-          pos += (ku > key || (ku == key && sel_idx[u] < idx)) ? 1 : 0;
-        }
-        if (pos < kk) {
-          topk_idx[row * k + pos] = idx + col_offset;
-          if (topk_score) topk_score[row * k + pos] = key_f64(key);
-        }
-      }
-      for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
-        topk_idx[row * k + t] = -1;
-        if (topk_score) topk_score[row * k + t] = -INFINITY;
-      }
-      return;
-    }
-    __syncthreads();   // a key repeated > kMaxCand times: fall through to the exact radix select
-  }
-
-  // ---- 3. top-k: radix select of the k-th largest key -----------------------------------
   if (threadIdx.x == 0) {
-    sh_prefix = 0ull;
-    sh_krem = kk;
-    sh_count = 0;
-    sh_eq_taken = 0;
+    sm.prefix = 0ull;
+    sm.krem = kk;
+    sm.count = 0;
+    sm.eq_taken = 0;
   }
   __syncthreads();
   for (int pass = 7; pass >= 0; --pass) {
-    hist[threadIdx.x] = 0;  // kRankThreads == 256 buckets
+    sm.hist[threadIdx.x] = 0;  // kRankThreads == 256 buckets
     __syncthreads();
-    const unsigned long long prefix = sh_prefix;
+    const unsigned long long prefix = sm.prefix;
     const int shift = pass * 8;
     const unsigned long long himask = pass == 7 ? 0ull : (~0ull << (shift + 8));
     for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
       unsigned long long key = rv.key(j);
-      if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+      if ((key & himask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 0xFF], 1);
     }
     __syncthreads();
     // find the bucket that holds the k-th largest key: warp 0 scans the 256 buckets from the top,
     // 8 buckets per lane + a shuffle scan (a single thread walking 256 buckets cost ~1.3 us per pass)
     if (threadIdx.x < 32) {
-      const int rem = sh_krem;
+      const int rem = sm.krem;
       int loc[8], tot = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {          // lane 0 owns buckets 255..248, lane 1 247..240, ...
-        loc[i] = hist[255 - (lane * 8 + i)];
+        loc[i] = sm.hist[255 - (lane * 8 + i)];
         tot += loc[i];
       }
       int incl = tot;
@@ -361,67 +179,307 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
           if (acc + loc[i] >= rem) { b = 255 - (lane * 8 + i); break; }
           acc += loc[i];
         }
-        sh_krem = rem - acc;  // still needed inside bucket b
-        sh_prefix = prefix | (static_cast<unsigned long long>(b) << shift);
+        sm.krem = rem - acc;  // still needed inside bucket b
+        sm.prefix = prefix | (static_cast<unsigned long long>(b) << shift);
       } else if (none && lane == 31) {
-        sh_krem = rem - (incl - loc[7]);
-        sh_prefix = prefix;                   // bucket 0
+        sm.krem = rem - (incl - loc[7]);
+        sm.prefix = prefix;                   // bucket 0
       }
     }
     __syncthreads();
   }
-  const unsigned long long thr = sh_prefix;  // exact k-th largest key
-  const int need_eq = sh_krem;               // how many == thr to take (lowest indices first)
+  const unsigned long long thr = sm.prefix;  // exact k-th largest key
+  const int need_eq = sm.krem;               // how many == thr to take (lowest indices first)
   // strictly-greater elements: unordered append
   for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
     unsigned long long key = rv.key(j);
     if (key > thr) {
-      int slot = atomicAdd(&sh_count, 1);
-      if (slot < kMaxK) { sel_keys[slot] = key; sel_idx[slot] = static_cast<int>(j); }
+      int slot = atomicAdd(&sm.count, 1);
+      if (slot < kMaxK) { sm.sel_keys[slot] = key; sm.sel_idx[slot] = static_cast<int>(j); }
     }
   }
   __syncthreads();
-  const int n_gt = sh_count;
+  const int n_gt = sm.count;
   // ties: ordered append, chunk by chunk
   for (int64_t base = 0; base < n_cols; base += kRankThreads) {
-    if (sh_eq_taken >= need_eq) break;
+    if (sm.eq_taken >= need_eq) break;
     int64_t j = base + threadIdx.x;
     bool eq = j < n_cols && rv.key(j) == thr;
     unsigned ballot = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) red[warp] = __popc(ballot);
+    if (lane == 0) sm.red[warp] = __popc(ballot);
     __syncthreads();
     int before = 0, total = 0;
     for (int w = 0; w < kRankThreads / 32; ++w) {
-      if (w < warp) before += red[w];
-      total += red[w];
+      if (w < warp) before += sm.red[w];
+      total += sm.red[w];
     }
     before += __popc(ballot & ((1u << lane) - 1u));
-    int taken = sh_eq_taken;
+    int taken = sm.eq_taken;
     if (eq && taken + before < need_eq) {
       int slot = n_gt + taken + before;
-      if (slot < kMaxK) { sel_keys[slot] = thr; sel_idx[slot] = static_cast<int>(j); }
+      if (slot < kMaxK) { sm.sel_keys[slot] = thr; sm.sel_idx[slot] = static_cast<int>(j); }
     }
     __syncthreads();
-    if (threadIdx.x == 0) sh_eq_taken = taken + total;
+    if (threadIdx.x == 0) sm.eq_taken = taken + total;
     __syncthreads();
   }
   // pad to a power of two and sort
   int n_pow = 1;
   while (n_pow < kk) n_pow <<= 1;
   for (int t = kk + threadIdx.x; t < n_pow; t += kRankThreads) {
-    sel_keys[t] = 0ull;
-    sel_idx[t] = 0x7FFFFFFF;
+    sm.sel_keys[t] = 0ull;
+    sm.sel_idx[t] = 0x7FFFFFFF;
   }
-  bitonic_sort_desc(sel_keys, sel_idx, n_pow);
+  bitonic_sort_desc(sm.sel_keys, sm.sel_idx, n_pow);
   for (int t = threadIdx.x; t < k; t += kRankThreads) {
     if (t < kk) {
-      topk_idx[row * k + t] = sel_idx[t] + col_offset;
-      if (topk_score) topk_score[row * k + t] = key_f64(sel_keys[t]);
+      topk_idx[row * k + t] = sm.sel_idx[t] + col_offset;
+      if (topk_score) topk_score[row * k + t] = key_f64(sm.sel_keys[t]);
     } else {
       topk_idx[row * k + t] = -1;
       if (topk_score) topk_score[row * k + t] = -INFINITY;
     }
   }
+}
+
+// Rows too long to stage: every pass re-reads global memory (L2 for rows up to a few MB).
+__global__ void __launch_bounds__(kRankThreads)
+rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
+                 int64_t n_cols, const int32_t* __restrict__ gt_col,
+                 const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
+                 int32_t col_offset, int k, int32_t* __restrict__ topk_idx,
+                 double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
+                 double* __restrict__ gt_score_out) {
+  __shared__ RankSmem sm;
+  const int64_t row = blockIdx.x;
+  RowView rv;
+  rv.a = single + row * ld;
+  rv.b = dual ? dual + row * ld : nullptr;
+  if (rank_out != nullptr) {
+    if (threadIdx.x == 0) gt_walk(rv, row, n_cols, gt_col, gt_score_in, prev_same, sm);
+    __syncthreads();
+    const unsigned long long gk = sm.gt_key;
+    int cnt = 0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+      if (rv.key(j) > gk) {
+        bool first = true;
+        if (prev_same) {
+          int32_t p = prev_same[j];
+          int32_t guard = 0;
+          while (p >= 0 && guard++ < (1 << 20)) {
+            if (rv.key(p) > gk) { first = false; break; }
+            p = prev_same[p];
+          }
+        }
+        cnt += first ? 1 : 0;
+      }
+    }
+    cnt = block_sum_int(cnt, sm.red);
+    if (threadIdx.x == 0) {
+      rank_out[row] = cnt;
+      if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
+    }
+  }
+  if (k <= 0 || topk_idx == nullptr) return;
+  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
+  radix_topk_row(rv, n_cols, kk, k, row, col_offset, topk_idx, topk_score, sm);
+}
+
+// Staged rows: see the header of this file.
+__global__ void __launch_bounds__(kRankThreads, 6)
+rank_topk_staged_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
+                        int64_t n_cols, const int32_t* __restrict__ gt_col,
+                        const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
+                        int32_t col_offset, int k, int32_t* __restrict__ topk_idx,
+                        double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
+                        double* __restrict__ gt_score_out) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ RankSmem sm;
+  unsigned int* cache = reinterpret_cast<unsigned int*>(dyn_smem);
+  const int64_t row = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RowView rv;
+  rv.a = single + row * ld;
+  rv.b = dual ? dual + row * ld : nullptr;
+  const bool want_rank = rank_out != nullptr;
+  const bool want_topk = k > 0 && topk_idx != nullptr;
+  const int kk = n_cols < k ? static_cast<int>(n_cols) : k;
+
+  // ---- 1. ground-truth score (thread 0) while the others start staging the row ---------------
+  if (want_rank && threadIdx.x == 0) gt_walk(rv, row, n_cols, gt_col, gt_score_in, prev_same, sm);
+
+  // ---- 2. stage the row as 32-bit keys, tracking the key range --------------------------------
+  unsigned int kmin = 0xFFFFFFFFu, kmax = 0u;
+  {
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
+                     (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
+    const int64_t n4 = vec ? n_cols / 4 : 0;
+    const float4* a4 = reinterpret_cast<const float4*>(rv.a);
+    const float4* b4 = reinterpret_cast<const float4*>(rv.b);
+#pragma unroll 4
+    for (int64_t q = threadIdx.x; q < n4; q += kRankThreads) {
+      float4 x = __ldg(a4 + q);
+      if (rv.b) {
+        const float4 y = __ldg(b4 + q);
+        x.x = __fadd_rn(x.x, y.x); x.y = __fadd_rn(x.y, y.y); x.z = __fadd_rn(x.z, y.z); x.w = __fadd_rn(x.w, y.w);
+      }
+      const uint4 kq = make_uint4(f32_key(x.x), f32_key(x.y), f32_key(x.z), f32_key(x.w));
+      *reinterpret_cast<uint4*>(cache + q * 4) = kq;
+      kmin = min(kmin, min(min(kq.x, kq.y), min(kq.z, kq.w)));
+      kmax = max(kmax, max(max(kq.x, kq.y), max(kq.z, kq.w)));
+    }
+    for (int64_t j = n4 * 4 + threadIdx.x; j < n_cols; j += kRankThreads) {
+      const unsigned int key = rv.key32(j);
+      cache[j] = key;
+      kmin = min(kmin, key);
+      kmax = max(kmax, key);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { sm.red32[0][warp] = kmin; sm.red32[1][warp] = kmax; }
+  }
+  for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
+  if (threadIdx.x == 0) { sm.count = 0; sm.ncand = 0; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kRankThreads / 32; ++w) {
+    kmin = min(kmin, sm.red32[0][w]);
+    kmax = max(kmax, sm.red32[1][w]);
+  }
+  const unsigned int range = kmax - kmin;
+  const int bits = range ? 32 - __clz(static_cast<int>(range)) : 0;
+  const int vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
+  const bool select = want_topk && kk > 0;
+
+  // ---- 3. one sweep: value histogram + distinct ids ahead of the ground truth ------------------
+  // A column beats s* when its fp32 key is more than two steps above that of s* (then the fp64
+  // scores differ too); within two steps the exact fp64 keys decide.
+  const unsigned long long gk = want_rank ? sm.gt_key : 0ull;
+  const long long gk32 = want_rank ? static_cast<long long>(sm.gt_key32) : 0ll;
+  auto beats = [&](int64_t j, unsigned int k32) -> bool {
+    const long long d = static_cast<long long>(k32) - gk32;
+    if (d > 2) return true;
+    if (d < -2) return false;
+    return rv.key(j) > gk;
+  };
+  if (want_rank || select) {
+    int cnt = 0;
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+      const unsigned int k32 = cache[j];
+      if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
+      if (want_rank && beats(j, k32)) {
+        bool first = true;
+        if (prev_same) {
+          int32_t p = prev_same[j];
+          int32_t guard = 0;
+          while (p >= 0 && guard++ < (1 << 20)) {
+            if (beats(p, cache[p])) { first = false; break; }
+            p = prev_same[p];
+          }
+        }
+        cnt += first ? 1 : 0;
+      }
+    }
+    if (want_rank) {
+      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the histogram
+      if (threadIdx.x == 0) {
+        rank_out[row] = cnt;
+        if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
+      }
+    } else {
+      __syncthreads();
+    }
+  }
+  if (!want_topk) return;
+
+  // ---- 4. threshold by value, 10 bits of the key range per level -------------------------------
+  bool ok = false;
+  unsigned int thr = 0u;
+  int n_cand = 0;
+  if (select) {
+    unsigned int base = kmin;
+    int shift = vshift, need = kk, above = 0;
+    unsigned int span = kValueBins;   // sub-bins the bin chosen at the previous level splits into
+    for (int level = 0; level < 4; ++level) {
+      if (level > 0) {
+        for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
+        __syncthreads();
+        for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+          const unsigned int k32 = cache[j];
+          const unsigned int d = (k32 - base) >> shift;
+          if (k32 >= base && d < span) atomicAdd(&sm.hist[d], 1);   // keys of the chosen bin only
+        }
+        __syncthreads();
+      }
+      if (warp == 0) {   // scan the bins from the top, 32 bins per lane
+        constexpr int kPer = kValueBins / 32;
+        int tot = 0;
+        const int top = kValueBins - 1 - lane * kPer;   // this lane owns bins top, top-1, ..., top-kPer+1
+#pragma unroll 8
+        for (int i = 0; i < kPer; ++i) tot += sm.hist[top - ((i + lane) & (kPer - 1))];   // rotated: no bank conflicts
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        int acc = incl - tot;
+        if (acc < need && incl >= need) {
+          for (int i = 0; i < kPer; ++i) {
+            const int c = sm.hist[top - i];
+            if (acc + c >= need) { sm.bin = top - i; sm.krem = acc; sm.ncand = c; break; }
+            acc += c;
+          }
+        }
+      }
+      __syncthreads();
+      const int bin = sm.bin, acc = sm.krem, c = sm.ncand;
+      n_cand = above + acc + c;
+      // accept once the candidate set is close to k (ordering it costs n_cand^2 / 256 steps per
+      // thread); at shift 0 the bin is a single key value and cannot be split further
+      if (n_cand <= kk + kCandSlack || (shift == 0 && n_cand <= kMaxCand)) {
+        thr = base + (static_cast<unsigned int>(bin) << shift);
+        ok = true;
+        break;
+      }
+      if (shift == 0) break;   // more than kMaxCand columns share one fp32 key: the radix path orders them
+      above += acc;
+      need -= acc;
+      base += static_cast<unsigned int>(bin) << shift;
+      span = 1u << (shift > kValueBinBits ? kValueBinBits : shift);
+      shift = shift > kValueBinBits ? shift - kValueBinBits : 0;
+    }
+  }
+  if (ok) {
+    // ---- 5. gather the candidates with their exact fp64 keys, order them by counting ----------
+    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
+      if (cache[j] >= thr) {
+        const int slot = atomicAdd(&sm.count, 1);
+        if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = static_cast<int>(j); }
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
+      const unsigned long long key = sm.sel_keys[t];
+      const int idx = sm.sel_idx[t];
+      int pos = 0;   // candidates that come first: larger key, or equal key and lower column
+      for (int u = 0; u < n_cand; ++u) {
+        const unsigned long long ku = sm.sel_keys[u];
+        pos += (ku > key || (ku == key && sm.sel_idx[u] < idx)) ? 1 : 0;
+      }
+      if (pos < kk) {
+        topk_idx[row * k + pos] = idx + col_offset;
+        if (topk_score) topk_score[row * k + pos] = key_f64(key);
+      }
+    }
+    for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
+      topk_idx[row * k + t] = -1;
+      if (topk_score) topk_score[row * k + t] = -INFINITY;
+    }
+    return;
+  }
+  __syncthreads();
+  radix_topk_row(rv, n_cols, kk, k, row, col_offset, topk_idx, topk_score, sm);
 }
 
 // Merge G per-shard candidate lists per row ([n_rows, n_cand] scores + global indices, -1 = empty)
@@ -559,18 +617,23 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
                (long long)n_cols);
   MADE_REQUIRE(k == 0 || topk_idx, "rank_topk: k>0 needs topk_idx");
   MADE_REQUIRE(!rank_out || gt_col || gt_score_in, "rank_topk: rank needs gt_col or gt_score_in");
-  int use_cache = n_cols <= kMaxSmemCols;
-  size_t smem = use_cache ? static_cast<size_t>(n_cols) * 8 : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(rank_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kMaxSmemCols * 8));
-    attr_set = true;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_cols <= kMaxSmemCols) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MADE_CUDA(cudaFuncSetAttribute(rank_topk_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kMaxSmemCols * 4));
+      attr_set = true;
+    }
+    const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);
+    rank_topk_staged_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
+        single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
+        gt_score_out);
+  } else {
+    rank_topk_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, 0, st>>>(
+        single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
+        gt_score_out);
   }
-  rank_topk_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem,
-                     static_cast<cudaStream_t>(stream)>>>(
-      single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, use_cache, topk_idx,
-      topk_score, rank_out, gt_score_out);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

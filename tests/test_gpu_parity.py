@@ -197,7 +197,8 @@ def test_rank_and_topk_exact(dev, n, n_dup, k):
     assert [x["topk_music_ids"][0] for x in res] == top1 or n_dup > 0
 
 
-@pytest.mark.parametrize("kind", ["clustered", "all_equal", "inf", "quantised", "similarity", "single_only", "long"])
+@pytest.mark.parametrize("kind", ["clustered", "all_equal", "inf", "quantised", "similarity", "single_only",
+                                  "fp32_ties", "long", "unstaged"])
 def test_topk_value_distributions(dev, kind):
     """The value-histogram fast path and the radix fallback must both give the exact top-k:
     score descending, lower column first on exact ties, for any distribution of a row's values."""
@@ -221,12 +222,23 @@ def test_topk_value_distributions(dev, kind):
         dual = torch.tanh(torch.randn(n, m, generator=g))
     elif kind == "single_only":
         single, dual = torch.rand(n, m, generator=g), None
-    else:                            # longer than the shared-memory stage: global-memory radix path
+    elif kind == "fp32_ties":        # sums that collide in fp32 but differ in fp64: the fp64 order must win
+        single = torch.full((n, m), 1.0) + torch.randint(0, 3, (n, m), generator=g).float() * 2.0 ** -23
+        dual = torch.randint(-8, 9, (n, m), generator=g).float() * 2.0 ** -30
+    elif kind == "long":             # 120 KB of staged keys
         m, k = 30000, 64
         single, dual = torch.randn(n, m, generator=g), torch.randn(n, m, generator=g)
+    else:                            # longer than the shared-memory stage: global-memory radix path
+        m, k = 50000, 64
+        single, dual = torch.randn(n, m, generator=g), torch.randn(n, m, generator=g)
     total = single.double() + (dual.double() if dual is not None else 0.0)
-    r = ops.rank_topk(single.to(dev), None if dual is None else dual.to(dev), k=k)
+    gt = torch.randint(0, m, (n,), generator=g, dtype=torch.int32)
+    r = ops.rank_topk(single.to(dev), None if dual is None else dual.to(dev), gt.to(dev), None, k=k)
     got_s, got_i = r["topk_score"].cpu(), r["topk_idx"].cpu().long()
+    # rank = columns whose fp64 score is strictly above the ground truth's (no repeated ids here)
+    gt_s = torch.gather(total, 1, gt.long().unsqueeze(1))
+    assert torch.equal(r["rank"].cpu().long(), (total > gt_s).sum(1))
+    assert torch.equal(r["gt_score"].cpu(), gt_s.squeeze(1))
     # reference order: stable sort of the negated scores = score descending, lower column first
     order = torch.sort(-total, dim=1, stable=True).indices[:, :k]
     assert torch.equal(got_i, order)
