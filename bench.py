@@ -133,7 +133,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -142,8 +142,18 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi takes 0.1 - 0.5 s to attach to the driver and has stalled a concurrent step for
+            # tens of ms while doing so: wait for its first sample so that this happens before the
+            # warm-up, not inside the timed region
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Timed region starts here: only samples taken from now on are reported."""
+        self.first = len(self.lines)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -159,7 +169,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.first:] or self.lines    # a region shorter than one period: keep the warm-up samples
+        for ln in lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 6:
                 continue
@@ -236,7 +247,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(on_host: bool, steps: int, warmup: int, xp_events=None):
+    def timed(on_host: bool, steps: int, warmup: int, xp_events=None, on_start=None):
         """Device time of `steps` back-to-back steps (CUDA events, barrier + synchronize on both sides,
         max over ranks).  Host-input steps end with a device->host read, so they are also timed one
         by one with the wall clock: the shared hosts of this pool stall a step now and then
@@ -244,6 +255,8 @@ def main():
         for _ in range(warmup):
             step(on_host)
         barrier()
+        if on_start:
+            on_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev.xpool_events = xp_events
         trace = os.environ.get("MADE_BENCH_TRACE")
@@ -271,7 +284,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     xp_events = []
-    ms_dev, _, _, _ = timed(False, args.steps, max(args.warmup, 3), xp_events)
+    ms_dev, _, _, _ = timed(False, args.steps, max(args.warmup, 3), xp_events, on_start=sampler.mark)
     launches = ev.launches
     clocks = sampler.stop()      # sampled during the device-resident timed region (20 ms period)
     e2e = None

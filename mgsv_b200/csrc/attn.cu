@@ -37,6 +37,8 @@ __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gs
 
 constexpr int kHeadDim = 32;
 constexpr int kHeadsPerCta = 4;
+constexpr int kWarpsPerHead = 2;   // the row tiles of a head alternate between two warps sharing its K/V slices
+constexpr int kMhaThreads = kHeadsPerCta * kWarpsPerHead * 32;
 constexpr int kKStride = 40;  // fp16 elements per K row in smem (80 B: conflict-free 4-byte frags)
 
 template <int LP>  // padded length, multiple of 16
@@ -54,7 +56,7 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&b)[2], const op_t* 
 }
 
 template <int LP>
-__global__ void __launch_bounds__(kHeadsPerCta * 32)
+__global__ void __launch_bounds__(kMhaThreads, 2)
 mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict__ K,
                 int64_t ldk, const op_t* __restrict__ V, int64_t ldv,
                 const float* __restrict__ key_mask, int L_in, const int32_t* __restrict__ seq_off,
@@ -67,13 +69,15 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int64_t b = blockIdx.x;
-  const int h = blockIdx.y * kHeadsPerCta + warp;
-  op_t* Ks = reinterpret_cast<op_t*>(attn_smem) + warp * S::kPerWarp;
+  const int hl = warp % kHeadsPerCta, part = warp / kHeadsPerCta;   // head within the CTA, which of its two warps
+  const int h = blockIdx.y * kHeadsPerCta + hl;
+  op_t* Ks = reinterpret_cast<op_t*>(attn_smem) + hl * S::kPerWarp;
   op_t* Vs = Ks + LP * kKStride;
   float* smask = reinterpret_cast<float*>(attn_smem + kHeadsPerCta * S::kPerWarp * 2);
   const int L = seq_off ? min(seq_len[b], LP) : L_in;
   const int64_t row0 = seq_off ? static_cast<int64_t>(seq_off[b]) : b * L_in;
   if (L <= 0) return;
+  const float scale2 = scale * 1.4426950408889634f;
 
   for (int i = threadIdx.x; i < LP; i += blockDim.x)
     smask[i] = (i < L && (seq_off != nullptr || key_mask[row0 + i] != 0.f)) ? 0.f : -INFINITY;
@@ -82,13 +86,16 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
   const op_t* Kg = K + row0 * ldk + h * kHeadDim;
   const op_t* Vg = V + row0 * ldv + h * kHeadDim;
   const int n_nt = (L + 7) >> 3, n_kk = (L + 15) >> 4;   // key tiles that hold at least one real key
-  for (int idx = lane; idx < n_kk * 64; idx += 32) {  // rows the MMAs touch; all copies in flight, one wait
+  for (int idx = lane + 32 * part; idx < n_kk * 64; idx += 32 * kWarpsPerHead) {  // rows the MMAs touch; all copies in flight, one wait
     const int key = idx >> 2, ch = idx & 3;
     const bool ok = key < L;
     const int kr = ok ? key : 0;
     cp_async_16_zfill(Ks + key * kKStride + ch * 8, Kg + kr * ldk + ch * 8, ok);
     cp_async_16_zfill(Vs + key * kKStride + ch * 8, Vg + kr * ldv + ch * 8, ok);
   }
+  // column 32 of the V slice (first pad column) = 1: the P.V MMA of a fifth n-tile then returns the row
+  // sums of the ROUNDED weights, i.e. exactly the divisor that makes the weights used sum to one
+  for (int key = lane + 32 * part; key < n_kk * 16; key += 32 * kWarpsPerHead) Vs[key * kKStride + kHeadDim] = f2op(1.0f);
   cp_async_wait_all();
   __syncthreads();
 
@@ -106,8 +113,8 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
     }
   };
   uint32_t qn[2][4];
-  load_q(0, qn);
-  for (int rt = 0; rt < KK; ++rt) {
+  if (part * 16 < L) load_q(part, qn);
+  for (int rt = part; rt < KK; rt += kWarpsPerHead) {
     const int r0 = rt * 16 + g, r1 = r0 + 8;
     if (rt * 16 >= L) break;
     uint32_t qa[2][4];
@@ -115,7 +122,7 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
       for (int i = 0; i < 4; ++i) qa[ks][i] = qn[ks][i];
-    if ((rt + 1) * 16 < L) load_q(rt + 1, qn);
+    if ((rt + kWarpsPerHead) * 16 < L) load_q(rt + kWarpsPerHead, qn);
     // ---- S = Q K^T ----
     float s[NT][4];
 #pragma unroll
@@ -136,10 +143,10 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const float m0 = smask[nt * 8 + 2 * t], m1 = smask[nt * 8 + 2 * t + 1];
-      s[nt][0] = s[nt][0] * scale + m0;
-      s[nt][1] = s[nt][1] * scale + m1;
-      s[nt][2] = s[nt][2] * scale + m0;
-      s[nt][3] = s[nt][3] * scale + m1;
+      s[nt][0] = fmaf(s[nt][0], scale2, m0);      // logits in log2 units: exp(x) = 2^(x * log2 e)
+      s[nt][1] = fmaf(s[nt][1], scale2, m1);
+      s[nt][2] = fmaf(s[nt][2], scale2, m0);
+      s[nt][3] = fmaf(s[nt][3], scale2, m1);
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -147,28 +154,17 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
     uint32_t pa[KK][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      // unnormalised weights, rounded to fp16 for the MMA; the divisor is the sum of the ROUNDED
-      // weights so that the weights used sum to one exactly
-      op2_t p01 = floats2op2(fast_exp(s[nt][0] - mx0), fast_exp(s[nt][1] - mx0));
-      op2_t p23 = floats2op2(fast_exp(s[nt][2] - mx1), fast_exp(s[nt][3] - mx1));
-      float2 f01 = op2_to_f2(p01), f23 = op2_to_f2(p23);
-      sum0 += f01.x + f01.y;
-      sum1 += f23.x + f23.y;
-      pa[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&p01);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
+      // unnormalised weights, rounded to fp16 for the MMA
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_op2(exp2_approx(s[nt][0] - mx0), exp2_approx(s[nt][1] - mx0));
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_op2(exp2_approx(s[nt][2] - mx1), exp2_approx(s[nt][3] - mx1));
     }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    // ---- O = P V ----
-    float o[4][4];
+    // ---- [O | row sums] = P [V | 1] ----
+    float o[5][4];
 #pragma unroll
-    for (int nd = 0; nd < 4; ++nd) {
+    for (int nd = 0; nd < 5; ++nd) {
       o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < KK; ++kk) {
@@ -178,6 +174,9 @@ mha_core_kernel(const op_t* __restrict__ Q, int64_t ldq, const op_t* __restrict_
         mma_f16_16816(o[nd], pa[kk], vb);
       }
     }
+    // column 0 of the fifth n-tile lives in the lanes with t == 0 (rows g and g + 8)
+    const float sum0 = __shfl_sync(0xffffffffu, o[4][0], lane & ~3);
+    const float sum1 = __shfl_sync(0xffffffffu, o[4][2], lane & ~3);
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     op_t* Og = O + row0 * ldo + h * kHeadDim;
 #pragma unroll
@@ -340,7 +339,7 @@ static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
     attr_set = true;
   }
   dim3 grid(static_cast<unsigned>(B), 8 / kHeadsPerCta);
-  mha_core_kernel<LP><<<grid, kHeadsPerCta * 32, AttnSmem<LP>::kBytes, st>>>(
+  mha_core_kernel<LP><<<grid, kMhaThreads, AttnSmem<LP>::kBytes, st>>>(
       Q, ldq, K, ldk, V, ldv, mask, L, seq_off, seq_len, 0.17677669529663687f /* 1/sqrt(32) */, O, ldo);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
