@@ -97,6 +97,26 @@ def cpu_reference_time(n_q_sample: int, n_m_sample: int, n_queries: int, n_track
     return best[0], best[1]
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it): keep a private handle to the real
+    stdout and point fd 1 at stderr, so that library chatter written to stdout during the run (NCCL's
+    version banner at NCCL_DEBUG >= VERSION, extension build logs) cannot land beside it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -122,7 +142,7 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -188,6 +208,7 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,7 +228,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # NCCL errors visible (its banner goes to stderr: claim_stdout)
         dist.init_process_group("nccl", device_id=dev)
 
     nq, nm = args.queries, args.tracks
@@ -384,7 +405,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
