@@ -360,8 +360,12 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     # DRAM traffic of the same launch shape from the committed `ncu --set full` capture (profiles/)
     traffic, traffic_src = None, None
-    cap = os.path.join(REPO, "profiles", "r01_g_xpool_v2_ncu_full_raw.csv")
-    if os.path.exists(cap) and xp_pairs:
+    # captures of this kernel, newest first: (file, (query, track) pairs of the captured launch)
+    caps = [("r01_h_xpool_ncu_full_raw.csv", 2000 * 1000), ("r01_g_xpool_v2_ncu_full_raw.csv", 2000 * 512)]
+    for cap_name, cap_pairs in caps:
+        cap = os.path.join(REPO, "profiles", cap_name)
+        if not (os.path.exists(cap) and xp_pairs):
+            continue
         import csv
         rows = list(csv.reader(open(cap)))
         col = {h: i for i, h in enumerate(rows[0])}
@@ -369,9 +373,11 @@ def main():
         tot = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(rows[2][col[key]].replace(",", "")) * unit[rows[1][col[key]]]
-        cap_pairs = 2000 * 512          # the capture's launch: 2000 queries x 512 tracks
-        traffic = tot * float(np.mean(xp_pairs)) / cap_pairs
-        traffic_src = "profiles/r01_g_xpool_v2_ncu_full_raw.csv (2000 x 512 launch), scaled by pairs per launch"
+        pairs_now = float(np.mean(xp_pairs))
+        traffic = tot * pairs_now / cap_pairs
+        traffic_src = f"profiles/{cap_name} (ncu --set full, launch of {cap_pairs} pairs)" + \
+            ("" if abs(pairs_now - cap_pairs) < 1 else ", scaled by pairs per launch")
+        break
     roofline = None
     if xp_ms:
         t_s = float(np.mean(xp_ms)) / 1e3                  # average launch duration
