@@ -55,6 +55,13 @@ def parse():
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # -------------------------------------------------------------------------------------------------
+# Sample of the workload the CPU arm runs per step.  The oracle's per-unit costs fall with the batch size
+# until the host threads are busy (measured on 8 cores: full-job time 64 s composed from a 48 x 256
+# sample, 35 s from 192 x 1024, 33 s from 384 x 2048), so the sample is large enough to sit on that
+# plateau: a smaller one would flatter the GPU/CPU ratio.
+CPU_SAMPLE_Q, CPU_SAMPLE_M = 192, 1024
+
+
 def cpu_reference_time(n_q_sample: int, n_m_sample: int, n_queries: int, n_tracks: int, repeats: int = 1):
     """Time the reference algorithm (oracle port, fp32, all host threads) on bounded samples of the
     workload and compose the full-job time from the measured per-unit costs (each stage is linear
@@ -124,15 +131,15 @@ def run_reference(args, rank: int):
     steps_ms = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        # one bounded sample per step: 48 queries x 256 tracks through every stage
-        tot, parts = cpu_reference_time(48, 256, args.queries, args.tracks, repeats=0)
+        # one bounded sample per step, through every stage
+        tot, parts = cpu_reference_time(CPU_SAMPLE_Q, CPU_SAMPLE_M, args.queries, args.tracks, repeats=0)
         if i >= args.warmup:
             steps_ms.append(tot * 1e3)
         if time.perf_counter() - t0 > 120 and len(steps_ms) >= 1:
             break
     ms = float(np.mean(steps_ms))
     value = args.queries / (ms / 1e3)
-    sample = ("per step: oracle port (reference algorithm, fp32) on 48 queries x 256 tracks through every stage; "
+    sample = (f"per step: oracle port (reference algorithm, fp32) on {CPU_SAMPLE_Q} queries x {CPU_SAMPLE_M} tracks through every stage; "
               "full 2000x4000 job time composed from the measured per-query / per-track / per-pair costs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -395,9 +402,9 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        tot, parts = cpu_reference_time(48, 256, nq, nm, repeats=1)
+        tot, parts = cpu_reference_time(CPU_SAMPLE_Q, CPU_SAMPLE_M, nq, nm, repeats=1)
         cpu_baseline = {"value": nq / tot, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": "oracle port (fp32, all host threads) on 48 queries x 256 tracks, best of 2; full-job "
+                        "sample": f"oracle port (fp32, all host threads) on {CPU_SAMPLE_Q} queries x {CPU_SAMPLE_M} tracks, best of 2; full-job "
                                   "time composed from measured per-query/per-track/per-pair costs",
                         "parts_us": {k: val * 1e6 for k, val in parts.items()}}
     if rank == 0:
