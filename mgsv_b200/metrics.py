@@ -27,6 +27,25 @@ def summarize_ranks(ind: np.ndarray) -> Dict[str, float]:
     return m
 
 
+def calc_similarity(video_feat_list, audio_feat_list, distance_type: str = "COS") -> np.ndarray:
+    """utils/util_test.py:10-29 — same arguments (lists of [bs, dim] blocks, tensors or numpy arrays) and
+    return value: the [val_len_v, val_len_m] numpy matrix, float32 for tensor blocks and float64 for
+    numpy blocks as modules/loss.py:52-61 produces them.  The reference loops over block pairs; rows
+    are normalised independently, so ONE cosine launch over the concatenated blocks gives the same
+    matrix."""
+    if len(video_feat_list) == 0 or len(audio_feat_list) == 0:
+        raise ValueError("need at least one array to concatenate")     # np.concatenate(()) in the reference
+    as_numpy = isinstance(video_feat_list[0], np.ndarray)
+    if as_numpy:
+        x = np.concatenate([np.asarray(b) for b in video_feat_list], axis=0)
+        y = np.concatenate([np.asarray(b) for b in audio_feat_list], axis=0)
+        return ops.cal_distance(x, y, distance_type)
+    x = torch.cat([b.detach() for b in video_feat_list], dim=0)
+    y = torch.cat([b.detach() for b in audio_feat_list], dim=0)
+    x = ops._to_cuda(x)
+    return ops.cal_distance(x, y.to(x.device), distance_type).cpu().numpy()
+
+
 def Recall_metrics(sim_single: torch.Tensor, sim_dual: Optional[torch.Tensor] = None, distance_type: str = "COS",
                    dedup: bool = True, all_music_ids_list: Optional[Sequence[str]] = None,
                    gt_music_ids: Optional[Sequence[str]] = None):

@@ -17,6 +17,15 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).contiguous()
 
 
+def _to_cuda(t: torch.Tensor) -> torch.Tensor:
+    """Host tensors handed to a reference-named free function: moved to the current CUDA device (there is
+    no CPU path; without a device this raises)."""
+    if t.is_cuda:
+        return t
+    _lib.require_cuda()
+    return t.to(torch.device("cuda", torch.cuda.current_device()))
+
+
 # ---------------------------------------------------------------------------------------------
 # music_detr/span_utils.py
 # ---------------------------------------------------------------------------------------------
@@ -185,11 +194,15 @@ def topk_merge(cand_score: torch.Tensor, cand_idx: torch.Tensor, k: int):
     return oi, os_
 
 
-def cal_distance(x: torch.Tensor, y: torch.Tensor, distance_type: str = "COS", out: Optional[torch.Tensor] = None,
-                 col_offset: int = 0) -> torch.Tensor:
-    """modules/loss.py:30-62, COS branch only (the shipped config; L2 raises ValueError)."""
+def cal_distance(x, y, distance_type: str = "COS", out: Optional[torch.Tensor] = None, col_offset: int = 0):
+    """modules/loss.py:30-62, COS branch only (the shipped config; L2 raises ValueError).
+    Tensors in -> fp32 CUDA tensor out.  numpy arrays in (the branch calc_similarity feeds,
+    loss.py:57-61) -> numpy float64 out, computed on the current CUDA device."""
     if distance_type != "COS":
         raise ValueError(f"distance_type={distance_type!r} is not supported by made_b200 (COS only)")
+    as_numpy = isinstance(x, np.ndarray)
+    if as_numpy:
+        x, y = _to_cuda(torch.from_numpy(np.ascontiguousarray(x))), _to_cuda(torch.from_numpy(np.ascontiguousarray(y)))
     assert x.shape[1] == y.shape[1], "The second dimension of x and y must be the same."
     x, y = _f32c(x), _f32c(y)
     if out is None:
@@ -197,7 +210,7 @@ def cal_distance(x: torch.Tensor, y: torch.Tensor, distance_type: str = "COS", o
         col_offset = 0
     _lib.check(_lib.load().made_cosine_sim(_lib.ptr(x), x.shape[0], _lib.ptr(y), y.shape[0], x.shape[1],
                                            out.data_ptr() + 4 * col_offset, out.stride(0), _lib.stream_ptr()))
-    return out
+    return out.cpu().numpy().astype(np.float64) if as_numpy else out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -257,6 +257,15 @@ def test_topk_merge_and_cosine(dev):
     np.testing.assert_allclose(got.cpu().numpy(), O.cal_distance_cos(x, y).numpy(), atol=1e-5, rtol=0)
     with pytest.raises(ValueError):
         ops.cal_distance(x.to(dev), y.to(dev), "L2")
+    # calc_similarity mirror (util_test.py:10-29): block lists, tensors -> float32, numpy -> float64
+    blocks_x, blocks_y = [x[:40], x[40:]], [y[:100], y[100:]]
+    ref = O.cal_distance_cos(x, y).numpy()
+    got = metrics.calc_similarity([b.to(dev) for b in blocks_x], [b.to(dev) for b in blocks_y])
+    assert got.dtype == np.float32 and got.shape == (70, 130)
+    np.testing.assert_allclose(got, ref, atol=1e-5, rtol=0)
+    got = metrics.calc_similarity([b.numpy() for b in blocks_x], [b.numpy() for b in blocks_y])
+    assert got.dtype == np.float64
+    np.testing.assert_allclose(got, ref, atol=1e-5, rtol=0)
     # >= 256 gallery rows: tcgen05 route (fp16 hi/lo split, K = 768) + SIMT tail, still fp32-accurate
     x, y = torch.randn(333, 256), torch.randn(600, 256)
     got = ops.cal_distance(x.to(dev), y.to(dev))

@@ -185,3 +185,33 @@ def test_save_results_json_schema(tmp_path):
     got = json.load(open(path))
     assert got == [dict(video_id="v1", music_id="m1", topk_mids=["m9"], gt_mid_rank=3, iou=0.1235, m_duration=120.0,
                         gt_st=5.043, gt_ed=15.988, pred_st=0, pred_ed=240)]
+
+
+def test_calc_similarity_mirror_host_logic(monkeypatch):
+    """utils/util_test.py:10-29: block lists in, one [val_len, val_len] numpy matrix out, float32 for tensor
+    blocks / float64 for numpy blocks.  The cosine kernel is replaced by torch here (CPU suite): only the
+    host logic of the mirror is under test; the GPU suite checks the same call against the oracle."""
+    from mgsv_b200 import metrics as M, ops
+    calls = []
+
+    def fake_cal_distance(x, y, distance_type="COS", out=None, col_offset=0):
+        calls.append((type(x), tuple(x.shape), tuple(y.shape)))
+        as_np = isinstance(x, np.ndarray)
+        xt, yt = torch.as_tensor(x, dtype=torch.float32), torch.as_tensor(y, dtype=torch.float32)
+        r = torch.nn.functional.normalize(xt, dim=1) @ torch.nn.functional.normalize(yt, dim=1).t()
+        return r.numpy().astype(np.float64) if as_np else r
+
+    monkeypatch.setattr(ops, "cal_distance", fake_cal_distance)
+    monkeypatch.setattr(ops, "_to_cuda", lambda t: t)
+    g = torch.Generator().manual_seed(5)
+    vb = [torch.randn(n, 256, generator=g) for n in (40, 40, 17)]
+    ab = [torch.randn(n, 256, generator=g) for n in (40, 57)]
+    ref = O.cal_distance_cos(torch.cat(vb), torch.cat(ab)).numpy()
+    got = M.calc_similarity(vb, ab)
+    assert got.dtype == np.float32 and got.shape == (97, 97) and len(calls) == 1
+    np.testing.assert_allclose(got, ref, atol=1e-6)
+    got64 = M.calc_similarity([b.numpy() for b in vb], [b.numpy() for b in ab])
+    assert got64.dtype == np.float64 and calls[-1][0] is np.ndarray
+    np.testing.assert_allclose(got64, ref, atol=1e-6)
+    with pytest.raises(ValueError):
+        M.calc_similarity([], ab)
