@@ -215,3 +215,33 @@ def test_calc_similarity_mirror_host_logic(monkeypatch):
     np.testing.assert_allclose(got64, ref, atol=1e-6)
     with pytest.raises(ValueError):
         M.calc_similarity([], ab)
+
+
+def test_bench_clock_sampler_reports_only_the_timed_region():
+    """bench.py's nvidia-smi sampler: samples before `mark()` (attach + warm-up) are dropped, throttle
+    reasons are collected, and a region shorter than one period falls back to the warm-up samples."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _Proc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.lines = ["1200, 1965, Not Active, Not Active, Not Active, Not Active"]      # warm-up: clocks still ramping
+    s.mark()
+    s.lines += ["1965, 1965, Not Active, Not Active, Not Active, Active",
+                "1950, 1965, Not Active, Not Active, Not Active, Not Active", "garbage"]
+    out = s.stop()
+    assert out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 2
+    assert out["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.lines = ["1965, 1965, Not Active, Not Active, Not Active, Not Active"]
+    s.mark()
+    assert s.stop()["samples"] == 1
+    s = bench.ClockSampler(0)                 # nvidia-smi missing
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
