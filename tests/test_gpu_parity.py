@@ -537,7 +537,7 @@ def test_full_size_job_properties(dev, engine, sd_fp32):
     # The 1e-3 bar (SIM_RTOL, relative to the matrix scale) holds per stage and on the reference's
     # fixtures (tests above).  Through the WHOLE pipeline the fp16 operand roundings of the encoders and
     # of the X-Pool operands add up to an error with rms ~2e-4 of the scale whose worst element grows
-    # with the number of pairs looked at (scripts/precision_study.py: ~5 sigma over 8192 pairs), so the
+    # with the number of pairs looked at (tests/tools/precision_study.py: ~5 sigma over 8192 pairs), so the
     # window is held to rms <= 5e-4 and max <= 2e-3 of the scale.
     for name, got, ref in (("single", a["single"][:64][:, ti.to(dev)], single),
                            ("dual", a["dual"][:64][:, ti.to(dev)], dual)):

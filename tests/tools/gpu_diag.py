@@ -1,6 +1,6 @@
 """GPU diagnostics: run one stage of the CUDA path against the CPU oracle and print error stats.
 
-    python scripts/gpu_diag.py <stage> [...]     stages: span rank gemm attn encode xpool detr
+    python tests/tools/gpu_diag.py <stage> [...]     stages: span rank gemm attn encode xpool detr
 
 Each stage is meant to be run under its own `timeout` (see scripts/gpu_diag.sh) so that a hang
 or a trap in one kernel does not take the others down.  Test infrastructure only.
@@ -14,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 
 from mgsv_b200 import _lib, ops, synth  # noqa: E402

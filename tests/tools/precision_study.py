@@ -2,7 +2,7 @@
 configurable rounding at every point where the CUDA path stores a 16-bit operand.  Used to decide
 which operands need fp16 (10-bit mantissa) instead of bf16 (7-bit).  Test infrastructure only.
 
-    python scripts/precision_study.py
+    python tests/tools/precision_study.py
 """
 from __future__ import annotations
 
@@ -11,7 +11,7 @@ import sys
 
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 
 from mgsv_b200 import synth  # noqa: E402

@@ -11,7 +11,7 @@ so the 128x256x96 Y MMA and the 256-column Y sweep of the epilogue become a 128x
 the algebra in fp64 and measures what rounding the new operands to fp16 costs, next to the current
 formulation ("Y in fp32 from fp16 operands").  Test infrastructure only.
 
-    python scripts/precision_study_noy.py
+    python tests/tools/precision_study_noy.py
 """
 from __future__ import annotations
 
@@ -20,9 +20,9 @@ import sys
 
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "scripts"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from mgsv_b200 import synth  # noqa: E402
 from oracle import made_oracle as O  # noqa: E402
