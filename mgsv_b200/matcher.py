@@ -46,9 +46,15 @@ class HungarianMatcher(nn.Module):
     def forward(self, outputs, targets):
         from scipy.optimize import linear_sum_assignment
         C, sizes = self.cost_matrix(outputs, targets)
-        C = C.cpu()
-        indices = [linear_sum_assignment(c[i]) for i, c in enumerate(C.split(sizes, -1))]
-        return [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in indices]
+        # the assignment itself stays scipy on the host like the reference (matcher.py:90-92): sample b is
+        # matched inside its own block of target columns (identity at one query / one target)
+        host = C.cpu().numpy()
+        pairs, col = [], 0
+        for b, n_tgt in enumerate(sizes):
+            rows, cols = linear_sum_assignment(host[b, :, col:col + n_tgt])
+            pairs.append((torch.as_tensor(rows, dtype=torch.int64), torch.as_tensor(cols, dtype=torch.int64)))
+            col += n_tgt
+        return pairs
 
 
 def build_matcher(args):
