@@ -245,3 +245,39 @@ def test_bench_clock_sampler_reports_only_the_timed_region():
     assert s.stop()["samples"] == 1
     s = bench.ClockSampler(0)                 # nvidia-smi missing
     assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_hungarian_matcher_mirror_host_logic(monkeypatch):
+    """music_detr/matcher.py:36-92 mirror: target filtering (width != 0), per-sample blocks of the cost
+    matrix, scipy assignment on the host.  The two kernels it calls are replaced by the oracle here (CPU
+    suite); the GPU suite runs the real ones (test_hungarian_matcher_mirror)."""
+    import types
+    from mgsv_b200 import matcher as M
+
+    def fake_postproc(logits, spans, *a, **k):
+        return None, None, logits.softmax(-1)[:, 0], None
+
+    def fake_cost(prob_fg, out_spans, tgt_spans, cost_span, cost_giou, cost_class):
+        giou = O.generalized_temporal_iou(O.span_cw_to_se(out_spans), O.span_cw_to_se(tgt_spans))
+        return cost_span * torch.cdist(out_spans, tgt_spans, p=1) - cost_giou * giou - cost_class * prob_fg[:, None]
+
+    monkeypatch.setattr(ops, "moment_postproc", fake_postproc)
+    monkeypatch.setattr(ops, "matcher_cost", fake_cost)
+    m = M.build_matcher(types.SimpleNamespace(span_loss_type="l1", max_snippet_num=100, fb_label="01"))
+    g = torch.Generator().manual_seed(1)
+    bs, nq = 6, 3
+    out = dict(pred_logits=torch.randn(bs, nq, 2, generator=g), pred_spans=torch.rand(bs, nq, 2, generator=g) * 0.3 + 0.1)
+    tg = torch.rand(bs, 2, 2, generator=g) * 0.3 + 0.1
+    tg[2, :, 1] = 0            # sample 2: no target survives the width filter
+    tg[4, 1, 1] = 0            # sample 4: one target
+    res = m(out, tg)
+    assert [len(r) for r, _ in res] == [2, 2, 0, 2, 1, 2]
+    C, sizes = m.cost_matrix(out, tg)
+    assert sizes == [2, 2, 0, 2, 1, 2] and tuple(C.shape) == (bs, nq, 9)
+    from scipy.optimize import linear_sum_assignment
+    col = 0
+    for b, n in enumerate(sizes):           # each sample is matched inside its own block of columns
+        r, c = linear_sum_assignment(C[b, :, col:col + n].numpy())
+        assert res[b][0].tolist() == r.tolist() and res[b][1].tolist() == c.tolist()
+        assert res[b][0].dtype == torch.int64
+        col += n
