@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MADE_ABI_VERSION 1
+#define MADE_ABI_VERSION 2
 
 #define MADE_OK 0
 #define MADE_EINVAL (-1)        /* bad shape / pointer / argument            */
@@ -38,6 +38,14 @@ extern "C" {
 
 #define MADE_VIDEO 0
 #define MADE_MUSIC 1
+
+/* Arithmetic of the similarity path (temporal encoders + X-Pool projections), DESIGN.md "numerics".
+ * FP16  : every GEMM operand is one fp16 value (fastest; similarity error ~2e-4 rms of the scale).
+ * SPLIT : the weights and token activations whose rounding dominates the similarity error travel as
+ *         fp16 (hi, lo) pairs and their GEMMs run 2-3 tcgen05 passes into one fp32 accumulator
+ *         (default; meets the 1e-3 similarity bar on the full 2000 x 4000 job). */
+#define MADE_PREC_FP16 0
+#define MADE_PREC_SPLIT 1
 
 typedef struct made_ctx made_ctx;
 
@@ -109,6 +117,11 @@ int made_ctx_destroy(made_ctx* ctx);
  * Packs fp16 GEMM operands and the folded X-Pool / decoder weights. */
 int made_ctx_load_weights(made_ctx* ctx, int n, const char* const* names, const float* const* host_ptrs,
                           const int64_t* numels, void* stream);
+/* MADE_PREC_* (default MADE_PREC_SPLIT); takes effect for the calls that follow. */
+int made_ctx_set_precision(made_ctx* ctx, int mode);
+/* Columns of a packed operand row of `dim` features in the context's precision mode (2*dim for
+ * (hi | lo) pairs): the row width of made_ingest_ragged's output. */
+int made_ctx_operand_width(const made_ctx* ctx, int dim);
 
 /* ---------------------------------------------------------------------------------------------
  * Ragged (token-packed) batches.  The reference computes every zero-padded position and masks it
@@ -132,12 +145,13 @@ int64_t made_ragged_index_words(int64_t B, int L);
 /* masks [B, L] float {0,1} (device) -> descriptor (3 small kernels on `stream`). */
 int made_ragged_build(const float* masks, int64_t B, int L, int32_t* idx_workspace, made_ragged* out, void* stream);
 /* Feature ingest = the masked_fill + cast at the top of forward_{video,audio}_encoder_feature
- * (model_Base.py:556 / :595): feats [B, L, dim] (fp32 / bf16 / fp16) -> out16_packed [<= B*L, dim] fp16
- * holding the valid rows only; rows with mask == 0 are NEVER READ.  `feats` may be device memory or
+ * (model_Base.py:556 / :595): feats [B, L, dim] (fp32 / bf16 / fp16) -> out16_packed
+ * [<= B*L, made_ctx_operand_width(ctx, dim)] fp16 holding the valid rows only (in MADE_PREC_SPLIT every row is
+ * [hi | lo]: the fp16 rounding of the features and what that rounding dropped); rows with mask == 0 are NEVER READ.  `feats` may be device memory or
  * pinned host memory (unified addressing: the kernel then pulls just the valid rows over PCIe).
  * dim % 8 == 0. */
-int made_ingest_ragged(const void* feats, int feats_dtype, const made_ragged* rb, int dim, void* out16_packed,
-                       void* stream);
+int made_ingest_ragged(made_ctx* ctx, const void* feats, int feats_dtype, const made_ragged* rb, int dim,
+                       void* out16_packed, void* stream);
 
 /* Host -> device transfer of a zero-padded feature tensor, valid rows only (the reference copies the
  * whole padded tensor per batch, test-MaDe.py:268-271).  host_feats [B, L, dim] and host_masks
@@ -174,12 +188,12 @@ int made_encode_ragged(made_ctx* ctx, int modality, const void* x16_packed, cons
 int made_gallery_prepare(made_ctx* ctx, const void* seg16, const float* seg_masks, int64_t N,
                          void* kz, void* gram, uint32_t* maskbits, void* stream);
 /* Per-query X-Pool operands (modules/transformer.py:164, 98; metrics.py:19):
- * video_feats [N,256] fp32 -> q [N,256] fp16 (q_proj(LN1(v))/16), vhat [N,256] fp16. */
-int made_query_prepare(made_ctx* ctx, const float* video_feats, int64_t N, void* q, void* vhat,
+ * video_feats [N,256] fp32 -> q [N,256] fp16 (q_proj(LN1(v))/16), vhat [N,256] fp32 (v / |v|). */
+int made_query_prepare(made_ctx* ctx, const float* video_feats, int64_t N, void* q, float* vhat,
                        void* stream);
 /* Transformer_XA + sim_matrix_music_pooling fused (modules/transformer.py:156-180,
  * modules/metrics.py:10-24): sim[v, col_offset + m] for v < N_v, m < N_m; sim row stride ld. */
-int made_xpool_score(made_ctx* ctx, const void* q, const void* vhat, int64_t n_queries,
+int made_xpool_score(made_ctx* ctx, const void* q, const float* vhat, int64_t n_queries,
                      const void* kz, const void* gram, const uint32_t* maskbits, int64_t n_tracks,
                      float* sim, int64_t ld, int64_t col_offset, void* stream);
 
@@ -218,6 +232,13 @@ int made_retrieval_loss(const float* dual, const float* single, int64_t ld, int 
 int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const float* bias,
                    const float* residual, int act, const float* ln_gamma, const float* ln_beta,
                    void* out16, float* out_f32, void* stream);
+/* The split-precision GEMM behind MADE_PREC_SPLIT.  W [N, 2K] = rows of [hi | lo] fp16 pairs; split = 1: A [M, K]
+ * plain fp16, C = A W_hi^T + A W_lo^T; split = 2: A [M, 2K] pairs too, C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T
+ * (three tcgen05 passes into one fp32 accumulator).  residual_pair [M, 2N] (nullable) = (hi | lo) pair added as
+ * hi + lo; exactly one of out_pair [M, 2N] ((hi | lo) pair of the result) / out_f32 [M, N]. */
+int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias,
+                        const void* residual_pair, int act, const float* ln_gamma, const float* ln_beta,
+                        void* out_pair, float* out_f32, void* stream);
 /* softmax(Q K^T / sqrt(32) + key mask) V for 8 heads of 32: q,k,v,out [B*L, 256] fp16. */
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B,
                   int L, void* out, void* stream);

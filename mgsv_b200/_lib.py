@@ -15,6 +15,8 @@ _LIB: Optional[C.CDLL] = None
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 VIDEO, MUSIC = 0, 1
+PREC_FP16, PREC_SPLIT = 0, 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -43,9 +45,11 @@ SIGNATURES = {
     "made_ctx_create": [C.POINTER(_p), _i32],
     "made_ctx_destroy": [_p],
     "made_ctx_load_weights": [_p, _i32, C.POINTER(C.c_char_p), C.POINTER(_p), C.POINTER(_i64), _p],
+    "made_ctx_set_precision": [_p, _i32],
+    "made_ctx_operand_width": [_p, _i32],
     "made_h2d_valid_rows": [_p, _i32, _p, _i64, _i32, _i32, _p, _i32, _p, C.POINTER(_i64), _p],
     "made_ragged_build": [_p, _i64, _i32, _p, C.POINTER(Ragged), _p],
-    "made_ingest_ragged": [_p, _i32, C.POINTER(Ragged), _i32, _p, _p],
+    "made_ingest_ragged": [_p, _p, _i32, C.POINTER(Ragged), _i32, _p, _p],
     "made_encode": [_p, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p],
     "made_encode_ragged": [_p, _i32, _p, C.POINTER(Ragged), _p, _p, _p, _p],
     "made_gallery_prepare": [_p, _p, _p, _i64, _p, _p, _p, _p],
@@ -55,6 +59,7 @@ SIGNATURES = {
     "made_detr_losses": [_p, _p, _p, _p, _p, _i64, _i32, _f, _f, _f, _p, _p],
     "made_retrieval_loss": [_p, _p, _i64, _i32, _f, _p, _p],
     "made_gemm_f16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
+    "made_gemm_f16_split": [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
     "made_mha_core": [_p, _p, _p, _p, _i64, _i32, _p, _p],
 }
 

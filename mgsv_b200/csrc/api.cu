@@ -28,6 +28,7 @@ uint16_t f2h(float f) {  // fp32 -> IEEE fp16 bits, round-to-nearest-even, satur
 
 struct Lin {            // y = x W^T + b, W [out,in] fp16 on device, b fp32
   op_t* w = nullptr;
+  op_t* w2 = nullptr;   // [out, 2*in] = [fp16(W) | fp16(W - fp16(W))]: the (hi, lo) pair of the split-precision GEMMs
   float* b = nullptr;
 };
 struct LNp {
@@ -62,6 +63,10 @@ struct made_ctx {
   std::vector<void*> allocs;
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0, ws_off = 0;
+  bool ws_dry = false;          // sizing pass of with_arena(): take() only advances the offset
+  int precision = MADE_PREC_SPLIT;
+  XpoolConsts xp_consts;        // folded X-Pool constants of THIS context's checkpoint
+  float* xp_c5 = nullptr;       // [5][256] weight vectors of the W5 columns (device)
 
   EncW enc[2];
   LNp xp_ln1;
@@ -93,9 +98,27 @@ struct made_ctx {
   template <typename T>
   T* take(size_t count) {
     size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
-    T* p = reinterpret_cast<T*>(ws + ws_off);
+    T* p = ws_dry ? nullptr : reinterpret_cast<T*>(ws + ws_off);
     ws_off += bytes;
     return p;
+  }
+  // Lays out a call's scratch buffers: `layout` (a sequence of take() calls) runs once as a sizing pass and
+  // once for real, so the reservation can never drift from what is taken.
+  template <typename F>
+  int with_arena(F&& layout) {
+    ws_dry = true;
+    ws_off = 0;
+    layout();
+    const size_t need = ws_off;
+    ws_dry = false;
+    int rc = reserve(need);
+    if (rc != MADE_OK) return rc;
+    layout();
+    if (ws_off > ws_bytes) {     // cannot happen: same take() sequence as the sizing pass
+      set_error("workspace arena overrun: %zu > %zu bytes", ws_off, ws_bytes);
+      return MADE_ESTATE;
+    }
+    return MADE_OK;
   }
 };
 
@@ -138,18 +161,35 @@ int up_op(made_ctx* c, const float* src, size_t n, op_t** dst) {
   return MADE_OK;
 }
 
-int up_lin(made_ctx* c, const float* w, const float* b, size_t out_f, size_t in_f, Lin* lin) {
+int up_lin(made_ctx* c, const float* w, const float* b, size_t out_f, size_t in_f, Lin* lin, bool split = false) {
   MADE_TRY(up_op(c, w, out_f * in_f, &lin->w));
   MADE_TRY(up_f32(c, b, out_f, &lin->b));
+  if (split) {     // rows of [hi | lo]: W = hi + lo to ~22 bits
+    std::vector<uint16_t> tmp(out_f * in_f * 2);
+    for (size_t r = 0; r < out_f; ++r)
+      for (size_t k = 0; k < in_f; ++k) {
+        const float x = w[r * in_f + k];
+        const uint16_t hi = f2h(x);
+        __half hh;
+        memcpy(&hh, &hi, 2);
+        tmp[r * 2 * in_f + k] = hi;
+        tmp[r * 2 * in_f + in_f + k] = f2h(x - __half2float(hh));
+      }
+    void* p = nullptr;
+    MADE_CUDA(cudaMalloc(&p, tmp.size() * 2));
+    c->allocs.push_back(p);
+    MADE_CUDA(cudaMemcpy(p, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+    lin->w2 = static_cast<op_t*>(p);
+  }
   return MADE_OK;
 }
 
 int load_lin(made_ctx* c, const std::string& prefix, size_t out_f, size_t in_f, Lin* lin,
-             const char* wname = ".weight", const char* bname = ".bias") {
+             const char* wname = ".weight", const char* bname = ".bias", bool split = false) {
   const std::vector<float>*w, *b;
   MADE_TRY(get(c, prefix + wname, out_f * in_f, &w));
   MADE_TRY(get(c, prefix + bname, out_f, &b));
-  return up_lin(c, w->data(), b->data(), out_f, in_f, lin);
+  return up_lin(c, w->data(), b->data(), out_f, in_f, lin, split);
 }
 
 int load_ln(made_ctx* c, const std::string& prefix, LNp* ln) {
@@ -182,14 +222,16 @@ int load_encoder(made_ctx* c, int modality) {
   e.L = vid ? LV : LM;
   e.din = vid ? 512 : 768;
   const std::string tr = vid ? "video_transformer" : "audio_transformer";
-  MADE_TRY(load_lin(c, vid ? "vit_proj" : "ast_proj", D, e.din, &e.proj));
+  // the four linears whose operand rounding dominates the similarity error carry (hi, lo) weight pairs
+  // (tests/tools/precision_pipeline.py); the FF branch is a small perturbation of the residual stream
+  MADE_TRY(load_lin(c, vid ? "vit_proj" : "ast_proj", D, e.din, &e.proj, ".weight", ".bias", true));
   MADE_TRY(load_ln(c, tr + ".layers.0.0", &e.ln1));
-  MADE_TRY(load_lin(c, tr + ".layers.0.1", 3 * D, D, &e.in_proj, ".in_proj_weight", ".in_proj_bias"));
-  MADE_TRY(load_lin(c, tr + ".layers.0.1.out_proj", D, D, &e.out_proj));
+  MADE_TRY(load_lin(c, tr + ".layers.0.1", 3 * D, D, &e.in_proj, ".in_proj_weight", ".in_proj_bias", true));
+  MADE_TRY(load_lin(c, tr + ".layers.0.1.out_proj", D, D, &e.out_proj, ".weight", ".bias", true));
   MADE_TRY(load_ln(c, tr + ".layers.0.2", &e.ln2));
   MADE_TRY(load_lin(c, tr + ".layers.0.3.0", DFF, D, &e.ff1));
   MADE_TRY(load_lin(c, tr + ".layers.0.3.3", D, DFF, &e.ff2));
-  MADE_TRY(load_lin(c, tr + ".final_linear", D, D, &e.fin));
+  MADE_TRY(load_lin(c, tr + ".final_linear", D, D, &e.fin, ".weight", ".bias", true));
   const std::vector<float>* pe;
   const size_t pe_len = vid ? 250 : 300;
   MADE_TRY(get(c, vid ? "video_position_embedding.pe" : "audio_position_embedding.pe", pe_len * D, &pe));
@@ -220,7 +262,7 @@ int load_xpool(made_ctx* c, cudaStream_t st) {
     std::vector<float> w(D * D), b(D);
     for (int i = 0; i < D * D; ++i) w[i] = (*wq)[i] * 0.0625f;
     for (int i = 0; i < D; ++i) b[i] = (*bq)[i] * 0.0625f;
-    MADE_TRY(up_lin(c, w.data(), b.data(), D, D, &c->xp_q));
+    MADE_TRY(up_lin(c, w.data(), b.data(), D, D, &c->xp_q, true));
   }
   // V'' = centre_d( Wo (Wv s + bv) + bo ),  Z'' = W' V'',  W' = (I + Wl) diag(gamma2)
   std::vector<double> Wo = to_d(wo->data(), D * D), Wv = to_d(wv->data(), D * D);
@@ -271,9 +313,12 @@ int load_xpool(made_ctx* c, cudaStream_t st) {
     b[D + i] = static_cast<float>(bvo[i]);
     b[2 * D + i] = static_cast<float>(bz[i]);
   }
-  MADE_TRY(up_lin(c, w.data(), b.data(), 3 * D, D, &c->xp_kvz));
-  MADE_TRY(xpool_set_constants(bprime.data(), g3->data(), b3->data(), st));
-  MADE_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  MADE_TRY(up_lin(c, w.data(), b.data(), 3 * D, D, &c->xp_kvz, true));
+  // folded constants live in the context (a second context with another checkpoint keeps its own)
+  std::vector<float> c5(5 * D);
+  xpool_fill_constants(bprime.data(), g3->data(), b3->data(), &c->xp_consts, c5.data());
+  MADE_TRY(up_f32(c, c5.data(), c5.size(), &c->xp_c5));
+  (void)st;
   return MADE_OK;
 }
 
@@ -484,42 +529,92 @@ int made_ragged_build(const float* masks, int64_t B, int L, int32_t* idx_workspa
   return MADE_OK;
 }
 
-int made_ingest_ragged(const void* feats, int feats_dtype, const made_ragged* rb, int dim, void* out16_packed,
-                       void* stream) {
+int made_ingest_ragged(made_ctx* c, const void* feats, int feats_dtype, const made_ragged* rb, int dim,
+                       void* out16_packed, void* stream) {
+  MADE_REQUIRE(c, "ingest_ragged: null made_ctx");
   MADE_REQUIRE(feats && rb && out16_packed, "ingest_ragged: null pointer");
   MADE_REQUIRE(feats_dtype >= MADE_DTYPE_F32 && feats_dtype <= MADE_DTYPE_F16, "ingest_ragged: bad dtype %d",
                feats_dtype);
   MADE_REQUIRE(dim > 0 && dim % 8 == 0, "ingest_ragged: dim=%d must be a positive multiple of 8", dim);
   if (rb->B == 0) return MADE_OK;
   return ingest_gather(feats, feats_dtype, to_ragged(rb), dim, static_cast<op_t*>(out16_packed),
-                       static_cast<cudaStream_t>(stream));
+                       c->precision == MADE_PREC_SPLIT, static_cast<cudaStream_t>(stream));
+}
+
+int made_ctx_set_precision(made_ctx* c, int mode) {
+  MADE_REQUIRE(c, "set_precision: null made_ctx");
+  MADE_REQUIRE(mode == MADE_PREC_FP16 || mode == MADE_PREC_SPLIT, "set_precision: unknown mode %d", mode);
+  c->precision = mode;
+  return MADE_OK;
+}
+
+int made_ctx_operand_width(const made_ctx* c, int dim) {
+  return c && c->precision == MADE_PREC_SPLIT ? 2 * dim : dim;
+}
+
+// Scratch of one encoder pass over T packed rows.  Split precision: token activations that feed a
+// K = 256 / K = din GEMM are (hi, lo) fp16 pairs, [T, 512] with the lo halves 256 columns to the right,
+// and double as the residual stream (hi + lo carries ~22 bits); fp16 mode keeps an fp32 copy instead.
+struct EncBufs {
+  op_t *x1 = nullptr, *qkv = nullptr, *att = nullptr, *x2 = nullptr, *h = nullptr, *x3 = nullptr;
+  float *x1f = nullptr, *x2f = nullptr, *seqf = nullptr;
+};
+static void encode_layout(made_ctx* c, int64_t T, EncBufs* b) {
+  const bool sp = c->precision == MADE_PREC_SPLIT;
+  const int64_t W = sp ? 2 * D : D;
+  b->x1 = c->take<op_t>(T * W);
+  b->x1f = sp ? nullptr : c->take<float>(T * D);
+  b->qkv = c->take<op_t>(T * 3 * D);
+  b->att = c->take<op_t>(T * D);
+  b->x2 = c->take<op_t>(T * W);
+  b->x2f = sp ? nullptr : c->take<float>(T * D);
+  b->h = c->take<op_t>(T * DFF);
+  b->x3 = c->take<op_t>(T * W);
+  b->seqf = c->take<float>(T * D);
 }
 
 // forward_{video,audio}_encoder_feature on a token-packed batch (valid tokens only).
-static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged& rb, void* seq16, float* seq_f32,
-                         float* pooled, cudaStream_t st) {
+static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged& rb, const EncBufs& bf, void* seq16,
+                         float* seq_f32, float* pooled, cudaStream_t st) {
   const EncW& e = c->enc[modality];
   const int64_t B = rb.B;
   const int64_t T = B * e.L;   // upper bound of the packed row count (the real count lives on the device)
-  op_t* x1 = c->take<op_t>(T * D);
-  float* x1f = c->take<float>(T * D);
-  op_t* qkv = c->take<op_t>(T * 3 * D);
-  op_t* att = c->take<op_t>(T * D);
-  op_t* x2 = c->take<op_t>(T * D);
-  float* x2f = c->take<float>(T * D);
-  op_t* h = c->take<op_t>(T * DFF);
-  op_t* x3 = c->take<op_t>(T * D);
-  float* seqf = c->take<float>(T * D);
+  const bool sp = c->precision == MADE_PREC_SPLIT;
+  const int64_t W = sp ? 2 * D : D;          // row stride of the (hi | lo) activation buffers
 
-  auto lin = [&](const op_t* A, int64_t lda, const Lin& w, int N, int K, GemmEpilogue ep) {
+  // A [T, K] (row stride lda; split_a: a (hi | lo) pair) x w -> N columns
+  auto lin = [&](const op_t* A, int64_t lda, bool split_a, const Lin& w, bool split_w, int N, int K, GemmEpilogue ep) {
     GemmParams p;
     p.M = T;
     p.N = N;
     p.K = K;
     p.m_dev = rb.total;
+    p.split = split_w ? (split_a ? 2 : 1) : 0;
     ep.bias = w.b;
     p.epi = ep;
-    return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
+    return gemm_f16_tc(A, lda, split_w ? w.w2 : w.w, split_w ? 2 * K : K, N, p, 256, st);
+  };
+  auto residual_from = [&](GemmEpilogue& ep, const op_t* pair, const float* f32) {
+    if (sp) {
+      ep.residual = pair;
+      ep.residual_lo = pair + D;
+      ep.residual_f32 = 0;
+      ep.res_ld = W;
+    } else {
+      ep.residual = f32;
+      ep.residual_f32 = 1;
+      ep.res_ld = D;
+    }
+  };
+  auto out_pair = [&](GemmEpilogue& ep, op_t* pair, float* f32) {
+    ep.out_h = pair;
+    ep.ld_h = W;
+    if (sp) {
+      ep.out_lo = pair + D;
+    } else {
+      ep.out_f32 = f32;
+      ep.ld_f32 = D;
+    }
   };
   {  // :559/598 projection, :533 += pe[position], Transformer_enhancement norm1 (:86)
     GemmEpilogue ep;
@@ -528,48 +623,39 @@ static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged
     ep.row_src = rb.tok_src;
     ep.ln_gamma = e.ln1.g;
     ep.ln_beta = e.ln1.b;
-    ep.out_h = x1;
-    ep.ld_h = D;
-    ep.out_f32 = x1f;
-    ep.ld_f32 = D;
-    MADE_TRY(lin(x0, e.din, e.proj, D, e.din, ep));
+    out_pair(ep, bf.x1, bf.x1f);
+    MADE_TRY(lin(x0, sp ? 2 * e.din : e.din, sp, e.proj, sp, D, e.din, ep));
   }
   {  // packed in_proj (nn.MultiheadAttention)
     GemmEpilogue ep;
-    ep.out_h = qkv;
+    ep.out_h = bf.qkv;
     ep.ld_h = 3 * D;
-    MADE_TRY(lin(x1, D, e.in_proj, 3 * D, D, ep));
+    MADE_TRY(lin(bf.x1, W, sp, e.in_proj, sp, 3 * D, D, ep));
   }
-  MADE_TRY(mha_core(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, nullptr, B, e.L, att, D, st, rb.seq_off,
-                    rb.seq_len));
+  MADE_TRY(mha_core(bf.qkv, 3 * D, bf.qkv + D, 3 * D, bf.qkv + 2 * D, 3 * D, nullptr, B, e.L, bf.att, D, st,
+                    rb.seq_off, rb.seq_len));
   {  // out_proj + residual (from the normed tensor, Q2) + norm2 (:87-88)
     GemmEpilogue ep;
-    ep.residual = x1f;
-    ep.residual_f32 = 1;
-    ep.res_ld = D;
+    residual_from(ep, bf.x1, bf.x1f);
     ep.ln_gamma = e.ln2.g;
     ep.ln_beta = e.ln2.b;
-    ep.out_h = x2;
-    ep.ld_h = D;
-    ep.out_f32 = x2f;
-    ep.ld_f32 = D;
-    MADE_TRY(lin(att, D, e.out_proj, D, D, ep));
+    out_pair(ep, bf.x2, bf.x2f);
+    MADE_TRY(lin(bf.att, D, false, e.out_proj, sp, D, D, ep));
   }
-  {  // FF: Linear -> GELU(erf)
+  {  // FF: Linear -> GELU(erf); plain fp16 operands in both modes
     GemmEpilogue ep;
     ep.act = 1;
-    ep.out_h = h;
+    ep.out_h = bf.h;
     ep.ld_h = DFF;
-    MADE_TRY(lin(x2, D, e.ff1, DFF, D, ep));
+    MADE_TRY(lin(bf.x2, W, false, e.ff1, false, DFF, D, ep));
   }
   {  // FF: Linear + residual (:89)
     GemmEpilogue ep;
-    ep.residual = x2f;
-    ep.residual_f32 = 1;
-    ep.res_ld = D;
-    ep.out_h = x3;
-    ep.ld_h = D;
-    MADE_TRY(lin(h, DFF, e.ff2, D, DFF, ep));
+    residual_from(ep, bf.x2, bf.x2f);
+    ep.out_h = bf.x3;
+    ep.ld_h = W;
+    if (sp) ep.out_lo = bf.x3 + D;
+    MADE_TRY(lin(bf.h, DFF, false, e.ff2, false, D, DFF, ep));
   }
   {  // final_linear (:91); masked_fill (:541) = padded rows of the output stay zero
     MADE_CUDA(cudaMemsetAsync(seq16, 0, static_cast<size_t>(T) * D * 2, st));
@@ -577,18 +663,14 @@ static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged
     ep.out_h = static_cast<op_t*>(seq16);
     ep.ld_h = D;
     ep.h_row_idx = rb.tok_src;      // scatter packed rows back to [B, L, 256]
-    ep.out_f32 = seqf;
+    ep.out_f32 = bf.seqf;
     ep.ld_f32 = D;
-    MADE_TRY(lin(x3, D, e.fin, D, D, ep));
+    MADE_TRY(lin(bf.x3, W, sp, e.fin, sp, D, D, ep));
   }
-  if (seq_f32) MADE_TRY(scatter_rows_f32(seqf, rb, seq_f32, st));
+  if (seq_f32) MADE_TRY(scatter_rows_f32(bf.seqf, rb, seq_f32, st));
   // masked mean + F.normalize (:579-580 / :615-616)
-  MADE_TRY(pool_norm_ragged(seqf, rb, pooled, st));
+  MADE_TRY(pool_norm_ragged(bf.seqf, rb, pooled, st));
   return MADE_OK;
-}
-
-static size_t encode_scratch_bytes(int64_t T) {
-  return padded(T * D, 2) * 4 + padded(T * D, 4) * 3 + padded(T * 3 * D, 2) + padded(T * DFF, 2);
 }
 
 int made_encode_ragged(made_ctx* c, int modality, const void* x16_packed, const made_ragged* rb, void* seq16,
@@ -602,8 +684,9 @@ int made_encode_ragged(made_ctx* c, int modality, const void* x16_packed, const 
   MADE_REQUIRE(rb->L == e.L, "encode_ragged: descriptor built for L=%d, modality needs L=%d", rb->L, e.L);
   const int64_t T = rb->B * e.L;
   MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
-  MADE_TRY(c->reserve(encode_scratch_bytes(T)));
-  return encode_packed(c, modality, static_cast<const op_t*>(x16_packed), to_ragged(rb), seq16, seq_f32, pooled,
+  EncBufs bf;
+  MADE_TRY(c->with_arena([&] { encode_layout(c, T, &bf); }));
+  return encode_packed(c, modality, static_cast<const op_t*>(x16_packed), to_ragged(rb), bf, seq16, seq_f32, pooled,
                        static_cast<cudaStream_t>(stream));
 }
 
@@ -619,14 +702,20 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   const EncW& e = c->enc[modality];
   const int64_t T = B * e.L;
   MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
-  MADE_TRY(c->reserve(padded(ragged_index_words(B, e.L), 4) + padded(T * e.din, 2) + encode_scratch_bytes(T)));
-  int32_t* idx = c->take<int32_t>(ragged_index_words(B, e.L));
-  op_t* x0 = c->take<op_t>(T * e.din);
+  const bool sp = c->precision == MADE_PREC_SPLIT;
+  int32_t* idx = nullptr;
+  op_t* x0 = nullptr;
+  EncBufs bf;
+  MADE_TRY(c->with_arena([&] {
+    idx = c->take<int32_t>(ragged_index_words(B, e.L));
+    x0 = c->take<op_t>(T * e.din * (sp ? 2 : 1));
+    encode_layout(c, T, &bf);
+  }));
   Ragged rb;
   MADE_TRY(ragged_build(masks, B, e.L, idx, &rb, st));
   // model_Base.py:556/595 masked_fill + cast: only the valid rows are read and packed
-  MADE_TRY(ingest_gather(feats, feats_dtype, rb, e.din, x0, st));
-  return encode_packed(c, modality, x0, rb, seq16, seq_f32, pooled, st);
+  MADE_TRY(ingest_gather(feats, feats_dtype, rb, e.din, x0, sp, st));
+  return encode_packed(c, modality, x0, rb, bf, seq16, seq_f32, pooled, st);
 }
 
 int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks, int64_t N, void* kz,
@@ -637,16 +726,23 @@ int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t T = N * LM;
   MADE_REQUIRE(T < (1LL << 31), "gallery_prepare: too many tracks in one call; chunk it");
-  MADE_TRY(c->reserve(padded(T * D, 2)));
-  op_t* sp = c->take<op_t>(T * D);
+  const bool sp = c->precision == MADE_PREC_SPLIT;
+  const int64_t W = sp ? 2 * D : D;
+  op_t* spn = nullptr;
+  MADE_TRY(c->with_arena([&] { spn = c->take<op_t>(T * W); }));
   // shared LayerNorm1 on the segments (modules/transformer.py:165)
-  MADE_TRY(layernorm_rows(seg16, 1, D, T, c->xp_ln1.g, c->xp_ln1.b, sp, nullptr, st));
+  MADE_TRY(layernorm_rows(seg16, 1, D, T, c->xp_ln1.g, c->xp_ln1.b, spn, W, sp ? spn + D : nullptr, nullptr, st));
   op_t* kzb = static_cast<op_t*>(kz);
   {
-    GemmEpilogue ep;
-    ep.out_h = kzb;
-    ep.ld_h = 3 * D;
-    MADE_TRY(linear(sp, D, c->xp_kvz, T, 3 * D, D, ep, st));
+    GemmParams p;
+    p.M = T;
+    p.N = 3 * D;
+    p.K = D;
+    p.split = sp ? 2 : 0;
+    p.epi.bias = c->xp_kvz.b;
+    p.epi.out_h = kzb;
+    p.epi.ld_h = 3 * D;
+    MADE_TRY(gemm_f16_tc(spn, W, sp ? c->xp_kvz.w2 : c->xp_kvz.w, sp ? 2 * D : D, 3 * D, p, 256, st));
   }
   {  // per-track Gram matrix G = V'' V''^T (96 x 96), batched over tracks -> columns 0..95 of [G | W5 | 0]
     GemmParams p;
@@ -661,33 +757,40 @@ int made_gallery_prepare(made_ctx* c, const void* seg16, const float* seg_masks,
     MADE_TRY(gemm_f16_tc(kzb + D, 3 * D, kzb + D, 3 * D, T, p, 96, st));
   }
   // W5 = Z'' . {1, b', g3^2, g3^2 b', g3 beta3} -> columns 96..100 (xpool.cu)
-  MADE_TRY(xpool_w5(kzb + 2 * D, 3 * D, T, static_cast<op_t*>(gram), st));
+  MADE_TRY(xpool_w5(kzb + 2 * D, 3 * D, T, c->xp_c5, static_cast<op_t*>(gram), st));
   MADE_TRY(mask_bits(seg_masks, N, maskbits, st));
   return MADE_OK;
 }
 
-int made_query_prepare(made_ctx* c, const float* video_feats, int64_t N, void* q, void* vhat, void* stream) {
+int made_query_prepare(made_ctx* c, const float* video_feats, int64_t N, void* q, float* vhat, void* stream) {
   CTX_READY(c);
   if (N == 0) return MADE_OK;
   MADE_REQUIRE(video_feats && q && vhat, "query_prepare: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MADE_TRY(c->reserve(padded(N * D, 2)));
-  op_t* vp = c->take<op_t>(N * D);
-  MADE_TRY(layernorm_rows(video_feats, 0, D, N, c->xp_ln1.g, c->xp_ln1.b, vp, nullptr, st));
-  GemmEpilogue ep;
-  ep.out_h = static_cast<op_t*>(q);
-  ep.ld_h = D;
-  MADE_TRY(linear(vp, D, c->xp_q, N, D, D, ep, st));
-  MADE_TRY(vhat_rows(video_feats, N, static_cast<__half*>(vhat), st));
+  const bool sp = c->precision == MADE_PREC_SPLIT;
+  const int64_t W = sp ? 2 * D : D;
+  op_t* vp = nullptr;
+  MADE_TRY(c->with_arena([&] { vp = c->take<op_t>(N * W); }));
+  MADE_TRY(layernorm_rows(video_feats, 0, D, N, c->xp_ln1.g, c->xp_ln1.b, vp, W, sp ? vp + D : nullptr, nullptr, st));
+  GemmParams p;
+  p.M = N;
+  p.N = D;
+  p.K = D;
+  p.split = sp ? 2 : 0;
+  p.epi.bias = c->xp_q.b;
+  p.epi.out_h = static_cast<op_t*>(q);
+  p.epi.ld_h = D;
+  MADE_TRY(gemm_f16_tc(vp, W, sp ? c->xp_q.w2 : c->xp_q.w, sp ? 2 * D : D, D, p, 256, st));
+  MADE_TRY(vhat_rows(video_feats, N, vhat, st));
   return MADE_OK;
 }
 
-int made_xpool_score(made_ctx* c, const void* q, const void* vhat, int64_t n_queries, const void* kz,
+int made_xpool_score(made_ctx* c, const void* q, const float* vhat, int64_t n_queries, const void* kz,
                      const void* gram, const uint32_t* maskbits, int64_t n_tracks, float* sim, int64_t ld,
                      int64_t col_offset, void* stream) {
   CTX_READY(c);
   MADE_REQUIRE(ld >= col_offset + n_tracks, "xpool_score: ld=%lld too small", (long long)ld);
-  return xpool_score(static_cast<const op_t*>(q), static_cast<const __half*>(vhat), n_queries,
+  return xpool_score(c->xp_consts, static_cast<const op_t*>(q), vhat, n_queries,
                      static_cast<const op_t*>(kz), 3 * D, 2 * D, static_cast<const op_t*>(gram),
                      maskbits, n_tracks, sim, ld, col_offset, static_cast<cudaStream_t>(stream));
 }
@@ -711,44 +814,46 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   const int64_t R = NDEC * B;
   const int64_t n_chunks = (B + Bc - 1) / Bc;
   const size_t idx_words = ragged_index_words(Bc, LD);
-  size_t need = padded(Tall * D, 2) * 2 + padded(Tall, 4) + padded(B, 4) * 2 +                  // mem, mp, mask, off, len
-                padded(idx_words, 4) * n_chunks +
-                padded(Tc * D, 2) * 7 + padded(Tc * 2 * D, 2) + padded(Tc * D, 4) * 2 + padded(Tc * DFF, 2) +
-                padded(B * D, 2) * 4 + padded(B * D, 4) * 2 + padded(B * 8 * D, 4) + padded(B * 8 * D, 2) +
-                padded(B * DFF, 2) + padded(R * D, 4) + padded(R * D, 2) * 3;
-  MADE_TRY(c->reserve(need));
   // Encoder output of every sequence, token-packed per encoder chunk: chunk k owns rows
   // [k * Tc, ...) of mem_all / mp_all, sequence b its chunk's rows [seq_off[b], + seq_len[b]).
-  op_t* mem_all = c->take<op_t>(Tall * D);     // memory, fp16
-  op_t* mp_all = c->take<op_t>(Tall * D);      // memory + pos
-  float* mask = c->take<float>(Tall);          // concatenated key mask [B, 146]
-  int32_t* row_off = c->take<int32_t>(B);      // first row of sequence b inside mem_all / mp_all
-  int32_t* row_len = c->take<int32_t>(B);
-  op_t* src = c->take<op_t>(Tc * D);
-  op_t* pos = c->take<op_t>(Tc * D);
-  op_t* srcpos = c->take<op_t>(Tc * D);
-  op_t* qk = c->take<op_t>(Tc * 2 * D);
-  op_t* v = c->take<op_t>(Tc * D);
-  op_t* att = c->take<op_t>(Tc * D);
-  op_t* s1 = c->take<op_t>(Tc * D);
-  float* s1f = c->take<float>(Tc * D);
-  op_t* hbuf = c->take<op_t>(Tc * DFF);
-  op_t* src2 = c->take<op_t>(Tc * D);
-  op_t* srcpos2 = c->take<op_t>(Tc * D);
-  float* srcf = c->take<float>(Tc * D);
-  op_t* tgt = c->take<op_t>(B * D);
-  op_t* t1 = c->take<op_t>(B * D);
-  float* t1f = c->take<float>(B * D);
-  float* qt = c->take<float>(B * 8 * D);
-  op_t* mbar = c->take<op_t>(B * 8 * D);
-  op_t* t2 = c->take<op_t>(B * D);
-  float* t2f = c->take<float>(B * D);
-  op_t* hdec = c->take<op_t>(B * DFF);
-  op_t* t3 = c->take<op_t>(B * D);
-  float* t3all = c->take<float>(R * D);
-  op_t* hsb = c->take<op_t>(R * D);
-  op_t* sp0 = c->take<op_t>(R * D);
-  op_t* sp1 = c->take<op_t>(R * D);
+  op_t *mem_all, *mp_all, *src, *pos, *srcpos, *qk, *v, *att, *s1, *hbuf, *src2, *srcpos2, *tgt, *t1, *mbar, *t2, *hdec,
+      *t3, *hsb, *sp0, *sp1;
+  float *mask, *s1f, *srcf, *t1f, *qt, *t2f, *t3all;
+  int32_t *row_off, *row_len;
+  std::vector<int32_t*> idx_chunk(static_cast<size_t>(n_chunks));
+  MADE_TRY(c->with_arena([&] {
+    mem_all = c->take<op_t>(Tall * D);     // memory, fp16
+    mp_all = c->take<op_t>(Tall * D);      // memory + pos
+    mask = c->take<float>(Tall);           // concatenated key mask [B, 146]
+    row_off = c->take<int32_t>(B);         // first row of sequence b inside mem_all / mp_all
+    row_len = c->take<int32_t>(B);
+    src = c->take<op_t>(Tc * D);
+    pos = c->take<op_t>(Tc * D);
+    srcpos = c->take<op_t>(Tc * D);
+    qk = c->take<op_t>(Tc * 2 * D);
+    v = c->take<op_t>(Tc * D);
+    att = c->take<op_t>(Tc * D);
+    s1 = c->take<op_t>(Tc * D);
+    s1f = c->take<float>(Tc * D);
+    hbuf = c->take<op_t>(Tc * DFF);
+    src2 = c->take<op_t>(Tc * D);
+    srcpos2 = c->take<op_t>(Tc * D);
+    srcf = c->take<float>(Tc * D);
+    tgt = c->take<op_t>(B * D);
+    t1 = c->take<op_t>(B * D);
+    t1f = c->take<float>(B * D);
+    qt = c->take<float>(B * 8 * D);
+    mbar = c->take<op_t>(B * 8 * D);
+    t2 = c->take<op_t>(B * D);
+    t2f = c->take<float>(B * D);
+    hdec = c->take<op_t>(B * DFF);
+    t3 = c->take<op_t>(B * D);
+    t3all = c->take<float>(R * D);
+    hsb = c->take<op_t>(R * D);
+    sp0 = c->take<op_t>(R * D);
+    sp1 = c->take<op_t>(R * D);
+    for (auto& ip : idx_chunk) ip = c->take<int32_t>(idx_words);
+  }));
 
   const op_t* fr = static_cast<const op_t*>(frame16);
   static_assert(NENC % 2 == 0, "the encoder ping-pong below ends in the (src, srcpos) buffers");
@@ -758,7 +863,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
     const int64_t nb = (B - b0) < Bc ? (B - b0) : Bc;
     const int64_t T = nb * LD;          // upper bound of this chunk's packed rows
     float* mask_c = mask + b0 * LD;
-    int32_t* idx = c->take<int32_t>(idx_words);
+    int32_t* idx = idx_chunk[static_cast<size_t>(ck)];
     Ragged rb;
     MADE_TRY(detr_mask(frame_masks + b0 * LV, seg_masks, track_idx ? track_idx + b0 : nullptr, b0, nb, mask_c, st));
     MADE_TRY(ragged_build(mask_c, nb, LD, idx, &rb, st));
@@ -911,7 +1016,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
     tinf = t3f;
   }
   // decoder.norm on every layer's output (:136), then the heads (model_Uni.py:131-149)
-  MADE_TRY(layernorm_rows(t3all, 0, D, R, c->dec_norm.g, c->dec_norm.b, hsb, hs, st));
+  MADE_TRY(layernorm_rows(t3all, 0, D, R, c->dec_norm.g, c->dec_norm.b, hsb, D, nullptr, hs, st));
   {
     GemmEpilogue ep;
     ep.act = 2;
@@ -964,6 +1069,40 @@ int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const f
   p.epi.ld_f32 = N;
   return gemm_f16_tc(static_cast<const op_t*>(A), K, static_cast<const op_t*>(W), K, N, p, 256,
                       static_cast<cudaStream_t>(stream));
+}
+
+int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias,
+                        const void* residual_pair, int act, const float* ln_gamma, const float* ln_beta, void* out_pair,
+                        float* out_f32, void* stream) {
+  MADE_REQUIRE(split == 1 || split == 2, "gemm_f16_split: split must be 1 (W pairs) or 2 (A and W pairs)");
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.split = split;
+  p.epi.bias = bias;
+  if (residual_pair) {
+    p.epi.residual = residual_pair;
+    p.epi.residual_lo = static_cast<const op_t*>(residual_pair) + N;
+    p.epi.residual_f32 = 0;
+    p.epi.res_ld = 2 * N;
+  }
+  p.epi.act = act;
+  p.epi.ln_gamma = ln_gamma;
+  p.epi.ln_beta = ln_beta;
+  if (out_pair) {
+    p.epi.out_h = static_cast<op_t*>(out_pair);
+    p.epi.out_lo = static_cast<op_t*>(out_pair) + N;
+    p.epi.ld_h = 2 * N;
+  }
+  if (out_f32 && !out_pair) {
+    p.epi.out_f32 = out_f32;
+    p.epi.ld_f32 = N;
+  }
+  MADE_REQUIRE(out_pair || out_f32, "gemm_f16_split: no output");
+  MADE_REQUIRE(!(out_pair && out_f32), "gemm_f16_split: one output");
+  return gemm_f16_tc(static_cast<const op_t*>(A), split == 2 ? 2 * K : K, static_cast<const op_t*>(W), 2 * K, N, p, 256,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B, int L, void* out,

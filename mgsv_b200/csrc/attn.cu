@@ -332,12 +332,7 @@ template <int LP>
 static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
                       const op_t* V, int64_t ldv, const float* mask, int64_t B, int L, const int32_t* seq_off,
                       const int32_t* seq_len, op_t* O, int64_t ldo, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(mha_core_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   AttnSmem<LP>::kBytes));
-    attr_set = true;
-  }
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&mha_core_kernel<LP>), static_cast<int>(AttnSmem<LP>::kBytes)));
   dim3 grid(static_cast<unsigned>(B), 8 / kHeadsPerCta);
   mha_core_kernel<LP><<<grid, kMhaThreads, AttnSmem<LP>::kBytes, st>>>(
       Q, ldq, K, ldk, V, ldv, mask, L, seq_off, seq_len, 0.17677669529663687f /* 1/sqrt(32) */, O, ldo);
@@ -363,11 +358,7 @@ int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const floa
   if (B == 0) return MADE_OK;
   MADE_REQUIRE(qt && mp && mem && (key_mask || (seq_off && seq_len)) && out && L > 0 && L <= 160,
                "dec_attn_folded: bad arguments");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(dec_attn_folded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
-    attr_set = true;
-  }
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&dec_attn_folded_kernel), static_cast<int>(kDecSmemBytes)));
   dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, kDecSmemBytes, st>>>(qt, mp, mem, key_mask, L, seq_off,
                                                                               seq_len, out);
   MADE_CHECK_LAUNCH();

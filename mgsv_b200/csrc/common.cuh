@@ -59,7 +59,11 @@ int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint6
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// multiprocessor count of the CURRENT device (cached per device)
 int sm_count();
+// opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (function attributes are per
+// device; done once per (kernel, device), thread-safe)
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------

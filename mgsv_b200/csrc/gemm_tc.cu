@@ -49,11 +49,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// low halves of eight values whose fp16-rounded high halves are `hi`: fp16(v - float(hi))
+__device__ __forceinline__ uint4 lo_of(const uint4& hi, const float* v) {
+  const op2_t* h = reinterpret_cast<const op2_t*>(&hi);
+  const float2 f0 = op2_to_f2(h[0]), f1 = op2_to_f2(h[1]), f2 = op2_to_f2(h[2]), f3 = op2_to_f2(h[3]);
+  return make_uint4(pack_op2(v[0] - f0.x, v[1] - f0.y), pack_op2(v[2] - f1.x, v[3] - f1.y),
+                    pack_op2(v[4] - f2.x, v[5] - f2.y), pack_op2(v[6] - f3.x, v[7] - f3.y));
+}
+
 template <int BN, bool WS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_oh, const __grid_constant__ CUtensorMap tmap_of,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_ol, const GemmParams p) {
   using Cfg = GemmCfg<BN, WS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,7 +85,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int64_t M = p.m_dev ? static_cast<int64_t>(__ldg(p.m_dev)) : p.M;   // ragged batches: rows actually present
   const int64_t m_tiles = (M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * n_blocks;
-  const int k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int kb_seg = (p.K + kBlockK - 1) / kBlockK;        // k blocks of one operand half
+  const int k_blocks = kb_seg * (1 + p.split);             // split: 2 or 3 passes over K accumulate into one tile
+  // pass s of a split GEMM: columns of the A / W tile of k block kb  (hi halves at 0, lo halves at K)
+  auto a_col = [&](int i) { return (p.split == 2 && i / kb_seg == 1 ? p.K : 0) + (i % kb_seg) * kBlockK; };
+  auto w_col = [&](int i) { return (p.split != 0 && i / kb_seg == p.split ? p.K : 0) + (i % kb_seg) * kBlockK; };
   // tile schedule: streaming = round-robin, m-major; WS = one contiguous n-major range per CTA
   const int64_t ws_per = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t ws_t0 = static_cast<int64_t>(blockIdx.x) * ws_per;
@@ -101,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (p.tma_store) {
       if (p.epi.out_h) tma_prefetch_desc(&tmap_oh);
       if (p.epi.out_f32) tma_prefetch_desc(&tmap_of);
+      if (p.epi.out_lo) tma_prefetch_desc(&tmap_ol);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -140,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (groups > 0) mbar_wait(w_empty, (groups - 1) & 1);
             mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(k_blocks) * Cfg::kBTileBytes);
             for (int kb = 0; kb < k_blocks; ++kb)
-              tma_load_2d(resident + kb * Cfg::kBTileBytes, &tmap_b, w_full, kb * kBlockK, row_b);
+              tma_load_2d(resident + kb * Cfg::kBTileBytes, &tmap_b, w_full, w_col(kb), row_b);
             cur_n = n_blk;
             ++groups;
           }
@@ -149,8 +162,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, row_a);
-          if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], kb * kBlockK, row_b);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col(kb), row_a);
+          if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], w_col(kb), row_b);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -266,10 +279,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if (e.out_h) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(stg_h + lane * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) =
-                  make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+            for (int i = 0; i < 4; ++i) {
+              const uint4 hi = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                          pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+              *reinterpret_cast<uint4*>(stg_h + lane * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) = hi;
+              if (e.out_lo)     // low halves: what the fp16 rounding of the high halves dropped (fp32 box reused)
+                *reinterpret_cast<uint4*>(stg_f + lane * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) = lo_of(hi, &v[8 * i]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -277,15 +293,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
             if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, wrow);
             if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, wrow);
+            if (e.out_lo && !h_first) tma_store_2d(&tmap_ol, stg_f, col0 - 32, wrow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else if (row_ok) {
           if (e.out_h) {
             uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
+            uint4* ol = e.out_lo ? reinterpret_cast<uint4*>(e.out_lo + hrow * e.ld_h + col0) : nullptr;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o[i] = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
-                                pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+            for (int i = 0; i < 4; ++i) {
+              const uint4 hi = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
+                                          pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
+              o[i] = hi;
+              if (ol) ol[i] = lo_of(hi, &v[8 * i]);
+            }
           }
           if (e.out_f32) {
             float4* o = reinterpret_cast<float4*>(e.out_f32 + grow * e.ld_f32 + col0);
@@ -367,6 +388,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             const uint4* r4 = reinterpret_cast<const uint4*>(
                 static_cast<const op_t*>(e.residual) + srow * e.res_ld + col0);
+            const uint4* l4 = e.residual_lo ? reinterpret_cast<const uint4*>(e.residual_lo + srow * e.res_ld + col0)
+                                            : nullptr;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 t = __ldg(r4 + i);
@@ -376,6 +399,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float2 f = op2_to_f2(h[jj]);
                 v[8 * i + 2 * jj] += f.x;
                 v[8 * i + 2 * jj + 1] += f.y;
+              }
+              if (l4) {
+                t = __ldg(l4 + i);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  float2 f = op2_to_f2(h[jj]);
+                  v[8 * i + 2 * jj] += f.x;
+                  v[8 * i + 2 * jj + 1] += f.y;
+                }
               }
             }
           }
@@ -463,19 +495,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 template <int BN, bool WS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& toh, const CUtensorMap& tof,
-                       const GemmParams& p, cudaStream_t stream) {
+                       const CUtensorMap& tol, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, WS>;
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget of an sm_100 CTA");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, WS>), Cfg::kSmemBytes));
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * (p.N / BN);
   int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
-  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, p);
+  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, tol, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -506,12 +533,18 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
   MADE_REQUIRE(e.out_h || e.out_f32 || e.out2_h, "gemm: no output");
   MADE_REQUIRE(p.m_valid >= 1 && p.m_valid <= 128 && p.m_stride >= 1 && p.m_stride <= 128,
                "gemm: bad tile geometry");
-  CUtensorMap ta, tb, toh, tof;
+  MADE_REQUIRE(p.split >= 0 && p.split <= 2, "gemm: split=%d", p.split);
+  MADE_REQUIRE(p.split == 0 || (p.K % kBlockK == 0 && ldb >= 2 * p.K && !p.b_batched && block_n == 256),
+               "gemm: split operands need K %% 64 == 0 and [hi | lo] rows of 2K columns");
+  MADE_REQUIRE(p.split != 2 || lda >= 2 * p.K, "gemm: split A needs lda >= 2K");
+  MADE_REQUIRE(!e.out_lo || e.out_h, "gemm: out_lo needs out_h");
+  CUtensorMap ta, tb, toh, tof, tol;
   memset(&toh, 0, sizeof(toh));
   memset(&tof, 0, sizeof(tof));
-  MADE_TRY(encode_tmap_2d_16b(&ta, A, static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M),
+  memset(&tol, 0, sizeof(tol));
+  MADE_TRY(encode_tmap_2d_16b(&ta, A, static_cast<uint64_t>(p.split == 2 ? 2 * p.K : p.K), static_cast<uint64_t>(p.M),
                                static_cast<uint64_t>(lda) * 2, kBlockK, kBlockM));
-  MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.K), static_cast<uint64_t>(w_rows),
+  MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.split ? 2 * p.K : p.K), static_cast<uint64_t>(w_rows),
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
   GemmParams pp = p;
   // outputs through TMA bulk stores whenever the tile is a plain [128 x 256] block of the output matrices
@@ -521,7 +554,8 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
   };
   pp.tma_store = tma_store_enabled && block_n == 256 && p.m_valid == 128 && p.m_stride == 128 && !e.h_row_idx &&
                  (e.out_h || e.out_f32) && (!e.out_h || aligned16(e.out_h, e.ld_h, 2)) &&
-                 (!e.out_f32 || aligned16(e.out_f32, e.ld_f32, 4));
+                 (!e.out_f32 || aligned16(e.out_f32, e.ld_f32, 4)) &&
+                 (!e.out_lo || (aligned16(e.out_lo, e.ld_h, 2) && !e.out_f32));
   if (p.n_store > 0 && p.n_store < p.N && !(pp.tma_store && !e.out2_h && !e.ln_gamma && !e.l2norm)) {
     set_error("gemm: a clipped output width needs the plain TMA-store epilogue");
     return MADE_EUNSUPPORTED;
@@ -534,17 +568,20 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
     if (e.out_f32)
       MADE_TRY(encode_tmap_2d(&tof, e.out_f32, 4, n_ext, static_cast<uint64_t>(p.M),
                               static_cast<uint64_t>(e.ld_f32) * 4, 32, 32));
+    if (e.out_lo)
+      MADE_TRY(encode_tmap_2d(&tol, e.out_lo, 2, n_ext, static_cast<uint64_t>(p.M),
+                              static_cast<uint64_t>(e.ld_h) * 2, 64, 32));
   }
   if (block_n == 256) {
     // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles;
     // its shared memory has no room for fp32 staging boxes, so fp32 outputs take the streaming variant
     const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
     const bool ws = p.K <= kWsKBlocks * kBlockK && !p.b_batched && m_tiles * (p.N / 256) >= 2 * sm_count() &&
-                    !(pp.tma_store && e.out_f32);
-    return ws ? launch_gemm<256, true>(ta, tb, toh, tof, pp, stream)
-              : launch_gemm<256, false>(ta, tb, toh, tof, pp, stream);
+                    !(pp.tma_store && (e.out_f32 || e.out_lo)) && p.split == 0;
+    return ws ? launch_gemm<256, true>(ta, tb, toh, tof, tol, pp, stream)
+              : launch_gemm<256, false>(ta, tb, toh, tof, tol, pp, stream);
   }
-  return launch_gemm<96, false>(ta, tb, toh, tof, pp, stream);
+  return launch_gemm<96, false>(ta, tb, toh, tof, tol, pp, stream);
 }
 
 }  // namespace made

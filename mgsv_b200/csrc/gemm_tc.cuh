@@ -16,6 +16,7 @@ struct GemmEpilogue {
   const int32_t* row_src = nullptr;     // ragged batches: tok_src (position of a packed row = tok_src % L)
   const int32_t* h_row_idx = nullptr;   // ragged batches: out_h row r is written to row h_row_idx[r] (scatter)
   const void* residual = nullptr;       // [M, N], row stride res_ld elements
+  const op_t* residual_lo = nullptr;    // fp16 residual given as a (hi, lo) pair: low halves, same stride
   int residual_f32 = 0;
   int64_t res_ld = 0;
   int act = 0;                          // 0 none, 1 GELU(erf), 2 ReLU
@@ -26,6 +27,8 @@ struct GemmEpilogue {
   const float* row_mask = nullptr;      // [M]; rows with mask == 0 are written as 0
   op_t* out_h = nullptr;
   int64_t ld_h = 0;
+  op_t* out_lo = nullptr;               // fp16(result - float(out_h)): the low half of a (hi, lo) pair, stride ld_h
+                                        // (TMA-store path: exclusive with out_f32, whose staging boxes it uses)
   float* out_f32 = nullptr;
   int64_t ld_f32 = 0;
   const op_t* add2 = nullptr;  // second output: fp16(result + add2[row, col])
@@ -42,6 +45,9 @@ struct GemmParams {
   int b_batched = 0;    // 1: B rows start at tile_m * m_stride (per-tile B, e.g. Gram matrix)
   const int32_t* m_dev = nullptr;   // device scalar: actual row count (<= M); M then only sizes the grid / TMA map
   int tma_store = 0;                // set by the launcher: out_h / out_f32 leave through TMA bulk stores
+  int split = 0;                    // fp16 (hi, lo) operand pairs, the lo halves K columns to the right of the hi halves:
+                                    // 1: W = [W_hi | W_lo] (ldb >= 2K)            C = A W_hi^T + A W_lo^T
+                                    // 2: also A = [A_hi | A_lo] (lda >= 2K)        C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T
   int n_store = 0;                  // > 0: only the first n_store (< N) output columns exist; W rows >= w_rows read as
                                     // zero and the TMA store clips the rest (needs the TMA-store path, else EUNSUPPORTED)
   GemmEpilogue epi;

@@ -10,8 +10,8 @@ namespace made {
 template <typename TIn>
 __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in, int64_t rows,
                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float eps, op_t* __restrict__ out_h,
-                                      float* __restrict__ out_f32) {
+                                      float eps, op_t* __restrict__ out_h, int64_t ld_out,
+                                      op_t* __restrict__ out_lo, float* __restrict__ out_f32) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -40,9 +40,20 @@ __global__ void layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * rstd * g[j] + bb[j];
-  if (out_h)
-    *reinterpret_cast<uint4*>(out_h + row * 256 + lane * 8) =
-        make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+  if (out_h) {
+    const uint4 hi = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(out_h + row * ld_out + lane * 8) = hi;
+    if (out_lo) {
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&hi);
+      uint32_t lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = op2_to_f2(hh[j]);
+        lo[j] = pack_op2(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+      }
+      *reinterpret_cast<uint4*>(out_lo + row * ld_out + lane * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
   if (out_f32) {
     float4* o = reinterpret_cast<float4*>(out_f32 + row * 256 + lane * 8);
     o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -93,8 +104,8 @@ __global__ void mask_bits_kernel(const float* __restrict__ mask, int64_t n, uint
   bits[i] = v;
 }
 
-// v_hat = v / |v| (modules/metrics.py:19) -> fp16.  Warp per row.
-__global__ void vhat_kernel(const float* __restrict__ v, int64_t rows, __half* __restrict__ out) {
+// v_hat = v / |v| (modules/metrics.py:19), fp32.  Warp per row.
+__global__ void vhat_kernel(const float* __restrict__ v, int64_t rows, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -103,23 +114,22 @@ __global__ void vhat_kernel(const float* __restrict__ v, int64_t rows, __half* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) { x[j] = v[row * 256 + lane * 8 + j]; s = fmaf(x[j], x[j], s); }
   const float nrm = sqrtf(warp_sum(s));
-  __half2 h[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[2 * j] / nrm, x[2 * j + 1] / nrm);
-  *reinterpret_cast<uint4*>(out + row * 256 + lane * 8) = *reinterpret_cast<uint4*>(h);
+  float4* o = reinterpret_cast<float4*>(out + row * 256 + lane * 8);
+  o[0] = make_float4(x[0] / nrm, x[1] / nrm, x[2] / nrm, x[3] / nrm);
+  o[1] = make_float4(x[4] / nrm, x[5] / nrm, x[6] / nrm, x[7] / nrm);
 }
 
 // ---- launchers ---------------------------------------------------------------------------
 int layernorm_rows(const void* in, int in_is_op, int64_t ld_in, int64_t rows, const float* gamma,
-                   const float* beta, op_t* out_h, float* out_f32, cudaStream_t st) {
+                   const float* beta, op_t* out_h, int64_t ld_out, op_t* out_lo, float* out_f32, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
   const unsigned blocks = static_cast<unsigned>(ceil_div64(rows, 8));
   if (in_is_op)
     layernorm_rows_kernel<op_t><<<blocks, 256, 0, st>>>(static_cast<const op_t*>(in), ld_in,
-                                                                 rows, gamma, beta, 1e-5f, out_h, out_f32);
+                                                                 rows, gamma, beta, 1e-5f, out_h, ld_out, out_lo, out_f32);
   else
     layernorm_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(in), ld_in, rows, gamma,
-                                                         beta, 1e-5f, out_h, out_f32);
+                                                         beta, 1e-5f, out_h, ld_out, out_lo, out_f32);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
@@ -141,7 +151,7 @@ int mask_bits(const float* mask, int64_t n, uint32_t* bits, cudaStream_t st) {
   return MADE_OK;
 }
 
-int vhat_rows(const float* v, int64_t rows, __half* out, cudaStream_t st) {
+int vhat_rows(const float* v, int64_t rows, float* out, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
   vhat_kernel<<<static_cast<unsigned>(ceil_div64(rows, 8)), 256, 0, st>>>(v, rows, out);
   MADE_CHECK_LAUNCH();

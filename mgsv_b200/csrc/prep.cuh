@@ -15,7 +15,8 @@ struct Ragged {
 };
 size_t ragged_index_words(int64_t B, int L);
 int ragged_build(const float* mask, int64_t B, int L, int32_t* idx, Ragged* out, cudaStream_t st);
-int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t* out, cudaStream_t st);
+// split: out rows are [hi | lo] pairs of 2*dim fp16 (lo = what the fp16 rounding of an fp32 input dropped)
+int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t* out, bool split, cudaStream_t st);
 int pool_norm_ragged(const float* seq_packed, const Ragged& rb, float* pooled, cudaStream_t st);
 int scatter_rows_f32(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
 int scatter_rows_f32_nozero(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
@@ -27,13 +28,15 @@ int detr_prep_ragged(const op_t* frame_out, const op_t* seg_out, const int32_t* 
                      cudaStream_t st);
 
 // prep.cu
+// out_h [rows, ld_out] fp16 (nullable), out_lo (nullable) = fp16(result - float(out_h)) with the same stride,
+// out_f32 [rows, 256] (nullable)
 int layernorm_rows(const void* in, int in_is_op, int64_t ld_in, int64_t rows, const float* gamma,
-                   const float* beta, op_t* out_h, float* out_f32, cudaStream_t st);
+                   const float* beta, op_t* out_h, int64_t ld_out, op_t* out_lo, float* out_f32, cudaStream_t st);
 int heads_final(const float* hs, const op_t* h2, int64_t rows, const float* w_cls,
                 const float* b_cls, const float* w_sp, const float* b_sp, float* logits, float* spans,
                 cudaStream_t st);
 int mask_bits(const float* mask, int64_t n, uint32_t* bits, cudaStream_t st);
-int vhat_rows(const float* v, int64_t rows, __half* out, cudaStream_t st);
+int vhat_rows(const float* v, int64_t rows, float* out, cudaStream_t st);
 
 // attn.cu
 int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
@@ -45,9 +48,19 @@ int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const floa
                     const int32_t* seq_len = nullptr);
 
 // xpool.cu
-int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st);
-int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, op_t* gw, cudaStream_t st);
-int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t* kz,
+struct XpoolConsts {    // folded X-Pool constants of one checkpoint (per made_ctx)
+  float bias[256];      // b' = (I + Wl) beta2 + bl
+  float gamma[256];     // gamma3
+  float gamma2[256];    // gamma3^2
+  float beta[256];      // beta3
+  // sums over the 256 features
+  float B1, B2;         // sum b', sum b'^2
+  float G2, G2b2, G2b;  // sum g^2, sum g^2 b'^2, sum g^2 b'
+  float Gbb, Gb, Bb;    // sum g beta b', sum g beta, sum beta^2
+};
+void xpool_fill_constants(const float* bias_prime, const float* gamma3, const float* beta3, XpoolConsts* h, float* c5);
+int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, const float* c5_dev, op_t* gw, cudaStream_t st);
+int xpool_score(const XpoolConsts& consts, const op_t* q, const float* vhat, int64_t n_queries, const op_t* kz,
                 int64_t ldkz, int z_col, const op_t* gram, const uint32_t* maskbits,
                 int64_t n_tracks, float* sim, int64_t ld, int64_t col_offset, cudaStream_t st);
 

@@ -87,7 +87,7 @@ __global__ void ragged_fill_kernel(const float* __restrict__ mask, int64_t B, in
 // packed row i <- cast(feats[tok_src[i], :])   (model_Base.py:556/595 masked_fill + cast, valid rows only)
 template <int kIn>
 __global__ void ingest_gather_kernel(const void* __restrict__ in_, const int32_t* __restrict__ tok_src,
-                                     const int32_t* __restrict__ total, int dim, op_t* __restrict__ out) {
+                                     const int32_t* __restrict__ total, int dim, op_t* __restrict__ out, int split) {
   const int vec = dim / 8;
   const int64_t n = static_cast<int64_t>(*total) * vec;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -111,8 +111,20 @@ __global__ void ingest_gather_kernel(const void* __restrict__ in_, const int32_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
     }
-    *reinterpret_cast<uint4*>(out + row * dim + c) =
-        make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+    const uint4 hi = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+    if (!split) {
+      *reinterpret_cast<uint4*>(out + row * dim + c) = hi;
+    } else {     // rows of [hi | lo]
+      const op2_t* hh = reinterpret_cast<const op2_t*>(&hi);
+      uint32_t lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = op2_to_f2(hh[j]);
+        lo[j] = pack_op2(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+      }
+      *reinterpret_cast<uint4*>(out + row * 2 * dim + c) = hi;
+      *reinterpret_cast<uint4*>(out + row * 2 * dim + dim + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -263,7 +275,7 @@ int ragged_build(const float* mask, int64_t B, int L, int32_t* idx, Ragged* out,
   return MADE_OK;
 }
 
-int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t* out, cudaStream_t st) {
+int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t* out, bool split, cudaStream_t st) {
   MADE_REQUIRE(dim % 8 == 0, "ingest: dim must be a multiple of 8");
   const int64_t max_items = rb.B * rb.L * (dim / 8);
   int64_t blocks = ceil_div64(max_items, 256);
@@ -278,11 +290,11 @@ int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t*
   if (blocks > cap) blocks = cap;
   const unsigned g = static_cast<unsigned>(blocks);
   if (in_dtype == MADE_DTYPE_F32)
-    ingest_gather_kernel<MADE_DTYPE_F32><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out);
+    ingest_gather_kernel<MADE_DTYPE_F32><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out, split ? 1 : 0);
   else if (in_dtype == MADE_DTYPE_BF16)
-    ingest_gather_kernel<MADE_DTYPE_BF16><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out);
+    ingest_gather_kernel<MADE_DTYPE_BF16><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out, split ? 1 : 0);
   else
-    ingest_gather_kernel<MADE_DTYPE_F16><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out);
+    ingest_gather_kernel<MADE_DTYPE_F16><<<g, 256, 0, st>>>(in, rb.tok_src, rb.total, dim, out, split ? 1 : 0);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

@@ -619,12 +619,7 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
   MADE_REQUIRE(!rank_out || gt_col || gt_score_in, "rank_topk: rank needs gt_col or gt_score_in");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_cols <= kMaxSmemCols) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      MADE_CUDA(cudaFuncSetAttribute(rank_topk_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kMaxSmemCols * 4));
-      attr_set = true;
-    }
+    MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&rank_topk_staged_kernel), static_cast<int>(kMaxSmemCols * 4)));
     const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);
     rank_topk_staged_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
         single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
@@ -647,12 +642,7 @@ int made_topk_merge(const double* cand_score, const int32_t* cand_idx, int64_t n
   int n_pow = 1;
   while (n_pow < n_cand) n_pow <<= 1;
   size_t smem = static_cast<size_t>(n_pow) * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   4096 * 12));
-    attr_set = true;
-  }
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&topk_merge_kernel), static_cast<int>(4096 * 12)));
   topk_merge_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem,
                       static_cast<cudaStream_t>(stream)>>>(cand_score, cand_idx, n_cand, k, out_idx,
                                                            out_score);

@@ -3,7 +3,9 @@
 #include <cstdio>
 #include <cstring>
 #include <condition_variable>
+#include <atomic>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -77,13 +79,31 @@ int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint6
 }
 
 int sm_count() {
-  static int n = 0;
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cache[kMaxDev];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;     // (kernel, device) -> bytes granted
+  int dev = 0;
+  MADE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return MADE_OK;
+  MADE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+  return MADE_OK;
 }
 
 // ---- small persistent host thread pool (fp32 -> fp16 conversion of host features) -----------------

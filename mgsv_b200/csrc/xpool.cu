@@ -50,22 +50,13 @@ constexpr uint32_t kColY = 0;      // 256 fp32 columns
 constexpr uint32_t kColT = 256;    // 112 fp32 columns [T | L]; also holds S before the softmax
 constexpr uint32_t kColV = 384;    // 128 columns: u = v_hat * gamma3 as packed fp16 pairs
 
-struct XpoolConsts {
-  float bias[kXD];      // b' = (I + Wl) beta2 + bl
-  float gamma[kXD];     // gamma3
-  float gamma2[kXD];    // gamma3^2
-  float beta[kXD];      // beta3
-  // sums over the 256 features
-  float B1, B2;         // sum b', sum b'^2
-  float G2, G2b2, G2b;  // sum g^2, sum g^2 b'^2, sum g^2 b'
-  float Gbb, Gb, Bb;    // sum g beta b', sum g beta, sum beta^2
-};
-__constant__ XpoolConsts c_xp;
+// XpoolConsts (prep.cuh) travels as a __grid_constant__ kernel parameter: parameters live in constant bank 0,
+// so gamma3^2 stays an immediate constant-bank FFMA operand in the Y sweep, and every made_ctx has its own copy.
 
 struct XpoolParams {
   int64_t n_queries, n_tracks;
   int q_tiles, slices;
-  const __half* vhat;          // [n_queries, 256] fp16
+  const float* vhat;           // [n_queries, 256] fp32: v / |v| (modules/metrics.py:19)
   const uint32_t* maskbits;    // [n_tracks, 4]
   float* sim;                  // [n_queries, ld]
   int64_t ld;
@@ -76,7 +67,7 @@ struct XpoolParams {
 // One sweep over half H of the Y accumulator of this thread's row: sum Y^2, sum g^2 Y^2, sum u Y.
 // H is a template parameter so that the gamma^2 constants are immediate constant-bank operands.
 template <int H>
-__device__ __forceinline__ void y_sweep(uint32_t lane_addr, float& s2, float& sg2, float& su) {
+__device__ __forceinline__ void y_sweep(const XpoolConsts& c_xp, uint32_t lane_addr, float& s2, float& sg2, float& su) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t y[32], uh[16];
@@ -100,7 +91,7 @@ __device__ __forceinline__ void y_sweep(uint32_t lane_addr, float& s2, float& sg
 __global__ void __launch_bounds__(kXThreads, 1)
 xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                    const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_g,
-                   const XpoolParams p) {
+                   const __grid_constant__ XpoolConsts c_xp, const XpoolParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -225,26 +216,28 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // ---- per-query constants and u = v_hat * gamma3 (fp16) -> TMEM, once ----
     float Cu1 = 0.f, Cu0 = 0.f, Cvb = 0.f;
     {
-      const uint4* src = reinterpret_cast<const uint4*>(p.vhat + (row_ok ? grow : 0) * kXD);
+      // v_hat arrives in fp32 and u = v_hat * gamma3 is rounded to fp16 ONCE (a fp16 v_hat would add a second
+      // rounding to the operand of the final dot product: tests/tools/precision_pipeline.py)
+      const float4* src = reinterpret_cast<const float4*>(p.vhat + (row_ok ? grow : 0) * kXD);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {          // 32 features per step
         uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 t = row_ok ? __ldg(src + c * 4 + i) : make_uint4(0, 0, 0, 0);
-          const uint32_t tt[4] = {t.x, t.y, t.z, t.w};
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = row_ok ? __ldg(src + c * 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float tt[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int f = c * 32 + i * 8 + j * 2;
-            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&tt[j]));
-            const __half2 uh = __floats2half2_rn(v.x * c_xp.gamma[f], v.y * c_xp.gamma[f + 1]);
+          for (int j = 0; j < 2; ++j) {
+            const int f = c * 32 + i * 4 + j * 2;
+            const float vx = tt[2 * j], vy = tt[2 * j + 1];
+            const __half2 uh = __floats2half2_rn(vx * c_xp.gamma[f], vy * c_xp.gamma[f + 1]);
             const float2 uf = __half22float2(uh);
             Cu1 = fmaf(uf.x, c_xp.bias[f], Cu1);
             Cu1 = fmaf(uf.y, c_xp.bias[f + 1], Cu1);
             Cu0 += uf.x + uf.y;
-            Cvb = fmaf(v.x, c_xp.beta[f], Cvb);
-            Cvb = fmaf(v.y, c_xp.beta[f + 1], Cvb);
-            w[i * 4 + j] = *reinterpret_cast<const uint32_t*>(&uh);
+            Cvb = fmaf(vx, c_xp.beta[f], Cvb);
+            Cvb = fmaf(vy, c_xp.beta[f + 1], Cvb);
+            w[i * 2 + j] = *reinterpret_cast<const uint32_t*>(&uh);
           }
         }
         if ((c >> 2) == h) tmem_st_x16(lane_addr + kColV + c * 16, w);   // own half of the columns
@@ -348,8 +341,8 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
       // ---------------- C. one sweep over this half of Y ----------------
       float s2 = 0.f, sg2 = 0.f, su = 0.f;
-      if (h == 0) y_sweep<0>(lane_addr, s2, sg2, su);
-      else y_sweep<1>(lane_addr, s2, sg2, su);
+      if (h == 0) y_sweep<0>(c_xp, lane_addr, s2, sg2, su);
+      else y_sweep<1>(c_xp, lane_addr, s2, sg2, su);
       tc_fence_before_sync();
       mbar_arrive(y_free);
 
@@ -395,10 +388,9 @@ xpool_score_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // the tensor core reproduces the five linear sums to fp32 accuracy: columns 96..100 = hi,
 // 101..105 = lo of the [G | W5 | 0] operand (106..111 zero).  Warp per row; the weight vectors live
 // in global memory (lane-indexed reads of __constant__ memory would serialise).
-__device__ float g_xp_c5[5][kXD];
-
 __global__ void __launch_bounds__(256)
-xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __restrict__ gw) {
+xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, const float* __restrict__ c5,
+                op_t* __restrict__ gw) {
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -407,8 +399,8 @@ xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __r
   float c[5][8];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    const float4 c0 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8]);
-    const float4 c1 = *reinterpret_cast<const float4*>(&g_xp_c5[k][lane * 8 + 4]);
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(c5 + k * kXD + lane * 8));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(c5 + k * kXD + lane * 8 + 4));
     c[k][0] = c0.x; c[k][1] = c0.y; c[k][2] = c0.z; c[k][3] = c0.w;
     c[k][4] = c1.x; c[k][5] = c1.y; c[k][6] = c1.z; c[k][7] = c1.w;
   }
@@ -447,8 +439,10 @@ xpool_w5_kernel(const op_t* __restrict__ z, int64_t ldz, int64_t rows, op_t* __r
   }
 }
 
-int xpool_set_constants(const float* bias_prime, const float* gamma3, const float* beta3, cudaStream_t st) {
-  static XpoolConsts h;   // host staging must outlive the async copy
+// Folded constants of one checkpoint (api.cu load_xpool): `h` is passed by value to every xpool_score launch,
+// `c5` ([5][256] fp32) is uploaded into the context's own device buffer for xpool_w5.
+void xpool_fill_constants(const float* bias_prime, const float* gamma3, const float* beta3, XpoolConsts* hp, float* c5) {
+  XpoolConsts& h = *hp;
   double B1 = 0, B2 = 0, G2 = 0, G2b2 = 0, G2b = 0, Gbb = 0, Gb = 0, Bb = 0;
   for (int i = 0; i < kXD; ++i) {
     const double b = bias_prime[i], g = gamma3[i], be = beta3[i];
@@ -458,46 +452,34 @@ int xpool_set_constants(const float* bias_prime, const float* gamma3, const floa
     h.beta[i] = beta3[i];
     B1 += b; B2 += b * b; G2 += g * g; G2b2 += g * g * b * b; G2b += g * g * b;
     Gbb += g * be * b; Gb += g * be; Bb += be * be;
+    c5[0 * kXD + i] = 1.0f;
+    c5[1 * kXD + i] = bias_prime[i];
+    c5[2 * kXD + i] = static_cast<float>(g * g);
+    c5[3 * kXD + i] = static_cast<float>(g * g * b);
+    c5[4 * kXD + i] = static_cast<float>(g * be);
   }
   h.B1 = static_cast<float>(B1); h.B2 = static_cast<float>(B2); h.G2 = static_cast<float>(G2);
   h.G2b2 = static_cast<float>(G2b2); h.G2b = static_cast<float>(G2b); h.Gbb = static_cast<float>(Gbb);
   h.Gb = static_cast<float>(Gb); h.Bb = static_cast<float>(Bb);
-  static float c5[5][kXD];
-  for (int i = 0; i < kXD; ++i) {
-    const double b = bias_prime[i], g = gamma3[i], be = beta3[i];
-    c5[0][i] = 1.0f;
-    c5[1][i] = bias_prime[i];
-    c5[2][i] = static_cast<float>(g * g);
-    c5[3][i] = static_cast<float>(g * g * b);
-    c5[4][i] = static_cast<float>(g * be);
-  }
-  MADE_CUDA(cudaMemcpyToSymbolAsync(c_xp, &h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
-  MADE_CUDA(cudaMemcpyToSymbolAsync(g_xp_c5, c5, sizeof(c5), 0, cudaMemcpyHostToDevice, st));
-  MADE_CUDA(cudaStreamSynchronize(st));
-  return MADE_OK;
 }
 
-int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, op_t* gw, cudaStream_t st) {
+int xpool_w5(const op_t* z, int64_t ldz, int64_t rows, const float* c5_dev, op_t* gw, cudaStream_t st) {
   if (rows == 0) return MADE_OK;
   const int64_t want = ceil_div64(rows, 8), cap = static_cast<int64_t>(sm_count()) * 3;   // persistent: 3 resident CTAs per SM (78 registers)
-  xpool_w5_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, st>>>(z, ldz, rows, gw);
+  xpool_w5_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, st>>>(z, ldz, rows, c5_dev, gw);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }
 
 // q [n_queries,256] fp16 (pre-scaled by 1/16), vhat fp16, kz [n_tracks*96, ldkz] fp16 with the K block
 // at column 0 and the Z'' block at column z_col, gw [n_tracks*96, 112] fp16 = [G | W5 | 0].
-int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t* kz,
+int xpool_score(const XpoolConsts& consts, const op_t* q, const float* vhat, int64_t n_queries, const op_t* kz,
                 int64_t ldkz, int z_col, const op_t* gw, const uint32_t* maskbits,
                 int64_t n_tracks, float* sim, int64_t ld, int64_t col_offset, cudaStream_t st) {
   if (n_queries == 0 || n_tracks == 0) return MADE_OK;
   MADE_REQUIRE(q && vhat && kz && gw && maskbits && sim, "xpool_score: null pointer");
   MADE_REQUIRE(n_tracks * kXL < (1LL << 31), "xpool_score: too many tracks for one launch");
-  static bool attr_set = false;
-  if (!attr_set) {
-    MADE_CUDA(cudaFuncSetAttribute(xpool_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXSmem));
-    attr_set = true;
-  }
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&xpool_score_kernel), static_cast<int>(kXSmem)));
   CUtensorMap tq, tk, tz, tg;
   const uint64_t T = static_cast<uint64_t>(n_tracks) * kXL;
   MADE_TRY(encode_tmap_2d_16b(&tq, q, kXD, static_cast<uint64_t>(n_queries), kXD * 2, 64, kXQ));
@@ -520,7 +502,7 @@ int xpool_score(const op_t* q, const __half* vhat, int64_t n_queries, const op_t
   p.col_offset = col_offset;
   p.ln2_eps = 1e-5f;
   p.ln3_eps = 1e-5f;
-  xpool_score_kernel<<<p.q_tiles * slices, kXThreads, kXSmem, st>>>(tq, tk, tz, tg, p);
+  xpool_score_kernel<<<p.q_tiles * slices, kXThreads, kXSmem, st>>>(tq, tk, tz, tg, consts, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

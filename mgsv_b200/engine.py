@@ -6,6 +6,7 @@ eager-PyTorch fallback: constructing an Engine without a CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -14,9 +15,19 @@ from . import _lib
 from . import config as cfg
 
 
+PRECISIONS = {"fp16": _lib.PREC_FP16, "split": _lib.PREC_SPLIT}
+
+
 class Engine:
-    def __init__(self, device: Optional[torch.device] = None):
+    def __init__(self, device: Optional[torch.device] = None, precision: Optional[str] = None):
+        """precision: "split" (default; fp16 (hi, lo) operand pairs where the similarity error is made —
+        meets the 1e-3 bar on the full job) or "fp16" (single fp16 operands everywhere, fastest).
+        MADE_PRECISION overrides the default."""
         _lib.require_cuda()
+        precision = precision or os.environ.get("MADE_PRECISION", "split")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        self.precision = precision
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("made_b200 needs a CUDA device; there is no CPU fallback")
@@ -26,6 +37,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self._lib.made_ctx_create(C.byref(h), self.device.index))
         self._h = h
+        _lib.check(self._lib.made_ctx_set_precision(self._h, PRECISIONS[precision]))
         self.loaded = False
 
     def close(self):
@@ -64,7 +76,7 @@ class Engine:
         beside scoring) needs its own context (21 MB of packed weights)."""
         if not self.loaded:
             raise RuntimeError("clone() needs loaded weights")
-        other = Engine(self.device)
+        other = Engine(self.device, self.precision)
         other.load_state_dict(self._weights)
         return other
 
@@ -123,11 +135,18 @@ class Engine:
         if dt is None:
             raise ValueError(f"unsupported feature dtype {feats.dtype}")
         B = feats.shape[0]
+        width = self.operand_width(din)
         if out is None:
-            out = torch.empty((B * L, din), dtype=torch.float16, device=self.device)
-        _lib.check(self._lib.made_ingest_ragged(_lib.ptr_any(feats), dt, C.byref(rb), din, _lib.ptr(out),
+            out = torch.empty((B * L, width), dtype=torch.float16, device=self.device)
+        elif out.shape[-1] != width or out.dtype != torch.float16:
+            raise ValueError(f"ingest: out must be fp16 with rows of {width} columns")
+        _lib.check(self._lib.made_ingest_ragged(self._h, _lib.ptr_any(feats), dt, C.byref(rb), din, _lib.ptr(out),
                                                 _lib.stream_ptr()))
         return out
+
+    def operand_width(self, dim: int) -> int:
+        """Columns of a packed operand row of `dim` features ((hi | lo) pairs in split precision)."""
+        return int(self._lib.made_ctx_operand_width(self._h, dim))
 
     def encode(self, modality: int, feats: torch.Tensor, masks: torch.Tensor, want_f32: bool = True,
                ragged=None, out=None):
@@ -146,7 +165,8 @@ class Engine:
             pooled = torch.empty((B, cfg.D_MODEL), dtype=torch.float32, device=dev)
         seq32 = torch.empty((B, L, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
         if ragged is not None:
-            if feats.dtype != torch.float16 or feats.dim() != 2 or feats.shape[1] != din or ragged.B != B:
+            if feats.dtype != torch.float16 or feats.dim() != 2 or feats.shape[1] != self.operand_width(din) \
+                    or ragged.B != B:
                 raise ValueError("ragged encode takes the packed fp16 output of Engine.ingest")
             _lib.check(self._lib.made_encode_ragged(self._h, modality, _lib.ptr(feats), C.byref(ragged), _lib.ptr(seq),
                                                     _lib.ptr(seq32), _lib.ptr(pooled), _lib.stream_ptr()))
@@ -184,7 +204,7 @@ class Engine:
         N = video_feats.shape[0]
         vf = video_feats.to(torch.float32).contiguous()
         q = torch.empty((N, cfg.D_MODEL), dtype=torch.float16, device=vf.device)
-        vhat = torch.empty((N, cfg.D_MODEL), dtype=torch.float16, device=vf.device)
+        vhat = torch.empty((N, cfg.D_MODEL), dtype=torch.float32, device=vf.device)
         _lib.check(self._lib.made_query_prepare(self._h, _lib.ptr(vf), N, _lib.ptr(q), _lib.ptr(vhat),
                                                 _lib.stream_ptr()))
         return q, vhat

@@ -229,6 +229,29 @@ def gemm_f16(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, act: in
     return out
 
 
+def split_pair(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [M, K] -> fp16 [M, 2K] rows of (hi | lo): hi = fp16(x), lo = fp16(x - hi) (what the split-precision
+    GEMMs consume; host-side helper for tests and packing, plain torch casts)."""
+    hi = x.to(torch.float16)
+    lo = (x.float() - hi.float()).to(torch.float16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def gemm_f16_split(a: torch.Tensor, w_pair: torch.Tensor, split: int, bias=None, residual_pair=None, act: int = 0,
+                   ln=None, out_pair: bool = False) -> torch.Tensor:
+    """a: [M, K] fp16 (split=1) or [M, 2K] (hi | lo) pairs (split=2); w_pair [N, 2K] pairs.
+    → fp32 [M, N], or the (hi | lo) fp16 pair [M, 2N] of the result with out_pair=True."""
+    N, K = w_pair.shape[0], w_pair.shape[1] // 2
+    M = a.shape[0]
+    out = torch.empty((M, 2 * N), dtype=torch.float16, device=a.device) if out_pair else \
+        torch.empty((M, N), dtype=torch.float32, device=a.device)
+    g, b = (ln if ln is not None else (None, None))
+    _lib.check(_lib.load().made_gemm_f16_split(
+        _lib.ptr(a), _lib.ptr(w_pair), M, N, K, split, _lib.ptr(bias), _lib.ptr(residual_pair), act, _lib.ptr(g),
+        _lib.ptr(b), _lib.ptr(out) if out_pair else None, None if out_pair else _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: torch.Tensor) -> torch.Tensor:
     """q,k,v [B,L,256] fp16, key_mask [B,L] float (1 = valid) → [B,L,256] fp16."""
     B, L, _ = q.shape

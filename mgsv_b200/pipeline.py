@@ -92,7 +92,8 @@ class GalleryEvaluator:
             key = (modality, slot)
             buf = self._stage.get(key)
             if buf is None or buf.shape[0] < (e - s) * L:
-                buf = torch.empty((max(chunk, e - s) * L, din), dtype=torch.float16, device=self.dev)
+                buf = torch.empty((max(chunk, e - s) * L, self.eng.operand_width(din)), dtype=torch.float16,
+                                  device=self.dev)
                 self._stage[key] = buf
             with torch.cuda.stream(self.ingest_stream):
                 self.ingest_stream.wait_event(start_ev)

@@ -311,6 +311,47 @@ def test_tcgen05_gemm_epilogues(dev):
         ops.gemm_f16(a.to(dev), w[:100].contiguous().to(dev), out_dtype=torch.float32)   # N % 256
 
 
+@pytest.mark.parametrize("M,N,K,split", [(1, 256, 64, 2), (300, 256, 256, 1), (1000, 768, 256, 2), (5000, 256, 768, 2),
+                                         (129, 256, 512, 1), (19000, 768, 256, 2)])
+def test_tcgen05_split_gemm(dev, M, N, K, split):
+    """fp16 (hi, lo) operand pairs: two or three tcgen05 passes into one fp32 accumulator reproduce the fp32
+    product of UN-rounded operands to ~2^-21 (the lo x lo term is dropped)."""
+    g = torch.Generator().manual_seed(M + N + K + split)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    a_in = ops.split_pair(a) if split == 2 else a.to(torch.float16)
+    a_eff = a.double() if split == 2 else a.to(torch.float16).double()
+    ref = a_eff @ w.double().t() + bias.double()
+    out = ops.gemm_f16_split(a_in.to(dev), ops.split_pair(w).to(dev), split, bias=bias.to(dev))
+    assert _rel(out, ref) < 3e-6
+    # a single fp16 pass of the same operands is ~500x worse: the test would catch a dropped pass
+    plain = ops.gemm_f16(a.to(torch.float16).to(dev), w.to(torch.float16).to(dev), bias=bias.to(dev),
+                         out_dtype=torch.float32)
+    if M >= 100:
+        assert _rel(plain, a.double() @ w.double().t() + bias.double()) > 1e-4
+
+
+def test_tcgen05_split_gemm_epilogues(dev):
+    """(hi | lo) pair outputs, pair residuals and the LayerNorm epilogue of the split GEMM."""
+    M, N, K = 1000, 256, 256
+    g = torch.Generator().manual_seed(5)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    base = a.double() @ w.double().t() + bias.double()
+    res_pair = ops.split_pair(res)
+    res_eff = res_pair[:, :N].double() + res_pair[:, N:].double()
+    pair = ops.gemm_f16_split(ops.split_pair(a).to(dev), ops.split_pair(w).to(dev), 2, bias=bias.to(dev),
+                              residual_pair=res_pair.to(dev), ln=(gam.to(dev), bet.to(dev)), out_pair=True)
+    ref = torch.nn.functional.layer_norm(base + res_eff, (N,), gam.double(), bet.double())
+    hi, lo = pair[:, :N].double().cpu(), pair[:, N:].double().cpu()
+    assert _rel(hi + lo, ref) < 3e-6                       # the pair carries ~22 bits
+    assert torch.equal(pair[:, :N].cpu(), (hi + lo).float().to(torch.float16)) or _rel(hi, ref) < 6e-4
+    out = ops.gemm_f16_split(a.to(torch.float16).to(dev), ops.split_pair(w).to(dev), 1, bias=bias.to(dev), act=2)
+    assert _rel(out, torch.relu(a.to(torch.float16).double() @ w.double().t() + bias.double())) < 3e-6
+
+
 @pytest.mark.parametrize("L", [50, 96, 146, 1, 17])
 def test_mha_core(dev, L):
     g = torch.Generator().manual_seed(L)
@@ -534,18 +575,19 @@ def test_full_size_job_properties(dev, engine, sd_fp32):
     so, mf = O.encode_music(sd_fp32, m["segment_feats"][ti], m["segment_mask"][ti])
     smask = m["segment_mask"][ti]
     single, dual, _ = O.gallery_similarity(sd_fp32, vf, mf, so * smask.unsqueeze(-1), smask)
-    # The 1e-3 bar (SIM_RTOL, relative to the matrix scale) holds per stage and on the reference's
-    # fixtures (tests above).  Through the WHOLE pipeline the fp16 operand roundings of the encoders and
-    # of the X-Pool operands add up to an error with rms ~2e-4 of the scale whose worst element grows
-    # with the number of pairs looked at (tests/tools/precision_study.py: ~5 sigma over 8192 pairs), so the
-    # window is held to rms <= 5e-4 and max <= 2e-3 of the scale.
+    # The 1e-3 bar (SIM_RTOL: max|d| <= 1e-3 * max|ref|, the north star's "1e-3 relative") holds through the WHOLE
+    # pipeline at full size in the default split precision; the per-element rule SURVEY.md section 7 proposes
+    # (|d| <= 1e-3 |ref| + 1e-5) is reported beside it.
     for name, got, ref in (("single", a["single"][:64][:, ti.to(dev)], single),
                            ("dual", a["dual"][:64][:, ti.to(dev)], dual)):
         d = (got.double().cpu() - ref.double()).abs()
         scale = ref.abs().max().item()
-        print(f"[parity] full-size job, {name} window: max|d| = {d.max().item():.3e} = {d.max().item() / scale:.2e}, "
-              f"rms = {d.pow(2).mean().sqrt().item() / scale:.2e} of max|ref| {scale:.3f}")
-        assert d.pow(2).mean().sqrt().item() <= 5e-4 * scale and d.max().item() <= 2e-3 * scale, name
+        per_elem = (d <= 1e-3 * ref.double().abs() + 1e-5).double().mean().item()
+        print(f"[parity] full-size job ({engine.precision}), {name} window: max|d| = {d.max().item():.3e} = "
+              f"{d.max().item() / scale:.2e}, rms = {d.pow(2).mean().sqrt().item() / scale:.2e} of max|ref| {scale:.3f}; "
+              f"per-element |d| <= 1e-3|ref| + 1e-5 holds for {100 * per_elem:.2f} % of the pairs")
+        assert d.max().item() <= SIM_RTOL * scale, name
+        assert d.pow(2).mean().sqrt().item() <= 2.5e-4 * scale, name
     # 3. rank and top-k are exactly those of double(single) + double(dual)
     total = a["single"].double() + a["dual"].double()
     gt_s = total.gather(1, gt.long().unsqueeze(1))

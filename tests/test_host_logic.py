@@ -71,7 +71,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/made_b200.h but not exported"
     assert set(_lib.SIGNATURES) | {"made_last_error_string", "made_ragged_index_words"} == declared
-    assert lib.made_abi_version() == 1
+    assert lib.made_abi_version() == 2
 
 
 def test_product_path_refuses_to_run_without_cuda():
