@@ -22,9 +22,18 @@ NQ, NM, K = 12, 20, 5
 
 
 def _cpu_rank_topk(single, dual, gt_col=None, prev_same=None, k=0, col_offset=0, gt_score_in=None, n_cols=None):
+    """CPU stand-in of ops.rank_topk with its dedup semantics (made_b200.h made_rank_topk): prev_same chains
+    group the columns of one music id; the GT score is the best column of the chain that ends at gt_col; the
+    rank counts the chains whose best column beats it."""
     tot = single.double() + dual.double()
-    n = tot.shape[0]
+    n, m = tot.shape
     out = dict(topk_idx=None, topk_score=None, rank=None, gt_score=None)
+    group = np.arange(m)
+    if prev_same is not None:
+        prev = prev_same.numpy()
+        for c in range(m):
+            if prev[c] >= 0:
+                group[c] = group[prev[c]]
     if gt_col is not None or gt_score_in is not None:
         if gt_score_in is not None:
             gs = gt_score_in.clone()
@@ -32,9 +41,12 @@ def _cpu_rank_topk(single, dual, gt_col=None, prev_same=None, k=0, col_offset=0,
             gs = torch.full((n,), float("-inf"), dtype=torch.float64)
             for i in range(n):
                 if gt_col[i] >= 0:
-                    gs[i] = tot[i, gt_col[i]]
+                    gs[i] = tot[i, torch.from_numpy(group == group[int(gt_col[i])])].max()
         out["gt_score"] = gs
-        out["rank"] = (tot > gs[:, None]).sum(1).to(torch.int32)
+        best = torch.full((n, m), float("-inf"), dtype=torch.float64)
+        for g in np.unique(group):
+            best[:, g] = tot[:, torch.from_numpy(group == g)].max(1).values
+        out["rank"] = (best > gs[:, None]).sum(1).to(torch.int32)
     if k > 0:
         kk = min(k, tot.shape[1])
         order = np.lexsort((np.broadcast_to(np.arange(tot.shape[1]), tot.shape), -tot.numpy()), axis=1)[:, :kk]
@@ -95,6 +107,18 @@ def _free_port():
     return p
 
 
+def _dup_ids():
+    """20 columns, 14 distinct ids: ids 3, 9 (straddling the uniform cut at column 10) and 15 repeat."""
+    ids = [f"m{i}" for i in range(NM)]
+    ids[4] = ids[3]
+    ids[10] = ids[9]
+    ids[11] = ids[9]
+    ids[16] = ids[15]
+    ids[17] = ids[15]
+    ids[18] = ids[15]
+    return ids
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(2)
@@ -112,8 +136,15 @@ def _worker(rank, world, port, q):
         tracks = {k: m[k][m0:m1] for k in ("segment_feats", "segment_mask", "gt_moment", "m_duration")}
         sh = ShardedEvaluator(_CpuEvaluator(sd, K), rank, world)
         out = sh.run(videos, tracks, gt_col, NQ, NM)
+        # the same job with repeated music ids: shards must not cut through an id, ranks are dedup ranks
+        ids2 = _dup_ids()
+        bounds = parallel.plan_track_shards(ids2, NM, world)
+        b0, b1 = bounds[rank]
+        tracks2 = {k: m[k][b0:b1] for k in ("segment_feats", "segment_mask", "gt_moment", "m_duration")}
+        sh2 = ShardedEvaluator(_CpuEvaluator(sd, K), rank, world, track_bounds=bounds)
+        out2 = sh2.run(videos, tracks2, gt_col, NQ, NM, music_ids=ids2, gather_results=False)
         q.put((rank, out["rank"].numpy(), out["topk_idx"].numpy(), out["topk_score"].numpy(),
-               out["iou"].numpy(), out["pred_st"].numpy(), out["q_range"]))
+               out["iou"].numpy(), out["pred_st"].numpy(), out["q_range"], out2["rank"].numpy(), bounds))
     finally:
         dist.destroy_process_group()
 
@@ -157,7 +188,15 @@ def test_sharded_equals_single_process():
     om = O.calc_output(sd, hs, fo)
     st, ed, sc = O.moment_postproc(om["pred_logits"], om["pred_spans"])
     ref_iou = O.detr_iou(st, ed, m["gt_moment"][gt_col], m["m_duration"][gt_col]).numpy()
-    for rank, rk, ti, ts, iou, pst, (q0, q1) in res:
+    # dedup ranks of the job with repeated ids (Recall_metrics(dedup=True) through the oracle)
+    ids2 = _dup_ids()
+    _, ref_ind2, _ = O.recall_metrics(total, ids2, gt_col)
+    assert parallel.plan_track_shards(ids2, NM, 2) == [(0, 12), (12, 20)]       # the cut moved past id m9
+    assert parallel.plan_track_shards(["a", "b", "a", "b"], 4, 2) == [(0, 4), (4, 4)]   # interleaved ids: one shard
+    assert list(parallel.order_tracks_by_id(["a", "b", "a", "b"])) == [0, 2, 1, 3]
+    for rank, rk, ti, ts, iou, pst, (q0, q1), rk2, bounds in res:
+        assert bounds == [(0, 12), (12, 20)]
+        assert np.array_equal(rk2, ref_ind2[q0:q1])               # owner-only results (gather_results=False)
         assert np.array_equal(rk, ref_rank)                       # ranks need both shards
         assert np.array_equal(ti, ref_top)
         np.testing.assert_allclose(ts, np.take_along_axis(total, ref_top, 1), rtol=0, atol=1e-6)  # fp32 BLAS blocking differs per shard size

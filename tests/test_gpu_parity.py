@@ -324,7 +324,7 @@ def test_tcgen05_split_gemm(dev, M, N, K, split):
     a_eff = a.double() if split == 2 else a.to(torch.float16).double()
     ref = a_eff @ w.double().t() + bias.double()
     out = ops.gemm_f16_split(a_in.to(dev), ops.split_pair(w).to(dev), split, bias=bias.to(dev))
-    assert _rel(out, ref) < 3e-6
+    assert _rel(out, ref) < 8e-6        # fp32 accumulation over up to 36 k-blocks; the lo x lo term is dropped
     # a single fp16 pass of the same operands is ~500x worse: the test would catch a dropped pass
     plain = ops.gemm_f16(a.to(torch.float16).to(dev), w.to(torch.float16).to(dev), bias=bias.to(dev),
                          out_dtype=torch.float32)
