@@ -239,6 +239,13 @@ int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const f
 int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias,
                         const void* residual_pair, int act, const float* ln_gamma, const float* ln_beta,
                         void* out_pair, float* out_f32, void* stream);
+/* The fused feed-forward block (256 -> 1024 -> 256, hidden activation kept on chip):
+ * out = [LayerNorm](act(x W1^T + b1) W2^T + b2 + residual).  x [M,256] fp16 (row stride ldx), W1 [1024,256],
+ * W2 [256,1024] fp16; act 1 = GELU(erf), 2 = ReLU; residual_pair (nullable) and out_pair are rows of
+ * [hi(256) | lo(256)] fp16 when has_lo, else plain [M,256] fp16 rows, with row strides res_ld / ld_out. */
+int made_ffn_fused(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2, const float* b2,
+                   int act, const void* residual_pair, int64_t res_ld, const float* ln_gamma, const float* ln_beta,
+                   void* out_pair, int64_t ld_out, int has_lo, int64_t M, void* stream);
 /* softmax(Q K^T / sqrt(32) + key mask) V for 8 heads of 32: q,k,v,out [B*L, 256] fp16. */
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B,
                   int L, void* out, void* stream);

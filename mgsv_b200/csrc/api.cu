@@ -1,6 +1,7 @@
 // C ABI entry points that own state: the model context (packed weights + workspace) and the
 // host-side orchestration of the encoder / X-Pool / DETR kernel sequences.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -452,6 +453,14 @@ int linear(const op_t* A, int64_t lda, const Lin& w, int64_t M, int N, int K, Ge
   return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
 }
 
+bool fused_ffn_enabled() {
+  static const bool enabled = [] {
+    const char* v = getenv("MADE_FUSED_FFN");
+    return !(v && v[0] == '0');
+  }();
+  return enabled;
+}
+
 #define CTX_READY(ctx)                                                       \
   do {                                                                       \
     if (!(ctx)) { set_error("null made_ctx"); return MADE_EINVAL; }          \
@@ -642,20 +651,41 @@ static int encode_packed(made_ctx* c, int modality, const op_t* x0, const Ragged
     out_pair(ep, bf.x2, bf.x2f);
     MADE_TRY(lin(bf.att, D, false, e.out_proj, sp, D, D, ep));
   }
-  {  // FF: Linear -> GELU(erf); plain fp16 operands in both modes
-    GemmEpilogue ep;
-    ep.act = 1;
-    ep.out_h = bf.h;
-    ep.ld_h = DFF;
-    MADE_TRY(lin(bf.x2, W, false, e.ff1, false, DFF, D, ep));
-  }
-  {  // FF: Linear + residual (:89)
-    GemmEpilogue ep;
-    residual_from(ep, bf.x2, bf.x2f);
-    ep.out_h = bf.x3;
-    ep.ld_h = W;
-    if (sp) ep.out_lo = bf.x3 + D;
-    MADE_TRY(lin(bf.h, DFF, false, e.ff2, false, D, DFF, ep));
+  if (fused_ffn_enabled()) {
+    // FF: Linear -> GELU(erf) -> Linear + residual (:89) in ONE kernel, hidden activation kept on chip; plain
+    // fp16 operands in both precision modes (the FF branch is a small perturbation of the residual stream)
+    if (sp) {
+      MADE_TRY(ffn_fused(bf.x2, W, e.ff1.w, e.ff1.b, e.ff2.w, e.ff2.b, 1, bf.x2, bf.x2 + D, W, nullptr, nullptr, bf.x3,
+                         bf.x3 + D, W, nullptr, 0, nullptr, 0, T, rb.total, st));
+    } else {
+      // fp16 mode keeps the residual stream in fp32 (x2f): the residual add stays in the unfused FF2 GEMM
+      GemmEpilogue ep;
+      ep.act = 1;
+      ep.out_h = bf.h;
+      ep.ld_h = DFF;
+      MADE_TRY(lin(bf.x2, W, false, e.ff1, false, DFF, D, ep));
+      GemmEpilogue ep2;
+      residual_from(ep2, bf.x2, bf.x2f);
+      ep2.out_h = bf.x3;
+      ep2.ld_h = W;
+      MADE_TRY(lin(bf.h, DFF, false, e.ff2, false, D, DFF, ep2));
+    }
+  } else {
+    {  // FF: Linear -> GELU(erf); plain fp16 operands in both modes
+      GemmEpilogue ep;
+      ep.act = 1;
+      ep.out_h = bf.h;
+      ep.ld_h = DFF;
+      MADE_TRY(lin(bf.x2, W, false, e.ff1, false, DFF, D, ep));
+    }
+    {  // FF: Linear + residual (:89)
+      GemmEpilogue ep;
+      residual_from(ep, bf.x2, bf.x2f);
+      ep.out_h = bf.x3;
+      ep.ld_h = W;
+      if (sp) ep.out_lo = bf.x3 + D;
+      MADE_TRY(lin(bf.h, DFF, false, e.ff2, false, D, DFF, ep));
+    }
   }
   {  // final_linear (:91); masked_fill (:541) = padded rows of the output stay zero
     MADE_CUDA(cudaMemsetAsync(seq16, 0, static_cast<size_t>(T) * D * 2, st));
@@ -816,9 +846,9 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   const size_t idx_words = ragged_index_words(Bc, LD);
   // Encoder output of every sequence, token-packed per encoder chunk: chunk k owns rows
   // [k * Tc, ...) of mem_all / mp_all, sequence b its chunk's rows [seq_off[b], + seq_len[b]).
-  op_t *mem_all, *mp_all, *src, *pos, *srcpos, *qk, *v, *att, *s1, *hbuf, *src2, *srcpos2, *tgt, *t1, *mbar, *t2, *hdec,
-      *t3, *hsb, *sp0, *sp1;
-  float *mask, *s1f, *srcf, *t1f, *qt, *t2f, *t3all;
+  op_t *mem_all, *mp_all, *src, *pos, *srcpos, *qk, *v, *att, *s1, *hbuf, *src2, *srcpos2, *lo1, *lo2, *tgt, *t1, *mbar, *t2,
+      *hdec, *t3, *hsb, *sp0, *sp1;
+  float *mask, *t1f, *qt, *t2f, *t3all;
   int32_t *row_off, *row_len;
   std::vector<int32_t*> idx_chunk(static_cast<size_t>(n_chunks));
   MADE_TRY(c->with_arena([&] {
@@ -833,12 +863,12 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
     qk = c->take<op_t>(Tc * 2 * D);
     v = c->take<op_t>(Tc * D);
     att = c->take<op_t>(Tc * D);
-    s1 = c->take<op_t>(Tc * D);
-    s1f = c->take<float>(Tc * D);
-    hbuf = c->take<op_t>(Tc * DFF);
+    s1 = c->take<op_t>(Tc * 2 * D);        // (hi | lo) pairs
+    hbuf = fused_ffn_enabled() ? nullptr : c->take<op_t>(Tc * DFF);
     src2 = c->take<op_t>(Tc * D);
     srcpos2 = c->take<op_t>(Tc * D);
-    srcf = c->take<float>(Tc * D);
+    lo1 = c->take<op_t>(Tc * D);           // low halves of the layer outputs (ping-pong)
+    lo2 = c->take<op_t>(Tc * D);
     tgt = c->take<op_t>(B * D);
     t1 = c->take<op_t>(B * D);
     t1f = c->take<float>(B * D);
@@ -880,7 +910,10 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       p.epi = ep;
       return gemm_f16_tc(A, lda, w.w, K, N, p, 256, st);
     };
+    // The residual stream travels as fp16 (hi, lo) pairs: s1 = [hi | lo] rows of 512, the layer output as the
+    // fp16 tensor the next GEMMs read (hi) plus a separate low-half buffer (~22 bits together; no fp32 copies).
     op_t *cur = src, *curpos = srcpos, *nxt = src2, *nxtpos = srcpos2;
+    op_t *cur_lo = nullptr, *nxt_lo = lo1;
     for (int l = 0; l < NENC; ++l) {
       const DetrEncW& w = c->denc[l];
       if (l == NENC - 1) {   // the last layer writes the memory straight into the all-sequence buffers
@@ -902,52 +935,53 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       MADE_TRY(mha_core(qk, 2 * D, qk + D, 2 * D, v, D, nullptr, nb, LD, att, D, st, rb.seq_off, rb.seq_len));
       {
         GemmEpilogue ep;
-        if (l == 0) {
-          ep.residual = cur;
-          ep.residual_f32 = 0;
-        } else {
-          ep.residual = srcf;
-          ep.residual_f32 = 1;
-        }
+        ep.residual = cur;
+        ep.residual_lo = cur_lo;      // layer 0: the fp16 input features are exact
+        ep.residual_f32 = 0;
         ep.res_ld = D;
         ep.ln_gamma = w.n1.g;
         ep.ln_beta = w.n1.b;
         ep.out_h = s1;
-        ep.ld_h = D;
-        ep.out_f32 = s1f;
-        ep.ld_f32 = D;
+        ep.out_lo = s1 + D;
+        ep.ld_h = 2 * D;
         MADE_TRY(lin(att, D, w.out, D, D, ep));
       }
-      {
-        GemmEpilogue ep;
-        ep.act = 2;
-        ep.out_h = hbuf;
-        ep.ld_h = DFF;
-        MADE_TRY(lin(s1, D, w.ff1, DFF, D, ep));
-      }
-      {
-        GemmEpilogue ep;
-        ep.residual = s1f;
-        ep.residual_f32 = 1;
-        ep.res_ld = D;
-        ep.ln_gamma = w.n2.g;
-        ep.ln_beta = w.n2.b;
-        ep.out_h = nxt;
-        ep.ld_h = D;
-        if (l < NENC - 1 || memory) {
-          ep.out_f32 = srcf;
-          ep.ld_f32 = D;
+      if (fused_ffn_enabled()) {
+        // linear2(relu(linear1(src))) + src -> norm2 (+ second output "+ pos") in one kernel, hidden on chip
+        MADE_TRY(ffn_fused(s1, 2 * D, w.ff1.w, w.ff1.b, w.ff2.w, w.ff2.b, 2, s1, s1 + D, 2 * D, w.n2.g, w.n2.b, nxt, nxt_lo,
+                           D, pos, D, nxtpos, D, T, rb.total, st));
+      } else {
+        {
+          GemmEpilogue ep;
+          ep.act = 2;
+          ep.out_h = hbuf;
+          ep.ld_h = DFF;
+          MADE_TRY(lin(s1, 2 * D, w.ff1, DFF, D, ep));
         }
-        ep.add2 = pos;
-        ep.add2_ld = D;
-        ep.out2_h = nxtpos;
-        ep.ld_out2 = D;
-        MADE_TRY(lin(hbuf, DFF, w.ff2, D, DFF, ep));
+        {
+          GemmEpilogue ep;
+          ep.residual = s1;
+          ep.residual_lo = s1 + D;
+          ep.residual_f32 = 0;
+          ep.res_ld = 2 * D;
+          ep.ln_gamma = w.n2.g;
+          ep.ln_beta = w.n2.b;
+          ep.out_h = nxt;
+          ep.out_lo = nxt_lo;
+          ep.ld_h = D;
+          ep.add2 = pos;
+          ep.add2_ld = D;
+          ep.out2_h = nxtpos;
+          ep.ld_out2 = D;
+          MADE_TRY(lin(hbuf, DFF, w.ff2, D, DFF, ep));
+        }
       }
       op_t* t = cur; cur = nxt; nxt = t;
       t = curpos; curpos = nxtpos; nxtpos = t;
+      cur_lo = nxt_lo;
+      nxt_lo = nxt_lo == lo1 ? lo2 : lo1;
     }
-    if (memory) MADE_TRY(scatter_rows_f32_nozero(srcf, rb, memory + b0 * LD * D, st));
+    if (memory) MADE_TRY(scatter_rows_pair_nozero(cur, cur_lo, rb, memory + b0 * LD * D, st));
   }
   // ---------------- decoder (forward_post :273-307), one moment query per sequence ----------------
   cast_f32_op_kernel<<<static_cast<unsigned>(ceil_div64(B * D, 256)), 256, 0, st>>>(video_feats, tgt, B * D);
@@ -1103,6 +1137,16 @@ int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, i
   MADE_REQUIRE(!(out_pair && out_f32), "gemm_f16_split: one output");
   return gemm_f16_tc(static_cast<const op_t*>(A), split == 2 ? 2 * K : K, static_cast<const op_t*>(W), 2 * K, N, p, 256,
                      static_cast<cudaStream_t>(stream));
+}
+
+int made_ffn_fused(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2, const float* b2, int act,
+                   const void* residual_pair, int64_t res_ld, const float* ln_gamma, const float* ln_beta, void* out_pair,
+                   int64_t ld_out, int has_lo, int64_t M, void* stream) {
+  const op_t* res = static_cast<const op_t*>(residual_pair);
+  op_t* out = static_cast<op_t*>(out_pair);
+  return ffn_fused(static_cast<const op_t*>(x), ldx, static_cast<const op_t*>(w1), b1, static_cast<const op_t*>(w2), b2,
+                   act, res, res && has_lo ? res + D : nullptr, res_ld, ln_gamma, ln_beta, out, has_lo ? out + D : nullptr,
+                   ld_out, nullptr, 0, nullptr, 0, M, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int made_mha_core(const void* q, const void* k, const void* v, const float* key_mask, int64_t B, int L, void* out,

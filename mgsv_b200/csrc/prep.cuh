@@ -20,6 +20,8 @@ int ingest_gather(const void* in, int in_dtype, const Ragged& rb, int dim, op_t*
 int pool_norm_ragged(const float* seq_packed, const Ragged& rb, float* pooled, cudaStream_t st);
 int scatter_rows_f32(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
 int scatter_rows_f32_nozero(const float* packed, const Ragged& rb, float* padded, cudaStream_t st);
+// padded[tok_src[i], :] = float(hi[i, :]) + float(lo[i, :])  (256-wide fp16 (hi, lo) pair rows; lo nullable)
+int scatter_rows_pair_nozero(const op_t* hi, const op_t* lo, const Ragged& rb, float* padded, cudaStream_t st);
 int offset_rows(const Ragged& rb, int32_t base, int32_t* row_off, int32_t* row_len, cudaStream_t st);
 int detr_mask(const float* frame_mask, const float* seg_mask, const int32_t* track_idx, int64_t seq_offset,
               int64_t B, float* mask_out, cudaStream_t st);
@@ -46,6 +48,12 @@ int mha_core(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
 int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const float* key_mask, int64_t B,
                     int L, op_t* out, cudaStream_t st, const int32_t* seq_off = nullptr,
                     const int32_t* seq_len = nullptr);
+
+// ffn_fused.cu — out = epilogue(act(x W1^T + b1) W2^T + b2 + residual), hidden activation kept on chip
+int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const op_t* w2, const float* b2, int act,
+              const op_t* res_hi, const op_t* res_lo, int64_t res_ld, const float* ln_gamma, const float* ln_beta,
+              op_t* out_hi, op_t* out_lo, int64_t ld_out, const op_t* add2, int64_t add2_ld, op_t* out2,
+              int64_t ld_out2, int64_t M, const int32_t* m_dev, cudaStream_t st);
 
 // xpool.cu
 struct XpoolConsts {    // folded X-Pool constants of one checkpoint (per made_ctx)

@@ -163,6 +163,31 @@ __global__ void scatter_rows_f32_kernel(const float* __restrict__ packed, const 
   }
 }
 
+// padded[tok_src[i], :] = hi[i, :] + lo[i, :]  (fp16 pair rows of 256 -> fp32)
+__global__ void scatter_rows_pair_kernel(const op_t* __restrict__ hi, const op_t* __restrict__ lo,
+                                         const int32_t* __restrict__ tok_src, const int32_t* __restrict__ total,
+                                         float* __restrict__ padded) {
+  const int lane = threadIdx.x & 31;
+  const int n = *total;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n;
+       row += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + row * 256 + lane * 8);
+    const op2_t* hh = reinterpret_cast<const op2_t*>(&h);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = op2_to_f2(hh[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    if (lo) {
+      const uint4 l = *reinterpret_cast<const uint4*>(lo + row * 256 + lane * 8);
+      const op2_t* ll = reinterpret_cast<const op2_t*>(&l);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = op2_to_f2(ll[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    }
+    float4* d = reinterpret_cast<float4*>(padded + static_cast<int64_t>(tok_src[row]) * 256 + lane * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 // ---- DETR input assembly on packed tokens (model_Uni.py:207-216 + position_encoding.py:51-71) ----
 // mask[b] = cat(frame_mask[b], seg_mask[track(b)])   [B,146]
 __global__ void detr_mask_kernel(const float* __restrict__ frame_mask, const float* __restrict__ seg_mask,
@@ -241,6 +266,12 @@ int offset_rows(const Ragged& rb, int32_t base, int32_t* row_off, int32_t* row_l
 
 int scatter_rows_f32_nozero(const float* packed, const Ragged& rb, float* padded, cudaStream_t st) {
   scatter_rows_f32_kernel<<<static_cast<unsigned>(sm_count() * 4), 256, 0, st>>>(packed, rb.tok_src, rb.total, padded);
+  MADE_CHECK_LAUNCH();
+  return MADE_OK;
+}
+
+int scatter_rows_pair_nozero(const op_t* hi, const op_t* lo, const Ragged& rb, float* padded, cudaStream_t st) {
+  scatter_rows_pair_kernel<<<static_cast<unsigned>(sm_count() * 4), 256, 0, st>>>(hi, lo, rb.tok_src, rb.total, padded);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
 }

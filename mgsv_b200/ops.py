@@ -252,6 +252,20 @@ def gemm_f16_split(a: torch.Tensor, w_pair: torch.Tensor, split: int, bias=None,
     return out
 
 
+def ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, act: int,
+              residual: Optional[torch.Tensor] = None, ln=None, pair: bool = False) -> torch.Tensor:
+    """Fused 256 -> 1024 -> 256 feed-forward block.  x [M, >=256] fp16 (first 256 columns are used), residual
+    [M,512] (hi | lo) pairs when pair else [M,256] fp16 → [M,512] pairs / [M,256] fp16."""
+    M = x.shape[0]
+    out = torch.empty((M, 512 if pair else 256), dtype=torch.float16, device=x.device)
+    g, b = (ln if ln is not None else (None, None))
+    _lib.check(_lib.load().made_ffn_fused(
+        _lib.ptr(x), x.stride(0), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), act, _lib.ptr(residual),
+        0 if residual is None else residual.stride(0), _lib.ptr(g), _lib.ptr(b), _lib.ptr(out), out.stride(0),
+        1 if pair else 0, M, _lib.stream_ptr()))
+    return out
+
+
 def mha_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask: torch.Tensor) -> torch.Tensor:
     """q,k,v [B,L,256] fp16, key_mask [B,L] float (1 = valid) → [B,L,256] fp16."""
     B, L, _ = q.shape

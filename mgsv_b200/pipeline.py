@@ -66,11 +66,19 @@ class GalleryEvaluator:
     # xpool_score = 1; cosine = 1; rank_topk = 1; detr_detect = per 2048-sequence encoder chunk
     # (mask 1 + ragged index 3 + prep 1 + row offsets 1 + enc 2*6 = 18) + cast 1 + dec 6*(5 GEMM +
     # attention) + LN 1 + heads 3 = 41 (the 6 D2D copies are not kernels); moment_postproc = 1.
+    # With the fused FFN kernel (default; MADE_FUSED_FFN=0 restores the two GEMMs): encode = 5 GEMM-class + attn + pool = 7
+    # in split precision, detr_chunk = 6 + 2 * (3 GEMM + attn + FFN) = 16.
     _K = dict(ingest=4, encode=8, gallery_prepare=4, query_prepare=3, xpool=1, cosine=1, rank=1, detr=41,
               detr_chunk=18, postproc=1)
 
     def _count(self, what: str, n: int = 1):
-        self.launches += self._K[what] * n
+        k = self._K[what]
+        if os.environ.get("MADE_FUSED_FFN", "1") != "0":
+            if what == "encode" and self.eng.precision == "split":
+                k = 7
+            elif what == "detr_chunk":
+                k = 16
+        self.launches += k * n
 
     # ---- feature ingest, one chunk ahead on the ingest stream ---------------------------------------
     def _ingest_iter(self, modality: int, feats: torch.Tensor, mask_d: torch.Tensor, chunk: int, mask_h=None):

@@ -352,6 +352,34 @@ def test_tcgen05_split_gemm_epilogues(dev):
     assert _rel(out, torch.relu(a.to(torch.float16).double() @ w.double().t() + bias.double())) < 3e-6
 
 
+@pytest.mark.parametrize("M,act,pair,ln", [(1, 1, True, False), (128, 1, True, False), (1000, 1, True, False),
+                                           (40000, 1, True, False), (5000, 2, False, True), (333, 2, True, True),
+                                           (20000, 1, False, False)])
+def test_fused_ffn(dev, M, act, pair, ln):
+    """act(x W1^T + b1) W2^T + b2 + residual [-> LayerNorm] with the hidden activation kept on chip, against fp64
+    on the same fp16 operands (the hidden activation is rounded to fp16 once, like the unfused path)."""
+    g = torch.Generator().manual_seed(M + act)
+    x = torch.randn(M, 256, generator=g).to(torch.float16)
+    w1 = (torch.randn(1024, 256, generator=g) / 16).to(torch.float16)
+    w2 = (torch.randn(256, 1024, generator=g) / 32).to(torch.float16)
+    b1, b2 = torch.randn(1024, generator=g) * 0.1, torch.randn(256, generator=g) * 0.1
+    res = torch.randn(M, 256, generator=g)
+    gam, bet = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    res_in = ops.split_pair(res) if pair else res.to(torch.float16)
+    res_eff = (res_in[:, :256].double() + res_in[:, 256:].double()) if pair else res_in.double()
+    pre = x.double() @ w1.double().t() + b1.double()
+    hid = (torch.nn.functional.gelu(pre) if act == 1 else torch.relu(pre)).to(torch.float16).double()
+    ref = hid @ w2.double().t() + b2.double() + res_eff
+    if ln:
+        ref = torch.nn.functional.layer_norm(ref, (256,), gam.double(), bet.double())
+    out = ops.ffn_fused(x.to(dev), w1.to(dev), b1.to(dev), w2.to(dev), b2.to(dev), act, residual=res_in.to(dev),
+                        ln=(gam.to(dev), bet.to(dev)) if ln else None, pair=pair).cpu()
+    got = (out[:, :256].double() + out[:, 256:].double()) if pair else out.double()
+    # a hidden value that sits on an fp16 rounding boundary may round the other way (erf approximation 1.5e-7):
+    # worth one fp16 ulp of one hidden unit times |w2| ~ 1e-5 of the output scale
+    assert _rel(got, ref) < (2e-5 if pair else 6e-4)
+
+
 @pytest.mark.parametrize("L", [50, 96, 146, 1, 17])
 def test_mha_core(dev, L):
     g = torch.Generator().manual_seed(L)
