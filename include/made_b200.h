@@ -54,6 +54,14 @@ int made_abi_version(void);
 /* MADE_OK iff `device` is an sm_100 part. */
 int made_device_check(int device);
 
+/* Kernel-family timing (bench.py's roofline): while enabled, the launchers of the tensor-core kernels bracket
+ * every launch with CUDA events on the launching stream.  made_prof_collect synchronises the device, sums the
+ * elapsed milliseconds and launch counts per family and clears the window.
+ * Families: 0 = gemm_tc_kernel, 1 = ffn_fused_kernel, 2 = xpool_score_kernel, 3 = attention kernels, 4 = rank / top-k. */
+#define MADE_PROF_KINDS 5
+int made_prof_enable(int on);
+int made_prof_collect(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
+
 /* ---------------------------------------------------------------------------------------------
  * span utilities — music_detr/span_utils.py, bit-exact fp32
  * ------------------------------------------------------------------------------------------- */

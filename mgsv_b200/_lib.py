@@ -32,6 +32,8 @@ class Ragged(C.Structure):
 SIGNATURES = {
     "made_abi_version": [],
     "made_device_check": [_i32],
+    "made_prof_enable": [_i32],
+    "made_prof_collect": [C.POINTER(C.c_double), C.POINTER(_i64), _i32],
     "made_span_cw_to_se": [_p, _p, _i64, _p],
     "made_span_se_to_cw": [_p, _p, _i64, _p],
     "made_span_iou": [_p, _p, _p, _p, _f, _i64, _p, _p],
@@ -97,6 +99,22 @@ def check(rc: int) -> None:
     if rc in (EINVAL, EUNSUPPORTED):
         raise ValueError(f"made_b200: {msg}")
     raise RuntimeError(f"made_b200 (code {rc}): {msg}")
+
+
+PROF_KINDS = ("gemm", "ffn", "xpool", "attn", "rank")
+
+
+def prof_enable(on: bool) -> None:
+    check(load().made_prof_enable(1 if on else 0))
+
+
+def prof_collect():
+    """→ {family: (total ms, launches)} of the window since the last collect (synchronises the device)."""
+    n = len(PROF_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (_i64 * n)()
+    check(load().made_prof_collect(ms, cnt, n))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -334,6 +334,7 @@ static int launch_mha(const op_t* Q, int64_t ldq, const op_t* K, int64_t ldk,
                       const int32_t* seq_len, op_t* O, int64_t ldo, cudaStream_t st) {
   MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&mha_core_kernel<LP>), static_cast<int>(AttnSmem<LP>::kBytes)));
   dim3 grid(static_cast<unsigned>(B), 8 / kHeadsPerCta);
+  ProfScope prof_scope(kProfAttn, st);
   mha_core_kernel<LP><<<grid, kMhaThreads, AttnSmem<LP>::kBytes, st>>>(
       Q, ldq, K, ldk, V, ldv, mask, L, seq_off, seq_len, 0.17677669529663687f /* 1/sqrt(32) */, O, ldo);
   MADE_CHECK_LAUNCH();
@@ -359,6 +360,7 @@ int dec_attn_folded(const float* qt, const op_t* mp, const op_t* mem, const floa
   MADE_REQUIRE(qt && mp && mem && (key_mask || (seq_off && seq_len)) && out && L > 0 && L <= 160,
                "dec_attn_folded: bad arguments");
   MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&dec_attn_folded_kernel), static_cast<int>(kDecSmemBytes)));
+  ProfScope prof_scope(kProfAttn, st);
   dec_attn_folded_kernel<<<static_cast<unsigned>(B), 256, kDecSmemBytes, st>>>(qt, mp, mem, key_mask, L, seq_off,
                                                                               seq_len, out);
   MADE_CHECK_LAUNCH();

@@ -65,6 +65,16 @@ int sm_count();
 // device; done once per (kernel, device), thread-safe)
 int ensure_dynamic_smem(const void* kernel, int bytes);
 
+// Kernel-family timing for bench.py (made_prof_*): when enabled, a launcher brackets its kernel with a pair of
+// CUDA events on the launching stream; made_prof_collect sums the elapsed times per family.
+enum ProfKind { kProfGemm = 0, kProfFfn = 1, kProfXpool = 2, kProfAttn = 3, kProfRank = 4, kProfKinds = 5 };
+struct ProfScope {      // RAII: records the closing event when the launcher returns
+  ProfScope(int kind, cudaStream_t st);
+  ~ProfScope();
+  int slot;
+  cudaStream_t st;
+};
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
 // device helpers

@@ -11,8 +11,10 @@
 //     Y   += h_j W2_j^T                 tcgen05.mma 128 x 256 x 128  -> TMEM (256 columns)
 //   out   = Y + b2 + residual [LayerNorm]   epilogue warps -> staging boxes -> TMA bulk stores
 // The MMA issuer runs GEMM 1 one slice ahead (G1(j+1) is issued before G2(j)), so the activation epilogue of slice
-// j overlaps tensor work on both sides of it.  W1 / W2 stream through a 3-stage ring of 32 KB (W1: two [128 x 64]
-// k-tiles per stage, W2: one [256 x 64] k-tile per stage): 1 MB of weights per tile from L2.
+// j overlaps tensor work on both sides of it.  W1 / W2 stream through a 4-stage ring of 32 KB (W1: two [128 x 64]
+// k-tiles per stage, W2: one [256 x 64] k-tile per stage): 1 MB of weights per tile from L2, and the ring holds the
+// operands of one G2 and one G1 step at once so that their L2 latency is hidden behind the previous step (a 3-stage
+// ring with two hidden buffers measured 36 us per tile, bound by exactly that latency; r02 profiles).
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 =
 // epilogue (thread = row, warps 4-7 the left half of the columns, warps 8-11 the right half).
 #include <cstring>
@@ -29,14 +31,14 @@ constexpr int kD = 256;            // model width
 constexpr int kHid = 1024;         // hidden width
 constexpr int kSl = 128;           // hidden columns per slice
 constexpr int kSlices = kHid / kSl;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kStageBytes = 32768;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kXBytes = kM * kD * 2;        // 64 KB: 4 k-slabs of [128 x 128 B]
 constexpr uint32_t kHBytes = kM * kSl * 2;       // 32 KB: 2 k-slabs of [128 x 128 B]
 constexpr uint32_t kSlab = kM * 128;             // 16 KB
-constexpr uint32_t kSmem = kXBytes + 2 * kHBytes + kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr uint32_t kSmem = kXBytes + kHBytes + kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 static_assert(kSmem <= 232448, "shared memory budget of an sm_100 CTA");
 
 // TMEM columns
@@ -88,21 +90,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
-  uint8_t* sH = sX + kXBytes;                   // 2 buffers; reused as the output staging boxes at the end of a tile
-  uint8_t* ring = sH + 2 * kHBytes;
+  uint8_t* sH = sX + kXBytes;                   // fp16 hidden slice; reused as the output staging boxes at the end of a tile
+  uint8_t* ring = sH + kHBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kStages * kStageBytes);
-  uint64_t* full = bars;                        // [3] weight stage landed
-  uint64_t* empty = bars + 3;                   // [3] MMAs that read the stage completed
-  uint64_t* x_full = bars + 6;
-  uint64_t* x_empty = bars + 7;                 // all GEMM-1 MMAs of the tile completed
-  uint64_t* hacc_full = bars + 8;               // [2] H accumulator of a slice complete
-  uint64_t* hacc_empty = bars + 10;             // [2] epilogue has read it (256 arrivals)
-  uint64_t* h_full = bars + 12;                 // [2] fp16 slice in shared memory (256 arrivals)
-  uint64_t* h_empty = bars + 14;                // [2] GEMM-2 MMAs that read it completed
+  uint64_t* full = bars;                        // [4] weight stage landed
+  uint64_t* empty = bars + 4;                   // [4] MMAs that read the stage completed
+  uint64_t* x_full = bars + 8;
+  uint64_t* x_empty = bars + 9;                 // all GEMM-1 MMAs of the tile completed
+  uint64_t* hacc_full = bars + 10;              // [2] H accumulator of a slice complete
+  uint64_t* hacc_empty = bars + 12;             // [2] epilogue has read it (256 arrivals)
+  uint64_t* h_full = bars + 14;                 // fp16 slice in shared memory (256 arrivals)
+  uint64_t* h_empty = bars + 15;                // GEMM-2 MMAs that read it completed
   uint64_t* y_full = bars + 16;
   uint64_t* y_empty = bars + 17;                // Y drained by the epilogue (256 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  // LayerNorm partial sums [2 stats][2 halves][128] alias the first 2 KB of the hidden buffers, which are idle
+  // LayerNorm partial sums [2 stats][2 halves][128] alias the first 2 KB of the hidden buffer, which is idle
   // between the last GEMM-2 MMA of a tile and the first staging-box write of its output epilogue
   float* ln_part = reinterpret_cast<float*>(sH);
 
@@ -128,9 +130,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     for (int i = 0; i < 2; ++i) {
       mbar_init(&hacc_full[i], 1);
       mbar_init(&hacc_empty[i], kEpiThreads);
-      mbar_init(&h_full[i], kEpiThreads);
-      mbar_init(&h_empty[i], 1);
     }
+    mbar_init(h_full, kEpiThreads);
+    mbar_init(h_empty, 1);
     mbar_init(y_full, 1);
     mbar_init(y_empty, kEpiThreads);
     fence_mbar_init();
@@ -215,9 +217,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (j == kSlices - 1) tc_commit(x_empty);
         };
         auto g2 = [&](int j) {
-          const int b = j & 1;
-          const uint32_t use = static_cast<uint32_t>(it * (kSlices / 2) + (j >> 1));
-          mbar_wait(&h_full[b], use & 1);
+          const uint32_t n = static_cast<uint32_t>(it * kSlices + j);
+          mbar_wait(h_full, n & 1);
           if (j == 0) mbar_wait(y_empty, (it & 1) ^ 1);
           tc_fence_after_sync();
           for (int h2 = 0; h2 < 2; ++h2) {
@@ -226,12 +227,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
             const uint32_t sb = smem_u32(ring + stage * kStageBytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss(tmem_base + kColY, umma_smem_desc(aH + b * kHBytes + h2 * kSlab + k * 32, 0, 1024),
+              umma_ss(tmem_base + kColY, umma_smem_desc(aH + h2 * kSlab + k * 32, 0, 1024),
                       umma_smem_desc(sb + k * 32, 0, 1024), idesc2, (j | h2 | k) != 0);
             tc_commit(&empty[stage]);
             advance();
           }
-          tc_commit(&h_empty[b]);
+          tc_commit(h_empty);
           if (j == kSlices - 1) tc_commit(y_full);
         };
         mbar_wait(x_full, it & 1);
@@ -252,8 +253,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sw = r & 7;
     const bool issuer = lane == 0;
-    uint8_t* stg_h = sH + ew * 8192;            // this warp's staging boxes: [32 rows][128 B] hi, then lo
-    uint8_t* stg_l = stg_h + 4096;
+    // this warp's staging boxes, one 32-column chunk each: [32 rows][64 B] hi, then lo; written with the 128-byte
+    // swizzle of the store's tensor map applied to the linear offset (16-byte unit index ^= bits 7..9 of the offset)
+    uint8_t* stg_h = sH + ew * 4096;
+    uint8_t* stg_l = stg_h + 2048;
+    uint32_t box_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t o = static_cast<uint32_t>(lane) * 64u + static_cast<uint32_t>(i) * 16u;
+      box_off[i] = o ^ (((o >> 7) & 7u) << 4);
+    }
     const bool do_ln = p.ln_gamma != nullptr;
 
     for (int64_t it = 0; it < my_tiles; ++it) {
@@ -289,20 +298,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           pk[2 * i] = pack_op2(v0, v1);
           pk[2 * i + 1] = pack_op2(v2, v3);
         }
-        // the GEMM-2 MMAs that read this buffer two slices ago have completed
-        mbar_wait(&h_empty[b], (use & 1) ^ 1);
+        // the GEMM-2 MMAs of the previous slice have finished reading the hidden buffer
+        const uint32_t n = static_cast<uint32_t>(it * kSlices + j);
+        mbar_wait(h_empty, (n & 1) ^ 1);
         // fp16 slice -> swizzled K-major A operand: this thread's 64 hidden columns = k-slab `half`, chunks 0..7
-        uint8_t* hrow = sH + b * kHBytes + half * kSlab + r * 128;
+        uint8_t* hrow = sH + half * kSlab + r * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<uint4*>(hrow + ((c ^ sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         fence_proxy_async_smem();
-        mbar_arrive(&h_full[b]);
+        mbar_arrive(h_full);
       }
       // ---------- output epilogue ----------
       mbar_wait(y_full, it & 1);
       tc_fence_after_sync();
-      // every GEMM-2 MMA of the tile has completed: both hidden buffers are free and become staging boxes
+      // every GEMM-2 MMA of the tile has completed: the hidden buffer is free and becomes the staging boxes
       float psum = 0.f, psq = 0.f;
       auto value_chunk = [&](int c, float (&v)[32]) {      // acc + b2 + residual for columns [32 c, +32)
         uint32_t acc[32];
@@ -342,18 +352,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           }
         }
       };
-      // emit chunk c (this thread's jl-th chunk): fill one half of the warp's 64-column box, store when full
+      // emit chunk c: fill the warp's 32-column boxes and hand them to the TMA engine
       auto emit = [&](int jl, int c, float (&v)[32]) {
-        const bool first = (jl & 1) == 0;
-        if (first) {
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-        }
+        (void)jl;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // previous stores have read the boxes
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint4 hi = make_uint4(pack_op2(v[8 * i], v[8 * i + 1]), pack_op2(v[8 * i + 2], v[8 * i + 3]),
                                       pack_op2(v[8 * i + 4], v[8 * i + 5]), pack_op2(v[8 * i + 6], v[8 * i + 7]));
-          *reinterpret_cast<uint4*>(stg_h + lane * 128 + ((((jl & 1) * 4 + i) ^ (lane & 7)) << 4)) = hi;
+          *reinterpret_cast<uint4*>(stg_h + box_off[i]) = hi;
           if (p.has_lo) {
             const op2_t* hh = reinterpret_cast<const op2_t*>(&hi);
             uint32_t lo[4];
@@ -362,8 +370,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
               const float2 f = op2_to_f2(hh[jj]);
               lo[jj] = pack_op2(v[8 * i + 2 * jj] - f.x, v[8 * i + 2 * jj + 1] - f.y);
             }
-            *reinterpret_cast<uint4*>(stg_l + lane * 128 + ((((jl & 1) * 4 + i) ^ (lane & 7)) << 4)) =
-                make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(stg_l + box_off[i]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           if (p.out2 && row_ok) {
             const uint4 t = __ldg(reinterpret_cast<const uint4*>(p.add2 + grow * p.add2_ld + c * 32) + i);
@@ -374,15 +381,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                            pack_op2(v[8 * i + 4] + f2.x, v[8 * i + 5] + f2.y), pack_op2(v[8 * i + 6] + f3.x, v[8 * i + 7] + f3.y));
           }
         }
-        if (!first) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (issuer) {
-            const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
-            tma_store_2d(&tm_oh, stg_h, c * 32 - 32, wrow);
-            if (p.has_lo) tma_store_2d(&tm_ol, stg_l, c * 32 - 32, wrow);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (issuer) {
+          const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
+          tma_store_2d(&tm_oh, stg_h, c * 32, wrow);
+          if (p.has_lo) tma_store_2d(&tm_ol, stg_l, c * 32, wrow);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
       if (!do_ln) {
@@ -440,8 +445,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       // Y is drained: the next tile's GEMM 2 may overwrite it
       tc_fence_before_sync();
       mbar_arrive(y_empty);
-      // the staging boxes alias the hidden buffers of the next tile: every warp's bulk stores must have
-      // finished reading them before anyone writes the next h_0 / h_1
+      // the staging boxes alias the hidden buffer of the next tile: every warp's bulk stores must have
+      // finished reading them before anyone writes the next h_0
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       named_bar_sync(1, kEpiThreads);
     }
@@ -476,9 +481,10 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
   MADE_TRY(encode_tmap_2d_16b(&tx, x, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ldx) * 2, 64, kM));
   MADE_TRY(encode_tmap_2d_16b(&tw1, w1, kD, kHid, kD * 2, 64, kSl));
   MADE_TRY(encode_tmap_2d_16b(&tw2, w2, kHid, kD, kHid * 2, 64, kD));
-  MADE_TRY(encode_tmap_2d(&toh, out_hi, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 64, 32));
+  // output boxes of 32 columns x 32 rows (64-byte rows, 128-byte swizzle pattern over the linear box offset)
+  MADE_TRY(encode_tmap_2d(&toh, out_hi, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32));
   if (out_lo)
-    MADE_TRY(encode_tmap_2d(&tol, out_lo, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 64, 32));
+    MADE_TRY(encode_tmap_2d(&tol, out_lo, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32));
   FfnParams p;
   p.M = M;
   p.m_dev = m_dev;
@@ -498,6 +504,7 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
   p.ld_out2 = ld_out2;
   const int64_t m_tiles = (M + kM - 1) / kM;
   const int grid = static_cast<int>(m_tiles < sm_count() ? m_tiles : sm_count());
+  ProfScope prof_scope(kProfFfn, st);
   ffn_fused_kernel<<<grid, kThreads, kSmem, st>>>(tx, tw1, tw2, toh, tol, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;

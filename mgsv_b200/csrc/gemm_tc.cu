@@ -502,6 +502,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * (p.N / BN);
   int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+  ProfScope prof_scope(kProfGemm, stream);
   gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, tol, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;

@@ -618,6 +618,7 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
   MADE_REQUIRE(k == 0 || topk_idx, "rank_topk: k>0 needs topk_idx");
   MADE_REQUIRE(!rank_out || gt_col || gt_score_in, "rank_topk: rank needs gt_col or gt_score_in");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof_scope(kProfRank, st);
   if (n_cols <= kMaxSmemCols) {
     MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&rank_topk_staged_kernel), static_cast<int>(kMaxSmemCols * 4)));
     const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);

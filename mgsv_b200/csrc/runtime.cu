@@ -106,6 +106,45 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
   return MADE_OK;
 }
 
+// ---- kernel-family profiler (bench.py roofline) ------------------------------------------------------------
+namespace {
+struct ProfRec {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind = 0;
+};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;       // records of the current window
+std::vector<ProfRec> g_prof_pool;  // events are recycled across windows
+}  // namespace
+
+ProfScope::ProfScope(int kind, cudaStream_t st_) : slot(-1), st(st_) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return;
+  }
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  ProfRec r;
+  if (!g_prof_pool.empty()) {
+    r = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return;
+  }
+  r.kind = kind;
+  cudaEventRecord(r.a, st);
+  slot = static_cast<int>(g_prof.size());
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (slot < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot].b, st);
+}
+
 // ---- small persistent host thread pool (fp32 -> fp16 conversion of host features) -----------------
 class HostPool {
  public:
@@ -202,6 +241,34 @@ extern "C" {
 const char* made_last_error_string(void) { return made::g_err; }
 
 int made_abi_version(void) { return MADE_ABI_VERSION; }
+
+int made_prof_enable(int on) {
+  made::g_prof_on.store(on ? 1 : 0);
+  return MADE_OK;
+}
+
+int made_prof_collect(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds) {
+  using namespace made;
+  MADE_REQUIRE(ms_by_kind && launches_by_kind && n_kinds >= kProfKinds, "prof_collect: need %d slots", (int)kProfKinds);
+  MADE_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (int i = 0; i < n_kinds; ++i) {
+    ms_by_kind[i] = 0.0;
+    launches_by_kind[i] = 0;
+  }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_kind[r.kind] += ms;
+      launches_by_kind[r.kind] += 1;
+    } else {
+      (void)cudaGetLastError();
+    }
+    g_prof_pool.push_back(r);
+  }
+  g_prof.clear();
+  return MADE_OK;
+}
 
 int made_h2d_valid_rows(const void* host_feats, int feats_dtype, const float* host_masks, int64_t B, int L,
                         int dim, void* host_stage16, int n_threads, void* dev_staging, int64_t* bytes_copied,

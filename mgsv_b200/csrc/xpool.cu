@@ -502,6 +502,7 @@ int xpool_score(const XpoolConsts& consts, const op_t* q, const float* vhat, int
   p.col_offset = col_offset;
   p.ln2_eps = 1e-5f;
   p.ln3_eps = 1e-5f;
+  ProfScope prof_scope(kProfXpool, st);
   xpool_score_kernel<<<p.q_tiles * slices, kXThreads, kXSmem, st>>>(tq, tk, tz, tg, consts, p);
   MADE_CHECK_LAUNCH();
   return MADE_OK;
