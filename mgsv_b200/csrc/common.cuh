@@ -55,9 +55,9 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
-// generic 2-D tiled map (elem_bytes 2 = fp16, 4 = fp32), 128-byte swizzle
+// generic 2-D tiled map (elem_bytes 2 = fp16, 4 = fp32); swizzle_bytes 128 (default) or 0 = dense box rows
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
-                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128);
 
 // multiprocessor count of the CURRENT device (cached per device)
 int sm_count();

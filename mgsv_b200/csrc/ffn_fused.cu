@@ -17,6 +17,7 @@
 // ring with two hidden buffers measured 36 us per tile, bound by exactly that latency; r02 profiles).
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 =
 // epilogue (thread = row, warps 4-7 the left half of the columns, warps 8-11 the right half).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -81,6 +82,8 @@ struct FfnParams {
   int64_t add2_ld;
   op_t* out2;
   int64_t ld_out2;
+  int debug;                    // bench-only ablations (MADE_FFN_DEBUG): 1 = no weight TMA traffic after the first ring
+                                // fill, 2 = output epilogue without global loads / stores, 4 = identity activation
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -148,24 +151,31 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t fills = 0;
+      bool skip = false;
       auto next_stage = [&]() -> uint8_t* {
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], kStageBytes);
+        skip = (p.debug & 1) && fills >= kStages;
+        ++fills;
+        if (skip) mbar_arrive(&full[stage]);      // ablation: stale weights, no L2 traffic
+        else mbar_arrive_expect_tx(&full[stage], kStageBytes);
         return ring + stage * kStageBytes;
       };
       auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
       auto load_w1 = [&](int j) {      // hidden rows [128 j, +128), 4 k-tiles of 64 -> 2 stages
         for (int h2 = 0; h2 < 2; ++h2) {
           uint8_t* s = next_stage();
-          tma_load_2d(s, &tm_w1, &full[stage], (2 * h2) * 64, j * kSl);
-          tma_load_2d(s + 16384, &tm_w1, &full[stage], (2 * h2 + 1) * 64, j * kSl);
+          if (!skip) {
+            tma_load_2d(s, &tm_w1, &full[stage], (2 * h2) * 64, j * kSl);
+            tma_load_2d(s + 16384, &tm_w1, &full[stage], (2 * h2 + 1) * 64, j * kSl);
+          }
           advance();
         }
       };
       auto load_w2 = [&](int j) {      // all 256 output rows, hidden columns [128 j, +128) -> 2 stages of one k-tile
         for (int h2 = 0; h2 < 2; ++h2) {
           uint8_t* s = next_stage();
-          tma_load_2d(s, &tm_w2, &full[stage], j * kSl + h2 * 64, 0);
+          if (!skip) tma_load_2d(s, &tm_w2, &full[stage], j * kSl + h2 * 64, 0);
           advance();
         }
       };
@@ -253,16 +263,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sw = r & 7;
     const bool issuer = lane == 0;
-    // this warp's staging boxes, one 32-column chunk each: [32 rows][64 B] hi, then lo; written with the 128-byte
-    // swizzle of the store's tensor map applied to the linear offset (16-byte unit index ^= bits 7..9 of the offset)
+    // this warp's staging boxes, one 32-column chunk each: dense [32 rows][64 B] hi, then lo (un-swizzled
+    // tensor maps: a 2 KB box is written once per tile chunk, the 4-way bank conflict of its 16-byte stores is noise)
     uint8_t* stg_h = sH + ew * 4096;
     uint8_t* stg_l = stg_h + 2048;
     uint32_t box_off[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t o = static_cast<uint32_t>(lane) * 64u + static_cast<uint32_t>(i) * 16u;
-      box_off[i] = o ^ (((o >> 7) & 7u) << 4);
-    }
+    for (int i = 0; i < 4; ++i) box_off[i] = static_cast<uint32_t>(lane) * 64u + static_cast<uint32_t>(i) * 16u;
     const bool do_ln = p.ln_gamma != nullptr;
 
     for (int64_t it = 0; it < my_tiles; ++it) {
@@ -290,7 +297,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t* src = i < 8 ? &a0[4 * i] : &a1[4 * (i - 8)];
           float v0 = __uint_as_float(src[0]) + bb.x, v1 = __uint_as_float(src[1]) + bb.y;
           float v2 = __uint_as_float(src[2]) + bb.z, v3 = __uint_as_float(src[3]) + bb.w;
-          if (p.act == 1) {
+          if (p.debug & 4) {
+          } else if (p.act == 1) {
             v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); v2 = gelu_erf_fast(v2); v3 = gelu_erf_fast(v3);
           } else {
             v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
@@ -310,11 +318,33 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_arrive(h_full);
       }
       // ---------- output epilogue ----------
+      // residual rows (thread = row: 16-byte pieces of 32 different rows per load instruction) are fetched one
+      // 32-column chunk ahead; the first chunk is requested before the wait for the last GEMM-2 step
+      uint4 rh[4], rl[4];
+      auto res_issue = [&](int c) {
+        if (p.res_hi) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + srow * p.res_ld + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rh[i] = __ldg(r4 + i);
+          if (p.res_lo) {
+            const uint4* l4 = reinterpret_cast<const uint4*>(p.res_lo + srow * p.res_ld + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rl[i] = __ldg(l4 + i);
+          }
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0u, 0u, 0u, 0u); rl[i] = make_uint4(0u, 0u, 0u, 0u); }
+      if (!(p.debug & 2)) res_issue(half * 4);
       mbar_wait(y_full, it & 1);
       tc_fence_after_sync();
       // every GEMM-2 MMA of the tile has completed: the hidden buffer is free and becomes the staging boxes
       float psum = 0.f, psq = 0.f;
-      auto value_chunk = [&](int c, float (&v)[32]) {      // acc + b2 + residual for columns [32 c, +32)
+      auto value_chunk = [&](int c, int c_next, float (&v)[32]) {      // acc + b2 + residual for columns [32 c, +32)
+        uint4 ch[4], cl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ch[i] = rh[i]; cl[i] = rl[i]; }
+        if (c_next >= 0) res_issue(c_next);      // the next chunk's residual rows travel while this chunk is processed
         uint32_t acc[32];
         tmem_ld_x32(lane_addr + kColY + c * 32, acc);
         tmem_wait_ld();
@@ -328,26 +358,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + t.w;
         }
         if (p.res_hi) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + srow * p.res_ld + c * 32);
-          const uint4* l4 = p.res_lo ? reinterpret_cast<const uint4*>(p.res_lo + srow * p.res_ld + c * 32) : nullptr;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint4 t = __ldg(r4 + i);
-            const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+            const op2_t* h = reinterpret_cast<const op2_t*>(&ch[i]);
+            const op2_t* l = reinterpret_cast<const op2_t*>(&cl[i]);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const float2 f = op2_to_f2(h[jj]);
-              v[8 * i + 2 * jj] += f.x;
-              v[8 * i + 2 * jj + 1] += f.y;
-            }
-            if (l4) {
-              t = __ldg(l4 + i);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float2 f = op2_to_f2(h[jj]);
-                v[8 * i + 2 * jj] += f.x;
-                v[8 * i + 2 * jj + 1] += f.y;
-              }
+              const float2 g = op2_to_f2(l[jj]);      // zeros when there is no low half
+              v[8 * i + 2 * jj] += f.x + g.x;
+              v[8 * i + 2 * jj + 1] += f.y + g.y;
             }
           }
         }
@@ -390,12 +410,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
-      if (!do_ln) {
+      if (p.debug & 2) {
+        // ablation: no output epilogue
+      } else if (!do_ln) {
 #pragma unroll 1
         for (int jl = 0; jl < 4; ++jl) {
           const int c = half * 4 + jl;
           float v[32];
-          value_chunk(c, v);
+          value_chunk(c, jl < 3 ? c + 1 : -1, v);
           emit(jl, c, v);
         }
       } else {
@@ -403,7 +425,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         for (int jl = 0; jl < 4; ++jl) {       // pass 1: values back into TMEM, row statistics
           const int c = half * 4 + jl;
           float v[32];
-          value_chunk(c, v);
+          value_chunk(c, jl < 3 ? c + 1 : -1, v);
           uint32_t st[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -481,10 +503,10 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
   MADE_TRY(encode_tmap_2d_16b(&tx, x, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ldx) * 2, 64, kM));
   MADE_TRY(encode_tmap_2d_16b(&tw1, w1, kD, kHid, kD * 2, 64, kSl));
   MADE_TRY(encode_tmap_2d_16b(&tw2, w2, kHid, kD, kHid * 2, 64, kD));
-  // output boxes of 32 columns x 32 rows (64-byte rows, 128-byte swizzle pattern over the linear box offset)
-  MADE_TRY(encode_tmap_2d(&toh, out_hi, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32));
+  // output boxes of 32 columns x 32 rows, dense 64-byte rows
+  MADE_TRY(encode_tmap_2d(&toh, out_hi, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32, 0));
   if (out_lo)
-    MADE_TRY(encode_tmap_2d(&tol, out_lo, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32));
+    MADE_TRY(encode_tmap_2d(&tol, out_lo, 2, kD, static_cast<uint64_t>(M), static_cast<uint64_t>(ld_out) * 2, 32, 32, 0));
   FfnParams p;
   p.M = M;
   p.m_dev = m_dev;
@@ -502,6 +524,10 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
   p.add2_ld = add2_ld;
   p.out2 = out2;
   p.ld_out2 = ld_out2;
+  {
+    const char* dbg = getenv("MADE_FFN_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const int64_t m_tiles = (M + kM - 1) / kM;
   const int grid = static_cast<int>(m_tiles < sm_count() ? m_tiles : sm_count());
   ProfScope prof_scope(kProfFfn, st);

@@ -50,7 +50,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
-                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -62,7 +62,8 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t 
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p esz=%d inner=%llu outer=%llu stride=%llu box=%ux%u",
@@ -75,7 +76,7 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t 
 
 int encode_tmap_2d_16b(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
-  return encode_tmap_2d(map, base, 2, inner, outer, row_stride_bytes, box_inner, box_outer);
+  return encode_tmap_2d(map, base, 2, inner, outer, row_stride_bytes, box_inner, box_outer, 128);
 }
 
 int sm_count() {

@@ -812,3 +812,27 @@ def test_span_se_to_cw_and_detr_iou_mirror(dev):
     ref = O.detr_iou(st, ed, gt, md)
     assert len(got) == n and got[0].dim() == 0
     assert np.array_equal(torch.stack(got).numpy(), ref.numpy())
+
+
+def test_gallery_index_streaming_search_equals_whole_matrix_path(dev, engine):
+    """configs[4] building block: a resident encoded gallery searched in score chunks with a running top-k
+    (sim[N_v, N_m] never materialised) returns exactly the ranks / top-k of the whole-matrix path."""
+    from mgsv_b200.index import GalleryIndex, ShardedIndex
+    from mgsv_b200.pipeline import GalleryEvaluator
+    nq, nm, k = 70, 333, 20
+    v, m, _ = synth.make_eval_set(nq, nm, synth.BASE_SEED + 51)
+    dv = {key: v[key].to(dev) for key in ("frame_feats", "frame_mask")}
+    dm = {key: m[key].to(dev) for key in ("segment_feats", "segment_mask", "gt_moment", "m_duration")}
+    gt = torch.tensor([(7 * i) % nm for i in range(nq)], dtype=torch.int32)
+    ev = GalleryEvaluator(engine, k=k, music_chunk=128, video_chunk=64)
+    ref = ev.run(dv, dm, gt.to(dev))
+    idx = GalleryIndex(ev, capacity=nm, score_chunk=100)         # 4 score chunks, the last one narrower than k + 13
+    for s in range(0, nm, 90):                                   # appended in uneven batches
+        idx.add(dm["segment_feats"][s:s + 90], dm["segment_mask"][s:s + 90])
+    assert idx.n == nm and idx.bytes_per_track > 200_000
+    out = ShardedIndex(idx, 0, 1).search(ref["video_feats"], k, gt_col=gt)
+    assert torch.equal(out["rank"], ref["rank"])
+    assert torch.equal(out["topk_idx"], ref["topk_idx"]) and torch.equal(out["topk_score"], ref["topk_score"])
+    # without ground truth: top-k only
+    out2 = idx.search(ref["video_feats"], k)
+    assert out2["count"] is None and torch.equal(out2["topk_idx"], ref["topk_idx"])
