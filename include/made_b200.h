@@ -43,9 +43,13 @@ extern "C" {
  * FP16  : every GEMM operand is one fp16 value (fastest; similarity error ~2e-4 rms of the scale).
  * SPLIT : the weights and token activations whose rounding dominates the similarity error travel as
  *         fp16 (hi, lo) pairs and their GEMMs run 2-3 tcgen05 passes into one fp32 accumulator
- *         (default; meets the 1e-3 similarity bar on the full 2000 x 4000 job). */
+ *         (default; meets the 1e-3 similarity bar on the full 2000 x 4000 job).
+ * FP32  : the temporal encoders run on the CUDA cores in the reference's own fp32 arithmetic (made_encode only;
+ *         with made_xpool_pooled + made_pooled_cosine for the X-Pool similarity this is the "1e-5 in fp32" mode:
+ *         exact, ~50x slower than SPLIT). */
 #define MADE_PREC_FP16 0
 #define MADE_PREC_SPLIT 1
+#define MADE_PREC_FP32 2
 
 typedef struct made_ctx made_ctx;
 
@@ -204,6 +208,18 @@ int made_query_prepare(made_ctx* ctx, const float* video_feats, int64_t N, void*
 int made_xpool_score(made_ctx* ctx, const void* q, const float* vhat, int64_t n_queries,
                      const void* kz, const void* gram, const uint32_t* maskbits, int64_t n_tracks,
                      float* sim, int64_t ld, int64_t col_offset, void* stream);
+
+/* Transformer_XA.forward MATERIALISED (modules/transformer.py:156-180), fp32 CUDA-core arithmetic:
+ * video_feats [N_v,256], seg_f32 [N_m,96,256] fp32, seg_masks [N_m,96] -> pooled [N_m, N_v, 256] fp32.
+ * The product path (made_xpool_score) never forms this tensor; this entry exists for callers that want it (the
+ * compat view of model.video_guided_to_music_pooling_cross_transformer) and for the fp32 precision mode.
+ * Chunk the tracks: scratch is N_m * N_v * 2.4 KB. */
+int made_xpool_pooled(made_ctx* ctx, const float* video_feats, int64_t n_q, const float* seg_f32, const float* seg_masks,
+                      int64_t n_m, float* pooled, void* stream);
+/* sim_matrix_music_pooling (modules/metrics.py:10-24) on a materialised pooled tensor:
+ * sim[v, col_offset + m] = < video[v]/|video[v]|, pooled[m,v]/|pooled[m,v]| >, fp32, sim row stride ld. */
+int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,
+                       int64_t col_offset, void* stream);
 
 /* Moment detection for B (query, track) pairs — model_Uni.py:207-227 + calc_output :117-150:
  * concat fusion, PositionEmbeddingSine, DETR encoder x2 / decoder x6, heads.

@@ -15,7 +15,7 @@ _LIB: Optional[C.CDLL] = None
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ESTATE = 0, -1, -2, -3, -4, -5
 F32, BF16, F16 = 0, 1, 2
 VIDEO, MUSIC = 0, 1
-PREC_FP16, PREC_SPLIT = 0, 1
+PREC_FP16, PREC_SPLIT, PREC_FP32 = 0, 1, 2
 ABI_VERSION = 2
 
 _p = C.c_void_p
@@ -57,6 +57,8 @@ SIGNATURES = {
     "made_gallery_prepare": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
     "made_xpool_score": [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _p],
+    "made_xpool_pooled": [_p, _p, _i64, _p, _p, _i64, _p, _p],
+    "made_pooled_cosine": [_p, _p, _i64, _i64, _p, _i64, _i64, _p],
     "made_detr_detect": [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "made_detr_losses": [_p, _p, _p, _p, _p, _i64, _i32, _f, _f, _f, _p, _p],
     "made_retrieval_loss": [_p, _p, _i64, _i32, _f, _p, _p],

@@ -66,6 +66,8 @@ struct made_ctx {
   size_t ws_bytes = 0, ws_off = 0;
   bool ws_dry = false;          // sizing pass of with_arena(): take() only advances the offset
   int precision = MADE_PREC_SPLIT;
+  ExactEncW xenc[2];            // raw fp32 weights for the fp32 CUDA-core path (exact_f32.cu)
+  ExactXpW xxp;
   XpoolConsts xp_consts;        // folded X-Pool constants of THIS context's checkpoint
   float* xp_c5 = nullptr;       // [5][256] weight vectors of the W5 columns (device)
 
@@ -216,6 +218,59 @@ std::vector<double> matmul(const std::vector<double>& A, const std::vector<doubl
 }
 std::vector<double> to_d(const float* p, size_t n) { return std::vector<double>(p, p + n); }
 std::vector<float> to_f(const std::vector<double>& v) { return std::vector<float>(v.begin(), v.end()); }
+
+int up_key(made_ctx* c, const std::string& key, size_t numel, const float** dst) {
+  const std::vector<float>* v;
+  MADE_TRY(get(c, key, numel, &v));
+  float* p = nullptr;
+  MADE_TRY(up_f32(c, v->data(), numel, &p));
+  *dst = p;
+  return MADE_OK;
+}
+
+int load_exact(made_ctx* c) {
+  for (int modality = 0; modality < 2; ++modality) {
+    ExactEncW& w = c->xenc[modality];
+    const bool vid = modality == MADE_VIDEO;
+    w.L = vid ? LV : LM;
+    w.din = vid ? 512 : 768;
+    const std::string tr = vid ? "video_transformer" : "audio_transformer";
+    const std::string pj = vid ? "vit_proj" : "ast_proj";
+    MADE_TRY(up_key(c, pj + ".weight", static_cast<size_t>(D) * w.din, &w.proj_w));
+    MADE_TRY(up_key(c, pj + ".bias", D, &w.proj_b));
+    w.pe = c->enc[modality].pe;
+    w.ln1_g = c->enc[modality].ln1.g; w.ln1_b = c->enc[modality].ln1.b;
+    w.ln2_g = c->enc[modality].ln2.g; w.ln2_b = c->enc[modality].ln2.b;
+    MADE_TRY(up_key(c, tr + ".layers.0.1.in_proj_weight", 3 * D * D, &w.in_w));
+    MADE_TRY(up_key(c, tr + ".layers.0.1.in_proj_bias", 3 * D, &w.in_b));
+    MADE_TRY(up_key(c, tr + ".layers.0.1.out_proj.weight", D * D, &w.out_w));
+    MADE_TRY(up_key(c, tr + ".layers.0.1.out_proj.bias", D, &w.out_b));
+    MADE_TRY(up_key(c, tr + ".layers.0.3.0.weight", DFF * D, &w.ff1_w));
+    MADE_TRY(up_key(c, tr + ".layers.0.3.0.bias", DFF, &w.ff1_b));
+    MADE_TRY(up_key(c, tr + ".layers.0.3.3.weight", D * DFF, &w.ff2_w));
+    MADE_TRY(up_key(c, tr + ".layers.0.3.3.bias", D, &w.ff2_b));
+    MADE_TRY(up_key(c, tr + ".final_linear.weight", D * D, &w.fin_w));
+    MADE_TRY(up_key(c, tr + ".final_linear.bias", D, &w.fin_b));
+  }
+  const std::string x = "video_guided_to_music_pooling_cross_transformer";
+  ExactXpW& w = c->xxp;
+  w.ln1_g = c->xp_ln1.g; w.ln1_b = c->xp_ln1.b;
+  MADE_TRY(up_key(c, x + ".layer_norm2.weight", D, &w.ln2_g));
+  MADE_TRY(up_key(c, x + ".layer_norm2.bias", D, &w.ln2_b));
+  MADE_TRY(up_key(c, x + ".layer_norm3.weight", D, &w.ln3_g));
+  MADE_TRY(up_key(c, x + ".layer_norm3.bias", D, &w.ln3_b));
+  MADE_TRY(up_key(c, x + ".cross_attn.q_proj.weight", D * D, &w.q_w));
+  MADE_TRY(up_key(c, x + ".cross_attn.q_proj.bias", D, &w.q_b));
+  MADE_TRY(up_key(c, x + ".cross_attn.k_proj.weight", D * D, &w.k_w));
+  MADE_TRY(up_key(c, x + ".cross_attn.k_proj.bias", D, &w.k_b));
+  MADE_TRY(up_key(c, x + ".cross_attn.v_proj.weight", D * D, &w.v_w));
+  MADE_TRY(up_key(c, x + ".cross_attn.v_proj.bias", D, &w.v_b));
+  MADE_TRY(up_key(c, x + ".cross_attn.out_proj.weight", D * D, &w.o_w));
+  MADE_TRY(up_key(c, x + ".cross_attn.out_proj.bias", D, &w.o_b));
+  MADE_TRY(up_key(c, x + ".linear_proj.weight", D * D, &w.l_w));
+  MADE_TRY(up_key(c, x + ".linear_proj.bias", D, &w.l_b));
+  return MADE_OK;
+}
 
 int load_encoder(made_ctx* c, int modality) {
   EncW& e = c->enc[modality];
@@ -504,6 +559,7 @@ int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const fl
   MADE_TRY(load_encoder(c, MADE_MUSIC));
   MADE_TRY(load_xpool(c, static_cast<cudaStream_t>(stream)));
   MADE_TRY(load_detr(c));
+  MADE_TRY(load_exact(c));
   c->host.clear();
   c->loaded = true;
   return MADE_OK;
@@ -552,7 +608,8 @@ int made_ingest_ragged(made_ctx* c, const void* feats, int feats_dtype, const ma
 
 int made_ctx_set_precision(made_ctx* c, int mode) {
   MADE_REQUIRE(c, "set_precision: null made_ctx");
-  MADE_REQUIRE(mode == MADE_PREC_FP16 || mode == MADE_PREC_SPLIT, "set_precision: unknown mode %d", mode);
+  MADE_REQUIRE(mode == MADE_PREC_FP16 || mode == MADE_PREC_SPLIT || mode == MADE_PREC_FP32, "set_precision: unknown mode %d",
+               mode);
   c->precision = mode;
   return MADE_OK;
 }
@@ -732,6 +789,20 @@ int made_encode(made_ctx* c, int modality, const void* feats, int feats_dtype, c
   const EncW& e = c->enc[modality];
   const int64_t T = B * e.L;
   MADE_REQUIRE(T < (1LL << 31), "encode: batch too large (%lld tokens); chunk the call", (long long)T);
+  if (c->precision == MADE_PREC_FP32) {
+    // fp32 CUDA-core path: the reference's arithmetic (exact_f32.cu); seq16 = fp16 cast of the fp32 output (DETR input)
+    float* ws = nullptr;
+    float* seqf = nullptr;
+    MADE_TRY(c->with_arena([&] {
+      ws = c->take<float>(exact_encode_ws_floats(B, e.L, e.din));
+      seqf = seq_f32 ? nullptr : c->take<float>(T * D);
+    }));
+    float* out32 = seq_f32 ? seq_f32 : seqf;
+    MADE_TRY(exact_encode(c->xenc[modality], feats, feats_dtype, masks, B, ws, out32, pooled, st));
+    cast_f32_op_kernel<<<static_cast<unsigned>(ceil_div64(T * D, 256)), 256, 0, st>>>(out32, static_cast<op_t*>(seq16), T * D);
+    MADE_CHECK_LAUNCH();
+    return MADE_OK;
+  }
   const bool sp = c->precision == MADE_PREC_SPLIT;
   int32_t* idx = nullptr;
   op_t* x0 = nullptr;
@@ -1103,6 +1174,24 @@ int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const f
   p.epi.ld_f32 = N;
   return gemm_f16_tc(static_cast<const op_t*>(A), K, static_cast<const op_t*>(W), K, N, p, 256,
                       static_cast<cudaStream_t>(stream));
+}
+
+int made_xpool_pooled(made_ctx* c, const float* video_feats, int64_t n_q, const float* seg_f32, const float* seg_masks,
+                      int64_t n_m, float* pooled, void* stream) {
+  CTX_READY(c);
+  if (n_q == 0 || n_m == 0) return MADE_OK;
+  MADE_REQUIRE(video_feats && seg_f32 && seg_masks && pooled, "xpool_pooled: null pointer");
+  MADE_REQUIRE(n_m * n_q < (1LL << 31) / 256 * 8, "xpool_pooled: %lld x %lld pairs in one call; chunk the tracks",
+               (long long)n_m, (long long)n_q);
+  float* ws = nullptr;
+  MADE_TRY(c->with_arena([&] { ws = c->take<float>(exact_xpool_ws_floats(n_q, n_m)); }));
+  return exact_xpool(c->xxp, video_feats, n_q, seg_f32, seg_masks, n_m, ws, pooled, static_cast<cudaStream_t>(stream));
+}
+
+int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,
+                       int64_t col_offset, void* stream) {
+  MADE_REQUIRE(video_feats && pooled && sim && ld >= col_offset + n_m, "pooled_cosine: bad arguments");
+  return exact_pooled_cosine(video_feats, pooled, n_q, n_m, sim, ld, col_offset, static_cast<cudaStream_t>(stream));
 }
 
 int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias,

@@ -55,6 +55,27 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
               op_t* out_hi, op_t* out_lo, int64_t ld_out, const op_t* add2, int64_t add2_ld, op_t* out2,
               int64_t ld_out2, int64_t M, const int32_t* m_dev, cudaStream_t st);
 
+// exact_f32.cu — fp32 CUDA-core path (MADE_PREC_FP32 and the materialised Transformer_XA output)
+struct ExactEncW {      // raw fp32 weights of one temporal encoder (device pointers)
+  int L = 0, din = 0;
+  const float *proj_w = nullptr, *proj_b = nullptr, *pe = nullptr, *ln1_g = nullptr, *ln1_b = nullptr, *in_w = nullptr,
+              *in_b = nullptr, *out_w = nullptr, *out_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *ff1_w = nullptr,
+              *ff1_b = nullptr, *ff2_w = nullptr, *ff2_b = nullptr, *fin_w = nullptr, *fin_b = nullptr;
+};
+struct ExactXpW {       // raw fp32 weights of Transformer_XA
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr,
+              *q_w = nullptr, *q_b = nullptr, *k_w = nullptr, *k_b = nullptr, *v_w = nullptr, *v_b = nullptr, *o_w = nullptr,
+              *o_b = nullptr, *l_w = nullptr, *l_b = nullptr;
+};
+size_t exact_encode_ws_floats(int64_t B, int L, int din);
+int exact_encode(const ExactEncW& w, const void* feats, int feats_dtype, const float* masks, int64_t B, float* ws,
+                 float* seq_f32, float* pooled, cudaStream_t st);
+size_t exact_xpool_ws_floats(int64_t n_q, int64_t n_m);
+int exact_xpool(const ExactXpW& w, const float* video, int64_t n_q, const float* seg, const float* seg_mask, int64_t n_m,
+                float* ws, float* pooled, cudaStream_t st);
+int exact_pooled_cosine(const float* video, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,
+                        int64_t col0, cudaStream_t st);
+
 // xpool.cu
 struct XpoolConsts {    // folded X-Pool constants of one checkpoint (per made_ctx)
   float bias[256];      // b' = (I + Wl) beta2 + bl

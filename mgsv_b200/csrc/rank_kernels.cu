@@ -8,6 +8,11 @@
 //   2. rank = number of DISTINCT music ids whose best column beats s* (strictly) — a column counts
 //      iff s > s* and no earlier column of the same id also has s > s* (prev_same chain),
 //   3. exact top-k, score descending, ties broken by the lower column index.
+// Tie rule (documented difference): the reference orders by np.argsort(sim)[:, ::-1] — an unstable sort, reversed —
+// so among EXACTLY equal float64 scores its order is implementation-defined (in practice the higher column first,
+// and an id tied with the ground truth may be counted ahead of it).  Here ties go to the lower column and only
+// strictly greater scores count for the rank.  Exact float64 ties need identical columns (a repeated track — which
+// dedup merges into one id anyway) or saturated scores; tests compare indices modulo exactly tied scores.
 //
 // Staged kernel (rows up to 49 152 columns): the row is read ONCE from HBM and kept in shared memory
 // as order-preserving 32-bit keys of fl32(single + dual).  Rounding is monotone, so a column that
@@ -32,7 +37,10 @@ constexpr int kValueBins = 1 << kValueBinBits;   // value-histogram bins of the 
 constexpr int kMaxCand = 512;                    // candidates the staged path orders (>= kMaxK + kCandSlack)
 constexpr int kCandSlack = 32;                   // refine the threshold while more than k + 32 keys pass it
 
+// NaN scores (an all-zero pooled row divides 0 by 0, exactly as the reference does) order BELOW every number:
+// key 0, so they never enter a top-k ahead of a real score and never count as beating the ground truth.
 __device__ __forceinline__ unsigned long long f64_key(double x) {
+  if (x != x) return 0ull;
   unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
@@ -41,6 +49,7 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
   return __longlong_as_double(static_cast<long long>(b));
 }
 __device__ __forceinline__ unsigned int f32_key(float x) {
+  if (x != x) return 0u;
   const unsigned int b = __float_as_uint(x);
   return (b >> 31) ? ~b : (b | 0x80000000u);
 }
@@ -657,7 +666,9 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
   MADE_REQUIRE(a && b && out && d > 0 && ld >= m, "cosine_sim: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int64_t m_tc = 0;
-  if (d == 256 && m >= 256 && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+  // One arithmetic for every gallery width: narrow calls (a last score chunk, the paired-track scores of the gallery
+  // index) must give the bits of the wide call, so the route depends on alignment only, never on m.
+  if (d == 256 && gemm_tma_store_enabled() && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     // tcgen05 route: every column when outputs leave through TMA stores (the last 256-wide tile reads
     // zero rows past the gallery and its store is clipped at column m), else the whole tiles only
     m_tc = gemm_tma_store_enabled() ? m : (m / 256) * 256;

@@ -15,14 +15,15 @@ from . import _lib
 from . import config as cfg
 
 
-PRECISIONS = {"fp16": _lib.PREC_FP16, "split": _lib.PREC_SPLIT}
+PRECISIONS = {"fp16": _lib.PREC_FP16, "split": _lib.PREC_SPLIT, "fp32": _lib.PREC_FP32}
 
 
 class Engine:
     def __init__(self, device: Optional[torch.device] = None, precision: Optional[str] = None):
         """precision: "split" (default; fp16 (hi, lo) operand pairs where the similarity error is made —
-        meets the 1e-3 bar on the full job) or "fp16" (single fp16 operands everywhere, fastest).
-        MADE_PRECISION overrides the default."""
+        meets the 1e-3 bar on the full job), "fp16" (single fp16 operands everywhere, fastest) or "fp32" (the
+        temporal encoders and X-Pool on the CUDA cores in the reference's fp32 arithmetic: the 1e-5 mode, ~50x
+        slower).  MADE_PRECISION overrides the default."""
         _lib.require_cuda()
         precision = precision or os.environ.get("MADE_PRECISION", "split")
         if precision not in PRECISIONS:
@@ -208,6 +209,28 @@ class Engine:
         _lib.check(self._lib.made_query_prepare(self._h, _lib.ptr(vf), N, _lib.ptr(q), _lib.ptr(vhat),
                                                 _lib.stream_ptr()))
         return q, vhat
+
+    def xpool_pooled(self, video_feats: torch.Tensor, segment_feats: torch.Tensor, segment_masks: torch.Tensor,
+                     out: Optional[torch.Tensor] = None, track_chunk: Optional[int] = None) -> torch.Tensor:
+        """Transformer_XA.forward MATERIALISED (modules/transformer.py:156-180): video_feats [N_v,256],
+        segment_feats [N_m,96,256], segment_masks [N_m,96] → [N_m, N_v, 256] fp32, in the reference's fp32
+        arithmetic on the CUDA cores.  The scoring path never forms this tensor (`xpool_score`); this is for callers
+        that want it and for the fp32 precision mode.  Tracks are processed `track_chunk` at a time (default:
+        ~256 MB of scratch)."""
+        dev = self.device
+        vf = video_feats.to(dev, torch.float32).contiguous()
+        sf = segment_feats.to(dev, torch.float32).contiguous()
+        sm = segment_masks.to(dev, torch.float32).contiguous()
+        n_q, n_m = vf.shape[0], sf.shape[0]
+        if out is None:
+            out = torch.empty((n_m, n_q, cfg.D_MODEL), dtype=torch.float32, device=dev)
+        if track_chunk is None:
+            track_chunk = max(1, min(n_m, (256 << 20) // max(1, n_q * 2432)))
+        for s in range(0, n_m, track_chunk):
+            e = min(n_m, s + track_chunk)
+            _lib.check(self._lib.made_xpool_pooled(self._h, _lib.ptr(vf), n_q, _lib.ptr(sf[s:e]), _lib.ptr(sm[s:e]), e - s,
+                                                   _lib.ptr(out[s:e]), _lib.stream_ptr()))
+        return out
 
     def xpool_score(self, q, vhat, kz, gram, bits, out: Optional[torch.Tensor] = None, col_offset: int = 0):
         n_q, n_m = q.shape[0], bits.shape[0]

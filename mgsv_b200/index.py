@@ -32,7 +32,7 @@ class GalleryIndex:
     def __init__(self, ev: GalleryEvaluator, capacity: int, score_chunk: int = 8192, col_offset: int = 0):
         """capacity: tracks this shard will hold; col_offset: global column of local track 0."""
         self.ev, self.eng, self.dev = ev, ev.eng, ev.dev
-        self.capacity, self.score_chunk, self.col_offset = int(capacity), int(score_chunk), int(col_offset)
+        self.capacity, self.score_chunk, self.col_offset = int(capacity), (int(score_chunk) + 3) // 4 * 4, int(col_offset)
         self.gal = ev.new_gallery(self.capacity)
         self.gal["mask"] = torch.zeros((self.capacity, cfg.L_M), dtype=torch.float32, device=self.dev)
         self.n = 0
@@ -78,12 +78,14 @@ class GalleryIndex:
         if qprep is None:
             qprep = self.eng.query_prepare(video_feats)
         q, vhat = qprep
+        # 16-byte aligned rows whatever the group size: the cosine then takes the same (tcgen05) route as the main pass
+        dual_buf = torch.empty((pair_chunk, (pair_chunk + 3) // 4 * 4), dtype=torch.float32, device=self.dev)
         for s in range(0, mine.numel(), pair_chunk):
             qi = mine[s:s + pair_chunk]
             sub = self._subgallery(loc[qi])
             single = self.eng.xpool_score(q[qi].contiguous(), vhat[qi].contiguous(), sub["kz"], sub["gram"], sub["bits"])
-            dual = ops.cal_distance(video_feats[qi].contiguous(), sub["pooled"])
-            out[qi] = single.diagonal().double() + dual.diagonal().double()
+            dual = ops.cal_distance(video_feats[qi].contiguous(), sub["pooled"], out=dual_buf[:qi.numel()])
+            out[qi] = single.diagonal().double() + dual[:, :qi.numel()].diagonal().double()
         return out
 
     @torch.no_grad()
@@ -95,7 +97,7 @@ class GalleryIndex:
             qprep = self.eng.query_prepare(video_feats)
         q, vhat = qprep
         L, g, C = cfg.L_M, self.gal, self.score_chunk
-        single = torch.empty((n_q, min(C, max(self.n, 1))), dtype=torch.float32, device=self.dev)
+        single = torch.empty((n_q, min(C, (max(self.n, 1) + 3) // 4 * 4)), dtype=torch.float32, device=self.dev)
         dual = torch.empty_like(single)
         run_i = run_s = None
         count = torch.zeros(n_q, dtype=torch.int32, device=self.dev) if gt_score is not None else None

@@ -34,6 +34,22 @@ def retrieval_loss(dual, single, logit_scale: float):
     return out[0]
 
 
+def clip_loss(sims, logit_scale: float):
+    """CLIPLoss (modules/loss.py:5-24): symmetric cross entropy of sims * exp(logit_scale) with diagonal labels,
+    forward value only.  CLIPLoss and InfoNCELoss (audio_id=None) are the same formula, and made_retrieval_loss
+    returns their sum over its two arguments: L(s) = (L(s) + L(s)) / 2, exact in floating point."""
+    s = sims.to(torch.float32)
+    if s.stride(1) != 1:
+        s = s.contiguous()
+    return retrieval_loss(s, s, logit_scale) * 0.5
+
+
+def info_nce_loss(sims, logit_scale: float):
+    """InfoNCELoss (modules/loss.py:66-123, the audio_id=None path) → (loss, logits_per_video, logits_per_audio)."""
+    logits = sims * float(torch.tensor(float(logit_scale)).exp())
+    return clip_loss(sims, logit_scale), logits, logits.t()
+
+
 def eval_losses(model, output_map, single, dual, spans_target):
     """→ loss_map with the reference's keys: retrieval_loss, localization_loss,
     localization_loss_dict (30 entries: 5 names x (final + 5 aux suffixes))."""

@@ -69,6 +69,30 @@ def Recall_metrics(sim_single: torch.Tensor, sim_dual: Optional[torch.Tensor] = 
     return summarize_ranks(ind), ind, results
 
 
+def Recall_metrics_matrix(sim_matrix, distance_type: str = "COS", dedup: bool = False, all_music_ids_list=None):
+    """utils/util_test.py:32-97 with the reference's own signature: `sim_matrix` is the [val_len, val_len] host
+    matrix test-MaDe.py:403 builds (float64 numpy = f64(single) + f64(dual); float32 numpy or a tensor work too).
+    The matrix is moved to the current CUDA device as an (fp32 hi, fp32 lo) pair whose float64 sum the rank kernel
+    forms — exact for float32 input, and within 2^-48 relative of a float64 entry (far below the spacing of any two
+    scores that differ at all in their float32 parts), so the ordering is the reference's argsort ordering up to
+    exact ties.  Returns (metrics, ind, ret_results_list) like the reference; `dedup=False` ranks by column."""
+    if isinstance(sim_matrix, torch.Tensor):
+        x = sim_matrix.detach()
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(sim_matrix))
+    if x.dim() != 2:
+        raise ValueError("sim_matrix must be [val_len, val_len]")
+    x = ops._to_cuda(x)
+    if x.dtype == torch.float64:
+        hi = x.to(torch.float32)
+        lo = (x - hi.to(torch.float64)).to(torch.float32)
+    else:
+        hi, lo = x.to(torch.float32).contiguous(), None
+    ids = all_music_ids_list if (all_music_ids_list is not None and len(all_music_ids_list) > 0) else None
+    return Recall_metrics(hi.contiguous(), None if lo is None else lo.contiguous(), distance_type,
+                          dedup=bool(dedup and ids is not None), all_music_ids_list=ids)
+
+
 def _f32(values) -> np.ndarray:
     if isinstance(values, torch.Tensor):
         return values.detach().to("cpu", torch.float32).numpy().reshape(-1)

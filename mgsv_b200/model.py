@@ -9,6 +9,7 @@ behave; the engine repacks them (fp16 operands, folded X-Pool/decoder weights) w
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -60,9 +61,20 @@ class _XPoolView(_Node):
         object.__setattr__(self, "_owner", owner)
 
     def forward(self, video_embeds, music_embeds, music_mask=None):
+        """Transformer_XA.forward (modules/transformer.py:156-180): video_embeds [N_v,256], music_embeds
+        [N_m,96,256] (the encoded segments), music_mask [N_m,96] → the MATERIALISED [N_m,N_v,256] fp32 tensor, on the
+        model's CUDA device, computed in the reference's fp32 arithmetic (`made_xpool_pooled`).  Inputs may live on
+        the CPU (test-MaDe.py:386-394 gathers them there); they are moved.  Above MADE_POOLED_CAP_GB (default 32 GiB
+        of output) this raises and points at `score_gallery`, which never forms the tensor."""
         return self._owner._xpool_pooled(video_embeds, music_embeds, music_mask)
 
-    def cpu(self):  # the reference moves this module to the CPU for gallery scoring; stay put
+    # test-MaDe.py:392/395 moves this sub-module to the CPU and back around the gallery stage.  The view computes on
+    # the model's CUDA device whatever the location of the fp32 master parameters, so moving is accepted and is a
+    # deliberate no-op (the parameters stay registered where the model holds them; state_dict is unchanged).
+    def cpu(self):
+        return self
+
+    def cuda(self, device=None):
         return self
 
     def to(self, *a, **k):
@@ -164,10 +176,21 @@ class Uni_model(nn.Module):
         return single, dual
 
     def _xpool_pooled(self, video_embeds, music_embeds, music_mask):
-        raise RuntimeError(
-            "made_b200 never materialises the [N_m, N_v, 256] pooled tensor; call "
-            "model.score_gallery(video_feats, music_feats, segment_feats, segment_masks) "
-            "(see INTEGRATION.md for the 3-line change to test-MaDe.py:392-403)")
+        if music_mask is None:
+            raise ValueError("Error: fusion_mask=0 (unmasked X-Pool) is not supported by made_b200 (shipped: fusion_mask=1)")
+        if video_embeds.dim() != 2 or music_embeds.dim() != 3 or music_embeds.shape[1:] != (cfg.L_M, cfg.D_MODEL) \
+                or video_embeds.shape[1] != cfg.D_MODEL or tuple(music_mask.shape) != tuple(music_embeds.shape[:2]):
+            raise ValueError(f"expected video_embeds [N_v,{cfg.D_MODEL}], music_embeds [N_m,{cfg.L_M},{cfg.D_MODEL}], "
+                             f"music_mask [N_m,{cfg.L_M}]; got {tuple(video_embeds.shape)}, {tuple(music_embeds.shape)}, "
+                             f"{tuple(music_mask.shape)}")
+        n_m, n_v = music_embeds.shape[0], video_embeds.shape[0]
+        cap = float(os.environ.get("MADE_POOLED_CAP_GB", "32")) * (1 << 30)
+        if n_m * n_v * cfg.D_MODEL * 4 > cap:
+            raise RuntimeError(
+                f"the materialised pooled tensor [{n_m}, {n_v}, 256] fp32 is {n_m * n_v * 1024 / 2**30:.1f} GiB "
+                f"(cap MADE_POOLED_CAP_GB = {cap / 2**30:.0f}); call model.score_gallery(video_feats, music_feats, "
+                "segment_feats, segment_masks), which scores the gallery without forming it (INTEGRATION.md)")
+        return self.engine().xpool_pooled(video_embeds, music_embeds, music_mask)
 
     # -- forward ---------------------------------------------------------------------------------
     @torch.no_grad()

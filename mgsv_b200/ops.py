@@ -17,6 +17,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).contiguous()
 
 
+def _default_device() -> torch.device:
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _to_cuda(t: torch.Tensor) -> torch.Tensor:
     """Host tensors handed to a reference-named free function: moved to the current CUDA device (there is
     no CPU path; without a device this raises)."""
@@ -64,7 +69,7 @@ def detr_iou(args, mr_results_list, device=None) -> List[torch.Tensor]:
     reference's list of 0-d tensors (on the host)."""
     if not mr_results_list:
         return []
-    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device) if device is not None else _default_device()
     st = torch.tensor([float(d["ranked_preds"][0][0]) for d in mr_results_list], dtype=torch.float32)
     ed = torch.tensor([float(d["ranked_preds"][0][1]) for d in mr_results_list], dtype=torch.float32)
     gt = torch.stack([torch.as_tensor(d["gt_moment"], dtype=torch.float32).reshape(-1, 2)[0] for d in mr_results_list])
@@ -211,6 +216,27 @@ def cal_distance(x, y, distance_type: str = "COS", out: Optional[torch.Tensor] =
     _lib.check(_lib.load().made_cosine_sim(_lib.ptr(x), x.shape[0], _lib.ptr(y), y.shape[0], x.shape[1],
                                            out.data_ptr() + 4 * col_offset, out.stride(0), _lib.stream_ptr()))
     return out.cpu().numpy().astype(np.float64) if as_numpy else out
+
+
+def sim_matrix_music_pooling(video_embeds: torch.Tensor, music_embeds_pooled: torch.Tensor,
+                             out: Optional[torch.Tensor] = None, col_offset: int = 0) -> torch.Tensor:
+    """modules/metrics.py:10-24 on a MATERIALISED pooled tensor: video_embeds [N_v,256], music_embeds_pooled
+    [N_m, N_v, 256] → sims [N_v, N_m] fp32 (row-wise cosine of every video with its conditioned pooled music
+    embedding).  Tensors are moved to the current CUDA device; the fused scoring path (`Engine.xpool_score`) never
+    needs this function."""
+    v = _f32c(_to_cuda(video_embeds))
+    p = _f32c(_to_cuda(music_embeds_pooled))
+    if p.dim() != 3 or p.shape[1] != v.shape[0] or p.shape[2] != v.shape[1]:
+        raise ValueError(f"expected pooled [N_m, {v.shape[0]}, {v.shape[1]}], got {tuple(p.shape)}")
+    if v.shape[1] != 256:
+        raise ValueError("sim_matrix_music_pooling: made_b200 is built for 256-d embeddings")
+    n_q, n_m = v.shape[0], p.shape[0]
+    if out is None:
+        out = torch.empty((n_q, n_m), dtype=torch.float32, device=v.device)
+        col_offset = 0
+    _lib.check(_lib.load().made_pooled_cosine(_lib.ptr(v), _lib.ptr(p), n_q, n_m, _lib.ptr(out), out.stride(0), col_offset,
+                                              _lib.stream_ptr()))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
