@@ -556,6 +556,10 @@ def test_cfg1_whole_job_vs_reference_fixture(dev, engine, golden_dir, sd_fp32):
         near = int((np.abs(ref_tot[r] - ref_tot[r, gt_cols[r]]) < tol).sum()) - 1
         assert diff[r] <= near, (r, diff[r], near)
     assert (diff <= 3).all() and (diff != 0).mean() < 0.15, (diff.max(), (diff != 0).mean())
+    print(f"[parity] cfg1 vs reference fixture: max|d| IoU {np.abs(out['iou'].cpu().numpy() - gold['iou']).max():.2e}, "
+          f"pred_st {np.abs(out['pred_st'].cpu().numpy() - gold['pred_st']).max():.2e} s, "
+          f"pred_ed {np.abs(out['pred_ed'].cpu().numpy() - gold['pred_ed']).max():.2e} s, "
+          f"score {np.abs(out['score'].cpu().numpy() - gold['pred_score']).max():.2e}")
     np.testing.assert_allclose(out["iou"].cpu().numpy(), gold["iou"], atol=4e-3)
     np.testing.assert_allclose(out["pred_st"].cpu().numpy(), gold["pred_st"], atol=0.1)      # seconds, of 240
     np.testing.assert_allclose(out["pred_ed"].cpu().numpy(), gold["pred_ed"], atol=0.1)
