@@ -210,12 +210,16 @@ int made_xpool_score(made_ctx* ctx, const void* q, const float* vhat, int64_t n_
                      float* sim, int64_t ld, int64_t col_offset, void* stream);
 
 /* Transformer_XA.forward MATERIALISED (modules/transformer.py:156-180), fp32 CUDA-core arithmetic:
- * video_feats [N_v,256], seg_f32 [N_m,96,256] fp32, seg_masks [N_m,96] -> pooled [N_m, N_v, 256] fp32.
+ * which = MADE_MUSIC: model.video_guided_to_music_pooling_cross_transformer — video_feats [N_v,256] (the guides),
+ *         seg_f32 [N_m,96,256] fp32, seg_masks [N_m,96] -> pooled [N_m, N_v, 256] fp32;
+ * which = MADE_VIDEO: model.music_guided_to_video_pooling_cross_transformer (vmr_fusion "XA-music-video",
+ *         model_Uni.py:24-28,203-204) — guides = music_feats [N_m,256] passed as `video_feats`, keys = frame features
+ *         [N_v,50,256] + masks [N_v,50] passed as `seg_f32` / `seg_masks` -> pooled [N_v, N_m, 256].
  * The product path (made_xpool_score) never forms this tensor; this entry exists for callers that want it (the
  * compat view of model.video_guided_to_music_pooling_cross_transformer) and for the fp32 precision mode.
  * Chunk the tracks: scratch is N_m * N_v * 2.4 KB. */
-int made_xpool_pooled(made_ctx* ctx, const float* video_feats, int64_t n_q, const float* seg_f32, const float* seg_masks,
-                      int64_t n_m, float* pooled, void* stream);
+int made_xpool_pooled(made_ctx* ctx, int which, const float* video_feats, int64_t n_q, const float* seg_f32,
+                      const float* seg_masks, int64_t n_m, float* pooled, void* stream);
 /* sim_matrix_music_pooling (modules/metrics.py:10-24) on a materialised pooled tensor:
  * sim[v, col_offset + m] = < video[v]/|video[v]|, pooled[m,v]/|pooled[m,v]| >, fp32, sim row stride ld. */
 int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,

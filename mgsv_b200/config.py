@@ -76,6 +76,11 @@ def default_args(**overrides) -> argparse.Namespace:
     return argparse.Namespace(**d)
 
 
+# flag values accepted beside the shipped one: vmr_fusion "XA-music-video" adds a second Transformer_XA whose output the
+# shipped vmr_loss never reads (model_Uni.py:203-204, 254-262), so the compute graph that produces outputs is unchanged
+_ALSO = {"vmr_fusion": ("XA-music-video",)}
+
+
 def check_args(args) -> None:
     """Raise ValueError unless `args` selects the shipped compute graph."""
     for k in _STRICT:
@@ -84,7 +89,7 @@ def check_args(args) -> None:
         got, want = getattr(args, k), SHIPPED[k]
         same = (float(got) == float(want)) if isinstance(want, (int, float)) and not isinstance(want, bool) \
             and isinstance(got, (int, float)) else (got == want)
-        if not same:
+        if not same and got not in _ALSO.get(k, ()):
             raise ValueError(
                 f"Error: args.{k}={got!r} is not supported by made_b200 "
                 f"(only the shipped MaDe config is built: {k}={want!r})")

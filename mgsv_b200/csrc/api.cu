@@ -67,7 +67,9 @@ struct made_ctx {
   bool ws_dry = false;          // sizing pass of with_arena(): take() only advances the offset
   int precision = MADE_PREC_SPLIT;
   ExactEncW xenc[2];            // raw fp32 weights for the fp32 CUDA-core path (exact_f32.cu)
-  ExactXpW xxp;
+  ExactXpW xxp;                 // video_guided_to_music_pooling_cross_transformer (keys = 96 segments)
+  ExactXpW xxp_video;           // music_guided_to_video_pooling_cross_transformer (vmr_fusion "XA-music-video"; keys = 50 frames)
+  bool has_xp_video = false;
   XpoolConsts xp_consts;        // folded X-Pool constants of THIS context's checkpoint
   float* xp_c5 = nullptr;       // [5][256] weight vectors of the W5 columns (device)
 
@@ -252,23 +254,29 @@ int load_exact(made_ctx* c) {
     MADE_TRY(up_key(c, tr + ".final_linear.weight", D * D, &w.fin_w));
     MADE_TRY(up_key(c, tr + ".final_linear.bias", D, &w.fin_b));
   }
-  const std::string x = "video_guided_to_music_pooling_cross_transformer";
-  ExactXpW& w = c->xxp;
-  w.ln1_g = c->xp_ln1.g; w.ln1_b = c->xp_ln1.b;
-  MADE_TRY(up_key(c, x + ".layer_norm2.weight", D, &w.ln2_g));
-  MADE_TRY(up_key(c, x + ".layer_norm2.bias", D, &w.ln2_b));
-  MADE_TRY(up_key(c, x + ".layer_norm3.weight", D, &w.ln3_g));
-  MADE_TRY(up_key(c, x + ".layer_norm3.bias", D, &w.ln3_b));
-  MADE_TRY(up_key(c, x + ".cross_attn.q_proj.weight", D * D, &w.q_w));
-  MADE_TRY(up_key(c, x + ".cross_attn.q_proj.bias", D, &w.q_b));
-  MADE_TRY(up_key(c, x + ".cross_attn.k_proj.weight", D * D, &w.k_w));
-  MADE_TRY(up_key(c, x + ".cross_attn.k_proj.bias", D, &w.k_b));
-  MADE_TRY(up_key(c, x + ".cross_attn.v_proj.weight", D * D, &w.v_w));
-  MADE_TRY(up_key(c, x + ".cross_attn.v_proj.bias", D, &w.v_b));
-  MADE_TRY(up_key(c, x + ".cross_attn.out_proj.weight", D * D, &w.o_w));
-  MADE_TRY(up_key(c, x + ".cross_attn.out_proj.bias", D, &w.o_b));
-  MADE_TRY(up_key(c, x + ".linear_proj.weight", D * D, &w.l_w));
-  MADE_TRY(up_key(c, x + ".linear_proj.bias", D, &w.l_b));
+  auto load_xa = [&](const std::string& x, ExactXpW& w) -> int {
+    MADE_TRY(up_key(c, x + ".layer_norm1.weight", D, &w.ln1_g));
+    MADE_TRY(up_key(c, x + ".layer_norm1.bias", D, &w.ln1_b));
+    MADE_TRY(up_key(c, x + ".layer_norm2.weight", D, &w.ln2_g));
+    MADE_TRY(up_key(c, x + ".layer_norm2.bias", D, &w.ln2_b));
+    MADE_TRY(up_key(c, x + ".layer_norm3.weight", D, &w.ln3_g));
+    MADE_TRY(up_key(c, x + ".layer_norm3.bias", D, &w.ln3_b));
+    MADE_TRY(up_key(c, x + ".cross_attn.q_proj.weight", D * D, &w.q_w));
+    MADE_TRY(up_key(c, x + ".cross_attn.q_proj.bias", D, &w.q_b));
+    MADE_TRY(up_key(c, x + ".cross_attn.k_proj.weight", D * D, &w.k_w));
+    MADE_TRY(up_key(c, x + ".cross_attn.k_proj.bias", D, &w.k_b));
+    MADE_TRY(up_key(c, x + ".cross_attn.v_proj.weight", D * D, &w.v_w));
+    MADE_TRY(up_key(c, x + ".cross_attn.v_proj.bias", D, &w.v_b));
+    MADE_TRY(up_key(c, x + ".cross_attn.out_proj.weight", D * D, &w.o_w));
+    MADE_TRY(up_key(c, x + ".cross_attn.out_proj.bias", D, &w.o_b));
+    MADE_TRY(up_key(c, x + ".linear_proj.weight", D * D, &w.l_w));
+    MADE_TRY(up_key(c, x + ".linear_proj.bias", D, &w.l_b));
+    return MADE_OK;
+  };
+  MADE_TRY(load_xa("video_guided_to_music_pooling_cross_transformer", c->xxp));
+  // the second X-Pool module exists only in checkpoints trained with vmr_fusion "XA-music-video" (model_Uni.py:24-28)
+  c->has_xp_video = c->host.count("music_guided_to_video_pooling_cross_transformer.linear_proj.weight") != 0;
+  if (c->has_xp_video) MADE_TRY(load_xa("music_guided_to_video_pooling_cross_transformer", c->xxp_video));
   return MADE_OK;
 }
 
@@ -1176,16 +1184,22 @@ int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const f
                       static_cast<cudaStream_t>(stream));
 }
 
-int made_xpool_pooled(made_ctx* c, const float* video_feats, int64_t n_q, const float* seg_f32, const float* seg_masks,
-                      int64_t n_m, float* pooled, void* stream) {
+int made_xpool_pooled(made_ctx* c, int which, const float* video_feats, int64_t n_q, const float* seg_f32,
+                      const float* seg_masks, int64_t n_m, float* pooled, void* stream) {
   CTX_READY(c);
+  MADE_REQUIRE(which == MADE_VIDEO || which == MADE_MUSIC, "xpool_pooled: which must be MADE_MUSIC (video-guided pooling of "
+               "music segments) or MADE_VIDEO (music-guided pooling of video frames)");
+  MADE_REQUIRE(which == MADE_MUSIC || c->has_xp_video, "xpool_pooled: the loaded checkpoint has no "
+               "music_guided_to_video_pooling_cross_transformer (vmr_fusion 'XA-music-video')");
   if (n_q == 0 || n_m == 0) return MADE_OK;
   MADE_REQUIRE(video_feats && seg_f32 && seg_masks && pooled, "xpool_pooled: null pointer");
+  const int Lk = which == MADE_MUSIC ? LM : LV;
   MADE_REQUIRE(n_m * n_q < (1LL << 31) / 256 * 8, "xpool_pooled: %lld x %lld pairs in one call; chunk the tracks",
                (long long)n_m, (long long)n_q);
   float* ws = nullptr;
-  MADE_TRY(c->with_arena([&] { ws = c->take<float>(exact_xpool_ws_floats(n_q, n_m)); }));
-  return exact_xpool(c->xxp, video_feats, n_q, seg_f32, seg_masks, n_m, ws, pooled, static_cast<cudaStream_t>(stream));
+  MADE_TRY(c->with_arena([&] { ws = c->take<float>(exact_xpool_ws_floats(n_q, n_m, Lk)); }));
+  return exact_xpool(which == MADE_MUSIC ? c->xxp : c->xxp_video, video_feats, n_q, seg_f32, seg_masks, n_m, Lk, ws, pooled,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,

@@ -210,8 +210,9 @@ pool_f32_kernel(float* __restrict__ seq, const float* __restrict__ mask, int L, 
   pooled[b * 256 + d] = v / fmaxf(sqrtf(tot), 1e-12f);
 }
 
-// rows of 96 logits per (track, query): masked softmax in place.  logits [n_tracks * n_q, 96], mask [n_tracks, 96]
-__global__ void softmax96_kernel(float* __restrict__ logits, const float* __restrict__ mask, int64_t n_q, int64_t rows) {
+// rows of L <= 96 logits per (key sequence, query): masked softmax in place.  logits [n_seq * n_q, L], mask [n_seq, L]
+__global__ void softmax_keys_kernel(float* __restrict__ logits, const float* __restrict__ mask, int64_t n_q, int64_t rows,
+                                    int L) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -221,7 +222,7 @@ __global__ void softmax96_kernel(float* __restrict__ logits, const float* __rest
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const int t = lane + 32 * j;
-    v[j] = mask[m * 96 + t] != 0.f ? logits[row * 96 + t] : -INFINITY;
+    v[j] = (t < L && mask[m * L + t] != 0.f) ? logits[row * L + t] : -INFINITY;
     mx = fmaxf(mx, v[j]);
   }
   mx = warp_max(mx);
@@ -230,7 +231,8 @@ __global__ void softmax96_kernel(float* __restrict__ logits, const float* __rest
   for (int j = 0; j < 3; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
   s = warp_sum(s);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) logits[row * 96 + lane + 32 * j] = v[j] / s;
+  for (int j = 0; j < 3; ++j)
+    if (lane + 32 * j < L) logits[row * L + lane + 32 * j] = v[j] / s;
 }
 
 // sim[v, col0 + m] = < video[v] / |video[v]|, pooled[m, v] / |pooled[m, v]| >   (modules/metrics.py:19-23); warp per pair
@@ -314,37 +316,38 @@ size_t exact_encode_ws_floats(int64_t B, int L, int din) {
   return T * (static_cast<size_t>(din) + 256 + 768 + 256 + 256 + 1024 + 256);
 }
 
-// Transformer_XA.forward (modules/transformer.py:156-180) materialised: pooled [n_m, n_q, 256].
-// ws: n_q*512 + n_m*96*768 + n_m*n_q*(96 + 256 + 256) floats.
+// Transformer_XA.forward (modules/transformer.py:156-180) materialised: pooled [n_m, n_q, 256] for n_m key sequences
+// of L <= 96 tokens (L = 96 music segments for the video-guided module, 50 frames for the music-guided one).
+// ws: n_q*512 + n_m*L*768 + n_m*n_q*(L + 256 + 256) floats.
 int exact_xpool(const ExactXpW& w, const float* video, int64_t n_q, const float* seg, const float* seg_mask, int64_t n_m,
-                float* ws, float* pooled, cudaStream_t st) {
+                int L, float* ws, float* pooled, cudaStream_t st) {
   float* vln = ws;                          // [n_q, 256]
   float* q = vln + n_q * 256;               // [n_q, 256]
   float* sln = q + n_q * 256;               // [n_m*96, 256]
-  float* kk = sln + n_m * 96 * 256;         // [n_m*96, 256]
-  float* vv = kk + n_m * 96 * 256;          // [n_m*96, 256]
-  float* logit = vv + n_m * 96 * 256;       // [n_m, n_q, 96]
-  float* att = logit + n_m * n_q * 96;      // [n_m, n_q, 256]
+  float* kk = sln + n_m * L * 256;         // [n_m*96, 256]
+  float* vv = kk + n_m * L * 256;          // [n_m*96, 256]
+  float* logit = vv + n_m * L * 256;       // [n_m, n_q, 96]
+  float* att = logit + n_m * n_q * L;      // [n_m, n_q, 256]
   float* o = att + n_m * n_q * 256;         // [n_m, n_q, 256]
   const int NQ = static_cast<int>(n_q);
   const int64_t R = n_m * n_q;
   MADE_TRY(layernorm_rows(video, 0, 256, n_q, w.ln1_g, w.ln1_b, nullptr, 256, nullptr, vln, st));
-  MADE_TRY(layernorm_rows(seg, 0, 256, n_m * 96, w.ln1_g, w.ln1_b, nullptr, 256, nullptr, sln, st));
+  MADE_TRY(layernorm_rows(seg, 0, 256, n_m * L, w.ln1_g, w.ln1_b, nullptr, 256, nullptr, sln, st));
   MADE_TRY(sgemm(linear_p(vln, 256, w.q_w, w.q_b, q, 256, NQ, 256, 256), 1, st));
-  MADE_TRY(sgemm(linear_p(sln, 256, w.k_w, w.k_b, kk, 256, static_cast<int>(n_m * 96), 256, 256), 1, st));
-  MADE_TRY(sgemm(linear_p(sln, 256, w.v_w, w.v_b, vv, 256, static_cast<int>(n_m * 96), 256, 256), 1, st));
+  MADE_TRY(sgemm(linear_p(sln, 256, w.k_w, w.k_b, kk, 256, static_cast<int>(n_m * L), 256, 256), 1, st));
+  MADE_TRY(sgemm(linear_p(sln, 256, w.v_w, w.v_b, vv, 256, static_cast<int>(n_m * L), 256, 256), 1, st));
   {   // logits[m] = q K_m^T / sqrt(256)   (:111)
     SgemmP p{};
-    p.A = q; p.lda = 256; p.sA = 0; p.B = kk; p.ldb = 256; p.sB = 96 * 256; p.b_nk = 1;
-    p.C = logit; p.ldc = 96; p.sC = n_q * 96; p.M = NQ; p.N = 96; p.K = 256; p.alpha = 0.0625f;
+    p.A = q; p.lda = 256; p.sA = 0; p.B = kk; p.ldb = 256; p.sB = static_cast<int64_t>(L) * 256; p.b_nk = 1;
+    p.C = logit; p.ldc = L; p.sC = n_q * L; p.M = NQ; p.N = L; p.K = 256; p.alpha = 0.0625f;
     MADE_TRY(sgemm(p, static_cast<int>(n_m), st));
   }
-  softmax96_kernel<<<static_cast<unsigned>(ceil_div64(R, 8)), 256, 0, st>>>(logit, seg_mask, n_q, R);
+  softmax_keys_kernel<<<static_cast<unsigned>(ceil_div64(R, 8)), 256, 0, st>>>(logit, seg_mask, n_q, R, L);
   MADE_CHECK_LAUNCH();
   {   // attention[m] = softmax V_m
     SgemmP p{};
-    p.A = logit; p.lda = 96; p.sA = n_q * 96; p.B = vv; p.ldb = 256; p.sB = 96 * 256; p.b_nk = 0;
-    p.C = att; p.ldc = 256; p.sC = n_q * 256; p.M = NQ; p.N = 256; p.K = 96; p.alpha = 1.f;
+    p.A = logit; p.lda = L; p.sA = n_q * L; p.B = vv; p.ldb = 256; p.sB = static_cast<int64_t>(L) * 256; p.b_nk = 0;
+    p.C = att; p.ldc = 256; p.sC = n_q * 256; p.M = NQ; p.N = 256; p.K = L; p.alpha = 1.f;
     MADE_TRY(sgemm(p, static_cast<int>(n_m), st));
   }
   MADE_TRY(sgemm(linear_p(att, 256, w.o_w, w.o_b, o, 256, static_cast<int>(R), 256, 256), 1, st));     // out_proj (:122)
@@ -358,8 +361,8 @@ int exact_xpool(const ExactXpW& w, const float* video, int64_t n_q, const float*
   return MADE_OK;
 }
 
-size_t exact_xpool_ws_floats(int64_t n_q, int64_t n_m) {
-  return static_cast<size_t>(n_q) * 512 + static_cast<size_t>(n_m) * 96 * 768 + static_cast<size_t>(n_m) * n_q * (96 + 256 + 256);
+size_t exact_xpool_ws_floats(int64_t n_q, int64_t n_m, int L) {
+  return static_cast<size_t>(n_q) * 512 + static_cast<size_t>(n_m) * L * 768 + static_cast<size_t>(n_m) * n_q * (L + 256 + 256);
 }
 
 int exact_pooled_cosine(const float* video, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,

@@ -70,9 +70,9 @@ struct ExactXpW {       // raw fp32 weights of Transformer_XA
 size_t exact_encode_ws_floats(int64_t B, int L, int din);
 int exact_encode(const ExactEncW& w, const void* feats, int feats_dtype, const float* masks, int64_t B, float* ws,
                  float* seq_f32, float* pooled, cudaStream_t st);
-size_t exact_xpool_ws_floats(int64_t n_q, int64_t n_m);
+size_t exact_xpool_ws_floats(int64_t n_q, int64_t n_m, int L);
 int exact_xpool(const ExactXpW& w, const float* video, int64_t n_q, const float* seg, const float* seg_mask, int64_t n_m,
-                float* ws, float* pooled, cudaStream_t st);
+                int L, float* ws, float* pooled, cudaStream_t st);
 int exact_pooled_cosine(const float* video, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,
                         int64_t col0, cudaStream_t st);
 

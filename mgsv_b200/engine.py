@@ -211,12 +211,15 @@ class Engine:
         return q, vhat
 
     def xpool_pooled(self, video_feats: torch.Tensor, segment_feats: torch.Tensor, segment_masks: torch.Tensor,
-                     out: Optional[torch.Tensor] = None, track_chunk: Optional[int] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, track_chunk: Optional[int] = None,
+                     which: int = _lib.MUSIC) -> torch.Tensor:
         """Transformer_XA.forward MATERIALISED (modules/transformer.py:156-180): video_feats [N_v,256],
         segment_feats [N_m,96,256], segment_masks [N_m,96] → [N_m, N_v, 256] fp32, in the reference's fp32
         arithmetic on the CUDA cores.  The scoring path never forms this tensor (`xpool_score`); this is for callers
         that want it and for the fp32 precision mode.  Tracks are processed `track_chunk` at a time (default:
-        ~256 MB of scratch)."""
+        ~256 MB of scratch).  `which=_lib.VIDEO` runs the second module of vmr_fusion "XA-music-video"
+        (model.music_guided_to_video_pooling_cross_transformer): guides = music_feats [N_m,256] in `video_feats`, keys =
+        frame features [N_v,50,256] + masks in `segment_feats` / `segment_masks` → [N_v, N_m, 256]."""
         dev = self.device
         vf = video_feats.to(dev, torch.float32).contiguous()
         sf = segment_feats.to(dev, torch.float32).contiguous()
@@ -228,7 +231,7 @@ class Engine:
             track_chunk = max(1, min(n_m, (256 << 20) // max(1, n_q * 2432)))
         for s in range(0, n_m, track_chunk):
             e = min(n_m, s + track_chunk)
-            _lib.check(self._lib.made_xpool_pooled(self._h, _lib.ptr(vf), n_q, _lib.ptr(sf[s:e]), _lib.ptr(sm[s:e]), e - s,
+            _lib.check(self._lib.made_xpool_pooled(self._h, which, _lib.ptr(vf), n_q, _lib.ptr(sf[s:e]), _lib.ptr(sm[s:e]), e - s,
                                                    _lib.ptr(out[s:e]), _lib.stream_ptr()))
         return out
 

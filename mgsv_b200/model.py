@@ -56,17 +56,19 @@ class _XPoolView(_Node):
     """`model.video_guided_to_music_pooling_cross_transformer`: parameter holder + thin
     compatibility callable (test-MaDe.py:392-395 calls it and moves it between devices)."""
 
-    def __init__(self, owner: "Uni_model"):
+    def __init__(self, owner: "Uni_model", which: int = _lib.MUSIC):
         super().__init__()
         object.__setattr__(self, "_owner", owner)
+        object.__setattr__(self, "_which", which)
 
     def forward(self, video_embeds, music_embeds, music_mask=None):
-        """Transformer_XA.forward (modules/transformer.py:156-180): video_embeds [N_v,256], music_embeds
+        """(For the second module of "XA-music-video" read: guides = music_feats, keys = frame features, [N_v,N_m,256].)
+        Transformer_XA.forward (modules/transformer.py:156-180): video_embeds [N_v,256], music_embeds
         [N_m,96,256] (the encoded segments), music_mask [N_m,96] → the MATERIALISED [N_m,N_v,256] fp32 tensor, on the
         model's CUDA device, computed in the reference's fp32 arithmetic (`made_xpool_pooled`).  Inputs may live on
         the CPU (test-MaDe.py:386-394 gathers them there); they are moved.  Above MADE_POOLED_CAP_GB (default 32 GiB
         of output) this raises and points at `score_gallery`, which never forms the tensor."""
-        return self._owner._xpool_pooled(video_embeds, music_embeds, music_mask)
+        return self._owner._xpool_pooled(video_embeds, music_embeds, music_mask, self._which)
 
     # test-MaDe.py:392/395 moves this sub-module to the CPU and back around the gallery stage.  The view computes on
     # the model's CUDA device whatever the location of the fp32 master parameters, so moving is accepted and is a
@@ -94,8 +96,11 @@ class Uni_model(nn.Module):
         # parameter tree under the reference's names
         self.add_module("video_guided_to_music_pooling_cross_transformer", _XPoolView(self))
         self.add_module("criterion", _Criterion())
+        self.xa_video = "video" in str(args.vmr_fusion)         # model_Uni.py:27-28: a second Transformer_XA
+        if self.xa_video:
+            self.add_module("music_guided_to_video_pooling_cross_transformer", _XPoolView(self, _lib.VIDEO))
         sd0 = None
-        for key, shape, kind in synth.state_dict_spec():
+        for key, shape, kind in synth.state_dict_spec() + (synth.xa_video_spec() if self.xa_video else []):
             parts = key.split(".")
             node = _ensure_path(self, parts[:-1])
             if kind in ("pe", "empty_weight"):
@@ -110,7 +115,7 @@ class Uni_model(nn.Module):
 
     # -- parameters ------------------------------------------------------------------------------
     def reset_parameters(self, seed: int = 0):
-        sd = synth.make_state_dict(seed)
+        sd = synth.make_state_dict(seed, xa_video=self.xa_video)
         with torch.no_grad():
             for k, v in self.state_dict().items():
                 v.copy_(sd[k])
@@ -142,7 +147,8 @@ class Uni_model(nn.Module):
         return self._group(("vit_proj.", "ast_proj.", "video_transformer.", "audio_transformer."))
 
     def get_matching_parameter(self):       # model_Uni.py:80-89
-        return self._group(("video_guided_to_music_pooling_cross_transformer.",)) + [self.logit_scale]
+        return self._group(("video_guided_to_music_pooling_cross_transformer.",
+                            "music_guided_to_video_pooling_cross_transformer.")) + [self.logit_scale]
 
     def get_detection_parameter(self):      # model_Uni.py:92-114
         return self._group(("detr_transformer.", "span_embed.", "class_embed.", "contrastive_align_projection_"))
@@ -175,13 +181,14 @@ class Uni_model(nn.Module):
         dual = ops.cal_distance(video_feats.to(dev), music_feats.to(dev))
         return single, dual
 
-    def _xpool_pooled(self, video_embeds, music_embeds, music_mask):
+    def _xpool_pooled(self, video_embeds, music_embeds, music_mask, which=_lib.MUSIC):
+        L_keys = cfg.L_M if which == _lib.MUSIC else cfg.L_V
         if music_mask is None:
             raise ValueError("Error: fusion_mask=0 (unmasked X-Pool) is not supported by made_b200 (shipped: fusion_mask=1)")
-        if video_embeds.dim() != 2 or music_embeds.dim() != 3 or music_embeds.shape[1:] != (cfg.L_M, cfg.D_MODEL) \
+        if video_embeds.dim() != 2 or music_embeds.dim() != 3 or music_embeds.shape[1:] != (L_keys, cfg.D_MODEL) \
                 or video_embeds.shape[1] != cfg.D_MODEL or tuple(music_mask.shape) != tuple(music_embeds.shape[:2]):
-            raise ValueError(f"expected video_embeds [N_v,{cfg.D_MODEL}], music_embeds [N_m,{cfg.L_M},{cfg.D_MODEL}], "
-                             f"music_mask [N_m,{cfg.L_M}]; got {tuple(video_embeds.shape)}, {tuple(music_embeds.shape)}, "
+            raise ValueError(f"expected video_embeds [N_v,{cfg.D_MODEL}], music_embeds [N_m,{L_keys},{cfg.D_MODEL}], "
+                             f"music_mask [N_m,{L_keys}]; got {tuple(video_embeds.shape)}, {tuple(music_embeds.shape)}, "
                              f"{tuple(music_mask.shape)}")
         n_m, n_v = music_embeds.shape[0], video_embeds.shape[0]
         cap = float(os.environ.get("MADE_POOLED_CAP_GB", "32")) * (1 << 30)
@@ -190,7 +197,7 @@ class Uni_model(nn.Module):
                 f"the materialised pooled tensor [{n_m}, {n_v}, 256] fp32 is {n_m * n_v * 1024 / 2**30:.1f} GiB "
                 f"(cap MADE_POOLED_CAP_GB = {cap / 2**30:.0f}); call model.score_gallery(video_feats, music_feats, "
                 "segment_feats, segment_masks), which scores the gallery without forming it (INTEGRATION.md)")
-        return self.engine().xpool_pooled(video_embeds, music_embeds, music_mask)
+        return self.engine().xpool_pooled(video_embeds, music_embeds, music_mask, which=which)
 
     # -- forward ---------------------------------------------------------------------------------
     @torch.no_grad()

@@ -239,6 +239,13 @@ def sim_matrix_music_pooling(video_embeds: torch.Tensor, music_embeds_pooled: to
     return out
 
 
+def sim_matrix_video_pooling(video_embeds_pooled: torch.Tensor, music_embeds: torch.Tensor) -> torch.Tensor:
+    """modules/metrics.py:26-41 (the `XA-*video*` fusions): video_embeds_pooled [N_v, N_m, 256] (every video pooled under
+    the guidance of every track), music_embeds [N_m, 256] → sims [N_v, N_m] fp32.  Same kernel as
+    `sim_matrix_music_pooling` with the roles of the two sides exchanged."""
+    return sim_matrix_music_pooling(music_embeds, video_embeds_pooled).t()
+
+
 # ---------------------------------------------------------------------------------------------
 # building blocks exported for tests
 # ---------------------------------------------------------------------------------------------

@@ -83,6 +83,17 @@ def state_dict_spec() -> List[Tuple[str, tuple, str]]:
     return s
 
 
+def xa_video_spec() -> List[Tuple[str, tuple, str]]:
+    """Extra keys of vmr_fusion "XA-music-video": a second Transformer_XA (model_Uni.py:27-28)."""
+    x = "music_guided_to_video_pooling_cross_transformer"
+    s: List[Tuple[str, tuple, str]] = []
+    for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        s += _lin(f"{x}.cross_attn.{n}", 256, 256, "eye")
+    s += _lin(f"{x}.linear_proj", 256, 256, "eye")
+    s += _ln(f"{x}.layer_norm1") + _ln(f"{x}.layer_norm2") + _ln(f"{x}.layer_norm3")
+    return s
+
+
 def sinusoid_pe(seq_len: int, dim: int = C.D_MODEL) -> torch.Tensor:
     """Buffer of model_Base.py:48-57 (sin on even, cos on odd channels), same op order, fp32."""
     pe = torch.zeros(seq_len, dim)
@@ -93,7 +104,7 @@ def sinusoid_pe(seq_len: int, dim: int = C.D_MODEL) -> torch.Tensor:
     return pe.unsqueeze(0)
 
 
-def make_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 0, xa_video: bool = False) -> Dict[str, torch.Tensor]:
     """Random-but-deterministic fp32 weights with reference key names.
 
     X-Pool linears are eye + 0.05*N(0,1) (the reference eye-initialises them,
@@ -102,7 +113,7 @@ def make_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, kind in state_dict_spec():
+    for key, shape, kind in state_dict_spec() + (xa_video_spec() if xa_video else []):
         if kind == "logit_scale":
             a = np.array(C.logit_scale_init(), dtype=np.float32)
         elif kind == "pe":

@@ -64,7 +64,7 @@ class _OracleEngine:
     def xpool_score(self, q, vhat, kz, gram, bits, out=None, col_offset=0):
         return O.sim_matrix_music_pooling(q, O.xpool(self.sd, q, kz, gram))
 
-    def xpool_pooled(self, video_feats, segment_feats, segment_masks, out=None, track_chunk=None):
+    def xpool_pooled(self, video_feats, segment_feats, segment_masks, out=None, track_chunk=None, which=1):
         return O.xpool(self.sd, video_feats.float(), segment_feats.float(), segment_masks.float())
 
 

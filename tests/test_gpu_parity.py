@@ -560,9 +560,11 @@ def test_cfg1_whole_job_vs_reference_fixture(dev, engine, golden_dir, sd_fp32):
           f"pred_st {np.abs(out['pred_st'].cpu().numpy() - gold['pred_st']).max():.2e} s, "
           f"pred_ed {np.abs(out['pred_ed'].cpu().numpy() - gold['pred_ed']).max():.2e} s, "
           f"score {np.abs(out['score'].cpu().numpy() - gold['pred_score']).max():.2e}")
-    np.testing.assert_allclose(out["iou"].cpu().numpy(), gold["iou"], atol=4e-3)
-    np.testing.assert_allclose(out["pred_st"].cpu().numpy(), gold["pred_st"], atol=0.1)      # seconds, of 240
-    np.testing.assert_allclose(out["pred_ed"].cpu().numpy(), gold["pred_ed"], atol=0.1)
+    # tolerances = ~2x the measured differences (split precision): IoU 6.1e-5, start 1.0e-2 s, end 1.6e-2 s of 240 s
+    # (6.6e-5 of the normalised span), score 3.5e-4.  Bit-exact spans are not attainable with 16-bit GEMM operands.
+    np.testing.assert_allclose(out["iou"].cpu().numpy(), gold["iou"], atol=2e-4)
+    np.testing.assert_allclose(out["pred_st"].cpu().numpy(), gold["pred_st"], atol=0.04)     # seconds, of 240
+    np.testing.assert_allclose(out["pred_ed"].cpu().numpy(), gold["pred_ed"], atol=0.04)
     np.testing.assert_allclose(out["score"].cpu().numpy(), gold["pred_score"], atol=1e-3)
     # the IoU kernel itself is exact: recompute from the GPU's spans with the oracle
     riou = O.detr_iou(out["pred_st"].cpu(), out["pred_ed"].cpu(), m["gt_moment"], m["m_duration"])
@@ -777,6 +779,39 @@ def test_retrieve_then_detect_matches_paired_detection(dev, engine):
     assert bool(torch.isfinite(spans).all()) and bool((spans[..., 1] >= spans[..., 0]).all())
 
 
+def test_retrieve_then_detect_vs_oracle(dev, engine, sd_fp32):
+    """Retrieve-then-detect against the ORACLE: for every (query, retrieved track) pair the device reports, the
+    reference's DETR (music_detr/transformer.py:51-81 + calc_output + test-MaDe.py:306-316) run on that pair gives the
+    same moment.  The retrieved indices themselves are the device's top-k (exactness of those: test_rank_and_topk_exact;
+    agreement with the oracle's ranking modulo near-ties: test_cfg1_whole_job_vs_reference_fixture)."""
+    from mgsv_b200.pipeline import GalleryEvaluator
+    nq, nm, kd = 24, 40, 3
+    v, m, ids = synth.make_eval_set(nq, nm, synth.BASE_SEED + 31)
+    ev = GalleryEvaluator(engine, k=8, music_chunk=16, video_chunk=16)
+    gt = torch.arange(nq, dtype=torch.int32)
+    out = ev.run({k: t.to(dev) for k, t in v.items()}, {k: t.to(dev) for k, t in m.items()}, gt, detect_topk=kd)
+    idx = out["topk_idx"][:, :kd].cpu().long()                       # [nq, kd] retrieved tracks
+    fo, vf = O.encode_video(sd_fp32, v["frame_feats"], v["frame_mask"])
+    so, mf = O.encode_music(sd_fp32, m["segment_feats"], m["segment_mask"])
+    qi = torch.arange(nq).repeat_interleave(kd)
+    ti = idx.reshape(-1)
+    src = torch.cat([fo[qi], so[ti]], 1)
+    mask = torch.cat([v["frame_mask"][qi], m["segment_mask"][ti]], 1)
+    hs, _ = O.detr_forward(sd_fp32, src, mask, O.position_embedding_sine(mask), vf[qi].unsqueeze(1))
+    om = O.calc_output(sd_fp32, hs, fo[qi])
+    st, ed, sc = O.moment_postproc(om["pred_logits"], om["pred_spans"])
+    spans = out["topk_spans"].cpu().reshape(-1, 2)
+    d_st, d_ed = (spans[:, 0] - st).abs().max().item(), (spans[:, 1] - ed).abs().max().item()
+    d_sc = (out["topk_span_score"].cpu().reshape(-1) - sc).abs().max().item()
+    print(f"[parity] retrieve-then-detect vs oracle ({nq} x top-{kd}): max|d| start {d_st:.2e} s, end {d_ed:.2e} s, score {d_sc:.2e}")
+    assert d_st < 0.05 and d_ed < 0.05 and d_sc < 1e-3                # seconds of 240; measured ~1e-2 s
+    # the oracle's own top-1 agrees wherever its margin exceeds the similarity tolerance
+    single, dual, total = O.gallery_similarity(sd_fp32, vf, mf, so, m["segment_mask"])
+    srt = np.sort(total, 1)
+    clear = (srt[:, -1] - srt[:, -2]) > 2 * SIM_RTOL * np.abs(total).max()
+    assert (idx[:, 0].numpy()[clear] == np.argmax(total, 1)[clear]).all()
+
+
 def test_hungarian_matcher_mirror(dev):
     """music_detr/matcher.py:36-92 with Q > 1 queries and a variable number of targets per sample."""
     from mgsv_b200.matcher import build_matcher
@@ -983,3 +1018,39 @@ def test_checkpoint_file_roundtrip(dev, sd_fp32, tmp_path):
     assert checkpoint.load_checkpoint(ref, str(tmp_path / "bare.bin")) == (0, 0.0)
     with pytest.raises(FileNotFoundError):
         checkpoint.load_checkpoint(ref, str(tmp_path / "missing.bin"))
+
+
+def test_xa_music_video_variant(dev, sd_fp32):
+    """vmr_fusion "XA-music-video" (model_Uni.py:24-28, 203-204): the checkpoint carries a second Transformer_XA
+    (music-guided pooling of the video frames).  With the shipped vmr_loss its output is computed and never read by
+    the reference, so every output equals the "XA-music" model's; the module itself is callable (materialised, fp32)
+    and `sim_matrix_video_pooling` (modules/metrics.py:26-41) runs on its output."""
+    from mgsv_b200.model import Uni_model
+    sd2 = synth.make_state_dict(0, xa_video=True)
+    assert set(sd2) - set(sd_fp32) == {k for k, _, _ in synth.xa_video_spec()} and all(torch.equal(sd2[k], sd_fp32[k]) for k in sd_fp32)
+    m2 = Uni_model(config.default_args(vmr_fusion="XA-music-video"), dev, None)
+    m2.load_state_dict(sd2)                                       # strict: every reference key, nothing else
+    m1 = Uni_model(config.default_args(), dev, None)
+    m1.load_state_dict(sd_fp32)
+    with pytest.raises(RuntimeError):
+        m1.load_state_dict(sd2)                                   # the plain model has no second module
+    assert not hasattr(m1, "music_guided_to_video_pooling_cross_transformer")
+    v, m, ids = synth.make_eval_set(6, 6, synth.BASE_SEED + 100)
+    a = [t.to(dev) for t in (v["frame_feats"], m["segment_feats"], v["frame_mask"], m["segment_mask"], m["spans_target"])]
+    o1, l1, f1, k1, _ = m1(*a)
+    o2, l2, f2, k2, _ = m2(*a)
+    assert torch.equal(o1["pred_spans"], o2["pred_spans"]) and torch.equal(o1["pred_logits"], o2["pred_logits"])
+    assert torch.equal(f1["video_feats"], f2["video_feats"]) and torch.equal(l1["retrieval_loss"], l2["retrieval_loss"])
+    # the second module, against the oracle's Transformer_XA with that module's weights
+    x_old, x_new = "music_guided_to_video_pooling_cross_transformer", "video_guided_to_music_pooling_cross_transformer"
+    sd_swapped = {k: t for k, t in sd2.items() if not k.startswith(x_new)}
+    sd_swapped.update({k.replace(x_old, x_new): t for k, t in sd2.items() if k.startswith(x_old)})
+    fo, vf = O.encode_video(sd_fp32, v["frame_feats"], v["frame_mask"])
+    so, mf = O.encode_music(sd_fp32, m["segment_feats"], m["segment_mask"])
+    ref = O.xpool(sd_swapped, mf, fo, v["frame_mask"])            # [N_v, N_m, 256]
+    got = m2.music_guided_to_video_pooling_cross_transformer(mf, fo, v["frame_mask"])
+    assert tuple(got.shape) == (6, 6, 256) and _rel(got, ref) < 2e-5
+    sims = ops.sim_matrix_video_pooling(got, mf.to(dev))
+    want = torch.einsum("vmd,md->vm", ref / ref.norm(dim=-1, keepdim=True), mf / mf.norm(dim=-1, keepdim=True))
+    assert _rel(sims, want) < 1e-5
+    assert len(m2.get_matching_parameter()) == 2 * 16 + 1

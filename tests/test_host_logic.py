@@ -102,6 +102,13 @@ def test_uni_model_interface_on_cpu():
     model.eval().float()
     with pytest.raises(ValueError):
         Uni_model(config.default_args(vmr_loss="dual"), torch.device("cpu"), None)
+    # vmr_fusion "XA-music-video": the second Transformer_XA's 16 tensors join the state_dict (model_Uni.py:27-28)
+    m2 = Uni_model(config.default_args(vmr_fusion="XA-music-video"), torch.device("cpu"), None)
+    extra = set(m2.state_dict()) - set(sd)
+    assert len(extra) == 16 and all(k.startswith("music_guided_to_video_pooling_cross_transformer.") for k in extra)
+    assert sum(p.numel() for p in m2.parameters()) == 10_534_917 + 330_496
+    with pytest.raises(ValueError):
+        Uni_model(config.default_args(vmr_fusion="XA-video"), torch.device("cpu"), None)
 
 
 def test_dedup_tables_and_rank_summary():
