@@ -447,8 +447,21 @@ def main():
     # kernel-family times: a second, shorter timed region with CUDA events around every tensor-core kernel launch
     # (on the launching stream); kept apart from the headline region so that its ~300 event records per step
     # cannot perturb `value`
+    # ... and run on ONE stream (no ingest / detection overlap): a kernel's event-bracketed duration otherwise includes the
+    # time it waits for SMs held by the other streams' kernels (6.6 ms of "GEMM time" in a 7.2 ms step)
     prof_steps = min(args.steps, 5)
-    ms_prof, _, _, _, prof = timed(step, False, prof_steps, 1, profile=True)
+    ev_serial = GalleryEvaluator(eng, k=TOPK, music_chunk=args.chunk, video_chunk=args.chunk, single_stream=True)
+    if sharded is not None:
+        serial_sharded = ShardedEvaluator(ev_serial, rank, world)
+
+        def step_serial(on_host: bool):
+            out = serial_sharded.run(dev_v, dev_m, gt_col, nq_total, nm, on_host=False, gather_results=False)
+            torch.cuda.synchronize()
+            return out
+    else:
+        def step_serial(on_host: bool):
+            return ev_serial.run(dev_v, dev_m, gt_col, on_host=False)
+    ms_prof, _, _, _, prof = timed(step_serial, False, prof_steps, 2, profile=True)
 
     strong = None
     if weak:     # the same 2000 x 4000 job on N GPUs, for the record
@@ -532,7 +545,8 @@ def main():
             "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
             "how": "algorithmic FLOPs of the family per step (SURVEY.md 8d dense formulation, attention and X-Pool pairs "
                    "excluded: 2.52 TF at 2000 x 4000) / summed CUDA-event duration of the family's launches per step "
-                   "(events on the launching stream around each launch, separate short timed region); rank 0's share at N > 1",
+                   "(events on the launching stream around each launch; separate short timed region in which the whole step "
+                   "runs on ONE stream so that no other stream's kernels share the SMs); rank 0's share at N > 1",
             "algorithmic_flops_per_step": alg, "executed_flops_per_step": exe,
             "executed_tflops": exe / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0,
             "executed_frac": exe / (gemm_ms / 1e3) / 1e12 / peak_tf if gemm_ms > 0 else 0.0,
@@ -547,8 +561,9 @@ def main():
                       "launches_per_step": xp_n, "share_of_step": xp_ms / ms_prof,
                       "algorithmic_flops_per_pair": F_XPOOL_PAIR, "executed_flops_per_pair": F_XPOOL_PAIR_EXEC},
             "other_families_ms_per_step": {"attention": per_step["attn"][0], "rank_topk": per_step["rank"][0]},
-            "streams_overlap_note": "gallery chunks, moment detection and ingest run on three streams, so family times "
-                                    "can sum to more than the step",
+            "serial_step_ms": ms_prof,
+            "streams_overlap_note": "family times come from a single-stream pass (serial_step_ms per step); the timed "
+                                    "headline step overlaps ingest, scoring and detection on three streams",
             "tensor_pipe_active_ncu": tensor_pipe_note(),
             "whole_step_tflops": F_TOTAL_JOB * (nq_total / N_QUERIES) / (ms_dev / 1e3) / 1e12 if nm == N_TRACKS else None,
         }

@@ -30,19 +30,21 @@ from .engine import Engine
 
 class GalleryEvaluator:
     def __init__(self, engine: Engine, k: int = 100, music_chunk: int = 1024, video_chunk: int = 1024,
-                 detr_chunk: int = 4096):
+                 detr_chunk: int = 4096, single_stream: bool = False):
+        """single_stream: ingest, scoring and detection all on the caller's stream (no overlap) — for per-kernel
+        timing, where concurrent kernels of other streams would inflate every event-bracketed duration."""
         self.eng = engine
         self.dev = engine.device
         self.k = k
         self.music_chunk = music_chunk
         self.video_chunk = video_chunk
         self.detr_chunk = detr_chunk
-        self.ingest_stream = torch.cuda.Stream(device=self.dev)
+        self.ingest_stream = torch.cuda.current_stream(self.dev) if single_stream else torch.cuda.Stream(device=self.dev)
         # moment detection is a long chain of small, latency-bound launches (one query per sequence in
         # the decoder): it runs on its own stream and made_ctx so that it fills the SMs left idle by /
         # beside the scoring kernels instead of serialising with them
-        self.detect_stream = torch.cuda.Stream(device=self.dev) if os.environ.get("MADE_DETECT_STREAM", "1") != "0" \
-            else None
+        self.detect_stream = torch.cuda.Stream(device=self.dev) \
+            if (os.environ.get("MADE_DETECT_STREAM", "1") != "0" and not single_stream) else None
         self._eng_detect = None
         # host inputs: "dma" = copy engines move the valid rows into a device staging buffer (no SM
         # involved, overlaps any kernel); "dma16" = host threads round the valid rows to fp16 first (half
