@@ -567,7 +567,8 @@ def main():
             "ffn_fused_ms_per_step": per_step["ffn"][0], "ffn_fused_launches_per_step": per_step["ffn"][1],
             "share_of_step": gemm_ms / ms_prof,
             "share_of_tensor_kernel_time": gemm_ms / fam_total if fam_total > 0 else None,
-            "traffic": None,
+            "traffic": None,     # a family of launches has no single per-launch figure: per-kernel DRAM bytes from the ncu
+                                 # --set full captures are in `tensor_pipe_active_ncu` (profiles/*_tensor_pipe.json)
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
             "xpool": {"kernel": "xpool_score_kernel", "achieved": xp_ach, "frac": xp_ach / peak_tf,
                       "executed_tflops": xp_exe, "executed_frac": xp_exe / peak_tf, "kernel_ms_per_step": xp_ms,
