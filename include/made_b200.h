@@ -220,6 +220,16 @@ int made_xpool_score(made_ctx* ctx, const void* q, const float* vhat, int64_t n_
  * Chunk the tracks: scratch is N_m * N_v * 2.4 KB. */
 int made_xpool_pooled(made_ctx* ctx, int which, const float* video_feats, int64_t n_q, const float* seg_f32,
                       const float* seg_masks, int64_t n_m, float* pooled, void* stream);
+/* mml_fusion "CA" (model_Uni.py:209-211; CrossTransformer, model/model_Base.py:169-213, CrossAttention :93-165,
+ * FeedForward :22-46): the music segments attend to the frames of the paired video before DETR.
+ * seg_f32 [B,96,256] / seg_masks [B,96] = encoded segments of the B pairs (queries), frame_f32 [B,50,256] /
+ * frame_masks [B,50] = encoded frames (keys, values) -> fused16 [B,96,256] fp16 (+ fused_f32, nullable), rows with
+ * seg_masks == 0 written as 0 (the masked_fill of :210).  The DETR input of this variant is `fused16` alone:
+ * call made_detr_detect with all-zero frame masks.  Needs a checkpoint that carries
+ * video_music_fusion_cross_transformer.* (MADE_ESTATE otherwise). */
+int made_ca_fuse(made_ctx* ctx, const float* seg_f32, const float* seg_masks, const float* frame_f32,
+                 const float* frame_masks, int64_t B, void* fused16, float* fused_f32, void* stream);
+
 /* sim_matrix_music_pooling (modules/metrics.py:10-24) on a materialised pooled tensor:
  * sim[v, col_offset + m] = < video[v]/|video[v]|, pooled[m,v]/|pooled[m,v]| >, fp32, sim row stride ld. */
 int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "made_query_prepare": [_p, _p, _i64, _p, _p, _p],
     "made_xpool_score": [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _p],
     "made_xpool_pooled": [_p, _i32, _p, _i64, _p, _p, _i64, _p, _p],
+    "made_ca_fuse": [_p, _p, _p, _p, _p, _i64, _p, _p, _p],
     "made_pooled_cosine": [_p, _p, _i64, _i64, _p, _i64, _i64, _p],
     "made_detr_detect": [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p],
     "made_detr_losses": [_p, _p, _p, _p, _p, _i64, _i32, _f, _f, _f, _p, _p],

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmade_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 SOURCES = ["runtime.cu", "span_kernels.cu", "rank_kernels.cu", "gemm_tc.cu", "attn.cu", "xpool.cu",
-           "prep.cu", "ragged.cu", "losses.cu", "ffn_fused.cu", "exact_f32.cu", "api.cu"]
+           "prep.cu", "ragged.cu", "losses.cu", "ffn_fused.cu", "exact_f32.cu", "ca_fusion.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

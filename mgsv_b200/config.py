@@ -78,7 +78,9 @@ def default_args(**overrides) -> argparse.Namespace:
 
 # flag values accepted beside the shipped one: vmr_fusion "XA-music-video" adds a second Transformer_XA whose output the
 # shipped vmr_loss never reads (model_Uni.py:203-204, 254-262), so the compute graph that produces outputs is unchanged
-_ALSO = {"vmr_fusion": ("XA-music-video",)}
+# mml_fusion "CA" (the argparse default of test-MaDe.py:80; the shipped script passes "concat") puts a CrossTransformer
+# between the encoders and DETR: built (`made_ca_fuse`), fp16 tcgen05 GEMMs + a CUDA-core cross-attention kernel.
+_ALSO = {"vmr_fusion": ("XA-music-video",), "mml_fusion": ("CA",)}
 
 
 def check_args(args) -> None:

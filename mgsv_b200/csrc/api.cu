@@ -70,6 +70,11 @@ struct made_ctx {
   ExactXpW xxp;                 // video_guided_to_music_pooling_cross_transformer (keys = 96 segments)
   ExactXpW xxp_video;           // music_guided_to_video_pooling_cross_transformer (vmr_fusion "XA-music-video"; keys = 50 frames)
   bool has_xp_video = false;
+  struct CaW {                  // video_music_fusion_cross_transformer (mml_fusion "CA", model_Base.py:169-213)
+    Lin to_q, to_kv, to_out, ff1, ff2, fin;     // to_q / to_kv have no bias (b stays null)
+    LNp ln_q, ln_c, ln_ff;
+  } ca;
+  bool has_ca = false;
   XpoolConsts xp_consts;        // folded X-Pool constants of THIS context's checkpoint
   float* xp_c5 = nullptr;       // [5][256] weight vectors of the W5 columns (device)
 
@@ -277,6 +282,26 @@ int load_exact(made_ctx* c) {
   // the second X-Pool module exists only in checkpoints trained with vmr_fusion "XA-music-video" (model_Uni.py:24-28)
   c->has_xp_video = c->host.count("music_guided_to_video_pooling_cross_transformer.linear_proj.weight") != 0;
   if (c->has_xp_video) MADE_TRY(load_xa("music_guided_to_video_pooling_cross_transformer", c->xxp_video));
+  return MADE_OK;
+}
+
+// mml_fusion "CA": the cross-attention fusion block, present only in checkpoints trained with that flag
+int load_ca(made_ctx* c) {
+  const std::string x = "video_music_fusion_cross_transformer";
+  c->has_ca = c->host.count(x + ".final_linear.weight") != 0;
+  if (!c->has_ca) return MADE_OK;
+  const std::vector<float>* w;
+  MADE_TRY(get(c, x + ".layers.0.0.to_q.weight", static_cast<size_t>(4 * D) * D, &w));
+  MADE_TRY(up_op(c, w->data(), w->size(), &c->ca.to_q.w));
+  MADE_TRY(get(c, x + ".layers.0.0.to_kv.weight", static_cast<size_t>(8 * D) * D, &w));
+  MADE_TRY(up_op(c, w->data(), w->size(), &c->ca.to_kv.w));
+  MADE_TRY(load_lin(c, x + ".layers.0.0.to_out.0", D, 4 * D, &c->ca.to_out));
+  MADE_TRY(load_lin(c, x + ".layers.0.1.net.0", DFF, D, &c->ca.ff1));
+  MADE_TRY(load_lin(c, x + ".layers.0.1.net.3", D, DFF, &c->ca.ff2));
+  MADE_TRY(load_lin(c, x + ".final_linear", D, D, &c->ca.fin));
+  MADE_TRY(load_ln(c, x + ".attention_query_layer_norms.0", &c->ca.ln_q));
+  MADE_TRY(load_ln(c, x + ".attention_context_layer_norms.0", &c->ca.ln_c));
+  MADE_TRY(load_ln(c, x + ".ff_layer_norms.0", &c->ca.ln_ff));
   return MADE_OK;
 }
 
@@ -568,6 +593,7 @@ int made_ctx_load_weights(made_ctx* c, int n, const char* const* names, const fl
   MADE_TRY(load_xpool(c, static_cast<cudaStream_t>(stream)));
   MADE_TRY(load_detr(c));
   MADE_TRY(load_exact(c));
+  MADE_TRY(load_ca(c));
   c->host.clear();
   c->loaded = true;
   return MADE_OK;
@@ -1200,6 +1226,72 @@ int made_xpool_pooled(made_ctx* c, int which, const float* video_feats, int64_t 
   MADE_TRY(c->with_arena([&] { ws = c->take<float>(exact_xpool_ws_floats(n_q, n_m, Lk)); }));
   return exact_xpool(which == MADE_MUSIC ? c->xxp : c->xxp_video, video_feats, n_q, seg_f32, seg_masks, n_m, Lk, ws, pooled,
                      static_cast<cudaStream_t>(stream));
+}
+
+int made_ca_fuse(made_ctx* c, const float* seg_f32, const float* seg_masks, const float* frame_f32, const float* frame_masks,
+                 int64_t B, void* fused16, float* fused_f32, void* stream) {
+  CTX_READY(c);
+  MADE_REQUIRE(c->has_ca, "ca_fuse: the loaded checkpoint has no video_music_fusion_cross_transformer (mml_fusion 'CA')");
+  if (B == 0) return MADE_OK;
+  MADE_REQUIRE(seg_f32 && seg_masks && frame_f32 && frame_masks && fused16, "ca_fuse: null pointer");
+  MADE_REQUIRE(B * LM < (1LL << 31) / (4 * D), "ca_fuse: batch too large; chunk the call");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t Tq = B * LM, Tk = B * LV;
+  op_t *nq, *nc, *q, *kv, *att, *nf, *h, *x2;
+  float* ax;
+  MADE_TRY(c->with_arena([&] {
+    nq = c->take<op_t>(Tq * D);
+    nc = c->take<op_t>(Tk * D);
+    q = c->take<op_t>(Tq * 4 * D);
+    kv = c->take<op_t>(Tk * 8 * D);
+    att = c->take<op_t>(Tq * 4 * D);
+    ax = c->take<float>(Tq * D);
+    nf = c->take<op_t>(Tq * D);
+    h = c->take<op_t>(Tq * DFF);
+    x2 = c->take<op_t>(Tq * D);
+  }));
+  const made_ctx::CaW& w = c->ca;
+  // CrossTransformer.forward (model_Base.py:199-213), depth 1
+  MADE_TRY(layernorm_rows(seg_f32, 0, D, Tq, w.ln_q.g, w.ln_q.b, nq, D, nullptr, nullptr, st));          // norm_x
+  MADE_TRY(layernorm_rows(frame_f32, 0, D, Tk, w.ln_c.g, w.ln_c.b, nc, D, nullptr, nullptr, st));        // norm_context
+  {
+    GemmEpilogue e;
+    e.out_h = q; e.ld_h = 4 * D;
+    MADE_TRY(linear(nq, D, w.to_q, Tq, 4 * D, D, e, st));                                                  // to_q (no bias)
+  }
+  {
+    GemmEpilogue e;
+    e.out_h = kv; e.ld_h = 8 * D;
+    MADE_TRY(linear(nc, D, w.to_kv, Tk, 8 * D, D, e, st));                                                 // to_kv (no bias)
+  }
+  MADE_TRY(ca_attention(q, kv, seg_masks, frame_masks, B, att, st));
+  {
+    GemmEpilogue e;                                                                                        // to_out + x
+    e.residual = seg_f32; e.residual_f32 = 1; e.res_ld = D;
+    e.out_f32 = ax; e.ld_f32 = D;
+    MADE_TRY(linear(att, 4 * D, w.to_out, Tq, D, 4 * D, e, st));
+  }
+  MADE_TRY(layernorm_rows(ax, 0, D, Tq, w.ln_ff.g, w.ln_ff.b, nf, D, nullptr, nullptr, st));              // ff_layer_norms
+  {
+    GemmEpilogue e;
+    e.act = 1;                                                                                             // nn.GELU()
+    e.out_h = h; e.ld_h = DFF;
+    MADE_TRY(linear(nf, D, w.ff1, Tq, DFF, D, e, st));
+  }
+  {
+    GemmEpilogue e;                                                                                        // ff(norm_x) + attn_x
+    e.residual = ax; e.residual_f32 = 1; e.res_ld = D;
+    e.out_h = x2; e.ld_h = D;
+    MADE_TRY(linear(h, DFF, w.ff2, Tq, D, DFF, e, st));
+  }
+  {
+    GemmEpilogue e;                                                                                        // final_linear,
+    e.row_mask = seg_masks;                                                                                // masked_fill (model_Uni.py:210)
+    e.out_h = static_cast<op_t*>(fused16); e.ld_h = D;
+    e.out_f32 = fused_f32; e.ld_f32 = D;
+    MADE_TRY(linear(x2, D, w.fin, Tq, D, D, e, st));
+  }
+  return MADE_OK;
 }
 
 int made_pooled_cosine(const float* video_feats, const float* pooled, int64_t n_q, int64_t n_m, float* sim, int64_t ld,

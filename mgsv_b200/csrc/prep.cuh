@@ -55,6 +55,10 @@ int ffn_fused(const op_t* x, int64_t ldx, const op_t* w1, const float* b1, const
               op_t* out_hi, op_t* out_lo, int64_t ld_out, const op_t* add2, int64_t add2_ld, op_t* out2,
               int64_t ld_out2, int64_t M, const int32_t* m_dev, cudaStream_t st);
 
+// ca_fusion.cu — cross-attention core of the mml_fusion "CA" variant (model_Base.py:127-165)
+int ca_attention(const op_t* q, const op_t* kv, const float* q_mask, const float* kv_mask, int64_t B, op_t* out,
+                 cudaStream_t st);
+
 // exact_f32.cu — fp32 CUDA-core path (MADE_PREC_FP32 and the materialised Transformer_XA output)
 struct ExactEncW {      // raw fp32 weights of one temporal encoder (device pointers)
   int L = 0, din = 0;

@@ -40,6 +40,7 @@ class Engine:
         self._h = h
         _lib.check(self._lib.made_ctx_set_precision(self._h, PRECISIONS[precision]))
         self.loaded = False
+        self.mml_fusion = "concat"      # "CA": moment detection runs on made_ca_fuse's output (set by Uni_model / the caller)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -79,6 +80,7 @@ class Engine:
             raise RuntimeError("clone() needs loaded weights")
         other = Engine(self.device, self.precision)
         other.load_state_dict(self._weights)
+        other.mml_fusion = self.mml_fusion
         return other
 
     # -----------------------------------------------------------------------------------------
@@ -234,6 +236,26 @@ class Engine:
             _lib.check(self._lib.made_xpool_pooled(self._h, which, _lib.ptr(vf), n_q, _lib.ptr(sf[s:e]), _lib.ptr(sm[s:e]), e - s,
                                                    _lib.ptr(out[s:e]), _lib.stream_ptr()))
         return out
+
+    def ca_fuse(self, segment_feats: torch.Tensor, segment_masks: torch.Tensor, frame_feats: torch.Tensor,
+                frame_masks: torch.Tensor, want_f32: bool = False):
+        """mml_fusion "CA" (model_Uni.py:209-211): CrossTransformer(segment_feats [B,96,256] as queries, frame_feats
+        [B,50,256] as keys / values, both masks) followed by the masked_fill of padded segments → (fused fp16
+        [B,96,256], fused fp32 or None).  DETR then runs on the fused segments alone."""
+        dev = self.device
+        sf = segment_feats.to(dev, torch.float32).contiguous()
+        ff = frame_feats.to(dev, torch.float32).contiguous()
+        sm = segment_masks.to(dev, torch.float32).contiguous()
+        fm = frame_masks.to(dev, torch.float32).contiguous()
+        B = sf.shape[0]
+        if tuple(sf.shape) != (B, cfg.L_M, cfg.D_MODEL) or tuple(ff.shape) != (B, cfg.L_V, cfg.D_MODEL) \
+                or tuple(sm.shape) != (B, cfg.L_M) or tuple(fm.shape) != (B, cfg.L_V):
+            raise ValueError("ca_fuse: expected segment_feats [B,96,256], frame_feats [B,50,256] and their masks")
+        out16 = torch.empty((B, cfg.L_M, cfg.D_MODEL), dtype=torch.float16, device=dev)
+        out32 = torch.empty((B, cfg.L_M, cfg.D_MODEL), dtype=torch.float32, device=dev) if want_f32 else None
+        _lib.check(self._lib.made_ca_fuse(self._h, _lib.ptr(sf), _lib.ptr(sm), _lib.ptr(ff), _lib.ptr(fm), B,
+                                          _lib.ptr(out16), _lib.ptr(out32), _lib.stream_ptr()))
+        return out16, out32
 
     def xpool_score(self, q, vhat, kz, gram, bits, out: Optional[torch.Tensor] = None, col_offset: int = 0):
         n_q, n_m = q.shape[0], bits.shape[0]

@@ -99,8 +99,10 @@ class Uni_model(nn.Module):
         self.xa_video = "video" in str(args.vmr_fusion)         # model_Uni.py:27-28: a second Transformer_XA
         if self.xa_video:
             self.add_module("music_guided_to_video_pooling_cross_transformer", _XPoolView(self, _lib.VIDEO))
+        self.ca_fusion = "CA" in str(args.mml_fusion)           # model_Uni.py:33-43: CrossTransformer before DETR
         sd0 = None
-        for key, shape, kind in synth.state_dict_spec() + (synth.xa_video_spec() if self.xa_video else []):
+        for key, shape, kind in synth.state_dict_spec() + (synth.xa_video_spec() if self.xa_video else []) + \
+                (synth.ca_spec() if self.ca_fusion else []):
             parts = key.split(".")
             node = _ensure_path(self, parts[:-1])
             if kind in ("pe", "empty_weight"):
@@ -115,7 +117,7 @@ class Uni_model(nn.Module):
 
     # -- parameters ------------------------------------------------------------------------------
     def reset_parameters(self, seed: int = 0):
-        sd = synth.make_state_dict(seed, xa_video=self.xa_video)
+        sd = synth.make_state_dict(seed, xa_video=self.xa_video, ca=self.ca_fusion)
         with torch.no_grad():
             for k, v in self.state_dict().items():
                 v.copy_(sd[k])
@@ -137,6 +139,7 @@ class Uni_model(nn.Module):
         ver = self._param_version()
         if self._packed_version != ver:
             self._engine.load_state_dict(self.state_dict())
+            self._engine.mml_fusion = "CA" if self.ca_fusion else "concat"
             self._packed_version = ver
         return self._engine
 
@@ -151,7 +154,8 @@ class Uni_model(nn.Module):
                             "music_guided_to_video_pooling_cross_transformer.")) + [self.logit_scale]
 
     def get_detection_parameter(self):      # model_Uni.py:92-114
-        return self._group(("detr_transformer.", "span_embed.", "class_embed.", "contrastive_align_projection_"))
+        return self._group(("video_music_fusion_cross_transformer.", "detr_transformer.", "span_embed.", "class_embed.",
+                            "contrastive_align_projection_"))
 
     # -- pieces ----------------------------------------------------------------------------------
     def forward_video_encoder_feature(self, frame_feats=None, frame_masks=None, video_ids=None):
@@ -212,8 +216,13 @@ class Uni_model(nn.Module):
         segment_masks = segment_masks.to(dev)
         frame_out, video_feats, _ = self.forward_video_encoder_feature(frame_feats, frame_masks)
         segment_out, music_feats, _ = self.forward_audio_encoder_feature(segment_feats, segment_masks)
-        det = eng.detr_detect(self._last_frame16, frame_masks, self._last_segment16, segment_masks,
-                              video_feats, want_proj=True)
+        if self.ca_fusion:      # model_Uni.py:209-213: the segments attend to the paired video's frames; DETR sees 96 tokens
+            fused16, _ = eng.ca_fuse(segment_out, segment_masks, frame_out, frame_masks)
+            det = eng.detr_detect(self._last_frame16, torch.zeros_like(frame_masks), fused16, segment_masks, video_feats,
+                                  want_proj=True)
+        else:
+            det = eng.detr_detect(self._last_frame16, frame_masks, self._last_segment16, segment_masks,
+                                  video_feats, want_proj=True)
         L = cfg.DETR_DEC_LAYERS
         output_map = {
             "pred_logits": det["pred_logits"][L - 1].unsqueeze(1),

@@ -253,8 +253,14 @@ class GalleryEvaluator:
             spans = torch.empty((n, 2), dtype=torch.float32, device=self.dev)
             for s in range(0, n, self.detr_chunk):
                 e = min(n, s + self.detr_chunk)
-                r = eng.detr_detect(frame_seq[s:e], frame_mask[s:e], gal["seq"], gal["mask"], video_feats[s:e],
-                                    track_idx=track_idx[s:e])
+                if eng.mml_fusion == "CA":      # model_Uni.py:209-213: cross-attention fusion, DETR over the 96 fused tokens
+                    sel = track_idx[s:e].long()
+                    seg_mask = gal["mask"][sel]
+                    fused16, _ = eng.ca_fuse(gal["seq"][sel], seg_mask, frame_seq[s:e], frame_mask[s:e])
+                    r = eng.detr_detect(frame_seq[s:e], torch.zeros_like(frame_mask[s:e]), fused16, seg_mask, video_feats[s:e])
+                else:
+                    r = eng.detr_detect(frame_seq[s:e], frame_mask[s:e], gal["seq"], gal["mask"], video_feats[s:e],
+                                        track_idx=track_idx[s:e])
                 spans[s:e] = r["pred_spans"][-1]
                 a, b, c, d = ops.moment_postproc(r["pred_logits"][-1], r["pred_spans"][-1], gt_moment[s:e],
                                                  m_duration[s:e])

@@ -94,6 +94,22 @@ def xa_video_spec() -> List[Tuple[str, tuple, str]]:
     return s
 
 
+def ca_spec() -> List[Tuple[str, tuple, str]]:
+    """Extra keys of mml_fusion "CA": video_music_fusion_cross_transformer = CrossTransformer(256, depth 1, 8 heads x
+    128, mlp 1024, out 256) (model_Uni.py:33-43; model/model_Base.py:169-197, :100-113, :22-31)."""
+    x = "video_music_fusion_cross_transformer"
+    s: List[Tuple[str, tuple, str]] = [
+        (f"{x}.layers.0.0.to_q.weight", (1024, 256), "xavier"),
+        (f"{x}.layers.0.0.to_kv.weight", (2048, 256), "xavier"),
+    ]
+    s += _lin(f"{x}.layers.0.0.to_out.0", 256, 1024, "xavier")
+    s += _lin(f"{x}.layers.0.1.net.0", 1024, 256, "xavier") + _lin(f"{x}.layers.0.1.net.3", 256, 1024, "xavier")
+    s += _ln(f"{x}.attention_query_layer_norms.0") + _ln(f"{x}.attention_context_layer_norms.0")
+    s += _ln(f"{x}.ff_layer_norms.0")
+    s += _lin(f"{x}.final_linear", 256, 256)
+    return s
+
+
 def sinusoid_pe(seq_len: int, dim: int = C.D_MODEL) -> torch.Tensor:
     """Buffer of model_Base.py:48-57 (sin on even, cos on odd channels), same op order, fp32."""
     pe = torch.zeros(seq_len, dim)
@@ -104,7 +120,7 @@ def sinusoid_pe(seq_len: int, dim: int = C.D_MODEL) -> torch.Tensor:
     return pe.unsqueeze(0)
 
 
-def make_state_dict(seed: int = 0, xa_video: bool = False) -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 0, xa_video: bool = False, ca: bool = False) -> Dict[str, torch.Tensor]:
     """Random-but-deterministic fp32 weights with reference key names.
 
     X-Pool linears are eye + 0.05*N(0,1) (the reference eye-initialises them,
@@ -113,7 +129,7 @@ def make_state_dict(seed: int = 0, xa_video: bool = False) -> Dict[str, torch.Te
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, kind in state_dict_spec() + (xa_video_spec() if xa_video else []):
+    for key, shape, kind in state_dict_spec() + (xa_video_spec() if xa_video else []) + (ca_spec() if ca else []):
         if kind == "logit_scale":
             a = np.array(C.logit_scale_init(), dtype=np.float32)
         elif kind == "pe":

@@ -39,10 +39,10 @@ def _stub_modules():
         sys.path.insert(0, REF)
 
 
-def build_reference_model(sd):
+def build_reference_model(sd, **overrides):
     _stub_modules()
     from model.model_Uni import Uni_model
-    args = C.default_args(name="oracle")
+    args = C.default_args(name="oracle", **overrides)
     logger = logging.getLogger("gen_golden")
     model = Uni_model(args, torch.device("cpu"), logger)
     model.vit_proj = nn.Linear(C.D_VIT, C.D_MODEL)   # model_Base.py:289 (not built for feature input)
@@ -100,6 +100,29 @@ def gen_forward_b8(model, sd):
     g["detr_pos"] = t2n(pos[:2])
     np.savez_compressed(os.path.join(GOLD, "forward_b8.npz"), **g)
     print("forward_b8:", {k: getattr(v_, "shape", None) for k, v_ in g.items()})
+
+
+@torch.no_grad()
+def gen_forward_b8_ca():
+    """mml_fusion "CA": the unmodified reference with its CrossTransformer fusion, same B = 8 batch."""
+    sd = synth.make_state_dict(0, ca=True)
+    model, args = build_reference_model(sd, mml_fusion="CA")
+    B = 8
+    v, m, ids = synth.make_eval_set(B, B, synth.BASE_SEED + 100)
+    out, loss, feat, mask, _ = model(
+        v["frame_feats"].clone(), m["segment_feats"].clone(), v["frame_mask"], m["segment_mask"],
+        m["spans_target"], v_duration=v["v_duration"], video_ids=ids["video_ids"],
+        music_ids=ids["music_ids"], is_train=False)
+    fused, _ = model.video_music_fusion_cross_transformer(feat["segment_feats"], feat["frame_feats"],
+                                                          q_mask=mask["segment_masks"], kv_mask=mask["frame_masks"])
+    fused = fused.masked_fill(mask["segment_masks"].unsqueeze(-1) == 0, 0)       # model_Uni.py:210
+    g = {"pred_logits": t2n(out["pred_logits"]), "pred_spans": t2n(out["pred_spans"]),
+         "proj_queries": t2n(out["proj_queries"]), "fused": t2n(fused),
+         "retrieval_loss": t2n(loss["retrieval_loss"]), "localization_loss": t2n(loss["localization_loss"])}
+    for i, aux in enumerate(out["aux_outputs"]):
+        g[f"aux{i}_pred_spans"] = t2n(aux["pred_spans"])
+    np.savez_compressed(os.path.join(GOLD, "forward_b8_ca.npz"), **g)
+    print("forward_b8_ca:", {k: getattr(v_, "shape", None) for k, v_ in g.items()})
 
 
 def _load_driver():
@@ -231,6 +254,7 @@ def main():
     gen_span_pairs()
     gen_forward_b8(model, sd)
     gen_cfg1(model, args, sd)
+    gen_forward_b8_ca()
 
 
 if __name__ == "__main__":

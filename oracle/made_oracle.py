@@ -347,16 +347,51 @@ def info_nce_loss(sims, logit_scale):
 
 
 # ---------------------------------------------------------------------------------------------
+# mml_fusion "CA": CrossTransformer (model/model_Base.py:169-213), CrossAttention (:93-165), FeedForward (:22-46)
+# ---------------------------------------------------------------------------------------------
+CA = "video_music_fusion_cross_transformer"
+
+
+def cross_transformer(sd: SD, query, context, q_mask, kv_mask, heads: int = 8):
+    """depth 1.  query [B,Lq,256], context [B,Lk,256], masks float {0,1} → [B,Lq,256] (before the caller's masked_fill)."""
+    x = query
+    nx = _ln(sd, f"{CA}.attention_query_layer_norms.0", x)                     # :203
+    nc = _ln(sd, f"{CA}.attention_context_layer_norms.0", context)            # :204
+    q = F.linear(nx, sd[f"{CA}.layers.0.0.to_q.weight"])                       # :135 (no bias)
+    k, v = F.linear(nc, sd[f"{CA}.layers.0.0.to_kv.weight"]).chunk(2, dim=-1)  # :136
+    B, Lq, inner = q.shape
+    dh = inner // heads
+    sp = lambda t: t.reshape(B, t.shape[1], heads, dh).permute(0, 2, 1, 3)     # 'b n (h d) -> b h n d'
+    q, k, v = sp(q), sp(k), sp(v)
+    dots = torch.matmul(q, k.transpose(-1, -2)) * dh ** -0.5                   # :140
+    dots = dots.masked_fill(kv_mask[:, None, None, :] == 0, float("-inf"))     # :158 (kv_mask before the softmax)
+    attn = torch.softmax(dots, dim=-1)
+    attn = attn.masked_fill(q_mask[:, None, :, None] == 0, 0)                  # :160 (q_mask after the softmax)
+    out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(B, Lq, inner)      # :162-163
+    x_res = _linear(sd, f"{CA}.layers.0.0.to_out.0", out)                      # :164
+    attn_x = x_res + x                                                         # :206
+    nf = _ln(sd, f"{CA}.ff_layer_norms.0", attn_x)                             # :207
+    ff = _linear(sd, f"{CA}.layers.0.1.net.3", F.gelu(_linear(sd, f"{CA}.layers.0.1.net.0", nf)))
+    x = ff + attn_x                                                            # :208
+    return _linear(sd, f"{CA}.final_linear", x)                                # :210
+
+
+# ---------------------------------------------------------------------------------------------
 # Uni_model.forward  (model_Uni.py:177-322)
 # ---------------------------------------------------------------------------------------------
 @torch.no_grad()
 def uni_forward(sd: SD, frame_feats, segment_feats, frame_masks, segment_masks, spans_target,
-                video_ids=None, music_ids=None, with_losses: bool = True):
+                video_ids=None, music_ids=None, with_losses: bool = True, mml_fusion: str = "concat"):
     frame_out, video_feats = encode_video(sd, frame_feats, frame_masks)
     segment_out, music_feats = encode_music(sd, segment_feats, segment_masks)
     pooled = xpool(sd, video_feats, segment_out, segment_masks)              # :201
-    src = torch.cat([frame_out, segment_out], dim=1)                         # :207
-    mask = torch.cat([frame_masks, segment_masks], dim=1)
+    if mml_fusion == "CA":                                                   # :209-211
+        src = cross_transformer(sd, segment_out, frame_out, segment_masks, frame_masks)
+        src = src.masked_fill(segment_masks.unsqueeze(-1) == 0, 0)
+        mask = segment_masks
+    else:
+        src = torch.cat([frame_out, segment_out], dim=1)                     # :207
+        mask = torch.cat([frame_masks, segment_masks], dim=1)
     pos = position_embedding_sine(mask)                                      # :216
     hs, memory = detr_forward(sd, src, mask, pos, video_feats.unsqueeze(1))  # :218-227
     output_map = calc_output(sd, hs, frame_out)

@@ -1054,3 +1054,40 @@ def test_xa_music_video_variant(dev, sd_fp32):
     want = torch.einsum("vmd,md->vm", ref / ref.norm(dim=-1, keepdim=True), mf / mf.norm(dim=-1, keepdim=True))
     assert _rel(sims, want) < 1e-5
     assert len(m2.get_matching_parameter()) == 2 * 16 + 1
+
+
+def test_ca_fusion_variant(dev, golden_dir):
+    """mml_fusion "CA" (model_Uni.py:33-43, 209-213): CrossTransformer fusion of the paired frames into the segments,
+    then DETR over the 96 fused tokens.  Against the unmodified reference's fixture and the oracle."""
+    from mgsv_b200.model import Uni_model
+    from mgsv_b200.pipeline import GalleryEvaluator
+    gold = np.load(os.path.join(golden_dir, "forward_b8_ca.npz"))
+    sd = synth.make_state_dict(0, ca=True)
+    model = Uni_model(config.default_args(mml_fusion="CA"), dev, None)
+    model.load_state_dict(sd)                                     # strict: the reference's keys, CA block included
+    assert sum(p.numel() for p in model.parameters()) == 10_534_917 + 1_641_728
+    v, m, ids = synth.make_eval_set(8, 8, synth.BASE_SEED + 100)
+    out, loss, feat, masks, _ = model(v["frame_feats"].to(dev), m["segment_feats"].to(dev), v["frame_mask"].to(dev),
+                                      m["segment_mask"].to(dev), m["spans_target"].to(dev))
+    eng = model.engine()
+    fused16, fused32 = eng.ca_fuse(feat["segment_feats"], masks["segment_masks"], feat["frame_feats"], masks["frame_masks"],
+                                   want_f32=True)
+    assert _rel(fused32, torch.from_numpy(gold["fused"])) < 2 * ACT_RTOL
+    assert bool((fused32[masks["segment_masks"] == 0] == 0).all())           # masked_fill of padded segments
+    d_sp = np.abs(out["pred_spans"].cpu().numpy() - gold["pred_spans"]).max()
+    d_lg = np.abs(out["pred_logits"].cpu().numpy() - gold["pred_logits"]).max()
+    print(f"[parity] CA variant vs reference fixture: fused rel {_rel(fused32, torch.from_numpy(gold['fused'])):.2e}, "
+          f"max|d| spans {d_sp:.2e}, logits {d_lg:.2e}")
+    assert d_sp < 1e-3 and d_lg < 5e-3
+    for i in range(5):
+        np.testing.assert_allclose(out["aux_outputs"][i]["pred_spans"].cpu().numpy(), gold[f"aux{i}_pred_spans"], atol=1e-3)
+    np.testing.assert_allclose(float(loss["localization_loss"]), float(gold["localization_loss"]), rtol=5e-3)
+    np.testing.assert_allclose(float(loss["retrieval_loss"]), float(gold["retrieval_loss"]), rtol=1e-3)
+    # the whole-job evaluator takes the same branch: paired detection == the model's forward on the same pairs
+    ev = GalleryEvaluator(eng, k=4, music_chunk=8, video_chunk=8)
+    r = ev.run({k: t.to(dev) for k, t in v.items()}, {k: t.to(dev) for k, t in m.items()}, torch.arange(8, dtype=torch.int32, device=dev))
+    assert (r["pred_spans"] - out["pred_spans"][:, 0]).abs().max().item() < 2e-3   # fp16 vs fp32 copy of the encoder output
+    # a plain checkpoint has no CA block: the entry refuses
+    plain = Uni_model(config.default_args(), dev, None)
+    with pytest.raises((RuntimeError, ValueError)):
+        plain.engine().ca_fuse(feat["segment_feats"], masks["segment_masks"], feat["frame_feats"], masks["frame_masks"])

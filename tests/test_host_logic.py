@@ -17,7 +17,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_check_args_accepts_shipped_and_rejects_other_branches():
     config.check_args(config.default_args())
-    for k, bad in (("vmr_fusion", "XA-video"), ("mml_fusion", "CA"), ("detr_dec_layers", 2),
+    for k, ok in (("vmr_fusion", "XA-music-video"), ("mml_fusion", "CA")):     # the two built variants beside the shipped config
+        config.check_args(config.default_args(**{k: ok}))
+    for k, bad in (("vmr_fusion", "XA-video"), ("mml_fusion", "add"), ("detr_dec_layers", 2),
                    ("agg_module", "mlp"), ("fusion_mask", 0), ("num_moment_queries", 5)):
         with pytest.raises(ValueError):
             config.check_args(config.default_args(**{k: bad}))

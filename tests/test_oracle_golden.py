@@ -104,3 +104,22 @@ def test_metrics_dedup_semantics():
     assert list(ind) == [0, 1, 0, 2]
     assert top1 == ["a", "c", "a", "a"]
     assert m["R1"] == 50.0
+
+
+def test_forward_b8_ca_variant(golden_dir):
+    """mml_fusion "CA": the oracle's CrossTransformer restatement against the unmodified reference's outputs."""
+    from mgsv_b200 import synth
+    from oracle import made_oracle as O
+    g = _g(golden_dir, "forward_b8_ca.npz")
+    sd = synth.make_state_dict(0, ca=True)
+    v, m, ids = synth.make_eval_set(8, 8, synth.BASE_SEED + 100)
+    out, loss, feat, mask, _ = O.uni_forward(sd, v["frame_feats"], m["segment_feats"], v["frame_mask"], m["segment_mask"],
+                                            m["spans_target"], mml_fusion="CA")
+    fused = O.cross_transformer(sd, feat["segment_feats"], feat["frame_feats"], m["segment_mask"], v["frame_mask"])
+    fused = fused.masked_fill(m["segment_mask"].unsqueeze(-1) == 0, 0)
+    np.testing.assert_allclose(fused.numpy(), g["fused"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(out["pred_spans"].numpy(), g["pred_spans"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(out["pred_logits"].numpy(), g["pred_logits"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(float(loss["localization_loss"]), float(g["localization_loss"]), rtol=1e-5)
+    for i in range(5):
+        np.testing.assert_allclose(out["aux_outputs"][i]["pred_spans"].numpy(), g[f"aux{i}_pred_spans"], atol=2e-6, rtol=0)
