@@ -1091,3 +1091,43 @@ def test_ca_fusion_variant(dev, golden_dir):
     plain = Uni_model(config.default_args(), dev, None)
     with pytest.raises((RuntimeError, ValueError)):
         plain.engine().ca_fuse(feat["segment_feats"], masks["segment_masks"], feat["frame_feats"], masks["frame_masks"])
+
+
+def test_workspace_arena_growth_and_two_contexts(dev, sd_fp32):
+    """Advisor findings of round 1: (1) a second call with a slightly larger batch must not run past the workspace
+    arena sized by the first (the arena is sized by a dry run of the same take() sequence; run this test under
+    compute-sanitizer to see the bounds: profiles/r02_*_memcheck.log); (2) the folded X-Pool constants belong to the
+    context, so two contexts with different weights in one process do not see each other's."""
+    from mgsv_b200.engine import Engine
+    v, m, ids = synth.make_eval_set(44, 44, synth.BASE_SEED + 100)
+    sd_b = synth.make_state_dict(7)
+    eng_a, eng_b = Engine(dev), Engine(dev)
+    eng_a.load_state_dict(sd_fp32)
+    eng_b.load_state_dict(sd_b)
+
+    def job(eng, n):
+        f16, _, vf = eng.encode(_lib.VIDEO, v["frame_feats"][:n].to(dev), v["frame_mask"][:n].to(dev))
+        s16, _, mf = eng.encode(_lib.MUSIC, m["segment_feats"][:n].to(dev), m["segment_mask"][:n].to(dev))
+        det = eng.detr_detect(f16, v["frame_mask"][:n].to(dev), s16, m["segment_mask"][:n].to(dev), vf)
+        kz, gram, bits = eng.gallery_prepare(s16, m["segment_mask"][:n].to(dev))
+        q, vhat = eng.query_prepare(vf)
+        return det["pred_spans"].clone(), eng.xpool_score(q, vhat, kz, gram, bits).clone()
+
+    sp40, sim40 = job(eng_a, 40)
+    sp44, sim44 = job(eng_a, 44)                # 1.1 x the batch on the same context: the arena must grow, not overflow
+    assert torch.equal(sp44[:, :40], sp40) and torch.equal(sim44[:40, :40], sim40)
+    fresh = Engine(dev)
+    fresh.load_state_dict(sd_fp32)
+    sp44f, sim44f = job(fresh, 44)
+    assert torch.equal(sp44, sp44f) and torch.equal(sim44, sim44f)
+    # two contexts, different checkpoints, interleaved calls
+    spb, simb = job(eng_b, 44)
+    sp_again, sim_again = job(eng_a, 44)
+    assert torch.equal(sim_again, sim44) and torch.equal(sp_again, sp44)
+    assert not torch.equal(simb, sim44)
+    only_b = Engine(dev)
+    only_b.load_state_dict(sd_b)
+    spb2, simb2 = job(only_b, 44)
+    assert torch.equal(simb, simb2) and torch.equal(spb, spb2)
+    for e in (eng_a, eng_b, fresh, only_b):
+        e.close()
