@@ -277,6 +277,11 @@ int made_gemm_f16(const void* A, const void* W, int64_t M, int N, int K, const f
 int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias,
                         const void* residual_pair, int act, const float* ln_gamma, const float* ln_beta,
                         void* out_pair, float* out_f32, void* stream);
+/* Same product with ONE plain fp16 output [M, N] and no row-wide epilogue: the shape of the encoder in_proj and the X-Pool
+ * operand projections.  MADE_GEMM_WS128=1 selects an experimental weight-stationary form on 128-column tiles (both
+ * halves of the weight pair of a tile column resident in shared memory; bit-identical results, measured slower). */
+int made_gemm_f16_split_h(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias, int act,
+                          void* out16, void* stream);
 /* The fused feed-forward block (256 -> 1024 -> 256, hidden activation kept on chip):
  * out = [LayerNorm](act(x W1^T + b1) W2^T + b2 + residual).  x [M,256] fp16 (row stride ldx), W1 [1024,256],
  * W2 [256,1024] fp16; act 1 = GELU(erf), 2 = ReLU; residual_pair (nullable) and out_pair are rows of

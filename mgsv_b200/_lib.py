@@ -65,6 +65,7 @@ SIGNATURES = {
     "made_retrieval_loss": [_p, _p, _i64, _i32, _f, _p, _p],
     "made_gemm_f16": [_p, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
     "made_gemm_f16_split": [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p],
+    "made_gemm_f16_split_h": [_p, _p, _i64, _i32, _i32, _i32, _p, _i32, _p, _p],
     "made_ffn_fused": [_p, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _p],
     "made_mha_core": [_p, _p, _p, _p, _i64, _i32, _p, _p],
 }

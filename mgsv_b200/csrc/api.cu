@@ -1334,6 +1334,23 @@ int made_gemm_f16_split(const void* A, const void* W, int64_t M, int N, int K, i
                      static_cast<cudaStream_t>(stream));
 }
 
+int made_gemm_f16_split_h(const void* A, const void* W, int64_t M, int N, int K, int split, const float* bias, int act,
+                          void* out16, void* stream) {
+  MADE_REQUIRE(split == 1 || split == 2, "gemm_f16_split_h: split must be 1 (W pairs) or 2 (A and W pairs)");
+  MADE_REQUIRE(out16, "gemm_f16_split_h: no output");
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.split = split;
+  p.epi.bias = bias;
+  p.epi.act = act;
+  p.epi.out_h = static_cast<op_t*>(out16);
+  p.epi.ld_h = N;
+  return gemm_f16_tc(static_cast<const op_t*>(A), split == 2 ? 2 * K : K, static_cast<const op_t*>(W), 2 * K, N, p, 256,
+                     static_cast<cudaStream_t>(stream));
+}
+
 int made_ffn_fused(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2, const float* b2, int act,
                    const void* residual_pair, int64_t res_ld, const float* ln_gamma, const float* ln_beta, void* out_pair,
                    int64_t ld_out, int has_lo, int64_t M, void* stream) {

@@ -166,6 +166,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2-D tiled prefetch into L2 (no shared memory, no completion to wait for): turns the HBM latency of a tile that will be
+// loaded a little later into an L2 hit
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c_inner,
                                              int32_t c_outer) {

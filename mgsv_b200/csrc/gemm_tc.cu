@@ -23,7 +23,11 @@ template <int BN, bool WS = false>
 struct GemmCfg {
   static constexpr int kBTileBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = WS ? kATileBytes : kATileBytes + kBTileBytes;
-  static constexpr int kResidentBytes = WS ? kWsKBlocks * kBTileBytes : 0;
+  // WS, BN = 256: the [256 x K] slice of a plain fp16 W (4 k-tiles).  WS, BN = 128: the [128 x K] slices of BOTH halves of
+  // a (hi | lo) weight pair (8 k-tiles, 128 KB too) — the weight-stationary form of the split-precision GEMMs, whose
+  // streaming form re-reads 1.1-1.7 MB of W tiles per 128 rows and is bound by that L2 -> SM traffic
+  static constexpr int kResidentTiles = WS ? (BN == 128 ? 2 * kWsKBlocks : kWsKBlocks) : 0;
+  static constexpr int kResidentBytes = kResidentTiles * kBTileBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;      // TMEM columns per acc stage
   static constexpr uint32_t kTmemCols = kAccStride * kAccStages;  // 256 or 512
   static constexpr int kChunks = BN / 32;
@@ -57,12 +61,16 @@ __device__ __forceinline__ uint4 lo_of(const uint4& hi, const float* v) {
                     pack_op2(v[4] - f2.x, v[5] - f2.y), pack_op2(v[6] - f3.x, v[7] - f3.y));
 }
 
+// clock64 stamps of CTA 0 (diagnostics; the pointer is null in production and the branch is warp-uniform)
+#define GEMM_TRACE(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64(); } while (0)
+
 template <int BN, bool WS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_oh, const __grid_constant__ CUtensorMap tmap_of,
                const __grid_constant__ CUtensorMap tmap_ol, const GemmParams p) {
   using Cfg = GemmCfg<BN, WS>;
+  if (threadIdx.x == 0) GEMM_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* resident = smem;                           // WS: W slice, kWsKBlocks tiles of [BN x 64]
@@ -134,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -151,17 +160,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if constexpr (WS) {
           if (n_blk != cur_n) {     // (re)load the resident W slice once the MMAs of the old one are done
             if (groups > 0) mbar_wait(w_empty, (groups - 1) & 1);
-            mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(k_blocks) * Cfg::kBTileBytes);
-            for (int kb = 0; kb < k_blocks; ++kb)
-              tma_load_2d(resident + kb * Cfg::kBTileBytes, &tmap_b, w_full, w_col(kb), row_b);
+            // every distinct [BN x 64] block of W once: the hi halves, then (split) the lo halves K columns to the right
+            const int n_w = kb_seg * (p.split ? 2 : 1);
+            mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(n_w) * Cfg::kBTileBytes);
+            for (int t = 0; t < n_w; ++t)
+              tma_load_2d(resident + t * Cfg::kBTileBytes, &tmap_b, w_full, (t / kb_seg) * p.K + (t % kb_seg) * kBlockK, row_b);
             cur_n = n_blk;
             ++groups;
+          }
+        }
+        // Optional (MADE_GEMM_L2_PREFETCH=1, off by default): pull the A tiles of this CTA's NEXT output tile into L2.
+        // Measured: no gain (23.6 us either way on the music-chunk GEMM) and +2 % on the whole job — the kernel is
+        // bound by the L2 -> SM traffic of its re-streamed W tiles, not by the HBM latency of A.
+        if (p.l2_prefetch && i + 1 < my_tiles) {
+          int64_t m_nx;
+          int n_nx;
+          decode(i + 1, m_nx, n_nx);
+          if (m_nx != m_blk) {
+            const int32_t row_nx = static_cast<int32_t>(m_nx * p.m_stride);
+            const int n_a = kb_seg * (p.split == 2 ? 2 : 1);
+            for (int kb = 0; kb < n_a; ++kb)
+              tma_prefetch_l2_2d(&tmap_a, (kb / kb_seg) * p.K + (kb % kb_seg) * kBlockK, row_nx);
           }
         }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (i == 0 && kb == 0) GEMM_TRACE(2);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col(kb), row_a);
           if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], w_col(kb), row_b);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -198,9 +224,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (it == 0 && kb == 0) GEMM_TRACE(3);
+          if (it == 0 && kb == k_blocks - 1) GEMM_TRACE(4);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-          const uint32_t sb = WS ? smem_u32(resident + kb * Cfg::kBTileBytes) : sa + kATileBytes;
+          // resident block of k block kb: its position inside the operand half (+ kb_seg for the lo halves)
+          const int widx = (p.split != 0 && kb / kb_seg == p.split ? kb_seg : 0) + kb % kb_seg;
+          const uint32_t sb = WS ? smem_u32(resident + widx * Cfg::kBTileBytes) : sa + kATileBytes;
           const uint64_t adesc = umma_smem_desc(sa, 0, 1024);
           const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
 #pragma unroll
@@ -254,6 +284,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = r_in_tile < p.m_valid && grow < M;
       const int64_t srow = row_ok ? grow : 0;   // safe row for loads
       mbar_wait(&tmem_full[as], aphase);
+      if (p.trace) {      // warp-uniform branch; reconverge before the warp-synchronous TMEM loads
+        if (threadIdx.x == 128 && it < 4) GEMM_TRACE(5 + 2 * static_cast<int>(it));
+        __syncwarp();
+      }
       tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + as * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
       float keep = 1.f;
@@ -264,13 +298,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       auto emit = [&](int j, int col0, float (&v)[32]) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
+        if (p.debug & 2) {
+          if (v[0] == 123456.f) stg_h[0] = 1;      // keep the values alive
+          return;
+        }
         if (tma_out) {
           const bool h_first = (j & 1) == 0;     // an fp16 box holds two chunks
           // the previous bulk stores of this half have finished READING the staging boxes
+          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(18 + 5 * j); __syncwarp(); }
           if (e.out_f32 || h_first) {      // a box is about to be overwritten
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
+          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(19 + 5 * j); __syncwarp(); }
           if (e.out_f32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -289,13 +329,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (issuer) {
+          if (issuer && !(p.debug & 1)) {
             const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
             if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, wrow);
             if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, wrow);
             if (e.out_lo && !h_first) tma_store_2d(&tmap_ol, stg_f, col0 - 32, wrow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(20 + 5 * j); __syncwarp(); }
         } else if (row_ok) {
           if (e.out_h) {
             uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
@@ -355,8 +396,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         uint32_t acc[32];
-        tmem_ld_x32(t_acc + c * 32, acc);
-        tmem_wait_ld();
+        if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(16 + 5 * j); __syncwarp(); }
+        if (p.debug & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = static_cast<uint32_t>(i + c);
+        } else {
+          tmem_ld_x32(t_acc + c * 32, acc);
+          tmem_wait_ld();
+        }
+        if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(17 + 5 * j); __syncwarp(); }
         const int col0 = n_blk * BN + c * 32;
         float v[32];
 #pragma unroll
@@ -480,9 +528,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (p.trace) {
+        if (threadIdx.x == 128 && it < 4) GEMM_TRACE(6 + 2 * static_cast<int>(it));
+        __syncwarp();
+      }
     }
     // the staging boxes must outlive the bulk stores that read them
+    if (p.trace) {
+      if (threadIdx.x == 128) GEMM_TRACE(13);
+      __syncwarp();
+    }
     if (tma_out && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.trace) {
+      if (threadIdx.x == 128) GEMM_TRACE(14);
+      __syncwarp();
+    }
   }
 
   tc_fence_before_sync();
@@ -490,6 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 2) {
     tc_fence_after_sync();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (threadIdx.x == 64) GEMM_TRACE(15);
   }
 }
 
@@ -508,6 +569,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return MADE_OK;
 }
 
+// MADE_GEMM_WS128=1 turns the weight-stationary 128-column form of the split GEMMs on (read per call).  OFF by default:
+// it moves 1.5x fewer bytes from L2 but is 2x SLOWER (N = 768, K = 256, split 2: 140 us against 72 us) — the mainloop
+// is bound by the round trip of a ring stage (TMA latency under load + MMA + commit, ~2 us) times the number of k
+// blocks over a 3-deep ring, not by bytes, and 128-column tiles double the k blocks per output.
+bool gemm_ws128_enabled() {
+  const char* v = getenv("MADE_GEMM_WS128");
+  return v && v[0] == '1';
+}
+
 bool gemm_tma_store_enabled() {
   static const bool enabled = [] {
     const char* v = getenv("MADE_GEMM_TMA_STORE");
@@ -515,6 +585,8 @@ bool gemm_tma_store_enabled() {
   }();
   return enabled;
 }
+
+static long long* g_gemm_trace = nullptr;     // diagnostics only (made_debug_gemm_trace)
 
 int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
                  int64_t w_rows, const GemmParams& p, int block_n, cudaStream_t stream) {
@@ -548,11 +620,26 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
   MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.split ? 2 * p.K : p.K), static_cast<uint64_t>(w_rows),
                                static_cast<uint64_t>(ldb) * 2, kBlockK, static_cast<uint32_t>(block_n)));
   GemmParams pp = p;
+  pp.trace = g_gemm_trace;
+  {
+    const char* pf = getenv("MADE_GEMM_L2_PREFETCH");
+    pp.l2_prefetch = (pf && atoi(pf) != 0) ? 1 : 0;
+    const char* dbg = getenv("MADE_GEMM_DEBUG");
+    pp.debug = dbg ? atoi(dbg) : 0;
+  }
   // outputs through TMA bulk stores whenever the tile is a plain [128 x 256] block of the output matrices
   const bool tma_store_enabled = gemm_tma_store_enabled();
   auto aligned16 = [](const void* ptr, int64_t ld, int esz) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * esz) % 16 == 0;
   };
+  // split-precision GEMMs without a row-wide epilogue (LayerNorm / L2) and with a plain fp16 output run weight-
+  // stationary on 128-column tiles: both halves of the weight pair of a tile column stay in shared memory
+  const int64_t m_tiles_all = (p.M + p.m_stride - 1) / p.m_stride;
+  const bool ws128 = block_n == 256 && p.split >= 1 && p.K <= kWsKBlocks * kBlockK && !p.b_batched && !e.ln_gamma && !e.l2norm &&
+                     !e.out_f32 && !e.out_lo && e.out_h && p.N % 128 == 0 && p.n_store == 0 && p.m_valid == 128 && p.m_stride == 128 &&
+                     m_tiles_all * (p.N / 128) >= 2 * sm_count() && gemm_ws128_enabled();
+  if (ws128) MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(2 * p.K), static_cast<uint64_t>(w_rows),
+                                          static_cast<uint64_t>(ldb) * 2, kBlockK, 128));
   pp.tma_store = tma_store_enabled && block_n == 256 && p.m_valid == 128 && p.m_stride == 128 && !e.h_row_idx &&
                  (e.out_h || e.out_f32) && (!e.out_h || aligned16(e.out_h, e.ld_h, 2)) &&
                  (!e.out_f32 || aligned16(e.out_f32, e.ld_f32, 4)) &&
@@ -573,6 +660,7 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
       MADE_TRY(encode_tmap_2d(&tol, e.out_lo, 2, n_ext, static_cast<uint64_t>(p.M),
                               static_cast<uint64_t>(e.ld_h) * 2, 64, 32));
   }
+  if (ws128) return launch_gemm<128, true>(ta, tb, toh, tof, tol, pp, stream);
   if (block_n == 256) {
     // weight-stationary when the [256 x K] slice fits next to the A ring and every CTA gets >= 2 tiles;
     // its shared memory has no room for fp32 staging boxes, so fp32 outputs take the streaming variant
@@ -586,3 +674,10 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
 }
 
 }  // namespace made
+
+// Diagnostics (not part of include/made_b200.h): device buffer of 16 int64 clock stamps written by CTA 0 of the
+// following GEMM launches; null turns tracing off.
+extern "C" int made_debug_gemm_trace(void* dev_buf) {
+  made::g_gemm_trace = static_cast<long long*>(dev_buf);
+  return 0;
+}

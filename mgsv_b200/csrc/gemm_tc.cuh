@@ -48,6 +48,10 @@ struct GemmParams {
   int split = 0;                    // fp16 (hi, lo) operand pairs, the lo halves K columns to the right of the hi halves:
                                     // 1: W = [W_hi | W_lo] (ldb >= 2K)            C = A W_hi^T + A W_lo^T
                                     // 2: also A = [A_hi | A_lo] (lda >= 2K)        C = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T
+  long long* trace = nullptr;       // diagnostics (scripts/diag_gemm_trace.py): clock64 stamps of CTA 0, null in production
+  int debug = 0;                    // bench-only ablations (MADE_GEMM_DEBUG): 1 no bulk stores, 2 no staging writes either,
+                                    // 4 no TMEM loads (results are wrong with any bit set)
+  int l2_prefetch = 0;              // the producer prefetches the A tiles of its next output tile into L2 (MADE_GEMM_L2_PREFETCH=1)
   int n_store = 0;                  // > 0: only the first n_store (< N) output columns exist; W rows >= w_rows read as
                                     // zero and the TMA store clips the rest (needs the TMA-store path, else EUNSUPPORTED)
   GemmEpilogue epi;

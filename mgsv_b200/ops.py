@@ -285,6 +285,16 @@ def gemm_f16_split(a: torch.Tensor, w_pair: torch.Tensor, split: int, bias=None,
     return out
 
 
+def gemm_f16_split_h(a: torch.Tensor, w_pair: torch.Tensor, split: int, bias=None, act: int = 0) -> torch.Tensor:
+    """Split-precision GEMM with one plain fp16 output [M, N] (no row-wide epilogue): weight-stationary when it can."""
+    N, K = w_pair.shape[0], w_pair.shape[1] // 2
+    M = a.shape[0]
+    out = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    _lib.check(_lib.load().made_gemm_f16_split_h(_lib.ptr(a), _lib.ptr(w_pair), M, N, K, split, _lib.ptr(bias), act,
+                                                 _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, act: int,
               residual: Optional[torch.Tensor] = None, ln=None, pair: bool = False) -> torch.Tensor:
     """Fused 256 -> 1024 -> 256 feed-forward block.  x [M, >=256] fp16 (first 256 columns are used), residual

@@ -35,6 +35,11 @@ for K, N in ((256, 256), (256, 768), (768, 256)):
         t(lambda: ops.gemm_f16(x, w, bias=bias, ln=(gam, bet)), "fp16: bias + LN, fp16 out")
         t(lambda: ops.gemm_f16(x, w, bias=bias, residual=res), "fp16: bias + fp32 residual, fp16 out")
         t(lambda: ops.gemm_f16(x, w, bias=bias, residual=res, ln=(gam, bet)), "fp16: bias + fp32 residual + LN, fp16 out")
+    for ws in ("1", "0"):
+        os.environ["MADE_GEMM_WS128"] = ws
+        t(lambda: ops.gemm_f16_split_h(x, wp, 1, bias=bias), f"split=1, fp16 out, weight-stationary={ws}")
+        t(lambda: ops.gemm_f16_split_h(xp, wp, 2, bias=bias), f"split=2, fp16 out, weight-stationary={ws}")
+    os.environ["MADE_GEMM_WS128"] = "0"
     t(lambda: ops.gemm_f16_split(x, wp, 1, bias=bias, out_pair=True), "split=1 (W pair): bias, pair out")
     t(lambda: ops.gemm_f16_split(xp, wp, 2, bias=bias, out_pair=True), "split=2 (A and W pairs): bias, pair out")
     if N == 256:

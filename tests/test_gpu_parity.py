@@ -332,6 +332,26 @@ def test_tcgen05_split_gemm(dev, M, N, K, split):
         assert _rel(plain, a.double() @ w.double().t() + bias.double()) > 1e-4
 
 
+@pytest.mark.parametrize("M,N,K,split", [(40000, 768, 256, 2), (40000, 256, 256, 1), (38017, 512, 192, 2), (300, 768, 256, 2)])
+def test_tcgen05_split_gemm_weight_stationary(dev, M, N, K, split):
+    """The (experimental, off by default) weight-stationary 128-column form of the split GEMMs returns the bits of the
+    streaming form, and both sit at fp16 output rounding of the fp32 product."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a32 = torch.randn(M, K, generator=g)
+    w32 = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(dev)
+    a = ops.split_pair(a32).to(dev) if split == 2 else a32.to(torch.float16).to(dev)
+    wp = ops.split_pair(w32).to(dev)
+    os.environ["MADE_GEMM_WS128"] = "1"
+    ws = ops.gemm_f16_split_h(a, wp, split, bias=bias, act=2)
+    os.environ["MADE_GEMM_WS128"] = "0"
+    st = ops.gemm_f16_split_h(a, wp, split, bias=bias, act=2)
+    assert torch.equal(ws, st)
+    a_eff = a32 if split == 2 else a32.to(torch.float16).float()
+    ref = torch.relu(a_eff.double() @ w32.double().t() + bias.cpu().double())
+    assert (ws.cpu().double() - ref).abs().max().item() <= 1.2e-3 * ref.abs().max().item()
+
+
 def test_tcgen05_split_gemm_epilogues(dev):
     """(hi | lo) pair outputs, pair residuals and the LayerNorm epilogue of the split GEMM."""
     M, N, K = 1000, 256, 256
