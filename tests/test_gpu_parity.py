@@ -650,6 +650,7 @@ def test_full_size_job_properties(dev, engine, sd_fp32):
               f"per-element |d| <= 1e-3|ref| + 1e-5 holds for {100 * per_elem:.2f} % of the pairs")
         assert d.max().item() <= SIM_RTOL * scale, name
         assert d.pow(2).mean().sqrt().item() <= 2.5e-4 * scale, name
+        assert per_elem >= 0.995, (name, per_elem)        # measured 99.80 % / 99.85 %: the rest are entries with |ref| < 0.01
     # 3. rank and top-k are exactly those of double(single) + double(dual)
     total = a["single"].double() + a["dual"].double()
     gt_s = total.gather(1, gt.long().unsqueeze(1))
