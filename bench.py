@@ -62,6 +62,8 @@ def parse():
                     "PCIe bound, and smaller chunks shorten the fill / drain of the copy-compute pipeline")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1 only")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--detect-topk", type=int, default=5, help="N = 1: also time retrieve-then-detect (DETR on the k best "
+                    "retrieved tracks of every query, SURVEY.md 8f rank 2); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-GPU parity check (N > 1)")
     return ap.parse_args()
@@ -477,6 +479,18 @@ def main():
                   "ms_per_step": s_ms, "value": nq / (s_ms / 1e3), "unit": UNIT}
         del sv, dsv
 
+    # ---- retrieve-then-detect (serving mode): the same job + one moment per (query, retrieved track) for the top-k ----
+    rtd = None
+    if world == 1 and args.detect_topk > 0:
+        kd = args.detect_topk
+        ms_rtd, _, _, _, _ = timed(lambda on_host: ev.run(dev_v, dev_m, gt_col, detect_topk=kd), False, min(args.steps, 5), 2)
+        rtd = {"k_det": kd, "ms_per_step": ms_rtd, "value": nq_total / (ms_rtd / 1e3), "unit": UNIT,
+               "extra_detections_per_step": nq_total * kd,
+               "extra_ms_per_1000_detections": (ms_rtd - ms_dev) / (nq_total * kd / 1e3),
+               "note": "configs[1] job + DETR moment detection on the k_det best retrieved tracks of every query "
+                       "(GalleryEvaluator.run(detect_topk=k)); checked against the oracle in "
+                       "tests/test_gpu_parity.py::test_retrieve_then_detect_vs_oracle"}
+
     e2e = None
     if not args.no_e2e:
         # reference point for the e2e number: plain pinned-host -> device copy rate of this box
@@ -606,6 +620,8 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if rtd is not None:
+            line["retrieve_then_detect"] = rtd
         if strong is not None:
             line["strong_same_job"] = strong
         if sharded_parity is not None:
