@@ -23,6 +23,13 @@ NVCC_FLAGS = [
 ]
 
 
+# MADE_DIAG=1 (with --force): compile the kernel diagnostics in — clock-stamp traces and ablation switches of the GEMM and
+# X-Pool kernels (scripts/diag_gemm_trace.py, diag_xpool_trace.py, MADE_GEMM_DEBUG / MADE_XPOOL_DEBUG).  The product
+# build carries none of their branches; rebuild with --force (and without MADE_DIAG) afterwards.
+if os.environ.get("MADE_DIAG") == "1":
+    NVCC_FLAGS += ["-DMADE_GEMM_DIAG", "-DMADE_XPOOL_DIAG", "-DMADE_XPOOL_TRACE"]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

@@ -61,8 +61,17 @@ __device__ __forceinline__ uint4 lo_of(const uint4& hi, const float* v) {
                     pack_op2(v[4] - f2.x, v[5] - f2.y), pack_op2(v[6] - f3.x, v[7] - f3.y));
 }
 
-// clock64 stamps of CTA 0 (diagnostics; the pointer is null in production and the branch is warp-uniform)
+// Diagnostics (scripts/diag_gemm_trace.py, MADE_GEMM_DEBUG ablations) are compiled in only with -DMADE_GEMM_DIAG
+// (`MADE_DIAG=1 python -m mgsv_b200.build`): the product kernel carries none of their branches.
+#ifdef MADE_GEMM_DIAG
 #define GEMM_TRACE(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64(); } while (0)
+#define GEMM_TRACING (p.trace != nullptr)
+#define GEMM_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define GEMM_TRACE(slot) do { } while (0)
+#define GEMM_TRACING false
+#define GEMM_DBG(bit) false
+#endif
 
 template <int BN, bool WS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -284,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = r_in_tile < p.m_valid && grow < M;
       const int64_t srow = row_ok ? grow : 0;   // safe row for loads
       mbar_wait(&tmem_full[as], aphase);
-      if (p.trace) {      // warp-uniform branch; reconverge before the warp-synchronous TMEM loads
+      if (GEMM_TRACING) {      // warp-uniform branch; reconverge before the warp-synchronous TMEM loads
         if (threadIdx.x == 128 && it < 4) GEMM_TRACE(5 + 2 * static_cast<int>(it));
         __syncwarp();
       }
@@ -298,19 +307,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       auto emit = [&](int j, int col0, float (&v)[32]) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
-        if (p.debug & 2) {
+        if (GEMM_DBG(2)) {
           if (v[0] == 123456.f) stg_h[0] = 1;      // keep the values alive
           return;
         }
         if (tma_out) {
           const bool h_first = (j & 1) == 0;     // an fp16 box holds two chunks
           // the previous bulk stores of this half have finished READING the staging boxes
-          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(18 + 5 * j); __syncwarp(); }
+          if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(18 + 5 * j); __syncwarp(); }
           if (e.out_f32 || h_first) {      // a box is about to be overwritten
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
-          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(19 + 5 * j); __syncwarp(); }
+          if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(19 + 5 * j); __syncwarp(); }
           if (e.out_f32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -329,14 +338,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (issuer && !(p.debug & 1)) {
+          if (issuer && !GEMM_DBG(1)) {
             const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
             if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, wrow);
             if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, wrow);
             if (e.out_lo && !h_first) tma_store_2d(&tmap_ol, stg_f, col0 - 32, wrow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(20 + 5 * j); __syncwarp(); }
+          if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(20 + 5 * j); __syncwarp(); }
         } else if (row_ok) {
           if (e.out_h) {
             uint4* o = reinterpret_cast<uint4*>(e.out_h + hrow * e.ld_h + col0);
@@ -396,15 +405,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         uint32_t acc[32];
-        if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(16 + 5 * j); __syncwarp(); }
-        if (p.debug & 4) {
+        if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(16 + 5 * j); __syncwarp(); }
+        if (GEMM_DBG(4)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] = static_cast<uint32_t>(i + c);
         } else {
           tmem_ld_x32(t_acc + c * 32, acc);
           tmem_wait_ld();
         }
-        if (p.trace) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(17 + 5 * j); __syncwarp(); }
+        if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(17 + 5 * j); __syncwarp(); }
         const int col0 = n_blk * BN + c * 32;
         float v[32];
 #pragma unroll
@@ -528,18 +537,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
-      if (p.trace) {
+      if (GEMM_TRACING) {
         if (threadIdx.x == 128 && it < 4) GEMM_TRACE(6 + 2 * static_cast<int>(it));
         __syncwarp();
       }
     }
     // the staging boxes must outlive the bulk stores that read them
-    if (p.trace) {
+    if (GEMM_TRACING) {
       if (threadIdx.x == 128) GEMM_TRACE(13);
       __syncwarp();
     }
     if (tma_out && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (p.trace) {
+    if (GEMM_TRACING) {
       if (threadIdx.x == 128) GEMM_TRACE(14);
       __syncwarp();
     }

@@ -143,6 +143,11 @@ __device__ __forceinline__ int xpool_nblk(const uint4& mb) {
 // trace slot: [track u][event e] of CTA 0, 24 events per track, 64 tracks.  Compiled in only with -DMADE_XPOOL_TRACE:
 // the single-lane stamps of the epilogue diverge a warp right before its warp-synchronous tcgen05.ld / bar.sync, which
 // is tolerable for a timing diagnostic and not for the product kernel.
+#ifdef MADE_XPOOL_DIAG
+#define XP_DBG(bit) ((p.debug & (bit)) != 0)      // MADE_XPOOL_DEBUG ablations (scripts/diag_xpool.py)
+#else
+#define XP_DBG(bit) false
+#endif
 #ifdef MADE_XPOOL_TRACE
 #define XP_TRACE(e) do { if (p.trace && blockIdx.x == 0 && u < 64) p.trace[u * 24 + (e)] = clock64(); __syncwarp(); } while (0)
 #else
@@ -208,7 +213,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
       uint32_t u = 0;
       uint4 mb_next = __ldg(reinterpret_cast<const uint4*>(p.maskbits + static_cast<int64_t>(slice) * 4));
       for (int64_t m = slice; m < p.n_tracks; m += p.slices, ++u) {
-        const int nb = (p.debug & 64) ? 5 : xpool_nblk(mb_next) - 1;        // rows [0, 16 (nb + 1)) of the track are fetched
+        const int nb = XP_DBG(64) ? 5 : xpool_nblk(mb_next) - 1;        // rows [0, 16 (nb + 1)) of the track are fetched
         if (m + p.slices < p.n_tracks) mb_next = __ldg(reinterpret_cast<const uint4*>(p.maskbits + (m + p.slices) * 4));
         const uint32_t blk_bytes = static_cast<uint32_t>(nb + 1) * 16 * 128;      // one slab's share
         const int32_t row = static_cast<int32_t>(m * kXL);
@@ -234,13 +239,13 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
       uint32_t u = 0;
       uint4 mb_next = __ldg(reinterpret_cast<const uint4*>(p.maskbits + static_cast<int64_t>(slice) * 4));
       for (int64_t m = slice; m < p.n_tracks; m += p.slices, ++u) {
-        const int nblk = (p.debug & 128) ? 6 : xpool_nblk(mb_next);          // 16-segment blocks up to the last valid segment
+        const int nblk = XP_DBG(128) ? 6 : xpool_nblk(mb_next);          // 16-segment blocks up to the last valid segment
         if (m + p.slices < p.n_tracks) mb_next = __ldg(reinterpret_cast<const uint4*>(p.maskbits + (m + p.slices) * 4));
         const uint32_t idesc_s = umma_idesc_f16(128, static_cast<uint32_t>(nblk) * 16, 0, 0);   // S = Q K^T (B K-major)
         mbar_wait(k_full, u & 1);
         mbar_wait(t_free, (u & 1) ^ 1);
         tc_fence_after_sync();
-        if (!(p.debug & 16)) {
+        if (!XP_DBG(16)) {
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
             const uint32_t off = (ks >> 2) * kSlabQ + (ks & 3) * 32;
@@ -255,7 +260,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
         mbar_wait(p_full, u & 1);
         mbar_wait(zg_full, u & 1);
         tc_fence_after_sync();
-        for (int ks = 0; ks < ((p.debug & 32) ? 0 : nblk); ++ks) {
+        for (int ks = 0; ks < (XP_DBG(32) ? 0 : nblk); ++ks) {
           const uint32_t offp = (ks >> 2) * kSlabQ + (ks & 3) * 32;      // P: K-major A, 16 k = 32 B
           const uint32_t offb = ks * 16 * 128;                            // 16 t-rows of 128 B
           umma_ss(tmem_base + kColT, umma_smem_desc(aP + offp, 0, 1024), umma_smem_desc(aG + offb, kSlabT, 1024),
@@ -264,7 +269,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
         tc_commit(t_full);                                                // the quadratic form can start
         mbar_wait(y_free, (u & 1) ^ 1);
         tc_fence_after_sync();
-        for (int ks = 0; ks < ((p.debug & 8) ? 0 : nblk); ++ks) {
+        for (int ks = 0; ks < (XP_DBG(8) ? 0 : nblk); ++ks) {
           const uint32_t offp = (ks >> 2) * kSlabQ + (ks & 3) * 32;
           const uint32_t offb = ks * 16 * 128;
           umma_ss(tmem_base + kColY, umma_smem_desc(aP + offp, 0, 1024), umma_smem_desc(aZ + offb, kSlabT, 1024),
@@ -333,7 +338,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
       const uint4 mb = mb_next;                   // the mask words of the next track are fetched a track ahead
       if (m + p.slices < p.n_tracks) mb_next = __ldg(reinterpret_cast<const uint4*>(p.maskbits + (m + p.slices) * 4));
 #endif
-      const int nblk = (p.debug & 128) ? 6 : xpool_nblk(mb);
+      const int nblk = XP_DBG(128) ? 6 : xpool_nblk(mb);
       const int n0 = (nblk + 1) >> 1;
       const int b0 = h ? n0 : 0;                  // first 16-segment block of this half
       const int nmine = h ? nblk - n0 : n0;       // 0..3 blocks
@@ -371,7 +376,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
         // P -> shared memory, 128B-swizzled K-major: logical 16-byte chunk c of row r sits at c ^ (r & 7)
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          if (j < nmine && !(p.debug & 2)) {
+          if (j < nmine && !XP_DBG(2)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const __half2 e = __floats2half2_rn(fast_exp(__uint_as_float(sv[j][2 * i]) - mx),
@@ -406,7 +411,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          if (j < nmine && !(p.debug & 4)) {
+          if (j < nmine && !XP_DBG(4)) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&pk[j * 8 + i]));
@@ -428,7 +433,7 @@ xpool_score_kernel(const __grid_constant__ XpoolMaps tm, const __grid_constant__
       if (threadIdx.x == 128) XP_TRACE(14);
       tc_fence_after_sync();
       float s2 = 0.f, sg2 = 0.f, su = 0.f;
-      if (!(p.debug & 1)) {
+      if (!XP_DBG(1)) {
         if (h == 0) y_sweep<0>(c_xp, lane_addr, s2, sg2, su);
         else y_sweep<1>(c_xp, lane_addr, s2, sg2, su);
       }

@@ -1,4 +1,5 @@
 """Clock-stamp timeline of CTA 0 of one tcgen05 GEMM launch (K = N = 256): where the fixed ~20 us go. Diagnostics."""
+# needs a diagnostics build: MADE_DIAG=1 python -m mgsv_b200.build --force  (rebuild without MADE_DIAG afterwards)
 import ctypes as C, os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

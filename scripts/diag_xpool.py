@@ -1,4 +1,5 @@
 """Ablation timings of the fused X-Pool kernel (MADE_XPOOL_DEBUG bits) at the bench's chunk shape. Diagnostics."""
+# needs a diagnostics build: MADE_DIAG=1 python -m mgsv_b200.build --force  (rebuild without MADE_DIAG afterwards)
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
