@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 # X-Pool kernels (scripts/diag_gemm_trace.py, diag_xpool_trace.py, MADE_GEMM_DEBUG / MADE_XPOOL_DEBUG).  The product
 # build carries none of their branches; rebuild with --force (and without MADE_DIAG) afterwards.
 if os.environ.get("MADE_DIAG") == "1":
-    NVCC_FLAGS += ["-DMADE_GEMM_DIAG", "-DMADE_XPOOL_DIAG", "-DMADE_XPOOL_TRACE"]
+    NVCC_FLAGS += ["-DMADE_GEMM_DIAG", "-DMADE_XPOOL_DIAG", "-DMADE_XPOOL_TRACE", "-DMADE_FFN_DIAG"]
 
 
 def _nvcc() -> str:

@@ -25,6 +25,13 @@
 
 namespace made {
 
+// MADE_FFN_DEBUG ablations (scripts/diag_ffn.py) exist only in a diagnostics build (MADE_DIAG=1)
+#ifdef MADE_FFN_DIAG
+#define FFN_DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define FFN_DBG(bit) false
+#endif
+
 namespace {
 
 constexpr int kM = 128;            // rows per tile
@@ -155,7 +162,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       bool skip = false;
       auto next_stage = [&]() -> uint8_t* {
         mbar_wait(&empty[stage], phase ^ 1);
-        skip = (p.debug & 1) && fills >= kStages;
+        skip = FFN_DBG(1) && fills >= kStages;
         ++fills;
         if (skip) mbar_arrive(&full[stage]);      // ablation: stale weights, no L2 traffic
         else mbar_arrive_expect_tx(&full[stage], kStageBytes);
@@ -297,7 +304,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           const uint32_t* src = i < 8 ? &a0[4 * i] : &a1[4 * (i - 8)];
           float v0 = __uint_as_float(src[0]) + bb.x, v1 = __uint_as_float(src[1]) + bb.y;
           float v2 = __uint_as_float(src[2]) + bb.z, v3 = __uint_as_float(src[3]) + bb.w;
-          if (p.debug & 4) {
+          if (FFN_DBG(4)) {
           } else if (p.act == 1) {
             v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); v2 = gelu_erf_fast(v2); v3 = gelu_erf_fast(v3);
           } else {
@@ -335,7 +342,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       };
 #pragma unroll
       for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0u, 0u, 0u, 0u); rl[i] = make_uint4(0u, 0u, 0u, 0u); }
-      if (!(p.debug & 2)) res_issue(half * 4);
+      if (!FFN_DBG(2)) res_issue(half * 4);
       mbar_wait(y_full, it & 1);
       tc_fence_after_sync();
       // every GEMM-2 MMA of the tile has completed: the hidden buffer is free and becomes the staging boxes
@@ -410,7 +417,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       };
-      if (p.debug & 2) {
+      if (FFN_DBG(2)) {
         // ablation: no output epilogue
       } else if (!do_ln) {
 #pragma unroll 1

@@ -1,4 +1,5 @@
 """Ablation timings of the fused FFN kernel (MADE_FFN_DEBUG bits) at the music-chunk size. Diagnostics."""
+# needs a diagnostics build: MADE_DIAG=1 python -m mgsv_b200.build --force  (rebuild without MADE_DIAG afterwards)
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
