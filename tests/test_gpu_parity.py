@@ -103,6 +103,42 @@ def test_span_kernels_bit_exact_vs_oracle(dev, n, m):
         assert np.array_equal(c.cpu().numpy(), O.matcher_cost(prob, a, tgt).numpy(), equal_nan=True)
 
 
+@pytest.mark.parametrize("kind", ["unit", "seconds", "edges", "tiny_and_huge"])
+def test_span_fast_division_path_is_bit_identical(dev, kind):
+    """CTAs whose spans all lie in the proven-safe range divide without the guards of __fdiv_rn (6 instead of 13
+    instructions per quotient); the bits must equal the guarded path's on every pair, NaNs included."""
+    g = torch.Generator().manual_seed({"unit": 1, "seconds": 2, "edges": 3, "tiny_and_huge": 4}[kind])
+    n, m = 2048, 4096
+    if kind == "unit":
+        a = torch.stack([torch.rand(n, generator=g), torch.rand(n, generator=g) * 0.3 + 0.01], 1)
+        b = torch.stack([torch.rand(m, generator=g), torch.rand(m, generator=g) * 0.3 + 0.01], 1)
+    elif kind == "seconds":
+        a = torch.stack([torch.rand(n, generator=g) * 240, torch.rand(n, generator=g) * 60], 1)
+        b = torch.stack([torch.rand(m, generator=g) * 240, torch.rand(m, generator=g) * 60], 1)
+    elif kind == "edges":      # zero widths, identical spans, touching spans, a quantised grid (many exact ties and 0/0)
+        a = torch.stack([torch.randint(0, 8, (n,), generator=g) / 8.0, torch.randint(0, 4, (n,), generator=g) / 8.0], 1)
+        b = torch.stack([torch.randint(0, 8, (m,), generator=g) / 8.0, torch.randint(0, 4, (m,), generator=g) / 8.0], 1)
+    else:                      # values at and beyond the borders of the safe range: some CTAs fast, some guarded
+        ea = torch.randint(-40, 41, (n,), generator=g).float()
+        eb = torch.randint(-40, 41, (m,), generator=g).float()
+        a = torch.stack([torch.rand(n, generator=g) * 2 ** ea, torch.rand(n, generator=g) * 2 ** ea], 1)
+        b = torch.stack([torch.rand(m, generator=g) * 2 ** eb, torch.rand(m, generator=g) * 2 ** eb], 1)
+        b[:1024] = torch.stack([torch.rand(1024, generator=g), torch.rand(1024, generator=g) * 0.2], 1)   # one all-safe CTA column
+        a[:64] = torch.stack([torch.rand(64, generator=g), torch.rand(64, generator=g) * 0.2], 1)
+    a, b = a.to(dev), b.to(dev)
+    sa, sb = ops.span_cw_to_se(a), ops.span_cw_to_se(b)
+    prob = torch.rand(n, generator=g).to(dev)
+    out = {}
+    for fast in ("1", "0"):
+        os.environ["MADE_SPAN_FAST"] = fast
+        out[fast] = (ops.generalized_temporal_iou(sa, sb, check=False), *ops.temporal_iou(sa, sb), ops.matcher_cost(prob, a, b))
+    os.environ.pop("MADE_SPAN_FAST")
+    for x, y in zip(out["1"], out["0"]):
+        assert torch.equal(x.view(torch.int32), y.view(torch.int32))          # bit patterns, NaN payloads included
+    if kind == "edges":
+        assert bool(torch.isnan(out["1"][0]).any())                            # 0/0 of two zero-width spans is there (Q10)
+
+
 def test_span_kernels_empty_and_errors(dev):
     e = torch.zeros((0, 2), device=dev)
     s = torch.tensor([[0.1, 0.5]], device=dev)
