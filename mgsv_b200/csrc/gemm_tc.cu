@@ -8,7 +8,6 @@ namespace made {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int kStages = 3;
 constexpr int kWarpBoxBytes = 32 * 128;              // one TMA store box: a warp's 32 rows x 128 bytes (swizzled)
 constexpr int kAccStages = 2;
 constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
@@ -19,9 +18,16 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 // WS = weight-stationary: the whole [BN x K<=256] slice of W stays in shared memory while the CTA
 // walks a contiguous range of M tiles (n-major tile order), so only A tiles stream through the ring.
 constexpr int kWsKBlocks = 4;                       // K <= 256
-template <int BN, bool WS = false>
+// PAIR = CTA pair (cta_group::2): the two CTAs of a 2-CTA cluster compute ONE [256 x BN] tile with 256-row MMAs issued by
+// the leader.  Each CTA stages its own 128 rows of A and only its own HALF of the W rows of a k block (32 instead of 48
+// KB from L2 per k block and CTA — these GEMMs are bound by the L2 -> SM operand traffic), holds the
+// accumulator of its 128 rows in its own TMEM and runs the unchanged epilogue on them.
+template <int BN, bool WS = false, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int kBTileBytes = BN * kBlockK * 2;
+  static_assert(!PAIR || (BN == 256 && !WS), "CTA pairs: 256-column streaming tiles only");
+  static constexpr int kStages = PAIR ? 4 : 3;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;               // W rows of a k block this CTA stages
+  static constexpr int kBTileBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = WS ? kATileBytes : kATileBytes + kBTileBytes;
   // WS, BN = 256: the [256 x K] slice of a plain fp16 W (4 k-tiles).  WS, BN = 128: the [128 x K] slices of BOTH halves of
   // a (hi | lo) weight pair (8 k-tiles, 128 KB too) — the weight-stationary form of the split-precision GEMMs, whose
@@ -32,7 +38,8 @@ struct GemmCfg {
   static constexpr uint32_t kTmemCols = kAccStride * kAccStages;  // 256 or 512
   static constexpr int kChunks = BN / 32;
   // dynamic smem: tiles + barriers + tmem slot + LN partials
-  static constexpr int kMiscBytes = 256 + 4 * 128 * 4;      // barriers + TMEM slot, LN partial sums
+  static constexpr int kVecFloats = 2048 + 2 * 256;         // bias [N <= 2048], LayerNorm gamma / beta [256] (epilogue copies)
+  static constexpr int kMiscBytes = 256 + 4 * 128 * 4 + kVecFloats * 4;      // barriers + TMEM slot, LN partial sums, vectors
   static constexpr int kStageOutOffset = ((kResidentBytes + kStages * kStageBytes + kMiscBytes + 1023) / 1024) * 1024;
   // the weight-stationary variant has room for the fp16 boxes only (fp32 outputs go to the streaming variant)
   static constexpr int kStageOutBytes = (WS ? 1 : 2) * kEpiWarps * kWarpBoxBytes;
@@ -73,12 +80,13 @@ __device__ __forceinline__ uint4 lo_of(const uint4& hi, const float* v) {
 #define GEMM_DBG(bit) false
 #endif
 
-template <int BN, bool WS>
+template <int BN, bool WS, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_oh, const __grid_constant__ CUtensorMap tmap_of,
                const __grid_constant__ CUtensorMap tmap_ol, const GemmParams p) {
-  using Cfg = GemmCfg<BN, WS>;
+  using Cfg = GemmCfg<BN, WS, PAIR>;
+  constexpr int kStages = Cfg::kStages;
   if (threadIdx.x == 0) GEMM_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,6 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* w_empty = w_full + 1;                     // WS: every MMA that reads the slice has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + 1);
   float* ln_part = reinterpret_cast<float*>(after + 256);   // [2 halves][2][128]
+  float* vec_s = ln_part + 4 * 128;                         // bias [<= 2048] | gamma [256] | beta [256]
   uint8_t* stage_out = smem + Cfg::kStageOutOffset;         // per epilogue warp: one fp16 box, then one fp32 box
 
   const int warp = threadIdx.x >> 5;
@@ -110,10 +119,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // tile schedule: streaming = round-robin, m-major; WS = one contiguous n-major range per CTA
   const int64_t ws_per = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t ws_t0 = static_cast<int64_t>(blockIdx.x) * ws_per;
-  const int64_t my_tiles = WS ? (ws_t0 >= n_tiles ? 0 : (n_tiles - ws_t0 < ws_per ? n_tiles - ws_t0 : ws_per))
-                              : (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // PAIR: the cluster (blockIdx.x / 2) walks [256 x BN] pair tiles round-robin; rank r of the pair owns rows 128 r ..
+  // of each (an odd tile count leaves the last pair's second half empty: its loads read zeros, its stores are clipped)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int64_t n_ptiles = ((m_tiles + 1) / 2) * n_blocks;
+  const int64_t n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int64_t my_tiles = PAIR ? (n_ptiles - cluster_id + n_clusters - 1) / n_clusters
+                           : WS ? (ws_t0 >= n_tiles ? 0 : (n_tiles - ws_t0 < ws_per ? n_tiles - ws_t0 : ws_per))
+                                : (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   auto decode = [&](int64_t i, int64_t& m_blk, int& n_blk) {
-    if constexpr (WS) {
+    if constexpr (PAIR) {
+      const int64_t t = cluster_id + i * n_clusters;
+      m_blk = (t / n_blocks) * 2 + cta_rank;
+      n_blk = static_cast<int>(t % n_blocks);
+    } else if constexpr (WS) {
       const int64_t t = ws_t0 + i;
       n_blk = static_cast<int>(t / m_tiles);
       m_blk = t % m_tiles;
@@ -140,15 +160,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);    // PAIR: the epilogue warps of both CTAs (leader's copy)
     }
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) GEMM_TRACE(1);
@@ -165,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int n_blk;
         decode(i, m_blk, n_blk);
         const int32_t row_a = static_cast<int32_t>(m_blk * p.m_stride);
-        const int32_t row_b = p.b_batched ? row_a : n_blk * BN;
+        const int32_t row_b = p.b_batched ? row_a : n_blk * BN + static_cast<int32_t>(cta_rank) * Cfg::kBRows;
         if constexpr (WS) {
           if (n_blk != cur_n) {     // (re)load the resident W slice once the MMAs of the old one are done
             if (groups > 0) mbar_wait(w_empty, (groups - 1) & 1);
@@ -195,18 +219,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (i == 0 && kb == 0) GEMM_TRACE(2);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col(kb), row_a);
-          if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], w_col(kb), row_b);
+          if constexpr (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the two stages
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(sa, &tmap_a, fb, a_col(kb), row_a);
+            tma_load_2d_pair(sa + kATileBytes, &tmap_b, fb, w_col(kb), row_b);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (i == 0 && kb == 0) GEMM_TRACE(2);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col(kb), row_a);
+            if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], w_col(kb), row_b);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1;
@@ -221,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         const int as = static_cast<int>(it & 1);
         const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[as], aphase ^ 1);
+        else mbar_wait(&tmem_empty[as], aphase ^ 1);
         if constexpr (WS) {
           if (n_blk != cur_n) {
             mbar_wait(w_full, groups & 1);
@@ -245,11 +278,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);
+          if constexpr (PAIR) tc_commit_pair(&empty_bar[stage]);     // the stage is free in BOTH CTAs
+          else tc_commit(&empty_bar[stage]);
           if (kb == k_blocks - 1) {
-            tc_commit(&tmem_full[as]);
+            if constexpr (PAIR) tc_commit_pair(&tmem_full[as]);
+            else tc_commit(&tmem_full[as]);
             if constexpr (WS) {
               if (n_next != n_blk) tc_commit(w_empty);   // last tile that reads this W slice
             }
@@ -282,6 +318,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* stg_f = stage_out + (kEpiWarps + ew) * kWarpBoxBytes;          // [32 rows][128 B] fp32 box (32 columns)
     const int swz = lane & 7;
 
+    // The CTA's shared memory leaves no L1: every __ldg in the epilogue is an L2 round trip (~1000 cycles under the
+    // operand traffic).  The vectors every row needs — bias, LayerNorm gamma / beta — are copied to shared memory once.
+    const bool bias_smem = e.bias != nullptr && p.N <= 2048;
+    float* gam_s = vec_s + 2048;
+    float* bet_s = gam_s + 256;
+    {
+      const int et = threadIdx.x - 4 * 32;
+      if (bias_smem)
+        for (int i = et; i < p.N; i += kEpiThreads) vec_s[i] = __ldg(e.bias + i);
+      if (do_ln && et < BN) {
+        gam_s[et] = __ldg(e.ln_gamma + et);
+        bet_s[et] = __ldg(e.ln_beta + et);
+      }
+      named_bar_sync(1, kEpiThreads);
+    }
+
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int as = static_cast<int>(it & 1);
       const uint32_t aphase = static_cast<uint32_t>((it >> 1) & 1);
@@ -305,8 +357,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       // final values of chunk j (columns col0..col0+31 of this thread's row) -> every requested output
       auto emit = [&](int j, int col0, float (&v)[32]) {
+        if (e.row_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= keep;
+          for (int i = 0; i < 32; ++i) v[i] *= keep;
+        }
         if (GEMM_DBG(2)) {
           if (v[0] == 123456.f) stg_h[0] = 1;      // keep the values alive
           return;
@@ -336,9 +390,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 *reinterpret_cast<uint4*>(stg_f + lane * 128 + ((((j & 1) * 4 + i) ^ swz) << 4)) = lo_of(hi, &v[8 * i]);
             }
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (issuer && !GEMM_DBG(1)) {
+          if (e.out_f32 || !h_first) {      // a store follows: the generic-proxy writes must be visible to the TMA engine
+            fence_proxy_async_smem();
+            __syncwarp();
+          }
+          if (issuer && !GEMM_DBG(1) && (e.out_f32 || !h_first)) {
             const int32_t wrow = static_cast<int32_t>(row0) + q * 32;
             if (e.out_f32) tma_store_2d(&tmap_of, stg_f, col0, wrow);
             if (e.out_h && !h_first) tma_store_2d(&tmap_oh, stg_h, col0 - 32, wrow);
@@ -382,28 +438,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
 
       float psum = 0.f, psq = 0.f;
-      // fp32 residual rows are fetched one 32-column chunk ahead of the chunk being processed, so their
-      // L2 latency overlaps the TMEM read / math / store of the previous chunk
+      // Row operands of the epilogue — the residual (fp32 row, or an fp16 (hi, lo) pair) or else the position table row —
+      // are fetched one 32-column chunk AHEAD of the chunk being processed: their L2 latency overlaps the TMEM read /
+      // math / store of the previous chunk instead of stalling every chunk
       const bool res32 = e.residual != nullptr && e.residual_f32;
+      const bool res16 = e.residual != nullptr && !e.residual_f32;
+      const bool tab_pre = e.row_table != nullptr && e.residual == nullptr;
       const float* res_row = res32 ? static_cast<const float*>(e.residual) + srow * e.res_ld + n_blk * BN : nullptr;
-      float4 rnext[8];
-      if (res32) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + chunk_of(0) * 32) + i);
+      const op_t* res_hi = res16 ? static_cast<const op_t*>(e.residual) + srow * e.res_ld + n_blk * BN : nullptr;
+      const op_t* res_lo = res16 && e.residual_lo ? e.residual_lo + srow * e.res_ld + n_blk * BN : nullptr;
+      const float* tab_row = nullptr;
+      if (e.row_table) {
+        const int64_t trow = (e.row_src ? static_cast<int64_t>(__ldg(e.row_src + srow)) : srow) % e.row_mod;
+        tab_row = e.row_table + trow * p.N + n_blk * BN;
       }
+      uint4 pre[8];
+      auto prefetch = [&](int c) {      // the row operand words of chunk c
+        if (res32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(res_row + c * 32) + i);
+        } else if (res16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(res_hi + c * 32) + i);
+          if (res_lo) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pre[4 + i] = __ldg(reinterpret_cast<const uint4*>(res_lo + c * 32) + i);
+          }
+        } else if (tab_pre) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(tab_row + c * 32) + i);
+        }
+      };
+      prefetch(chunk_of(0));
       // ---------- pass 1: x = act(acc + bias + table + residual); store or stash ----------
       for (int j = 0; j < n_my; ++j) {
         const int c = chunk_of(j);
-        float4 rcur[8];
-        if (res32) {
+        uint4 cur[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          if (j + 1 < n_my) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              rnext[i] = __ldg(reinterpret_cast<const float4*>(res_row + chunk_of(j + 1) * 32) + i);
-          }
-        }
+        for (int i = 0; i < 8; ++i) cur[i] = pre[i];
+        if (j + 1 < n_my) prefetch(chunk_of(j + 1));
         uint32_t acc[32];
         if (GEMM_TRACING) { if (threadIdx.x == 128 && it == 1) GEMM_TRACE(16 + 5 * j); __syncwarp(); }
         if (GEMM_DBG(4)) {
@@ -419,52 +492,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
         if (e.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 t = __ldg(b4 + i);
-            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-          }
-        }
-        if (e.row_table) {
-          const int64_t trow = (e.row_src ? static_cast<int64_t>(__ldg(e.row_src + srow)) : srow) % e.row_mod;
-          const float4* t4 = reinterpret_cast<const float4*>(e.row_table + trow * p.N + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 t = __ldg(t4 + i);
-            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-          }
-        }
-        if (e.residual) {
-          if (e.residual_f32) {
+          if (bias_smem) {
+            const float4* b4 = reinterpret_cast<const float4*>(vec_s + col0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 t = rcur[i];
+              const float4 t = b4[i];
               v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
             }
           } else {
-            const uint4* r4 = reinterpret_cast<const uint4*>(
-                static_cast<const op_t*>(e.residual) + srow * e.res_ld + col0);
-            const uint4* l4 = e.residual_lo ? reinterpret_cast<const uint4*>(e.residual_lo + srow * e.res_ld + col0)
-                                            : nullptr;
+            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 t = __ldg(r4 + i);
-              const op2_t* h = reinterpret_cast<const op2_t*>(&t);
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(b4 + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+        }
+        if (e.row_table) {
+          if (tab_pre) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += __uint_as_float(cur[i].x); v[4 * i + 1] += __uint_as_float(cur[i].y);
+              v[4 * i + 2] += __uint_as_float(cur[i].z); v[4 * i + 3] += __uint_as_float(cur[i].w);
+            }
+          } else {
+            const float4* t4 = reinterpret_cast<const float4*>(tab_row + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(t4 + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+        }
+        if (res32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[4 * i] += __uint_as_float(cur[i].x); v[4 * i + 1] += __uint_as_float(cur[i].y);
+            v[4 * i + 2] += __uint_as_float(cur[i].z); v[4 * i + 3] += __uint_as_float(cur[i].w);
+          }
+        } else if (res16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const op2_t* h = reinterpret_cast<const op2_t*>(&cur[i]);
+            const op2_t* l = reinterpret_cast<const op2_t*>(&cur[4 + i]);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float2 f = op2_to_f2(h[jj]);
+              v[8 * i + 2 * jj] += f.x;
+              v[8 * i + 2 * jj + 1] += f.y;
+            }
+            if (res_lo) {
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
-                float2 f = op2_to_f2(h[jj]);
+                const float2 f = op2_to_f2(l[jj]);
                 v[8 * i + 2 * jj] += f.x;
                 v[8 * i + 2 * jj + 1] += f.y;
-              }
-              if (l4) {
-                t = __ldg(l4 + i);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  float2 f = op2_to_f2(h[jj]);
-                  v[8 * i + 2 * jj] += f.x;
-                  v[8 * i + 2 * jj + 1] += f.y;
-                }
               }
             }
           }
@@ -514,11 +596,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int col0 = n_blk * BN + c * 32;
           float v[32];
           if (do_ln) {
-            const float4* g4 = reinterpret_cast<const float4*>(e.ln_gamma + col0);
-            const float4* b4 = reinterpret_cast<const float4*>(e.ln_beta + col0);
+            const float4* g4 = reinterpret_cast<const float4*>(gam_s + c * 32);      // N == BN: column = c * 32
+            const float4* b4 = reinterpret_cast<const float4*>(bet_s + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 g = __ldg(g4 + i), bb = __ldg(b4 + i);
+              const float4 g = g4[i], bb = b4[i];
               v[4 * i] = (__uint_as_float(acc[4 * i]) - mean) * scale * g.x + bb.x;
               v[4 * i + 1] = (__uint_as_float(acc[4 * i + 1]) - mean) * scale * g.y + bb.y;
               v[4 * i + 2] = (__uint_as_float(acc[4 * i + 2]) - mean) * scale * g.z + bb.z;
@@ -536,7 +618,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // release the accumulator stage
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));   // the leader's copy
+        else mbar_arrive(&tmem_empty[as]);
+      }
       if (GEMM_TRACING) {
         if (threadIdx.x == 128 && it < 4) GEMM_TRACE(6 + 2 * static_cast<int>(it));
         __syncwarp();
@@ -555,27 +640,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // neither CTA leaves while the other may still touch its memory
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     if (threadIdx.x == 64) GEMM_TRACE(15);
   }
 }
 
-template <int BN, bool WS>
+template <int BN, bool WS, bool PAIR = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& toh, const CUtensorMap& tof,
                        const CUtensorMap& tol, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, WS>;
+  using Cfg = GemmCfg<BN, WS, PAIR>;
   static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget of an sm_100 CTA");
-  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, WS>), Cfg::kSmemBytes));
+  MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, WS, PAIR>), Cfg::kSmemBytes));
   const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
-  const int64_t n_tiles = m_tiles * (p.N / BN);
-  int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
   ProfScope prof_scope(kProfGemm, stream);
-  gemm_tc_kernel<BN, WS><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, tol, p);
+  if constexpr (PAIR) {
+    const int64_t n_ptiles = ((m_tiles + 1) / 2) * (p.N / BN);
+    const int64_t max_pairs = sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * (n_ptiles < max_pairs ? n_ptiles : max_pairs)));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    MADE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, WS, PAIR>, ta, tb, toh, tof, tol, p));
+  } else {
+    const int64_t n_tiles = m_tiles * (p.N / BN);
+    int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+    gemm_tc_kernel<BN, WS, PAIR><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, tol, p);
+  }
   MADE_CHECK_LAUNCH();
   return MADE_OK;
+}
+
+// MADE_GEMM_PAIR=0 turns the CTA-pair form off (read per call: the A/B switch of the parity test and of the benchmarks)
+bool gemm_pair_enabled() {
+  const char* v = getenv("MADE_GEMM_PAIR");
+  return !(v && v[0] == '0');
 }
 
 // MADE_GEMM_WS128=1 turns the weight-stationary 128-column form of the split GEMMs on (read per call).  OFF by default:
@@ -676,8 +787,16 @@ int gemm_f16_tc(const op_t* A, int64_t lda, const op_t* W, int64_t ldb,
     const int64_t m_tiles = (p.M + p.m_stride - 1) / p.m_stride;
     const bool ws = p.K <= kWsKBlocks * kBlockK && !p.b_batched && m_tiles * (p.N / 256) >= 2 * sm_count() &&
                     !(pp.tma_store && (e.out_f32 || e.out_lo)) && p.split == 0;
-    return ws ? launch_gemm<256, true>(ta, tb, toh, tof, tol, pp, stream)
-              : launch_gemm<256, false>(ta, tb, toh, tof, tol, pp, stream);
+    if (ws) return launch_gemm<256, true>(ta, tb, toh, tof, tol, pp, stream);
+    // CTA pairs when there are at least two waves of [256 x 256] pair tiles: every CTA stages half of the W rows
+    const bool pair = !p.b_batched && p.m_stride == 128 && p.m_valid == 128 && w_rows >= p.N &&
+                      ((m_tiles + 1) / 2) * (p.N / 256) >= sm_count() && gemm_pair_enabled();
+    if (pair) {
+      MADE_TRY(encode_tmap_2d_16b(&tb, W, static_cast<uint64_t>(p.split ? 2 * p.K : p.K), static_cast<uint64_t>(w_rows),
+                                   static_cast<uint64_t>(ldb) * 2, kBlockK, 128));
+      return launch_gemm<256, false, true>(ta, tb, toh, tof, tol, pp, stream);
+    }
+    return launch_gemm<256, false>(ta, tb, toh, tof, tol, pp, stream);
   }
   return launch_gemm<96, false>(ta, tb, toh, tof, tol, pp, stream);
 }
