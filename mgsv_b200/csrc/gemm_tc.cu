@@ -112,10 +112,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int64_t m_tiles = (M + p.m_stride - 1) / p.m_stride;
   const int64_t n_tiles = m_tiles * n_blocks;
   const int kb_seg = (p.K + kBlockK - 1) / kBlockK;        // k blocks of one operand half
-  const int k_blocks = kb_seg * (1 + p.split);             // split: 2 or 3 passes over K accumulate into one tile
-  // pass s of a split GEMM: columns of the A / W tile of k block kb  (hi halves at 0, lo halves at K)
-  auto a_col = [&](int i) { return (p.split == 2 && i / kb_seg == 1 ? p.K : 0) + (i % kb_seg) * kBlockK; };
-  auto w_col = [&](int i) { return (p.split != 0 && i / kb_seg == p.split ? p.K : 0) + (i % kb_seg) * kBlockK; };
+  // pass s of a split GEMM reads the A / W halves at these column offsets (hi halves at 0, lo halves at K).  The
+  // producer and the MMA issuer are ONE thread each: their per-k-block code is a serial chain of dependent
+  // instructions, so it is kept free of divisions (a profile showed the producer 70 % busy with index arithmetic and
+  // the k blocks arriving ~800 cycles apart because of it)
+  auto a_off = [&](int pass) { return (p.split == 2 && pass == 1) ? p.K : 0; };
+  auto w_off = [&](int pass) { return (p.split != 0 && pass == p.split) ? p.K : 0; };
   // tile schedule: streaming = round-robin, m-major; WS = one contiguous n-major range per CTA
   const int64_t ws_per = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t ws_t0 = static_cast<int64_t>(blockIdx.x) * ws_per;
@@ -184,6 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int cur_n = -1;
       uint32_t groups = 0;
+      const uint32_t full_bar_leader = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0;
       for (int64_t i = 0; i < my_tiles; ++i) {
         int64_t m_blk;
         int n_blk;
@@ -216,22 +219,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_prefetch_l2_2d(&tmap_a, (kb / kb_seg) * p.K + (kb % kb_seg) * kBlockK, row_nx);
           }
         }
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
-          if constexpr (PAIR) {
-            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the two stages
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_pair(sa, &tmap_a, fb, a_col(kb), row_a);
-            tma_load_2d_pair(sa + kATileBytes, &tmap_b, fb, w_col(kb), row_b);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if (i == 0 && kb == 0) GEMM_TRACE(2);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], a_col(kb), row_a);
-            if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], w_col(kb), row_b);
+        for (int pass = 0; pass <= p.split; ++pass) {
+          int ca = a_off(pass), cw = w_off(pass);
+          for (int ks = 0; ks < kb_seg; ++ks, ca += kBlockK, cw += kBlockK) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+            if constexpr (PAIR) {
+              // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the two stages
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t fb = full_bar_leader + stage * 8;
+              tma_load_2d_pair(sa, &tmap_a, fb, ca, row_a);
+              tma_load_2d_pair(sa + kATileBytes, &tmap_b, fb, cw, row_b);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              if (i == 0 && pass == 0 && ks == 0) GEMM_TRACE(2);
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], ca, row_a);
+              if constexpr (!WS) tma_load_2d(sa + kATileBytes, &tmap_b, &full_bar[stage], cw, row_b);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -239,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * kBlockM : kBlockM, BN, 0, 0);
+      const uint32_t tiles_u32 = smem_u32(tiles), resident_u32 = smem_u32(resident);
       int stage = 0;
       uint32_t phase = 0;
       int cur_n = -1;
@@ -264,33 +271,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          if (it == 0 && kb == 0) GEMM_TRACE(3);
-          if (it == 0 && kb == k_blocks - 1) GEMM_TRACE(4);
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(tiles + stage * Cfg::kStageBytes);
-          // resident block of k block kb: its position inside the operand half (+ kb_seg for the lo halves)
-          const int widx = (p.split != 0 && kb / kb_seg == p.split ? kb_seg : 0) + kb % kb_seg;
-          const uint32_t sb = WS ? smem_u32(resident + widx * Cfg::kBTileBytes) : sa + kATileBytes;
-          const uint64_t adesc = umma_smem_desc(sa, 0, 1024);
-          const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
+        for (int pass = 0; pass <= p.split; ++pass) {
+          // resident block of a k block: its position inside the operand half (+ kb_seg for the lo halves)
+          const int wbase = (p.split != 0 && pass == p.split) ? kb_seg : 0;
+          for (int ks = 0; ks < kb_seg; ++ks) {
+            const bool first = (pass | ks) == 0, last = pass == p.split && ks == kb_seg - 1;
+            mbar_wait(&full_bar[stage], phase);
+            if (it == 0 && first) GEMM_TRACE(3);
+            if (it == 0 && last) GEMM_TRACE(4);
+            tc_fence_after_sync();
+            const uint32_t sa = tiles_u32 + stage * Cfg::kStageBytes;
+            const uint32_t sb = WS ? resident_u32 + (wbase + ks) * Cfg::kBTileBytes : sa + kATileBytes;
+            const uint64_t adesc = umma_smem_desc(sa, 0, 1024);
+            const uint64_t bdesc = umma_smem_desc(sb, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
-            if constexpr (PAIR) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
-          if constexpr (PAIR) tc_commit_pair(&empty_bar[stage]);     // the stage is free in BOTH CTAs
-          else tc_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) {
-            if constexpr (PAIR) tc_commit_pair(&tmem_full[as]);
-            else tc_commit(&tmem_full[as]);
-            if constexpr (WS) {
-              if (n_next != n_blk) tc_commit(w_empty);   // last tile that reads this W slice
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr>>4)
+              if constexpr (PAIR) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !first || k != 0);
+              else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !first || k != 0);
             }
+            if constexpr (PAIR) tc_commit_pair(&empty_bar[stage]);     // the stage is free in BOTH CTAs
+            else tc_commit(&empty_bar[stage]);
+            if (last) {
+              if constexpr (PAIR) tc_commit_pair(&tmem_full[as]);
+              else tc_commit(&tmem_full[as]);
+              if constexpr (WS) {
+                if (n_next != n_blk) tc_commit(w_empty);   // last tile that reads this W slice
+              }
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -683,10 +693,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return MADE_OK;
 }
 
-// MADE_GEMM_PAIR=0 turns the CTA-pair form off (read per call: the A/B switch of the parity test and of the benchmarks)
+// MADE_GEMM_PAIR=1 turns the CTA-pair form on (read per call).  OFF by default: it is bit-identical and moves a third
+// fewer operand bytes from L2 to the SMs, but these GEMMs are bound by the HBM traffic of their activations (K = N = 256
+// on (hi, lo) pairs: 192 flop per byte, the ridge of the machine), so it measures within +-3 % of the single-CTA form
+// (scripts/diag_gemm_pair.py).
 bool gemm_pair_enabled() {
   const char* v = getenv("MADE_GEMM_PAIR");
-  return !(v && v[0] == '0');
+  return v && v[0] == '1';
 }
 
 // MADE_GEMM_WS128=1 turns the weight-stationary 128-column form of the split GEMMs on (read per call).  OFF by default:

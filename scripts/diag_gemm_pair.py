@@ -35,9 +35,9 @@ for M, N, K, split, pair_out in cases:
         a = ops.split_pair(a32).to(dev) if split == 2 else a32.to(torch.float16).to(dev)
         w = ops.split_pair(w32).to(dev)
         if pair_out == "ln_res":      # out_proj-style epilogue: pair residual + LayerNorm, pair out
-            res = ops.split_pair(torch.randn(M, N, generator=g)).to(dev)
+            rp = ops.split_pair(torch.randn(M, N, generator=g)).to(dev)
             gam, bet = torch.randn(N, generator=g).to(dev), torch.randn(N, generator=g).to(dev)
-            f = lambda: ops.gemm_f16_split(a, w, split, bias=bias, residual_pair=res, ln=(gam, bet), out_pair=True)
+            f = lambda: ops.gemm_f16_split(a, w, split, bias=bias, residual_pair=rp, ln=(gam, bet), out_pair=True)
         else:
             f = (lambda: ops.gemm_f16_split(a, w, split, bias=bias, out_pair=True)) if pair_out else \
                 (lambda: ops.gemm_f16_split_h(a, w, split, bias=bias, act=0))
