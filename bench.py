@@ -57,7 +57,8 @@ def parse():
     ap.add_argument("--impl", default="made_b200", choices=["made_b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries (per GPU with --scaling weak)")
     ap.add_argument("--tracks", type=int, default=N_TRACKS)
-    ap.add_argument("--chunk", type=int, default=1000, help="tracks / videos per ingest+encode chunk")
+    ap.add_argument("--chunk", type=int, default=2000, help="tracks / videos per ingest+encode chunk (device-resident steps; "
+                    "2000: 6 - 7 waves of 128-row tiles per GEMM launch, half the launches of 1000)")
     ap.add_argument("--e2e-chunk", type=int, default=500, help="chunk size of the host-input (e2e) steps: the e2e step is "
                     "PCIe bound, and smaller chunks shorten the fill / drain of the copy-compute pipeline")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1 only")
@@ -305,6 +306,21 @@ def tensor_pipe_note():
         cands = sorted(f for f in os.listdir(os.path.join(REPO, "profiles")) if f.endswith("_tensor_pipe.json"))
         if cands:
             return json.load(open(os.path.join(REPO, "profiles", cands[-1])))
+    except Exception:
+        pass
+    return None
+
+
+def step_dram_note():
+    """ncu DRAM bytes of one step per kernel (newest committed profiles/*_step_dram.json: `dram__bytes_read.sum +
+    dram__bytes_write.sum` of every launch between two rank_topk kernels)."""
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(REPO, "profiles")) if f.endswith("_step_dram.json"))
+        if cands:
+            d = json.load(open(os.path.join(REPO, "profiles", cands[-1])))
+            d.pop("per_kernel", None)
+            d["file"] = "profiles/" + cands[-1]
+            return d
     except Exception:
         pass
     return None
@@ -558,6 +574,7 @@ def main():
         peaks = json.load(open(pk_path))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     roofline = None
+    dram = step_dram_note()
     if prof:
         per_step = {k: (ms / prof_steps, n / prof_steps) for k, (ms, n) in prof.items()}
         gemm_ms = per_step["gemm"][0] + per_step["ffn"][0]
@@ -587,8 +604,23 @@ def main():
             "ffn_fused_ms_per_step": per_step["ffn"][0], "ffn_fused_launches_per_step": per_step["ffn"][1],
             "share_of_step": gemm_ms / ms_prof,
             "share_of_tensor_kernel_time": gemm_ms / fam_total if fam_total > 0 else None,
-            "traffic": None,     # a family of launches has no single per-launch figure: per-kernel DRAM bytes from the ncu
-                                 # --set full captures are in `tensor_pipe_active_ncu` (profiles/*_tensor_pipe.json)
+            # DRAM bytes of the family per launch (average over the step's launches) from the committed ncu launch list;
+            # `hbm_view` relates the family's DRAM bytes per step to its live kernel time
+            "traffic": (dram["gemm_family"]["dram_read_bytes"] + dram["gemm_family"]["dram_write_bytes"]) /
+                       max(dram["gemm_family"]["launches"], 1) if dram and world == 1 else None,
+            "hbm_view": {"dram_bytes_per_step_ncu": dram["gemm_family"]["dram_read_bytes"] + dram["gemm_family"]["dram_write_bytes"],
+                         "achieved_gbs": (dram["gemm_family"]["dram_read_bytes"] + dram["gemm_family"]["dram_write_bytes"]) /
+                                         (gemm_ms / 1e3) / 1e9,
+                         "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+                         "frac": (dram["gemm_family"]["dram_read_bytes"] + dram["gemm_family"]["dram_write_bytes"]) /
+                                 (gemm_ms / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                         "whole_step_dram_bytes_ncu": dram["step_dram_bytes"],
+                         "whole_step_frac": dram["step_dram_bytes"] / (ms_dev / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                         "source": dram["file"],
+                         "note": "K = N = 256 linears on (hi, lo) activation pairs move 2 KB per row for 0.39 MFLOP (3 passes): "
+                                 "192 flop per byte, the ridge of this machine (1413 TF/s / 6.46 TB/s = 219) - the family is "
+                                 "neither tensor- nor HBM-saturated; DESIGN.md 4.1 lists what bounds a tile"}
+                        if dram and world == 1 and gemm_ms > 0 else None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
             "xpool": {"kernel": "xpool_score_kernel", "achieved": xp_ach, "frac": xp_ach / peak_tf,
                       "executed_tflops": xp_exe, "executed_frac": xp_exe / peak_tf, "kernel_ms_per_step": xp_ms,

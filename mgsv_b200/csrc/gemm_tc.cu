@@ -20,7 +20,8 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kWsKBlocks = 4;                       // K <= 256
 // PAIR = CTA pair (cta_group::2): the two CTAs of a 2-CTA cluster compute ONE [256 x BN] tile with 256-row MMAs issued by
 // the leader.  Each CTA stages its own 128 rows of A and only its own HALF of the W rows of a k block (32 instead of 48
-// KB from L2 per k block and CTA — these GEMMs are bound by the L2 -> SM operand traffic), holds the
+// KB per k block and CTA: the TMA engine of one SM delivers ~64 B per cycle, so a 48 KB k block takes ~770 cycles against
+// 512 cycles of MMA; a pair's mainloop runs at 7.6 k instead of 9.2 k cycles per split-2 tile), holds the
 // accumulator of its 128 rows in its own TMEM and runs the unchanged epilogue on them.
 template <int BN, bool WS = false, bool PAIR = false>
 struct GemmCfg {
@@ -31,7 +32,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = WS ? kATileBytes : kATileBytes + kBTileBytes;
   // WS, BN = 256: the [256 x K] slice of a plain fp16 W (4 k-tiles).  WS, BN = 128: the [128 x K] slices of BOTH halves of
   // a (hi | lo) weight pair (8 k-tiles, 128 KB too) — the weight-stationary form of the split-precision GEMMs, whose
-  // streaming form re-reads 1.1-1.7 MB of W tiles per 128 rows and is bound by that L2 -> SM traffic
+  // streaming form re-reads 1.1-1.7 MB of W tiles per 128 rows
   static constexpr int kResidentTiles = WS ? (BN == 128 ? 2 * kWsKBlocks : kWsKBlocks) : 0;
   static constexpr int kResidentBytes = kResidentTiles * kBTileBytes;
   static constexpr int kAccStride = BN <= 128 ? 128 : 256;      // TMEM columns per acc stage
@@ -173,8 +174,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   tc_fence_before_sync();
+  __syncthreads();
   if constexpr (PAIR) cluster_sync_all();     // the peer's barriers exist before anything signals them
-  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) GEMM_TRACE(1);
@@ -206,8 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         // Optional (MADE_GEMM_L2_PREFETCH=1, off by default): pull the A tiles of this CTA's NEXT output tile into L2.
-        // Measured: no gain (23.6 us either way on the music-chunk GEMM) and +2 % on the whole job — the kernel is
-        // bound by the L2 -> SM traffic of its re-streamed W tiles, not by the HBM latency of A.
+        // Measured: no gain on L2-resident operands (23.6 us either way on the music-chunk GEMM) and 3 - 7 % SLOWER on
+        // operands streamed from HBM (303 k rows: 147 -> 157 us), +2 % on the whole job: the HBM latency of A is not
+        // what bounds the mainloop.
         if (p.l2_prefetch && i + 1 < my_tiles) {
           int64_t m_nx;
           int n_nx;
@@ -650,8 +652,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   tc_fence_before_sync();
+  __syncthreads();
   if constexpr (PAIR) cluster_sync_all();     // neither CTA leaves while the other may still touch its memory
-  else __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
     if constexpr (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
@@ -693,10 +695,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return MADE_OK;
 }
 
-// MADE_GEMM_PAIR=1 turns the CTA-pair form on (read per call).  OFF by default: it is bit-identical and moves a third
-// fewer operand bytes from L2 to the SMs, but these GEMMs are bound by the HBM traffic of their activations (K = N = 256
-// on (hi, lo) pairs: 192 flop per byte, the ridge of the machine), so it measures within +-3 % of the single-CTA form
-// (scripts/diag_gemm_pair.py).
+// MADE_GEMM_PAIR=1 turns the CTA-pair form on (read per call).  OFF by default: it is bit-identical and its mainloop is
+// faster (7.6 k against 9.2 k cycles per split-2 tile on L2-resident operands), but a tile's EPILOGUE takes 9.5 - 12 k
+// cycles and is what a tile waits for there, and on operands streamed from HBM both forms sit at the same 7 us per tile
+// with the epilogue emptied — so it measures within +-3 % of the single-CTA form (scripts/diag_gemm_pair.py,
+// diag_gemm_ablate.py, diag_gemm_trace2.py).
 bool gemm_pair_enabled() {
   const char* v = getenv("MADE_GEMM_PAIR");
   return v && v[0] == '1';

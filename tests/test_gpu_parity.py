@@ -388,6 +388,36 @@ def test_tcgen05_split_gemm_weight_stationary(dev, M, N, K, split):
     assert (ws.cpu().double() - ref).abs().max().item() <= 1.2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,split", [(40000, 768, 256, 2), (56000, 256, 256, 1), (38017, 256, 768, 2), (37900, 512, 256, 0)])
+def test_tcgen05_gemm_cta_pair_form_is_bit_identical(dev, M, N, K, split):
+    """The opt-in CTA-pair form (cta_group::2: 256-row MMAs issued by the leader of a 2-CTA cluster, each CTA staging
+    its own rows of A and half of the W rows; an odd tile count leaves the last pair half empty) returns the bits of
+    the single-CTA form."""
+    g = torch.Generator().manual_seed(M + N + K + split)
+    a32 = torch.randn(M, K, generator=g)
+    w32 = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(dev)
+    if split == 0:
+        a, w = a32.to(torch.float16).to(dev), w32.to(torch.float16).to(dev)
+        f = lambda: ops.gemm_f16(a, w, bias=bias, out_dtype=torch.float32)
+    else:
+        a = ops.split_pair(a32).to(dev) if split == 2 else a32.to(torch.float16).to(dev)
+        w = ops.split_pair(w32).to(dev)
+        f = lambda: ops.gemm_f16_split(a, w, split, bias=bias, out_pair=True)
+    try:
+        os.environ["MADE_GEMM_PAIR"] = "1"
+        pair = f()
+    finally:
+        os.environ.pop("MADE_GEMM_PAIR")
+    single = f()
+    assert torch.equal(pair, single)
+    a_eff = a32.double() if split == 2 else a32.to(torch.float16).double()
+    w_eff = w32.double() if split else w32.to(torch.float16).double()
+    ref = a_eff @ w_eff.t() + bias.cpu().double()
+    got = pair.double().cpu() if split == 0 else pair[:, :N].double().cpu() + pair[:, N:].double().cpu()
+    assert _rel(got, ref) < 8e-6
+
+
 def test_tcgen05_split_gemm_epilogues(dev):
     """(hi | lo) pair outputs, pair residuals and the LayerNorm epilogue of the split GEMM."""
     M, N, K = 1000, 256, 256
