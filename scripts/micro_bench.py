@@ -31,6 +31,26 @@ def timed(fn, reps=10, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+def timed_graph(fn, launches=32, reps=10):
+    """Per-launch time of `launches` back-to-back calls replayed from ONE CUDA graph: the device-side cost of a small
+    kernel without the ~20 us of Python / ctypes / allocator time a single eager call spends on the host."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(launches):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * launches)
+
+
 def main():
     dev = torch.device("cuda:0")
     peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
@@ -52,6 +72,16 @@ def main():
         rec(f"giou {n}x{m}", timed(lambda: ops.generalized_temporal_iou(se_a, se_b, check=False)), n * m * 4 + (n + m) * 8, note)
         rec(f"matcher_cost {n}x{m}", timed(lambda: ops.matcher_cost(prob, a, b)), n * m * 4 + (n + m) * 8 + n * 4, note)
         rec(f"temporal_iou {n}x{m}", timed(lambda: ops.temporal_iou(se_a, se_b)), 2 * n * m * 4 + (n + m) * 8, note)
+        if n == 1000:      # configs[2] itself: 1M pairs per call, 32 calls replayed from one CUDA graph
+            gnote = "configs[2]: 1M pairs per launch, 32 launches in one CUDA graph (device time per launch)"
+            for nme, fn, nb in (("giou", lambda: ops.generalized_temporal_iou(se_a, se_b, check=False), n * m * 4 + (n + m) * 8),
+                                ("matcher_cost", lambda: ops.matcher_cost(prob, a, b), n * m * 4 + (n + m) * 8 + n * 4),
+                                ("temporal_iou", lambda: ops.temporal_iou(se_a, se_b), 2 * n * m * 4 + (n + m) * 8)):
+                try:
+                    rec(f"{nme} {n}x{m} (graph)", timed_graph(fn), nb, gnote)
+                except Exception as exc:      # a host-side check inside the op that cannot be captured
+                    sys.stderr.write(f"graph timing of {nme} skipped: {exc}\n")
+                    torch.cuda.synchronize()
     for nq, nm in ((2000, 4000), (8192, 16384)):
         single = torch.randn(nq, nm, device=dev)
         dual = torch.randn(nq, nm, device=dev)
