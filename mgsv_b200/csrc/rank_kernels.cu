@@ -666,9 +666,14 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
   MADE_REQUIRE(a && b && out && d > 0 && ld >= m, "cosine_sim: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int64_t m_tc = 0;
-  // One arithmetic for every gallery width: narrow calls (a last score chunk, the paired-track scores of the gallery
-  // index) must give the bits of the wide call, so the route depends on alignment only, never on m.
-  if (d == 256 && gemm_tma_store_enabled() && (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+  // One arithmetic for every gallery width AND every output placement: narrow calls (a last score chunk, the
+  // paired-track scores of the gallery index) and calls into a matrix whose row pitch or column offset is not a
+  // multiple of 4 floats (a gallery shard cut between two music ids) must give the bits of the wide aligned call —
+  // the sharded path is compared with the single-GPU path bit for bit.  The TMA store needs 16-byte alignment, so an
+  // unaligned destination is served through an aligned scratch matrix and one strided device copy.
+  if (d == 256 && gemm_tma_store_enabled()) {
+    const bool aligned = (ld % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int64_t ld_tc = aligned ? ld : ((m + 3) / 4) * 4;
     // tcgen05 route: every column when outputs leave through TMA stores (the last 256-wide tile reads
     // zero rows past the gallery and its store is clipped at column m), else the whole tiles only
     m_tc = gemm_tma_store_enabled() ? m : (m / 256) * 256;
@@ -686,6 +691,9 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
       pool_ready_dev = dev;
     }
     op_t *a16 = nullptr, *b16 = nullptr;
+    float* out_tc = out;
+    if (!aligned)
+      MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&out_tc), static_cast<size_t>(n) * ld_tc * sizeof(float), st));
     MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&a16), static_cast<size_t>(n) * 768 * 2, st));
     MADE_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&b16), static_cast<size_t>(m_tc) * 768 * 2, st));
     cos_split_kernel<<<static_cast<unsigned>(ceil_div64(n, 8)), 256, 0, st>>>(a, n, 0, a16);
@@ -697,11 +705,17 @@ int made_cosine_sim(const float* a, int64_t n, const float* b, int64_t m, int d,
     p.N = static_cast<int>(ceil_div64(m_tc, 256) * 256);
     p.n_store = static_cast<int>(m_tc);
     p.K = 768;
-    p.epi.out_f32 = out;
-    p.epi.ld_f32 = ld;
+    p.epi.out_f32 = out_tc;
+    p.epi.ld_f32 = ld_tc;
     int rc = gemm_f16_tc(a16, 768, b16, 768, m_tc, p, 256, st);
     MADE_CUDA(cudaFreeAsync(a16, st));
     MADE_CUDA(cudaFreeAsync(b16, st));
+    if (!aligned) {
+      if (rc == MADE_OK)
+        MADE_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(ld) * sizeof(float), out_tc, static_cast<size_t>(ld_tc) * sizeof(float),
+                                    static_cast<size_t>(m) * sizeof(float), static_cast<size_t>(n), cudaMemcpyDeviceToDevice, st));
+      MADE_CUDA(cudaFreeAsync(out_tc, st));
+    }
     MADE_TRY(rc);
   }
   if (m_tc < m) {   // remaining columns (and every non-256-d call): fp32 SIMT tiles

@@ -310,6 +310,22 @@ def test_topk_merge_and_cosine(dev):
     np.testing.assert_allclose(got.cpu().numpy(), O.cal_distance_cos(x, y).numpy(), atol=2e-6, rtol=0)
 
 
+def test_cosine_bits_do_not_depend_on_the_output_placement(dev):
+    """A gallery shard cut between two music ids gives similarity matrices whose width / column offset is not a
+    multiple of 4 floats; the dual-tower cosine must then return the bits of the aligned full-width call (the sharded
+    path is compared with the single-GPU path bit for bit, tests/test_gpu_sharded.py)."""
+    g = torch.Generator().manual_seed(11)
+    x, y = torch.randn(300, 256, generator=g).to(dev), torch.randn(520, 256, generator=g).to(dev)
+    full = ops.cal_distance(x, y)                                   # [300, 520], aligned
+    for m0, m1 in ((0, 261), (261, 520), (3, 258), (130, 131)):
+        part = ops.cal_distance(x, y[m0:m1].contiguous())            # row pitch m1 - m0: not a multiple of 4
+        assert torch.equal(part, full[:, m0:m1]), (m0, m1)
+        wide = torch.zeros((300, 523), dtype=torch.float32, device=dev)
+        ops.cal_distance(x, y[m0:m1].contiguous(), out=wide, col_offset=m0 + 1)   # odd pitch, odd column offset
+        assert torch.equal(wide[:, m0 + 1:m1 + 1], full[:, m0:m1]), (m0, m1)
+        assert float(wide[:, :m0 + 1].abs().sum()) == 0.0 and float(wide[:, m1 + 1:].abs().sum()) == 0.0
+
+
 # ---------------------------------------------------------------------------------------------
 # building blocks
 # ---------------------------------------------------------------------------------------------
