@@ -209,7 +209,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // Optional (MADE_GEMM_L2_PREFETCH=1, off by default): pull the A tiles of this CTA's NEXT output tile into L2.
         // Measured: no gain on L2-resident operands (23.6 us either way on the music-chunk GEMM) and 3 - 7 % SLOWER on
         // operands streamed from HBM (303 k rows: 147 -> 157 us), +2 % on the whole job: the HBM latency of A is not
-        // what bounds the mainloop.
+        // what bounds the mainloop.  ONE linear `cp.async.bulk.prefetch.L2` of the next tile's
+        // contiguous rows instead of the tensor-map prefetches measured the same (145 -> 153 us).
         if (p.l2_prefetch && i + 1 < my_tiles) {
           int64_t m_nx;
           int n_nx;
