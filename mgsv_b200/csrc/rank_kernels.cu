@@ -322,11 +322,11 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   {
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
                      (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
-    const int64_t n4 = vec ? n_cols / 4 : 0;
+    const int n4 = vec ? static_cast<int>(n_cols / 4) : 0;      // staged rows have <= 49152 columns: 32-bit indices
     const float4* a4 = reinterpret_cast<const float4*>(rv.a);
     const float4* b4 = reinterpret_cast<const float4*>(rv.b);
 #pragma unroll 4
-    for (int64_t q = threadIdx.x; q < n4; q += kRankThreads) {
+    for (int q = threadIdx.x; q < n4; q += kRankThreads) {
       float4 x = __ldg(a4 + q);
       if (rv.b) {
         const float4 y = __ldg(b4 + q);
@@ -337,7 +337,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       kmin = min(kmin, min(min(kq.x, kq.y), min(kq.z, kq.w)));
       kmax = max(kmax, max(max(kq.x, kq.y), max(kq.z, kq.w)));
     }
-    for (int64_t j = n4 * 4 + threadIdx.x; j < n_cols; j += kRankThreads) {
+    for (int j = n4 * 4 + threadIdx.x; j < static_cast<int>(n_cols); j += kRankThreads) {
       const unsigned int key = rv.key32(j);
       cache[j] = key;
       kmin = min(kmin, key);
@@ -364,29 +364,51 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   // A column beats s* when its fp32 key is more than two steps above that of s* (then the fp64
   // scores differ too); within two steps the exact fp64 keys decide.
   const unsigned long long gk = want_rank ? sm.gt_key : 0ull;
-  const long long gk32 = want_rank ? static_cast<long long>(sm.gt_key32) : 0ll;
-  auto beats = [&](int64_t j, unsigned int k32) -> bool {
-    const long long d = static_cast<long long>(k32) - gk32;
-    if (d > 2) return true;
-    if (d < -2) return false;
+  const unsigned int gk32 = want_rank ? sm.gt_key32 : 0u;
+  // k32 > g_hi: more than two fp32 steps above s* (beats it); k32 < g_lo: more than two below (does not); saturated
+  // bounds make the impossible side unreachable
+  const unsigned int g_hi = gk32 > 0xFFFFFFFDu ? 0xFFFFFFFFu : gk32 + 2u;
+  const unsigned int g_lo = gk32 < 2u ? 0u : gk32 - 2u;
+  auto beats = [&](int j, unsigned int k32) -> bool {
+    if (k32 > g_hi) return true;
+    if (k32 < g_lo) return false;
     return rv.key(j) > gk;
   };
+  const int nc = static_cast<int>(n_cols);
+  const int nv = nc >> 2;                      // the row as 16-byte words of four keys (the staging buffer is 16-byte aligned)
+  const uint4* cache4 = reinterpret_cast<const uint4*>(cache);
   if (want_rank || select) {
     int cnt = 0;
-    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-      const unsigned int k32 = cache[j];
-      if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
-      if (want_rank && beats(j, k32)) {
-        bool first = true;
-        if (prev_same) {
+    if (prev_same == nullptr) {
+      // lean sweep (distinct ids): four keys per shared-memory load, two compares per key for the rank, the exact fp64
+      // keys only within two fp32 steps of s*
+      auto one = [&](int j, unsigned int k32) {
+        if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
+        if (want_rank) {
+          if (k32 > g_hi) ++cnt;
+          else if (k32 >= g_lo && rv.key(j) > gk) ++cnt;
+        }
+      };
+#pragma unroll 2
+      for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+        const uint4 kq = cache4[q];
+        one(4 * q, kq.x); one(4 * q + 1, kq.y); one(4 * q + 2, kq.z); one(4 * q + 3, kq.w);
+      }
+      for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) one(j, cache[j]);
+    } else {
+      for (int j = threadIdx.x; j < nc; j += kRankThreads) {
+        const unsigned int k32 = cache[j];
+        if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
+        if (want_rank && beats(j, k32)) {
+          bool first = true;
           int32_t p = prev_same[j];
           int32_t guard = 0;
           while (p >= 0 && guard++ < (1 << 20)) {
             if (beats(p, cache[p])) { first = false; break; }
             p = prev_same[p];
           }
+          cnt += first ? 1 : 0;
         }
-        cnt += first ? 1 : 0;
       }
     }
     if (want_rank) {
@@ -413,11 +435,15 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       if (level > 0) {
         for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
         __syncthreads();
-        for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-          const unsigned int k32 = cache[j];
+        auto refine = [&](unsigned int k32) {
           const unsigned int d = (k32 - base) >> shift;
           if (k32 >= base && d < span) atomicAdd(&sm.hist[d], 1);   // keys of the chosen bin only
+        };
+        for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+          const uint4 kq = cache4[q];
+          refine(kq.x); refine(kq.y); refine(kq.z); refine(kq.w);
         }
+        for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) refine(cache[j]);
         __syncthreads();
       }
       if (warp == 0) {   // scan the bins from the top, 32 bins per lane
@@ -461,12 +487,21 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   }
   if (ok) {
     // ---- 5. gather the candidates with their exact fp64 keys, order them by counting ----------
-    for (int64_t j = threadIdx.x; j < n_cols; j += kRankThreads) {
-      if (cache[j] >= thr) {
-        const int slot = atomicAdd(&sm.count, 1);
-        if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = static_cast<int>(j); }
+    auto take = [&](int j) {
+      const int slot = atomicAdd(&sm.count, 1);
+      if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
+    };
+    for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+      const uint4 kq = cache4[q];
+      if (max(max(kq.x, kq.y), max(kq.z, kq.w)) >= thr) {      // ~k of the n columns pass: one compare per four keys
+        if (kq.x >= thr) take(4 * q);
+        if (kq.y >= thr) take(4 * q + 1);
+        if (kq.z >= thr) take(4 * q + 2);
+        if (kq.w >= thr) take(4 * q + 3);
       }
     }
+    for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads)
+      if (cache[j] >= thr) take(j);
     __syncthreads();
     for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
       const unsigned long long key = sm.sel_keys[t];
