@@ -690,6 +690,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   } else {
     const int64_t n_tiles = m_tiles * (p.N / BN);
     int grid = static_cast<int>(n_tiles < sm_count() ? n_tiles : sm_count());
+#ifdef MADE_GEMM_DIAG
+    if (const char* g = getenv("MADE_GEMM_GRID")) grid = atoi(g) > 0 && atoi(g) < grid ? atoi(g) : grid;   // diagnostics: fewer CTAs
+#endif
     gemm_tc_kernel<BN, WS, PAIR><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, toh, tof, tol, p);
   }
   MADE_CHECK_LAUNCH();
