@@ -20,8 +20,9 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kWsKBlocks = 4;                       // K <= 256
 // PAIR = CTA pair (cta_group::2): the two CTAs of a 2-CTA cluster compute ONE [256 x BN] tile with 256-row MMAs issued by
 // the leader.  Each CTA stages its own 128 rows of A and only its own HALF of the W rows of a k block (32 instead of 48
-// KB per k block and CTA: the TMA engine of one SM delivers ~64 B per cycle, so a 48 KB k block takes ~770 cycles against
-// 512 cycles of MMA; a pair's mainloop runs at 7.6 k instead of 9.2 k cycles per split-2 tile), holds the
+// KB per k block and CTA.  A single-CTA k block moves 48 KB into shared memory and its four MMAs read 48 KB back: 96 KB
+// through a 128 B / cycle shared memory = 750 cycles against 512 cycles of MMA (measured: 767); a pair moves 64 KB
+// per CTA and its mainloop runs at 7.6 k instead of 9.2 k cycles per split-2 tile), holds the
 // accumulator of its 128 rows in its own TMEM and runs the unchanged epilogue on them.
 template <int BN, bool WS = false, bool PAIR = false>
 struct GemmCfg {
