@@ -139,6 +139,25 @@ def test_shard_bounds_partition():
                 assert (own[b[r][0]:b[r][1]] == r).all()
 
 
+def test_ingest_chunk_bounds_partition_every_size():
+    """Host inputs are ingested in tapered chunks (small first chunks so the copy engine starts early, small last chunks
+    so little work is left after the last copy): whatever the taper, the chunks tile [0, n) in order without gaps."""
+    from mgsv_b200.pipeline import GalleryEvaluator
+    for n in (0, 1, 31, 64, 65, 499, 500, 999, 1000, 2000, 4000, 4001):
+        for chunk in (32, 500, 1024, 2000):
+            for head in (False, True):
+                for tail in (False, True):
+                    b = GalleryEvaluator._chunk_bounds(n, chunk, head, tail)
+                    assert (b == []) == (n == 0)
+                    if b:
+                        assert b[0][0] == 0 and b[-1][1] == n
+                        assert all(e > s for s, e in b) and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+                        assert max(e - s for s, e in b) <= chunk
+    assert GalleryEvaluator._chunk_bounds(4000, 500, False, False) == [(s, s + 500) for s in range(0, 4000, 500)]
+    assert GalleryEvaluator._chunk_bounds(4000, 500, False, True)[-3:] == [(3500, 3750), (3750, 3875), (3875, 4000)]
+    assert GalleryEvaluator._chunk_bounds(2000, 500, True, False)[:3] == [(0, 62), (62, 187), (187, 437)]
+
+
 def test_feature_store_reads_reference_file_layout(tmp_path):
     """dataloaders/dataloader_MGSV_EC_feature.py:46-75: {id}.pt files + CSV -> one batch schema."""
     import pandas as pd
