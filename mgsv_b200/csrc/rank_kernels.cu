@@ -18,12 +18,18 @@
 // as order-preserving 32-bit keys of fl32(single + dual).  Rounding is monotone, so a column that
 // beats another in fp64 never has the smaller fp32 key: the fp32 keys select a SUPERSET of the true
 // top-k and decide every rank comparison that is more than two fp32 steps away from s*; only the
-// <= k + 32 selected columns and the near-ties of s* are re-read (L2) and compared in fp64.  The
-// k-th largest key is located by value: a 1024-bin histogram over the row's key range, refined 10
-// bits at a time while more than k + 32 keys sit at or above the chosen bin; the candidates are then
-// ordered by counting.  A typical score row costs three sweeps of shared memory.
-// Rows where more than 512 columns tie around rank k, and rows too long to stage, take the exact
-// 8-pass MSB radix select on the 64-bit keys (re-reading global memory) + a bitonic sort instead.
+// selected columns and the near-ties of s* are re-read (L2) and compared in fp64.  The candidate
+// threshold comes from GROUP MAXIMA: while staging, every thread tracks the maximum key of its own
+// columns; the k-th largest of those 256 (or 1024) maxima bounds the k-th largest key from below and
+// leaves ~1.3 k columns at or above it, so a 1024-bin histogram of the maxima alone (1 - 4 shared-
+// memory atomics per thread instead of one per column: ATOMS costs 2 cycles per lane, and the
+// per-column histogram was 2/3 of the kernel) replaces the histogram of the row.  One sweep of the
+// staged keys then counts the rank and gathers the candidates, which are ordered by counting.
+// Rows where more than 512 columns pass that threshold (heavy ties) fall back to the per-column
+// value histogram (refined 10 bits at a time while more than k + 32 keys sit at or above the chosen
+// bin); rows where more than 512 columns share one fp32 key around rank k, and rows too long to
+// stage, take the exact 8-pass MSB radix select on the 64-bit keys (re-reading global memory) + a
+// bitonic sort instead.
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -71,7 +77,7 @@ struct RowView {
 struct RankSmem {
   int hist[kValueBins];                     // value histogram / the 256 radix buckets
   int red[kRankThreads / 32];
-  unsigned int red32[2][kRankThreads / 32];
+  unsigned int red32[3][kRankThreads / 32];
   unsigned long long sel_keys[kMaxCand];
   int sel_idx[kMaxCand];
   unsigned long long prefix, gt_key;
@@ -294,6 +300,31 @@ rank_topk_kernel(const float* __restrict__ single, const float* __restrict__ dua
   radix_topk_row(rv, n_cols, kk, k, row, col_offset, topk_idx, topk_score, sm);
 }
 
+// Warp 0 scans the value histogram from the top bin down (32 bins per lane + a shuffle scan) for the bin that holds
+// the need-th largest item: sm.bin = that bin, sm.krem = items in the bins above it, sm.ncand = items in it.  sm.bin is
+// left untouched when the histogram holds fewer than `need` items.
+__device__ __forceinline__ void scan_hist_from_top(RankSmem& sm, int need, int lane) {
+  constexpr int kPer = kValueBins / 32;
+  int tot = 0;
+  const int top = kValueBins - 1 - lane * kPer;   // this lane owns bins top, top-1, ..., top-kPer+1
+#pragma unroll 8
+  for (int i = 0; i < kPer; ++i) tot += sm.hist[top - ((i + lane) & (kPer - 1))];   // rotated: no bank conflicts
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  int acc = incl - tot;
+  if (acc < need && incl >= need) {
+    for (int i = 0; i < kPer; ++i) {
+      const int c = sm.hist[top - i];
+      if (acc + c >= need) { sm.bin = top - i; sm.krem = acc; sm.ncand = c; break; }
+      acc += c;
+    }
+  }
+}
+
 // Staged rows: see the header of this file.
 __global__ void __launch_bounds__(kRankThreads, 6)
 rank_topk_staged_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
@@ -301,7 +332,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
                         const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
                         int32_t col_offset, int k, int32_t* __restrict__ topk_idx,
                         double* __restrict__ topk_score, int32_t* __restrict__ rank_out,
-                        double* __restrict__ gt_score_out) {
+                        double* __restrict__ gt_score_out, int use_group_maxima) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ RankSmem sm;
   unsigned int* cache = reinterpret_cast<unsigned int*>(dyn_smem);
@@ -317,8 +348,14 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   // ---- 1. ground-truth score (thread 0) while the others start staging the row ---------------
   if (want_rank && threadIdx.x == 0) gt_walk(rv, row, n_cols, gt_col, gt_score_in, prev_same, sm);
 
-  // ---- 2. stage the row as 32-bit keys, tracking the key range --------------------------------
+  // ---- 2. stage the row as 32-bit keys, tracking the key range and the maximum of each of this thread's four
+  //         column groups (group c of thread t = component c of the 16-byte words t, t + 256, ...) ----------------
   unsigned int kmin = 0xFFFFFFFFu, kmax = 0u;
+  uint4 gmax = make_uint4(0u, 0u, 0u, 0u);
+  // the threshold items: the 256 thread maxima, or all 1024 component maxima when k or the row length asks for more groups
+  const int per = (kk > 128 || n_cols < 2048) ? 4 : 1;
+  unsigned int gm[4];
+  unsigned int imin = 0xFFFFFFFFu;               // smallest threshold item of the row
   {
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
                      (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
@@ -335,32 +372,39 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       const uint4 kq = make_uint4(f32_key(x.x), f32_key(x.y), f32_key(x.z), f32_key(x.w));
       *reinterpret_cast<uint4*>(cache + q * 4) = kq;
       kmin = min(kmin, min(min(kq.x, kq.y), min(kq.z, kq.w)));
-      kmax = max(kmax, max(max(kq.x, kq.y), max(kq.z, kq.w)));
+      gmax.x = max(gmax.x, kq.x); gmax.y = max(gmax.y, kq.y); gmax.z = max(gmax.z, kq.z); gmax.w = max(gmax.w, kq.w);
     }
     for (int j = n4 * 4 + threadIdx.x; j < static_cast<int>(n_cols); j += kRankThreads) {
       const unsigned int key = rv.key32(j);
       cache[j] = key;
       kmin = min(kmin, key);
-      kmax = max(kmax, key);
+      gmax.x = max(gmax.x, key);
     }
+    kmax = max(max(gmax.x, gmax.y), max(gmax.z, gmax.w));
+    gm[0] = per == 1 ? kmax : gmax.x;
+    gm[1] = gmax.y; gm[2] = gmax.z; gm[3] = gmax.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < per && gm[i] != 0u) imin = min(imin, gm[i]);   // key 0 = an empty group (or one of NaN scores only): not an item
     kmin = __reduce_min_sync(0xffffffffu, kmin);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
-    if (lane == 0) { sm.red32[0][warp] = kmin; sm.red32[1][warp] = kmax; }
+    imin = __reduce_min_sync(0xffffffffu, imin);
+    if (lane == 0) { sm.red32[0][warp] = kmin; sm.red32[1][warp] = kmax; sm.red32[2][warp] = imin; }
   }
   for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
-  if (threadIdx.x == 0) { sm.count = 0; sm.ncand = 0; }
+  if (threadIdx.x == 0) { sm.count = 0; sm.ncand = 0; sm.bin = -1; }
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < kRankThreads / 32; ++w) {
     kmin = min(kmin, sm.red32[0][w]);
     kmax = max(kmax, sm.red32[1][w]);
+    imin = min(imin, sm.red32[2][w]);
   }
   const unsigned int range = kmax - kmin;
   const int bits = range ? 32 - __clz(static_cast<int>(range)) : 0;
   const int vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
   const bool select = want_topk && kk > 0;
 
-  // ---- 3. one sweep: value histogram + distinct ids ahead of the ground truth ------------------
   // A column beats s* when its fp32 key is more than two steps above that of s* (then the fp64
   // scores differ too); within two steps the exact fp64 keys decide.
   const unsigned long long gk = want_rank ? sm.gt_key : 0ull;
@@ -377,14 +421,22 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   const int nc = static_cast<int>(n_cols);
   const int nv = nc >> 2;                      // the row as 16-byte words of four keys (the staging buffer is 16-byte aligned)
   const uint4* cache4 = reinterpret_cast<const uint4*>(cache);
-  if (want_rank || select) {
+  auto take = [&](int j) {                     // a top-k candidate: its exact fp64 key, fetched from L2
+    const int slot = atomicAdd(&sm.count, 1);
+    if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
+  };
+  // One sweep over the staged keys.  do_rank: count the distinct ids ahead of the ground truth.  With a candidate
+  // threshold (gather): append the columns at or above it; without one: fill the value histogram (one shared-memory
+  // atomic per column - 2 cycles per lane on this machine, the cost the group-maxima threshold exists to avoid).
+  auto sweep = [&](bool do_rank, bool gather, unsigned int thr) {
+    const bool fill = select && !gather;
     int cnt = 0;
     if (prev_same == nullptr) {
       // lean sweep (distinct ids): four keys per shared-memory load, two compares per key for the rank, the exact fp64
       // keys only within two fp32 steps of s*
       auto one = [&](int j, unsigned int k32) {
-        if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
-        if (want_rank) {
+        if (fill) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
+        if (do_rank) {
           if (k32 > g_hi) ++cnt;
           else if (k32 >= g_lo && rv.key(j) > gk) ++cnt;
         }
@@ -393,13 +445,24 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       for (int q = threadIdx.x; q < nv; q += kRankThreads) {
         const uint4 kq = cache4[q];
         one(4 * q, kq.x); one(4 * q + 1, kq.y); one(4 * q + 2, kq.z); one(4 * q + 3, kq.w);
+        if (gather && max(max(kq.x, kq.y), max(kq.z, kq.w)) >= thr) {   // ~k of the n columns pass: one compare per four keys
+          if (kq.x >= thr) take(4 * q);
+          if (kq.y >= thr) take(4 * q + 1);
+          if (kq.z >= thr) take(4 * q + 2);
+          if (kq.w >= thr) take(4 * q + 3);
+        }
       }
-      for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) one(j, cache[j]);
+      for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) {
+        const unsigned int k32 = cache[j];
+        one(j, k32);
+        if (gather && k32 >= thr) take(j);
+      }
     } else {
       for (int j = threadIdx.x; j < nc; j += kRankThreads) {
         const unsigned int k32 = cache[j];
-        if (select) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
-        if (want_rank && beats(j, k32)) {
+        if (fill) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
+        if (gather && k32 >= thr) take(j);
+        if (do_rank && beats(j, k32)) {
           bool first = true;
           int32_t p = prev_same[j];
           int32_t guard = 0;
@@ -411,8 +474,8 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
         }
       }
     }
-    if (want_rank) {
-      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the histogram
+    if (do_rank) {
+      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the histogram / the candidates
       if (threadIdx.x == 0) {
         rank_out[row] = cnt;
         if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
@@ -420,10 +483,91 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     } else {
       __syncthreads();
     }
+  };
+  // Order n_cand gathered candidates by counting (score descending, lower column first) and write the best kk.
+  auto order_and_write = [&](int n_cand) {
+    for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
+      const unsigned long long key = sm.sel_keys[t];
+      const int idx = sm.sel_idx[t];
+      int pos = 0;   // candidates that come first: larger key, or equal key and lower column
+      for (int u = 0; u < n_cand; ++u) {
+        const unsigned long long ku = sm.sel_keys[u];
+        pos += (ku > key || (ku == key && sm.sel_idx[u] < idx)) ? 1 : 0;
+      }
+      if (pos < kk) {
+        topk_idx[row * k + pos] = idx + col_offset;
+        if (topk_score) topk_score[row * k + pos] = key_f64(key);
+      }
+    }
+    for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
+      topk_idx[row * k + t] = -1;
+      if (topk_score) topk_score[row * k + t] = -INFINITY;
+    }
+  };
+
+  // ---- 3. candidate threshold from the group maxima ------------------------------------------------------------
+  // The kk-th largest of G group maxima is a lower bound of the kk-th largest key (the kk groups at or above it hold
+  // kk distinct columns), and about -G ln(1 - kk / G) keys of a row lie at or above it (126 for kk = 100, G = 256):
+  // locating it takes a histogram of G items instead of n_cols, and ONE sweep then serves the rank and gathers the
+  // candidates.  G = 256 (the thread maxima) for kk <= 128 on rows of 2048+ columns, else the 1024 component maxima.
+  // The threshold is the low edge of the value bin that holds that maximum; the 1024 bins span the maxima only (a
+  // fraction of the row's key range: float keys are logarithmic in the value), refined 10 bits at a time while more
+  // than 8 maxima share the bin.
+  bool rank_done = false;
+  if (select && use_group_maxima && imin <= kmax) {
+    const unsigned int mrange = kmax - imin;
+    const int mbits = mrange ? 32 - __clz(static_cast<int>(mrange)) : 0;
+    unsigned int base = imin, thr_g = 0u;
+    int shift = mbits > kValueBinBits ? mbits - kValueBinBits : 0, need = kk;
+    unsigned int span = kValueBins;
+    bool have = false;
+    for (int level = 0; level < 4; ++level) {
+      if (level > 0) {
+        for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
+        __syncthreads();
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // leaving a group out (key 0, see above) only lowers the threshold
+        if (i < per && gm[i] != 0u && gm[i] >= base) {
+          const unsigned int d = (gm[i] - base) >> shift;
+          if (d < span) atomicAdd(&sm.hist[d], 1);
+        }
+      }
+      __syncthreads();
+      if (warp == 0) scan_hist_from_top(sm, need, lane);
+      __syncthreads();
+      const int bin = sm.bin, acc = sm.krem, c = sm.ncand;
+      if (bin < 0) break;                       // level 0 only: fewer than kk non-empty groups (a short row)
+      thr_g = base + (static_cast<unsigned int>(bin) << shift);
+      have = true;
+      if (c <= 8 || shift == 0) break;
+      need -= acc;
+      base = thr_g;
+      span = 1u << (shift > kValueBinBits ? kValueBinBits : shift);
+      shift = shift > kValueBinBits ? shift - kValueBinBits : 0;
+    }
+    if (have) {
+      sweep(want_rank, true, thr_g);
+      const int n_cand = sm.count;
+      if (n_cand <= kMaxCand) {
+        order_and_write(n_cand);
+        return;
+      }
+      rank_done = true;                         // too many columns at the threshold (heavy ties): the histogram path decides
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
+    if (threadIdx.x == 0) sm.count = 0;
+    __syncthreads();
   }
+
+  // ---- 4. one sweep: value histogram + distinct ids ahead of the ground truth ------------------
+  const bool rank_here = want_rank && !rank_done;
+  if (rank_here || select) sweep(rank_here, false, 0u);
   if (!want_topk) return;
 
-  // ---- 4. threshold by value, 10 bits of the key range per level -------------------------------
+  // ---- 5. threshold by value, 10 bits of the key range per level -------------------------------
   bool ok = false;
   unsigned int thr = 0u;
   int n_cand = 0;
@@ -446,27 +590,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
         for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) refine(cache[j]);
         __syncthreads();
       }
-      if (warp == 0) {   // scan the bins from the top, 32 bins per lane
-        constexpr int kPer = kValueBins / 32;
-        int tot = 0;
-        const int top = kValueBins - 1 - lane * kPer;   // this lane owns bins top, top-1, ..., top-kPer+1
-#pragma unroll 8
-        for (int i = 0; i < kPer; ++i) tot += sm.hist[top - ((i + lane) & (kPer - 1))];   // rotated: no bank conflicts
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        int acc = incl - tot;
-        if (acc < need && incl >= need) {
-          for (int i = 0; i < kPer; ++i) {
-            const int c = sm.hist[top - i];
-            if (acc + c >= need) { sm.bin = top - i; sm.krem = acc; sm.ncand = c; break; }
-            acc += c;
-          }
-        }
-      }
+      if (warp == 0) scan_hist_from_top(sm, need, lane);
       __syncthreads();
       const int bin = sm.bin, acc = sm.krem, c = sm.ncand;
       n_cand = above + acc + c;
@@ -486,11 +610,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     }
   }
   if (ok) {
-    // ---- 5. gather the candidates with their exact fp64 keys, order them by counting ----------
-    auto take = [&](int j) {
-      const int slot = atomicAdd(&sm.count, 1);
-      if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
-    };
+    // ---- 6. gather the candidates with their exact fp64 keys, order them by counting ----------
     for (int q = threadIdx.x; q < nv; q += kRankThreads) {
       const uint4 kq = cache4[q];
       if (max(max(kq.x, kq.y), max(kq.z, kq.w)) >= thr) {      // ~k of the n columns pass: one compare per four keys
@@ -503,23 +623,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads)
       if (cache[j] >= thr) take(j);
     __syncthreads();
-    for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
-      const unsigned long long key = sm.sel_keys[t];
-      const int idx = sm.sel_idx[t];
-      int pos = 0;   // candidates that come first: larger key, or equal key and lower column
-      for (int u = 0; u < n_cand; ++u) {
-        const unsigned long long ku = sm.sel_keys[u];
-        pos += (ku > key || (ku == key && sm.sel_idx[u] < idx)) ? 1 : 0;
-      }
-      if (pos < kk) {
-        topk_idx[row * k + pos] = idx + col_offset;
-        if (topk_score) topk_score[row * k + pos] = key_f64(key);
-      }
-    }
-    for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
-      topk_idx[row * k + t] = -1;
-      if (topk_score) topk_score[row * k + t] = -INFINITY;
-    }
+    order_and_write(n_cand);
     return;
   }
   __syncthreads();
@@ -666,9 +770,14 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
   if (n_cols <= kMaxSmemCols) {
     MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&rank_topk_staged_kernel), static_cast<int>(kMaxSmemCols * 4)));
     const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);
+    // MADE_RANK_GROUP_MAXIMA=0: the full value histogram decides every row (A/B switch; results are identical)
+    static const int use_group_maxima = [] {
+      const char* v = getenv("MADE_RANK_GROUP_MAXIMA");
+      return (v && v[0] == '0') ? 0 : 1;
+    }();
     rank_topk_staged_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
         single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
-        gt_score_out);
+        gt_score_out, use_group_maxima);
   } else {
     rank_topk_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, 0, st>>>(
         single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
