@@ -1096,6 +1096,7 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
   for (int l = 0; l < NDEC; ++l) {
     const DetrDecW& w = c->ddec[l];
     float* t3f = t3all + static_cast<size_t>(l) * B * D;
+    op_t* tout = (l & 1) ? tgt : t3;   // the layer's fp16 output ping-pongs between two buffers: the next layer reads it as `tin`
     {
       GemmEpilogue ep;   // self-attention on a single query (folded) + norm1
       ep.residual = tinf;
@@ -1143,15 +1144,13 @@ int made_detr_detect(made_ctx* c, const void* frame16, const float* frame_masks,
       ep.res_ld = D;
       ep.ln_gamma = w.n3.g;
       ep.ln_beta = w.n3.b;
-      ep.out_h = t3;
+      ep.out_h = tout;
       ep.ld_h = D;
       ep.out_f32 = t3f;
       ep.ld_f32 = D;
       MADE_TRY(linear(hdec, DFF, w.ff2, B, D, DFF, ep, st));
     }
-    // t3 is consumed by the next layer's first GEMM before this layer's buffers are rewritten
-    MADE_CUDA(cudaMemcpyAsync(tgt, t3, static_cast<size_t>(B) * D * 2, cudaMemcpyDeviceToDevice, st));
-    tin = tgt;
+    tin = tout;
     tinf = t3f;
   }
   // decoder.norm on every layer's output (:136), then the heads (model_Uni.py:131-149)

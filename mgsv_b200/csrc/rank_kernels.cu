@@ -771,10 +771,8 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
     MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&rank_topk_staged_kernel), static_cast<int>(kMaxSmemCols * 4)));
     const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);
     // MADE_RANK_GROUP_MAXIMA=0: the full value histogram decides every row (A/B switch; results are identical)
-    static const int use_group_maxima = [] {
-      const char* v = getenv("MADE_RANK_GROUP_MAXIMA");
-      return (v && v[0] == '0') ? 0 : 1;
-    }();
+    const char* gmx = getenv("MADE_RANK_GROUP_MAXIMA");
+    const int use_group_maxima = (gmx && gmx[0] == '0') ? 0 : 1;
     rank_topk_staged_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
         single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
         gt_score_out, use_group_maxima);

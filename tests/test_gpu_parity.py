@@ -129,14 +129,18 @@ def test_span_fast_division_path_is_bit_identical(dev, kind):
     sa, sb = ops.span_cw_to_se(a), ops.span_cw_to_se(b)
     prob = torch.rand(n, generator=g).to(dev)
     out = {}
-    for fast in ("1", "0"):
-        os.environ["MADE_SPAN_FAST"] = fast
-        out[fast] = (ops.generalized_temporal_iou(sa, sb, check=False), *ops.temporal_iou(sa, sb), ops.matcher_cost(prob, a, b))
+    # fast + packed (two columns per FADD2 / FMUL2 / FFMA2, the default), fast scalar, guarded
+    for fast, packed in (("1", "1"), ("1", "0"), ("0", "1")):
+        os.environ["MADE_SPAN_FAST"], os.environ["MADE_SPAN_PACKED"] = fast, packed
+        out[fast + packed] = (ops.generalized_temporal_iou(sa, sb, check=False), *ops.temporal_iou(sa, sb),
+                              ops.matcher_cost(prob, a, b))
     os.environ.pop("MADE_SPAN_FAST")
-    for x, y in zip(out["1"], out["0"]):
-        assert torch.equal(x.view(torch.int32), y.view(torch.int32))          # bit patterns, NaN payloads included
+    os.environ.pop("MADE_SPAN_PACKED")
+    for other in ("10", "01"):
+        for x, y in zip(out["11"], out[other]):
+            assert torch.equal(x.view(torch.int32), y.view(torch.int32))      # bit patterns, NaN payloads included
     if kind == "edges":
-        assert bool(torch.isnan(out["1"][0]).any())                            # 0/0 of two zero-width spans is there (Q10)
+        assert bool(torch.isnan(out["11"][0]).any())                           # 0/0 of two zero-width spans is there (Q10)
 
 
 def test_span_kernels_empty_and_errors(dev):
@@ -279,6 +283,44 @@ def test_topk_value_distributions(dev, kind):
     order = torch.sort(-total, dim=1, stable=True).indices[:, :k]
     assert torch.equal(got_i, order)
     assert torch.equal(got_s, torch.gather(total, 1, order))
+
+
+@pytest.mark.parametrize("n_cols,k", [(16384, 100), (4000, 100), (4000, 256), (2048, 128), (2047, 129), (1000, 100),
+                                      (300, 100), (256, 100), (100, 100), (37, 100), (49152, 256), (4001, 1)])
+def test_topk_group_maxima_threshold(dev, n_cols, k):
+    """The candidate threshold taken from the per-thread group maxima (default) and the per-column value histogram
+    (MADE_RANK_GROUP_MAXIMA=0) must give the same exact top-k and rank, on rows with NaN and -inf scores too."""
+    g = torch.Generator().manual_seed(n_cols + k)
+    n = 24
+    single, dual = torch.randn(n, n_cols, generator=g), 0.3 * torch.randn(n, n_cols, generator=g)
+    single[1, ::3] = float("nan")                       # NaN orders below every number
+    single[2, 1::2] = float("-inf")
+    single[3] = single[3].round()                       # heavy ties: more candidates than the gather holds
+    dual[3] = 0.0
+    single[4, : n_cols // 2] = float("nan")            # whole groups of NaN scores
+    gt = torch.randint(0, n_cols, (n,), generator=g, dtype=torch.int32)
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["MADE_RANK_GROUP_MAXIMA"] = mode
+        out[mode] = ops.rank_topk(single.to(dev), dual.to(dev), gt.to(dev), None, k=k)
+    os.environ.pop("MADE_RANK_GROUP_MAXIMA")
+    for key in ("topk_idx", "rank"):
+        assert torch.equal(out["1"][key], out["0"][key]), key
+    for key in ("topk_score", "gt_score"):
+        assert torch.equal(out["1"][key].view(torch.int64), out["0"][key].view(torch.int64)), key
+    total = single.double() + dual.double()
+    keyed = torch.where(torch.isnan(total), torch.full_like(total, float("-inf")), total)
+    kk = min(k, n_cols)
+    order = torch.sort(-keyed, dim=1, stable=True).indices[:, :kk]
+    got_i = out["1"]["topk_idx"].cpu().long()
+    clean = ~torch.isnan(total).any(1) & ~torch.isinf(total).any(1)     # NaN / -inf rows: ties among the keys of NaN and -inf
+    assert torch.equal(got_i[clean][:, :kk], order[clean])
+    assert torch.equal(out["1"]["topk_score"].cpu()[clean][:, :kk], torch.gather(total, 1, order)[clean])
+    if k > n_cols:
+        assert bool((got_i[:, kk:] == -1).all())
+    gt_s = torch.gather(total, 1, gt.long().unsqueeze(1))
+    ok = ~torch.isnan(gt_s.squeeze(1))
+    assert torch.equal(out["1"]["rank"].cpu().long()[ok], (total > gt_s).sum(1)[ok])
 
 
 def test_topk_merge_and_cosine(dev):
