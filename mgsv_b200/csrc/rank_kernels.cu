@@ -101,13 +101,19 @@ __device__ __forceinline__ int block_sum_int(int v, int* red) {
   return t;
 }
 
-// bitonic sort of n (power of two) (key, idx) pairs: key descending, idx ascending
+// bitonic sort of n (power of two) (key, idx) pairs: key descending, idx ascending.  Called by the whole CTA
+// (blockDim.x a multiple of 32).  A compare-exchange step of stride <= 32 stays inside the 64-element segment
+// [64 w, 64 w + 64) of the warp w = t / 32 that owns it, so consecutive narrow steps only need a warp barrier; the CTA
+// barrier is kept where a step reads what other warps wrote (27 of the 28 steps of a 128-element sort are narrow).
 __device__ void bitonic_sort_desc(unsigned long long* keys, int* idx, int n) {
+  bool prev_wide = true;   // the input was written by arbitrary threads
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
+      const bool wide = stride > 32;
+      if (wide || prev_wide) __syncthreads(); else __syncwarp();
+      prev_wide = wide;
       for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
-        int lo = (t / stride) * stride * 2 + (t % stride);
+        int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         int hi = lo + stride;
         bool desc_block = ((lo & size) == 0);
         unsigned long long kl = keys[lo], kh = keys[hi];
@@ -348,14 +354,10 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   // ---- 1. ground-truth score (thread 0) while the others start staging the row ---------------
   if (want_rank && threadIdx.x == 0) gt_walk(rv, row, n_cols, gt_col, gt_score_in, prev_same, sm);
 
-  // ---- 2. stage the row as 32-bit keys, tracking the key range and the maximum of each of this thread's four
-  //         column groups (group c of thread t = component c of the 16-byte words t, t + 256, ...) ----------------
-  unsigned int kmin = 0xFFFFFFFFu, kmax = 0u;
+  // ---- 2. stage the row as 32-bit keys, tracking the maximum of each of this thread's four column groups
+  //         (group c of thread t = component c of the 16-byte words t, t + 256, ...: 1024 groups per row) --------
   uint4 gmax = make_uint4(0u, 0u, 0u, 0u);
-  // the threshold items: the 256 thread maxima, or all 1024 component maxima when k or the row length asks for more groups
-  const int per = (kk > 128 || n_cols < 2048) ? 4 : 1;
-  unsigned int gm[4];
-  unsigned int imin = 0xFFFFFFFFu;               // smallest threshold item of the row
+  unsigned int kmax = 0u, imin = 0xFFFFFFFFu;    // largest key of the row, smallest non-empty group maximum
   {
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(single) & 15) == 0) &&
                      (!dual || (reinterpret_cast<uintptr_t>(dual) & 15) == 0);
@@ -371,38 +373,31 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       }
       const uint4 kq = make_uint4(f32_key(x.x), f32_key(x.y), f32_key(x.z), f32_key(x.w));
       *reinterpret_cast<uint4*>(cache + q * 4) = kq;
-      kmin = min(kmin, min(min(kq.x, kq.y), min(kq.z, kq.w)));
       gmax.x = max(gmax.x, kq.x); gmax.y = max(gmax.y, kq.y); gmax.z = max(gmax.z, kq.z); gmax.w = max(gmax.w, kq.w);
     }
     for (int j = n4 * 4 + threadIdx.x; j < static_cast<int>(n_cols); j += kRankThreads) {
       const unsigned int key = rv.key32(j);
       cache[j] = key;
-      kmin = min(kmin, key);
       gmax.x = max(gmax.x, key);
     }
     kmax = max(max(gmax.x, gmax.y), max(gmax.z, gmax.w));
-    gm[0] = per == 1 ? kmax : gmax.x;
-    gm[1] = gmax.y; gm[2] = gmax.z; gm[3] = gmax.w;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (i < per && gm[i] != 0u) imin = min(imin, gm[i]);   // key 0 = an empty group (or one of NaN scores only): not an item
-    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    // key 0 = an empty group (or one of NaN scores only): not a threshold item
+    if (gmax.x != 0u) imin = gmax.x;
+    if (gmax.y != 0u) imin = min(imin, gmax.y);
+    if (gmax.z != 0u) imin = min(imin, gmax.z);
+    if (gmax.w != 0u) imin = min(imin, gmax.w);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     imin = __reduce_min_sync(0xffffffffu, imin);
-    if (lane == 0) { sm.red32[0][warp] = kmin; sm.red32[1][warp] = kmax; sm.red32[2][warp] = imin; }
+    if (lane == 0) { sm.red32[0][warp] = kmax; sm.red32[1][warp] = imin; }
   }
   for (int t = threadIdx.x; t < kValueBins; t += kRankThreads) sm.hist[t] = 0;
   if (threadIdx.x == 0) { sm.count = 0; sm.ncand = 0; sm.bin = -1; }
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < kRankThreads / 32; ++w) {
-    kmin = min(kmin, sm.red32[0][w]);
-    kmax = max(kmax, sm.red32[1][w]);
-    imin = min(imin, sm.red32[2][w]);
+    kmax = max(kmax, sm.red32[0][w]);
+    imin = min(imin, sm.red32[1][w]);
   }
-  const unsigned int range = kmax - kmin;
-  const int bits = range ? 32 - __clz(static_cast<int>(range)) : 0;
-  const int vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
   const bool select = want_topk && kk > 0;
 
   // A column beats s* when its fp32 key is more than two steps above that of s* (then the fp64
@@ -413,6 +408,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   // bounds make the impossible side unreachable
   const unsigned int g_hi = gk32 > 0xFFFFFFFDu ? 0xFFFFFFFFu : gk32 + 2u;
   const unsigned int g_lo = gk32 < 2u ? 0u : gk32 - 2u;
+  const unsigned int g_win = g_hi - g_lo;      // k32 - g_lo <= g_win (unsigned): within two steps of s*
   auto beats = [&](int j, unsigned int k32) -> bool {
     if (k32 > g_hi) return true;
     if (k32 < g_lo) return false;
@@ -425,42 +421,35 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     const int slot = atomicAdd(&sm.count, 1);
     if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
   };
-  // One sweep over the staged keys.  do_rank: count the distinct ids ahead of the ground truth.  With a candidate
-  // threshold (gather): append the columns at or above it; without one: fill the value histogram (one shared-memory
-  // atomic per column - 2 cycles per lane on this machine, the cost the group-maxima threshold exists to avoid).
+  // One sweep over the staged keys.  do_rank: count the distinct ids ahead of the ground truth; gather: append the
+  // columns at or above the candidate threshold.  The common case of a key is two compares: the exact fp64 compare
+  // (keys within two fp32 steps of s*) and the append (~k of the n columns) sit behind ONE rarely taken branch per
+  // four keys.
   auto sweep = [&](bool do_rank, bool gather, unsigned int thr) {
-    const bool fill = select && !gather;
     int cnt = 0;
     if (prev_same == nullptr) {
-      // lean sweep (distinct ids): four keys per shared-memory load, two compares per key for the rank, the exact fp64
-      // keys only within two fp32 steps of s*
-      auto one = [&](int j, unsigned int k32) {
-        if (fill) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
-        if (do_rank) {
-          if (k32 > g_hi) ++cnt;
-          else if (k32 >= g_lo && rv.key(j) > gk) ++cnt;
-        }
+      auto rare = [&](int j, unsigned int k32) {
+        if (do_rank && k32 - g_lo <= g_win && rv.key(j) > gk) ++cnt;
+        if (gather && k32 >= thr) take(j);
       };
 #pragma unroll 2
       for (int q = threadIdx.x; q < nv; q += kRankThreads) {
         const uint4 kq = cache4[q];
-        one(4 * q, kq.x); one(4 * q + 1, kq.y); one(4 * q + 2, kq.z); one(4 * q + 3, kq.w);
-        if (gather && max(max(kq.x, kq.y), max(kq.z, kq.w)) >= thr) {   // ~k of the n columns pass: one compare per four keys
-          if (kq.x >= thr) take(4 * q);
-          if (kq.y >= thr) take(4 * q + 1);
-          if (kq.z >= thr) take(4 * q + 2);
-          if (kq.w >= thr) take(4 * q + 3);
+        if (do_rank) cnt += (kq.x > g_hi ? 1 : 0) + (kq.y > g_hi ? 1 : 0) + (kq.z > g_hi ? 1 : 0) + (kq.w > g_hi ? 1 : 0);
+        const unsigned int near = min(min(kq.x - g_lo, kq.y - g_lo), min(kq.z - g_lo, kq.w - g_lo));
+        const unsigned int top = max(max(kq.x, kq.y), max(kq.z, kq.w));
+        if ((do_rank && near <= g_win) || (gather && top >= thr)) {
+          rare(4 * q, kq.x); rare(4 * q + 1, kq.y); rare(4 * q + 2, kq.z); rare(4 * q + 3, kq.w);
         }
       }
       for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) {
         const unsigned int k32 = cache[j];
-        one(j, k32);
-        if (gather && k32 >= thr) take(j);
+        if (do_rank && k32 > g_hi) ++cnt;
+        rare(j, k32);
       }
     } else {
       for (int j = threadIdx.x; j < nc; j += kRankThreads) {
         const unsigned int k32 = cache[j];
-        if (fill) atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1);
         if (gather && k32 >= thr) take(j);
         if (do_rank && beats(j, k32)) {
           bool first = true;
@@ -475,7 +464,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       }
     }
     if (do_rank) {
-      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the histogram / the candidates
+      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the candidates
       if (threadIdx.x == 0) {
         rank_out[row] = cnt;
         if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
@@ -484,37 +473,36 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       __syncthreads();
     }
   };
-  // Order n_cand gathered candidates by counting (score descending, lower column first) and write the best kk.
+  // Order the n_cand <= kMaxCand gathered candidates (score descending, lower column first) and write the best kk.
   auto order_and_write = [&](int n_cand) {
-    for (int t = threadIdx.x; t < n_cand; t += kRankThreads) {
-      const unsigned long long key = sm.sel_keys[t];
-      const int idx = sm.sel_idx[t];
-      int pos = 0;   // candidates that come first: larger key, or equal key and lower column
-      for (int u = 0; u < n_cand; ++u) {
-        const unsigned long long ku = sm.sel_keys[u];
-        pos += (ku > key || (ku == key && sm.sel_idx[u] < idx)) ? 1 : 0;
-      }
-      if (pos < kk) {
-        topk_idx[row * k + pos] = idx + col_offset;
-        if (topk_score) topk_score[row * k + pos] = key_f64(key);
-      }
+    int n_pow = 32;
+    while (n_pow < n_cand) n_pow <<= 1;
+    for (int t = n_cand + threadIdx.x; t < n_pow; t += kRankThreads) {
+      sm.sel_keys[t] = 0ull;
+      sm.sel_idx[t] = 0x7FFFFFFF;
     }
-    for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
-      topk_idx[row * k + t] = -1;
-      if (topk_score) topk_score[row * k + t] = -INFINITY;
+    bitonic_sort_desc(sm.sel_keys, sm.sel_idx, n_pow);
+    for (int t = threadIdx.x; t < k; t += kRankThreads) {
+      if (t < kk) {
+        topk_idx[row * k + t] = sm.sel_idx[t] + col_offset;
+        if (topk_score) topk_score[row * k + t] = key_f64(sm.sel_keys[t]);
+      } else {
+        topk_idx[row * k + t] = -1;
+        if (topk_score) topk_score[row * k + t] = -INFINITY;
+      }
     }
   };
 
   // ---- 3. candidate threshold from the group maxima ------------------------------------------------------------
-  // The kk-th largest of G group maxima is a lower bound of the kk-th largest key (the kk groups at or above it hold
-  // kk distinct columns), and about -G ln(1 - kk / G) keys of a row lie at or above it (126 for kk = 100, G = 256):
-  // locating it takes a histogram of G items instead of n_cols, and ONE sweep then serves the rank and gathers the
-  // candidates.  G = 256 (the thread maxima) for kk <= 128 on rows of 2048+ columns, else the 1024 component maxima.
-  // The threshold is the low edge of the value bin that holds that maximum; the 1024 bins span the maxima only (a
-  // fraction of the row's key range: float keys are logarithmic in the value), refined 10 bits at a time while more
-  // than 8 maxima share the bin.
+  // The kk-th largest of the G = 1024 group maxima is a lower bound of the kk-th largest key (the kk groups at or
+  // above it hold kk distinct columns), and about -G ln(1 - kk / G) keys of a row lie at or above it (105 for
+  // kk = 100): locating it takes a histogram of G items instead of n_cols, and ONE sweep then serves the rank and
+  // gathers the candidates.  The threshold is the low edge of the value bin that holds that maximum; the 1024 bins
+  // span the maxima only (a fraction of the row's key range: float keys are logarithmic in the value), refined 10 bits
+  // at a time while more than 8 maxima share the bin.
   bool rank_done = false;
   if (select && use_group_maxima && imin <= kmax) {
+    const unsigned int gm[4] = {gmax.x, gmax.y, gmax.z, gmax.w};
     const unsigned int mrange = kmax - imin;
     const int mbits = mrange ? 32 - __clz(static_cast<int>(mrange)) : 0;
     unsigned int base = imin, thr_g = 0u;
@@ -529,7 +517,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         // leaving a group out (key 0, see above) only lowers the threshold
-        if (i < per && gm[i] != 0u && gm[i] >= base) {
+        if (gm[i] != 0u && gm[i] >= base) {
           const unsigned int d = (gm[i] - base) >> shift;
           if (d < span) atomicAdd(&sm.hist[d], 1);
         }
@@ -562,9 +550,8 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     __syncthreads();
   }
 
-  // ---- 4. one sweep: value histogram + distinct ids ahead of the ground truth ------------------
-  const bool rank_here = want_rank && !rank_done;
-  if (rank_here || select) sweep(rank_here, false, 0u);
+  // ---- 4. rows the group maxima do not settle: the rank sweep, then the per-column value histogram ---------------
+  if (want_rank && !rank_done) sweep(true, false, 0u);
   if (!want_topk) return;
 
   // ---- 5. threshold by value, 10 bits of the key range per level -------------------------------
@@ -572,6 +559,28 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   unsigned int thr = 0u;
   int n_cand = 0;
   if (select) {
+    unsigned int kmin = 0xFFFFFFFFu;
+    for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+      const uint4 kq = cache4[q];
+      kmin = min(kmin, min(min(kq.x, kq.y), min(kq.z, kq.w)));
+    }
+    for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) kmin = min(kmin, cache[j]);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    __syncthreads();                                         // red32 / bin of the sections above are no longer read
+    if (lane == 0) sm.red32[2][warp] = kmin;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kRankThreads / 32; ++w) kmin = min(kmin, sm.red32[2][w]);
+    const unsigned int range = kmax - kmin;
+    const int bits = range ? 32 - __clz(static_cast<int>(range)) : 0;
+    const int vshift = bits > kValueBinBits ? bits - kValueBinBits : 0;   // (range >> vshift) < kValueBins
+    auto fill = [&](unsigned int k32) { atomicAdd(&sm.hist[(k32 - kmin) >> vshift], 1); };
+    for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+      const uint4 kq = cache4[q];
+      fill(kq.x); fill(kq.y); fill(kq.z); fill(kq.w);
+    }
+    for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) fill(cache[j]);
+    __syncthreads();
     unsigned int base = kmin;
     int shift = vshift, need = kk, above = 0;
     unsigned int span = kValueBins;   // sub-bins the bin chosen at the previous level splits into
@@ -594,8 +603,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       __syncthreads();
       const int bin = sm.bin, acc = sm.krem, c = sm.ncand;
       n_cand = above + acc + c;
-      // accept once the candidate set is close to k (ordering it costs n_cand^2 / 256 steps per
-      // thread); at shift 0 the bin is a single key value and cannot be split further
+      // accept once the candidate set is close to k; at shift 0 the bin is a single key value and cannot be split further
       if (n_cand <= kk + kCandSlack || (shift == 0 && n_cand <= kMaxCand)) {
         thr = base + (static_cast<unsigned int>(bin) << shift);
         ok = true;
@@ -610,19 +618,8 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     }
   }
   if (ok) {
-    // ---- 6. gather the candidates with their exact fp64 keys, order them by counting ----------
-    for (int q = threadIdx.x; q < nv; q += kRankThreads) {
-      const uint4 kq = cache4[q];
-      if (max(max(kq.x, kq.y), max(kq.z, kq.w)) >= thr) {      // ~k of the n columns pass: one compare per four keys
-        if (kq.x >= thr) take(4 * q);
-        if (kq.y >= thr) take(4 * q + 1);
-        if (kq.z >= thr) take(4 * q + 2);
-        if (kq.w >= thr) take(4 * q + 3);
-      }
-    }
-    for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads)
-      if (cache[j] >= thr) take(j);
-    __syncthreads();
+    // ---- 6. gather the candidates with their exact fp64 keys, order them ----------
+    sweep(false, true, thr);
     order_and_write(n_cand);
     return;
   }

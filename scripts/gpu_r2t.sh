@@ -1,0 +1,23 @@
+#!/bin/bash
+# round 2, session 4, call C: rank / top-k tests, micro bench, ncu --set full of rank_topk (8192 x 16384)
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 -k "rank or topk or recall or sharded or gallery or full_size or index" 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python scripts/micro_bench.py > gpurun_out/micro_bench_new.json 2> gpurun_out/mb_new.err
+python - <<'P'
+import json
+d = json.load(open("gpurun_out/micro_bench_new.json"))
+for r in d["kernels"]:
+    if "16384" in r["kernel"] or "rank" in r["kernel"] or "postproc" in r["kernel"]:
+        print(f"{r['kernel']:34s} {r['ms']:.4f} ms {r['gbs']:.0f} GB/s {100*r['frac_of_hbm_peak']:.1f} %")
+P
+prof() {  # name, kernel regex, skip, script
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/prof_$1 python $4 > gpurun_out/prof_$1.log 2>&1
+  ncu -i gpurun_out/prof_$1.ncu-rep --page raw --csv > gpurun_out/prof_$1_raw.csv 2>/dev/null
+  ncu -i gpurun_out/prof_$1.ncu-rep --page source --csv > gpurun_out/prof_$1_source.csv 2>/dev/null
+  python scripts/ncu_source_summary.py gpurun_out/prof_$1_source.csv 30 > gpurun_out/prof_$1_source_summary.txt 2>&1
+  find gpurun_out -name "prof_$1.ncu-rep" -size +20M -delete
+}
+prof rank rank_topk_staged 1 scripts/diag_rank_ncu.py
+head -5 gpurun_out/prof_rank_source_summary.txt
