@@ -30,6 +30,8 @@
 // bin); rows where more than 512 columns share one fp32 key around rank k, and rows too long to
 // stage, take the exact 8-pass MSB radix select on the 64-bit keys (re-reading global memory) + a
 // bitonic sort instead.
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -55,9 +57,10 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
   return __longlong_as_double(static_cast<long long>(b));
 }
 __device__ __forceinline__ unsigned int f32_key(float x) {
-  if (x != x) return 0u;
   const unsigned int b = __float_as_uint(x);
-  return (b >> 31) ? ~b : (b | 0x80000000u);
+  // negative: ~b, positive: b | 0x80000000 (= b ^ 0x80000000, the sign bit being clear): one shift, one three-input logic op
+  const unsigned int key = b ^ (static_cast<unsigned int>(static_cast<int>(b) >> 31) | 0x80000000u);
+  return x != x ? 0u : key;
 }
 
 // exact 64-bit keys of one row, read from global memory
@@ -107,11 +110,13 @@ __device__ __forceinline__ int block_sum_int(int v, int* red) {
 // barrier is kept where a step reads what other warps wrote (27 of the 28 steps of a 128-element sort are narrow).
 __device__ void bitonic_sort_desc(unsigned long long* keys, int* idx, int n) {
   bool prev_wide = true;   // the input was written by arbitrary threads
+  const bool idle = static_cast<int>(threadIdx.x & ~31u) >= n / 2;   // a warp without a compare-exchange in any step
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       const bool wide = stride > 32;
-      if (wide || prev_wide) __syncthreads(); else __syncwarp();
+      if (wide || prev_wide) __syncthreads(); else if (!idle) __syncwarp();
       prev_wide = wide;
+      if (idle) continue;
       for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
         int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         int hi = lo + stride;
@@ -421,26 +426,41 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     const int slot = atomicAdd(&sm.count, 1);
     if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
   };
+  constexpr std::true_type kYes{};
+  constexpr std::false_type kNo{};
   // One sweep over the staged keys.  do_rank: count the distinct ids ahead of the ground truth; gather: append the
   // columns at or above the candidate threshold.  The common case of a key is two compares: the exact fp64 compare
   // (keys within two fp32 steps of s*) and the append (~k of the n columns) sit behind ONE rarely taken branch per
   // four keys.
-  auto sweep = [&](bool do_rank, bool gather, unsigned int thr) {
+  auto sweep = [&](auto do_rank_t, auto gather_t, unsigned int thr) {
+    constexpr bool do_rank = decltype(do_rank_t)::value, gather = decltype(gather_t)::value;   // compile-time: no flag tests in the loops
     int cnt = 0;
     if (prev_same == nullptr) {
       auto rare = [&](int j, unsigned int k32) {
         if (do_rank && k32 - g_lo <= g_win && rv.key(j) > gk) ++cnt;
         if (gather && k32 >= thr) take(j);
       };
+      // A 16-byte word with a rare key only sets a bit (its iteration number: rows of <= 49152 columns give a thread
+      // <= 48 words); the words are revisited after the loop.  Rare per thread is not rare per warp - ~k of the n / 4
+      // words hold a candidate, more than half of the warp iterations have one in some lane - and the revisit costs a
+      // warp as many passes as its busiest lane has words (2 - 3) instead of one pass per such iteration.
+      unsigned long long revisit = 0ull;
+      int it = 0;
 #pragma unroll 2
-      for (int q = threadIdx.x; q < nv; q += kRankThreads) {
+      for (int q = threadIdx.x; q < nv; q += kRankThreads, ++it) {
         const uint4 kq = cache4[q];
         if (do_rank) cnt += (kq.x > g_hi ? 1 : 0) + (kq.y > g_hi ? 1 : 0) + (kq.z > g_hi ? 1 : 0) + (kq.w > g_hi ? 1 : 0);
         const unsigned int near = min(min(kq.x - g_lo, kq.y - g_lo), min(kq.z - g_lo, kq.w - g_lo));
         const unsigned int top = max(max(kq.x, kq.y), max(kq.z, kq.w));
-        if ((do_rank && near <= g_win) || (gather && top >= thr)) {
-          rare(4 * q, kq.x); rare(4 * q + 1, kq.y); rare(4 * q + 2, kq.z); rare(4 * q + 3, kq.w);
-        }
+        const bool hit = (do_rank && near <= g_win) || (gather && top >= thr);
+        revisit |= static_cast<unsigned long long>(hit ? 1u : 0u) << it;
+      }
+      while (revisit) {
+        const int b = __ffsll(static_cast<long long>(revisit)) - 1;
+        revisit &= revisit - 1ull;
+        const int q = threadIdx.x + b * kRankThreads;
+        const uint4 kq = cache4[q];
+        rare(4 * q, kq.x); rare(4 * q + 1, kq.y); rare(4 * q + 2, kq.z); rare(4 * q + 3, kq.w);
       }
       for (int j = nv * 4 + threadIdx.x; j < nc; j += kRankThreads) {
         const unsigned int k32 = cache[j];
@@ -536,7 +556,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       shift = shift > kValueBinBits ? shift - kValueBinBits : 0;
     }
     if (have) {
-      sweep(want_rank, true, thr_g);
+      if (want_rank) sweep(kYes, kYes, thr_g); else sweep(kNo, kYes, thr_g);
       const int n_cand = sm.count;
       if (n_cand <= kMaxCand) {
         order_and_write(n_cand);
@@ -551,7 +571,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   }
 
   // ---- 4. rows the group maxima do not settle: the rank sweep, then the per-column value histogram ---------------
-  if (want_rank && !rank_done) sweep(true, false, 0u);
+  if (want_rank && !rank_done) sweep(kYes, kNo, 0u);
   if (!want_topk) return;
 
   // ---- 5. threshold by value, 10 bits of the key range per level -------------------------------
@@ -619,7 +639,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   }
   if (ok) {
     // ---- 6. gather the candidates with their exact fp64 keys, order them ----------
-    sweep(false, true, thr);
+    sweep(kNo, kYes, thr);
     order_and_write(n_cand);
     return;
   }
