@@ -336,8 +336,12 @@ __device__ __forceinline__ void scan_hist_from_top(RankSmem& sm, int need, int l
   }
 }
 
-// Staged rows: see the header of this file.
-__global__ void __launch_bounds__(kRankThreads, 6)
+// Staged rows: see the header of this file.  WIDE (rows of more than 8192 columns, whose 32+ KB of keys leave room for
+// at most 3 - 6 CTAs per SM anyway): 3 CTAs per SM, 85 registers, EIGHT 16-byte word pairs in flight per thread while
+// staging (64 KB per CTA; with four, a 128 KB row took four HBM round trips and staging was 40 % of the kernel).
+// Otherwise 7 CTAs per SM: the job's own 2000 rows fit in two waves of 148 x 7 instead of three of 148 x 6.
+template <bool WIDE>
+__global__ void __launch_bounds__(kRankThreads, WIDE ? 3 : 7)
 rank_topk_staged_kernel(const float* __restrict__ single, const float* __restrict__ dual, int64_t ld,
                         int64_t n_cols, const int32_t* __restrict__ gt_col,
                         const double* __restrict__ gt_score_in, const int32_t* __restrict__ prev_same,
@@ -369,7 +373,7 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
     const int n4 = vec ? static_cast<int>(n_cols / 4) : 0;      // staged rows have <= 49152 columns: 32-bit indices
     const float4* a4 = reinterpret_cast<const float4*>(rv.a);
     const float4* b4 = reinterpret_cast<const float4*>(rv.b);
-#pragma unroll 4
+#pragma unroll (WIDE ? 8 : 4)
     for (int q = threadIdx.x; q < n4; q += kRankThreads) {
       float4 x = __ldg(a4 + q);
       if (rv.b) {
@@ -493,23 +497,58 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       __syncthreads();
     }
   };
-  // Order the n_cand <= kMaxCand gathered candidates (score descending, lower column first) and write the best kk.
+  // Order the n_cand <= kMaxCand gathered candidates (score descending, lower column first) and write the best kk: every
+  // candidate's position is the number of candidates that come before it.  The count runs on the HIGH words of the fp64
+  // keys (sign, exponent, 20 mantissa bits: one broadcast 4-byte shared-memory load and two compares per pair), split
+  // over 256 / n threads per candidate; only a candidate that shares its high word with another one (a relative
+  // score difference below 1e-6) recounts with the full keys and the column tie rule.  Two barriers instead of the
+  // 28 dependent compare-exchange steps of a 128-element bitonic sort (a quarter of the kernel on long rows).
   auto order_and_write = [&](int n_cand) {
     int n_pow = 32;
     while (n_pow < n_cand) n_pow <<= 1;
-    for (int t = n_cand + threadIdx.x; t < n_pow; t += kRankThreads) {
-      sm.sel_keys[t] = 0ull;
-      sm.sel_idx[t] = 0x7FFFFFFF;
-    }
-    bitonic_sort_desc(sm.sel_keys, sm.sel_idx, n_pow);
-    for (int t = threadIdx.x; t < k; t += kRankThreads) {
-      if (t < kk) {
-        topk_idx[row * k + t] = sm.sel_idx[t] + col_offset;
-        if (topk_score) topk_score[row * k + t] = key_f64(sm.sel_keys[t]);
-      } else {
-        topk_idx[row * k + t] = -1;
-        if (topk_score) topk_score[row * k + t] = -INFINITY;
+    const int parts = n_pow <= kRankThreads ? kRankThreads / n_pow : 1;   // n_pow >= 32: the lanes of a warp share one part
+    const int part = parts > 1 ? static_cast<int>(threadIdx.x) / n_pow : 0;
+    const int per = (n_cand + parts - 1) / parts;
+    const int u0 = part * per, u1 = min(n_cand, u0 + per);
+    const uint2* k2 = reinterpret_cast<const uint2*>(sm.sel_keys);   // .y = high word (little endian)
+    int* partial = sm.hist;                                            // [parts][n_pow] (<= 512 entries), free after the sweep
+    for (int c = static_cast<int>(threadIdx.x) & (n_pow - 1); c < n_pow; c += kRankThreads) {
+      int gt = 0, eq = 0;
+      if (c < n_cand) {
+        const unsigned int khi = k2[c].y;
+#pragma unroll 8
+        for (int u = u0; u < u1; ++u) {
+          const unsigned int h = k2[u].y;
+          gt += h > khi ? 1 : 0;
+          eq += h == khi ? 1 : 0;
+        }
       }
+      partial[part * n_pow + c] = gt | (eq << 16);
+    }
+    __syncthreads();
+    if (part == 0) {
+      for (int c = static_cast<int>(threadIdx.x) & (n_pow - 1); c < n_cand; c += kRankThreads) {
+        int acc = 0;
+        for (int p = 0; p < parts; ++p) acc += partial[p * n_pow + c];
+        int pos = acc & 0xFFFF;
+        const unsigned long long key = sm.sel_keys[c];
+        if ((acc >> 16) != 1) {      // another candidate shares the high word: exact recount (larger key, or equal key and lower column)
+          const int idx = sm.sel_idx[c];
+          pos = 0;
+          for (int u = 0; u < n_cand; ++u) {
+            const unsigned long long ku = sm.sel_keys[u];
+            pos += (ku > key || (ku == key && sm.sel_idx[u] < idx)) ? 1 : 0;
+          }
+        }
+        if (pos < kk) {
+          topk_idx[row * k + pos] = sm.sel_idx[c] + col_offset;
+          if (topk_score) topk_score[row * k + pos] = key_f64(key);
+        }
+      }
+    }
+    for (int t = kk + threadIdx.x; t < k; t += kRankThreads) {
+      topk_idx[row * k + t] = -1;
+      if (topk_score) topk_score[row * k + t] = -INFINITY;
     }
   };
 
@@ -785,14 +824,22 @@ int made_rank_topk(const float* single, const float* dual, int64_t ld, int64_t n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof_scope(kProfRank, st);
   if (n_cols <= kMaxSmemCols) {
-    MADE_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&rank_topk_staged_kernel), static_cast<int>(kMaxSmemCols * 4)));
+    const bool wide = n_cols > 8192;
+    MADE_TRY(ensure_dynamic_smem(wide ? reinterpret_cast<const void*>(&rank_topk_staged_kernel<true>)
+                                      : reinterpret_cast<const void*>(&rank_topk_staged_kernel<false>),
+                                 static_cast<int>(kMaxSmemCols * 4)));
     const size_t smem = (static_cast<size_t>(n_cols) * 4 + 15) & ~static_cast<size_t>(15);
     // MADE_RANK_GROUP_MAXIMA=0: the full value histogram decides every row (A/B switch; results are identical)
     const char* gmx = getenv("MADE_RANK_GROUP_MAXIMA");
     const int use_group_maxima = (gmx && gmx[0] == '0') ? 0 : 1;
-    rank_topk_staged_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
-        single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
-        gt_score_out, use_group_maxima);
+    if (wide)
+      rank_topk_staged_kernel<true><<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
+          single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
+          gt_score_out, use_group_maxima);
+    else
+      rank_topk_staged_kernel<false><<<static_cast<unsigned>(n_rows), kRankThreads, smem, st>>>(
+          single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
+          gt_score_out, use_group_maxima);
   } else {
     rank_topk_kernel<<<static_cast<unsigned>(n_rows), kRankThreads, 0, st>>>(
         single, dual, ld, n_cols, gt_col, gt_score_in, prev_same, col_offset, k, topk_idx, topk_score, rank_out,
