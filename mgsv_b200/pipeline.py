@@ -116,11 +116,13 @@ class GalleryEvaluator:
         return bounds
 
     def _ingest_iter(self, modality: int, feats: torch.Tensor, mask_d: torch.Tensor, chunk: int, mask_h=None,
-                     taper_head: bool = False, taper_tail: bool = False):
+                     taper_head: bool = False, taper_tail: bool = False, prime: int = 0):
         """Yield (start, end, x16, rb, release) per chunk: x16 = token-packed fp16 features of rows
         start:end (valid tokens only) with their ragged descriptor rb, ready on the compute stream;
         call release() after the last kernel that reads x16 has been enqueued so the ingest stream
-        may refill the buffer."""
+        may refill the buffer.  prime > 0: the first `prime` (<= 3, the staging slots) chunks are issued at once and the
+        generator then yields None ONCE; the caller resumes it when it wants the chunks (run() queues the head of
+        the gallery on the copy engine before the queries' many small copies, see there)."""
         n = feats.shape[0]
         L, din = feats.shape[1], feats.shape[2]
         on_host = not feats.is_cuda and os.environ.get("MADE_TAPER", "1") != "0"
@@ -187,11 +189,21 @@ class GalleryEvaluator:
             ready[i] = (x16, rb, keep, ev, key)
             self._count("ingest")
 
-        if bounds:
-            issue(0)
+        issued = 0
+
+        def issue_upto(j):      # chunks are issued in order, each once
+            nonlocal issued
+            while issued <= j and issued < len(bounds):
+                issue(issued)
+                issued += 1
+
+        issue_upto(0)
+        if prime > 0:
+            issue_upto(min(prime, 3) - 1)
+            yield None
         for i, (s, e) in enumerate(bounds):
-            if i == 0 and len(bounds) > 1:
-                issue(1)
+            if i == 0:
+                issue_upto(1)
             x16, rb, keep, ev, key = ready.pop(i)
             cur.wait_event(ev)
 
@@ -204,8 +216,7 @@ class GalleryEvaluator:
             yield s, e, x16, rb, release
             # chunk i's kernels are enqueued by now: only then spend host time (batched copy setup,
             # optional fp16 rounding) on chunk i + 2, so the device never waits for the host
-            if i >= 0 and i + 2 < len(bounds):
-                issue(i + 2)
+            issue_upto(i + 2)
 
     # ---- stages -----------------------------------------------------------------------------------
     def encode_queries(self, frame_feats, frame_mask):
@@ -228,17 +239,26 @@ class GalleryEvaluator:
                     gram=torch.empty((n * cfg.L_M, cfg.XPOOL_G_COLS), dtype=torch.float16, device=dev),
                     bits=torch.empty((n, 4), dtype=torch.int32, device=dev))
 
-    def encode_gallery(self, segment_feats, segment_mask, on_chunk=None):
+    def start_gallery(self, segment_feats, segment_mask, prime: int = 0):
+        """Allocate the gallery and set up its ingest; prime > 0 queues the first chunks' host->device copies (and
+        their ingest kernels) right away.  Returns what `encode_gallery(..., started=...)` continues from."""
+        gal = self.new_gallery(segment_feats.shape[0])
+        mask_d = self._to_dev(segment_mask).to(torch.float32)
+        gal["mask"] = mask_d
+        it = self._ingest_iter(_lib.MUSIC, segment_feats, mask_d, self.music_chunk, segment_mask,
+                               taper_head=prime > 0, taper_tail=True, prime=prime)
+        if prime > 0:
+            next(it)
+        return gal, it
+
+    def encode_gallery(self, segment_feats, segment_mask, on_chunk=None, started=None):
         """Encode the gallery chunk by chunk; `on_chunk(gal, s, e)` runs right after chunk [s,e) has
         its encoded segments and X-Pool operands enqueued (used to score / detect while later chunks
         are still being ingested)."""
-        n = segment_feats.shape[0]
         L = cfg.L_M
-        gal = self.new_gallery(n)
-        mask_d = self._to_dev(segment_mask).to(torch.float32)
-        gal["mask"] = mask_d
-        for s, e, x16, rb, release in self._ingest_iter(_lib.MUSIC, segment_feats, mask_d, self.music_chunk,
-                                                        segment_mask, taper_tail=True):
+        gal, it = started if started is not None else self.start_gallery(segment_feats, segment_mask)
+        mask_d = gal["mask"]
+        for s, e, x16, rb, release in it:
             self.eng.encode(_lib.MUSIC, x16, mask_d[s:e], want_f32=False, ragged=rb,
                             out=(gal["seq"][s:e], gal["pooled"][s:e]))
             release()
@@ -375,6 +395,15 @@ class GalleryEvaluator:
         else:                         # per-track ground truth (synthetic sets): query i <-> track gt_col[i]
             gt_moment_q = self._to_dev(tracks["gt_moment"])[idx64]
             m_dur_q = self._to_dev(tracks["m_duration"])[idx64]
+        # Host inputs through the copy engines: the queries' copies are 2000 small entries (47 KB per video) whose
+        # submission, not the link, bounds the first milliseconds of the step.  The head of the gallery (three tapered
+        # chunks, ~1.5 ms of link time in ~440 large entries) is queued on the copy engine FIRST, so the link is busy
+        # while the host submits the queries' entries; the kernels keep their order (queries, then gallery chunks).
+        # MADE_PRIME_GALLERY=0 = the A/B switch.  Results do not depend on it (chunking is invisible, tests).
+        seg = tracks["segment_feats"]
+        prime = 3 if (on_host and not seg.is_cuda and self.h2d_mode in ("dma", "dma16") and
+                      os.environ.get("MADE_PRIME_GALLERY", "1") != "0") else 0
+        started = self.start_gallery(seg, tracks["segment_mask"], prime) if prime else None
         frame_seq, video_feats, frame_mask = self.encode_queries(videos["frame_feats"], videos["frame_mask"])
         qprep = self.eng.query_prepare(video_feats)
         self._count("query_prepare")
@@ -387,7 +416,7 @@ class GalleryEvaluator:
             if "det" not in state and last_needed < e:
                 state["det"] = self.detect(frame_seq, frame_mask, gal, video_feats, gt_col_d, gt_moment_q, m_dur_q)
 
-        gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_chunk)
+        gal = self.encode_gallery(tracks["segment_feats"], tracks["segment_mask"], on_chunk, started=started)
         rk = ops.rank_topk(single, dual, gt_col_d, prev_d, k=self.k)
         self._count("rank")
         self.join_detect()

@@ -727,10 +727,16 @@ def test_whole_job_from_pinned_host_buffers_matches_device_resident(dev, engine)
     a = ev.run({k: t.to(dev) for k, t in v.items()}, {k: t.to(dev) for k, t in m.items()}, gt.to(dev))
     hv = {k: t.pin_memory() for k, t in v.items()}
     hm = {k: t.pin_memory() for k, t in m.items()}
-    b = ev.to_host(ev.run(hv, hm, gt, on_host=True))
-    assert ev.launches > 0
-    for k in ("rank", "topk_idx", "iou", "pred_st", "pred_ed", "score"):
-        assert torch.equal(a[k].cpu(), b[k]), k
+    # default: the head of the gallery is queued on the copy engine before the queries' copies; "0": queries first
+    for prime in ("1", "0"):
+        os.environ["MADE_PRIME_GALLERY"] = prime
+        try:
+            b = ev.to_host(ev.run(hv, hm, gt, on_host=True))
+        finally:
+            os.environ.pop("MADE_PRIME_GALLERY")
+        assert ev.launches > 0
+        for k in ("rank", "topk_idx", "iou", "pred_st", "pred_ed", "score"):
+            assert torch.equal(a[k].cpu(), b[k]), (prime, k)
 
 
 def test_full_size_job_properties(dev, engine, sd_fp32):
