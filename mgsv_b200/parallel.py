@@ -205,10 +205,17 @@ class ShardedEvaluator:
         perm_d = torch.from_numpy(perm).to(dev, non_blocking=True)
         prev_d = None if prev_local is None else torch.from_numpy(prev_local).to(dev, non_blocking=True)
         gt = torch.from_numpy(gt_last).to(dev, non_blocking=True).to(torch.int32)
+        # host inputs: the head of the gallery shard goes to the copy engine before the queries' many small copies
+        # (GalleryEvaluator.run, same switch)
+        seg = tracks["segment_feats"]
+        prime = 3 if (on_host and dev.type == "cuda" and not seg.is_cuda and ev.h2d_mode in ("dma", "dma16") and
+                      os.environ.get("MADE_PRIME_GALLERY", "1") != "0") else 0
+        started = ev.start_gallery(seg, tracks["segment_mask"], prime) if prime else None
         frame_seq, vf_local, frame_mask = ev.encode_queries(videos["frame_feats"], videos["frame_mask"])
         video_feats = self._all_gather_cat(vf_local, q_sizes)                      # exchange 1
         mark("plan+encode_queries+all_gather_q")
-        gal = ev.encode_gallery(tracks["segment_feats"], tracks["segment_mask"])
+        gal = ev.encode_gallery(seg, tracks["segment_mask"], started=started) if started is not None else \
+            ev.encode_gallery(seg, tracks["segment_mask"])
         mark("encode_gallery")
         # ---- exchange 2: every query's paired track -> the rank that detects it, one packed byte row per pair ----
         gtm = tracks["gt_moment"].to(dev, non_blocking=True).reshape(-1, 2).to(torch.float32)
