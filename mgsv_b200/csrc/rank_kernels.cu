@@ -449,9 +449,12 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   const int nc = static_cast<int>(n_cols);
   const int nv = nc >> 2;                      // the row as 16-byte words of four keys (the staging buffer is 16-byte aligned)
   const uint4* cache4 = reinterpret_cast<const uint4*>(cache);
-  auto take = [&](int j) {                     // a top-k candidate: its exact fp64 key, fetched from L2
+  // a top-k candidate: only its column is recorded here.  The exact fp64 keys are fetched (L2) by order_and_write, one
+  // candidate per thread in ONE round trip: fetched here, a thread with three candidates spent three dependent round
+  // trips on them while the other 255 waited at the barrier behind the sweep.
+  auto take = [&](int j) {
     const int slot = atomicAdd(&sm.count, 1);
-    if (slot < kMaxCand) { sm.sel_keys[slot] = rv.key(j); sm.sel_idx[slot] = j; }
+    if (slot < kMaxCand) sm.sel_idx[slot] = j;
   };
   constexpr std::true_type kYes{};
   constexpr std::false_type kNo{};
@@ -527,6 +530,8 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
   // score difference below 1e-6) recounts with the full keys and the column tie rule.  Two barriers instead of the
   // 28 dependent compare-exchange steps of a 128-element bitonic sort (a quarter of the kernel on long rows).
   auto order_and_write = [&](int n_cand) {
+    for (int t = threadIdx.x; t < n_cand; t += kRankThreads) sm.sel_keys[t] = rv.key(sm.sel_idx[t]);
+    __syncthreads();
     int n_pow = 32;
     while (n_pow < n_cand) n_pow <<= 1;
     const int parts = n_pow <= kRankThreads ? kRankThreads / n_pow : 1;   // n_pow >= 32: the lanes of a warp share one part
