@@ -514,13 +514,16 @@ rank_topk_staged_kernel(const float* __restrict__ single, const float* __restric
       }
     }
     if (do_rank) {
-      cnt = block_sum_int(cnt, sm.red);   // its barriers also publish the candidates
-      if (threadIdx.x == 0) {
-        rank_out[row] = cnt;
-        if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
-      }
-    } else {
-      __syncthreads();
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) sm.red[warp] = cnt;
+    }
+    __syncthreads();                        // ONE barrier publishes the candidates and the warps' counts
+    if (do_rank && threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kRankThreads / 32; ++w) tot += sm.red[w];
+      rank_out[row] = tot;
+      if (gt_score_out) gt_score_out[row] = gk ? key_f64(gk) : -INFINITY;
     }
   };
   // Order the n_cand <= kMaxCand gathered candidates (score descending, lower column first) and write the best kk: every
