@@ -1,7 +1,9 @@
 """CPU tests: host logic, ABI surface, metric bookkeeping (no CUDA compute calls)."""
 import ctypes
+import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -309,3 +311,24 @@ def test_hungarian_matcher_mirror_host_logic(monkeypatch):
         assert res[b][0].tolist() == r.tolist() and res[b][1].tolist() == c.tolist()
         assert res[b][0].dtype == torch.int64
         col += n
+
+
+def test_step_dram_record_is_reproducible_from_the_committed_launch_list():
+    """`bench.py` copies the newest profiles/*_step_dram.json into its roofline record (`hbm_view`); that file must be
+    what scripts/step_dram.py makes of the committed ncu launch list it names."""
+    import subprocess
+    prof = os.path.join(REPO, "profiles")
+    newest = sorted(f for f in os.listdir(prof) if f.endswith("_step_dram.json"))[-1]
+    rec = json.load(open(os.path.join(prof, newest)))
+    src = rec["source"].split(" ")[0]
+    assert os.path.exists(os.path.join(REPO, src)), src
+    out = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "step_dram.py"), os.path.join(REPO, src)],
+                         capture_output=True, text=True, check=True).stdout
+    again = json.loads(out)
+    for key in ("step_launches", "step_kernel_us", "step_dram_bytes"):
+        assert again[key] == pytest.approx(rec[key]), key
+    assert again["gemm_family"]["launches"] == rec["gemm_family"]["launches"]
+    assert again["gemm_family"]["us"] == pytest.approx(rec["gemm_family"]["us"])
+    # the family is the step's largest share, and the step is one whole job: its last launch is the rank / top-k kernel
+    assert 0.4 < again["gemm_family"]["us"] / again["step_kernel_us"] < 0.7
+    assert any(k.startswith("rank_topk_staged_kernel") for k in again["per_kernel"])
