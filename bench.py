@@ -59,8 +59,9 @@ def parse():
     ap.add_argument("--tracks", type=int, default=N_TRACKS)
     ap.add_argument("--chunk", type=int, default=2000, help="tracks / videos per ingest+encode chunk (device-resident steps; "
                     "2000: 6 - 7 waves of 128-row tiles per GEMM launch, half the launches of 1000)")
-    ap.add_argument("--e2e-chunk", type=int, default=500, help="chunk size of the host-input (e2e) steps: the e2e step is "
-                    "PCIe bound, and smaller chunks shorten the fill / drain of the copy-compute pipeline")
+    ap.add_argument("--e2e-chunk", type=int, default=768, help="chunk size of the host-input (e2e) steps: the e2e step is "
+                    "PCIe bound, and smaller chunks shorten the fill / drain of the copy-compute pipeline (measured with "
+                    "the gallery-first copy order, ms per step: 256 15.6, 384 15.6, 512 14.9, 768 14.7, 1000 15.6)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1 only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--detect-topk", type=int, default=5, help="N = 1: also time retrieve-then-detect (DETR on the k best "

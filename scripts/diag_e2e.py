@@ -13,9 +13,12 @@ hv = {k: v[k].contiguous().pin_memory() for k in ("frame_feats", "frame_mask")}
 hm = {k: m[k].contiguous().pin_memory() for k in ("segment_feats", "segment_mask", "gt_moment", "m_duration")}
 gt = torch.arange(nq, dtype=torch.int32)
 eng = Engine(dev); eng.load_state_dict(synth.make_state_dict(0))
-for mode in sys.argv[1:] or ["dma", "zerocopy"]:
-    ev = GalleryEvaluator(eng, k=100, music_chunk=512, video_chunk=512)
+# MADE_DIAG_CHUNKS=384,512,1000: sweep the ingest chunk size (tracks / videos per host->device copy + encode chunk)
+chunks = [int(c) for c in os.environ.get("MADE_DIAG_CHUNKS", "512").split(",")]
+for mode, chunk in [(mo, c) for mo in (sys.argv[1:] or ["dma", "zerocopy"]) for c in chunks]:
+    ev = GalleryEvaluator(eng, k=100, music_chunk=chunk, video_chunk=chunk)
     ev.h2d_mode = mode
+    mode = f"{mode} chunk {chunk}"
     ts = []
     for it in range(30):
         t0 = time.perf_counter()
