@@ -539,7 +539,10 @@ def main():
             else:
                 out = ev_e2e.run(host_v, host_m, gt_col, on_host=True)
             return ev_e2e.to_host(out)
-        ms_e2e, wall_e2e, med_e2e, max_e2e, _ = timed(step_e2e, True, args.steps, 3)
+        # the first steps of a process run 0.3 - 0.6 ms slow (staging buffers, pinned pages, allocator pools): 10 untimed
+        # warm-up steps instead of 3 (scripts/diag_e2e.py: 15.5 15.2 15.2 14.9 14.9 ... per step)
+        e2e_warm = max(args.warmup, 10)
+        ms_e2e, wall_e2e, med_e2e, max_e2e, _ = timed(step_e2e, True, args.steps, e2e_warm)
         ev.h2d_mode = ev_e2e.h2d_mode
         # every host-input step ends with a synchronous device->host read, so its wall time is its
         # end-to-end time: median and max are reported beside the mean
@@ -558,7 +561,7 @@ def main():
         e2e = {"value": nq_total / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                "statistic": "K back-to-back steps between CUDA events (each step ends with its device->host read)",
                "ms_per_step_median": med_e2e, "ms_per_step_max": max_e2e, "host_jitter_seen": bool(jitter),
-               "wall_ms_per_step": wall_e2e,
+               "wall_ms_per_step": wall_e2e, "warmup_steps": e2e_warm,
                "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[2].item()),
                "h2d_bytes_if_padded_rows_were_copied": int(tot[1].item()),
                "h2d_link_gbs_measured": link_gbs, "h2d_mode": ev.h2d_mode, "chunk": args.e2e_chunk,

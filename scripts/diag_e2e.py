@@ -20,11 +20,14 @@ for mode, chunk in [(mo, c) for mo in (sys.argv[1:] or ["dma", "zerocopy"]) for 
     ev.h2d_mode = mode
     mode = f"{mode} chunk {chunk}"
     ts = []
-    for it in range(30):
+    for it in range(int(os.environ.get("MADE_DIAG_STEPS", "30"))):
         t0 = time.perf_counter()
         out = ev.to_host(ev.run(hv, hm, gt, on_host=True))
         ts.append(1e3 * (time.perf_counter() - t0))
     print(mode, " ".join(f"{t:.1f}" for t in ts), flush=True)
+    tt = sorted(ts[6:])
+    print(mode, f"after 6 warm-up steps: mean {sum(tt) / len(tt):.2f} median {tt[len(tt) // 2]:.2f} max {tt[-1]:.2f} "
+                f"steps above 1.05 x median: {sum(1 for t in tt if t > 1.05 * tt[len(tt) // 2])} of {len(tt)}", flush=True)
     # CPU-side enqueue cost of one step (no sync until the end)
     torch.cuda.synchronize()
     t0 = time.perf_counter(); o = ev.run(hv, hm, gt, on_host=True); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
